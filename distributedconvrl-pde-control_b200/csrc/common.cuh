@@ -1,0 +1,87 @@
+// Shared device-side helpers for the pdeb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pdeb200 {
+
+template <typename T> struct V2;
+template <> struct V2<float>  { using type = float2;  static __host__ __device__ float2  make(float a, float b)   { return make_float2(a, b); } };
+template <> struct V2<double> { using type = double2; static __host__ __device__ double2 make(double a, double b) { return make_double2(a, b); } };
+
+constexpr int kMaxLayers = 4;       // Dense layers per network (reference uses 2 or 3)
+constexpr int kFusedActorMaxWidth = 64;
+
+// Sparse (ELL) gather table: row i = sum_j w[j][i] * x[idx[j][i]], j < nnz_max.
+// j-major so that threads owning consecutive rows read consecutive addresses.
+// Padding entries have w = 0 and idx = a valid index.
+template <typename T>
+struct EllTable {
+    const int* idx;
+    const T* w;
+    int nnz_max;
+    int n_rows;
+};
+
+// A Flux Chain of Dense layers, float32, device resident.
+// params: per layer W (column-major (out,in), i.e. W[o + out*i]) then b (out).
+struct NetDev {
+    const float* params;
+    int n_layers;
+    int sizes[kMaxLayers + 1];
+    int acts[kMaxLayers];
+    int offs[kMaxLayers];           // offset of layer l's W in params
+};
+
+__device__ __forceinline__ float act_apply(int kind, float v) {
+    if (kind == 1) return v > 0.f ? v : 0.f;         // relu
+    if (kind == 2) return tanhf(v);                  // tanh
+    return v;
+}
+
+// Per-column MLP forward in registers/local memory (actor widths <= kFusedActorMaxWidth).
+// x: in/out scratch of size kFusedActorMaxWidth (input in x[0..sizes[0])).
+// Restates Flux Dense: y = act.(W*x .+ b)   (src/PDEagent.jl:18-30).
+__device__ __forceinline__ void mlp_forward_small(const NetDev& net, float* x, float* h) {
+    float* in = x;
+    float* out = h;
+    for (int l = 0; l < net.n_layers; ++l) {
+        const int ni = net.sizes[l], no = net.sizes[l + 1];
+        const float* W = net.params + net.offs[l];
+        const float* b = W + ni * no;
+        for (int o = 0; o < no; ++o) {
+            float acc = 0.f;
+            for (int i = 0; i < ni; ++i) acc = fmaf(__ldg(W + o + no * i), in[i], acc);
+            out[o] = act_apply(net.acts[l], acc + __ldg(b + o));
+        }
+        float* tmp = in; in = out; out = tmp;
+    }
+    if (in != x) {
+        const int no = net.sizes[net.n_layers];
+        for (int o = 0; o < no; ++o) x[o] = in[o];
+    }
+}
+
+template <typename T> __device__ __forceinline__ T pow_t(T a, T b);
+template <> __device__ __forceinline__ float  pow_t<float>(float a, float b)    { return powf(a, b); }
+template <> __device__ __forceinline__ double pow_t<double>(double a, double b) { return pow(a, b); }
+
+template <typename T> __device__ __forceinline__ T clamp_t(T v, T lim) { return v < -lim ? -lim : (v > lim ? lim : v); }
+
+// Parameters shared by every environment kernel (KS / KSeg / NS): observation and
+// reward assembly restating featurize / reward_function of the setup files.
+template <typename T>
+struct ObsRewardParams {
+    int n_sensors, n_act, fields;         // fields: 1 (KS, NS) or 2 (KSeg u,v)
+    int window, temporal, memory, a_rows; // a_rows = 1 + memory
+    int obs_rows;                         // ns
+    int mono;
+    int spa;                              // NS: sensors per axis (2-D window), 0 for 1-D
+    int check_max;
+    T obs_scale, r_gain, r_pow, r_div, r_offset, a_pun, da_pun, max_value;
+    double dt, te;
+    const int* a2s;                       // [n_act], 0-based
+    const T* sens_sum;                    // [n_sensors] sum of each sensor basis (for r_offset)
+};
+
+}  // namespace pdeb200

@@ -1,0 +1,138 @@
+// Host-side context shared by the translation units of libpdeb200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/pdeb200.h"
+#include "common.cuh"
+
+namespace pdeb200 {
+
+struct HostNet {
+    int n_layers = 0;
+    int sizes[kMaxLayers + 1] = {0};
+    int acts[kMaxLayers] = {0};
+    int offs[kMaxLayers] = {0};
+    int n_params = 0;
+    float* d_params = nullptr;      // weights
+    float* d_m = nullptr;           // ADAM first moment
+    float* d_v = nullptr;           // ADAM second moment
+    double beta_p[2] = {0.9, 0.999};  // running beta powers (Flux ADAM state `βp`)
+    NetDev dev() const {
+        NetDev n;
+        n.params = d_params; n.n_layers = n_layers;
+        for (int i = 0; i <= kMaxLayers; ++i) n.sizes[i] = sizes[i];
+        for (int i = 0; i < kMaxLayers; ++i) { n.acts[i] = acts[i]; n.offs[i] = offs[i]; }
+        return n;
+    }
+};
+
+struct EllHost {
+    int* d_idx = nullptr;
+    void* d_w = nullptr;
+    int nnz_max = 0, n_rows = 0;
+};
+
+}  // namespace pdeb200
+
+struct pdeb200_ctx {
+    pdeb200_config cfg;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    mutable std::string err;
+    size_t esz = 8;                 // sizeof(T)
+    int npts = 0;                   // grid points per field
+    int y_elems = 0;                // scalars of T per environment in env.y
+    int p_elems = 0;                // scalars of T per environment in env.p
+    int fields = 1;
+    int obs_rows = 0, n_cols = 0, a_rows = 1, n_rew = 0, wrows = 1;
+    int64_t launches = 0;
+    bool bases_set = false, y0_set = false;
+
+    // environment arrays
+    void *y = nullptr, *y0 = nullptr, *p = nullptr, *state = nullptr, *action = nullptr, *action_in = nullptr,
+         *delta_action = nullptr, *reward = nullptr, *sensors = nullptr;
+    uint8_t* done = nullptr; double* time = nullptr; int* steps = nullptr;
+    uint8_t* d_mask = nullptr; double* d_rsum = nullptr; void* d_noise = nullptr;
+
+    // bases
+    pdeb200::EllHost sens, actT;
+    int* d_a2s = nullptr; void* d_sens_sum = nullptr;
+
+    // KS spectral constants
+    int N1 = 0, N2 = 0;
+    void *tw12 = nullptr, *tw21 = nullptr, *c1 = nullptr, *cN = nullptr, *ainvh = nullptr, *hm = nullptr;
+
+    // problem-specific opaque state (KSeg / NS translation units)
+    void* prob = nullptr;
+
+    // networks + replay + ddpg
+    pdeb200::HostNet nets[4];
+    float* d_grads = nullptr; int n_grads = 0; float* d_losses = nullptr;
+    void* agent = nullptr;
+
+    // timing
+    bool timing = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
+};
+
+namespace pdeb200 {
+
+extern thread_local std::string g_last_error;
+
+inline int32_t fail(const pdeb200_ctx* c, int32_t code, const std::string& msg) {
+    if (c) c->err = msg;
+    g_last_error = msg;
+    return code;
+}
+
+#define PDEB_CUDA(ctx, expr)                                                                         \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess)                                                                      \
+            return pdeb200::fail(ctx, PDEB200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+template <typename T> struct DT;
+template <> struct DT<float>  { static constexpr int id = PDEB200_F32; };
+template <> struct DT<double> { static constexpr int id = PDEB200_F64; };
+
+template <typename T>
+inline ObsRewardParams<T> make_obs_params(const pdeb200_ctx* c) {
+    ObsRewardParams<T> P;
+    const pdeb200_config& g = c->cfg;
+    P.n_sensors = g.n_sensors; P.n_act = g.n_actuators; P.fields = c->fields;
+    P.window = g.window_size; P.temporal = g.temporal_steps; P.memory = g.memory_size; P.a_rows = c->a_rows;
+    P.obs_rows = c->obs_rows; P.mono = g.mono; P.spa = (g.problem == PDEB200_NS2D) ? g.sensors_per_axis : 0;
+    P.check_max = g.check_max_value;
+    P.obs_scale = (T)g.obs_scale; P.r_gain = (T)g.reward_gain; P.r_pow = (T)g.reward_pow; P.r_div = (T)g.reward_div;
+    P.r_offset = (T)g.reward_offset; P.a_pun = (T)g.action_punish; P.da_pun = (T)g.delta_action_punish;
+    P.max_value = (T)g.max_value; P.dt = g.dt; P.te = g.te;
+    P.a2s = c->d_a2s; P.sens_sum = (const T*)c->d_sens_sum;
+    return P;
+}
+
+// problem back-ends (one translation unit each)
+int32_t ks_setup(pdeb200_ctx* c);
+int32_t ks_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum);
+int32_t ks_cost(const pdeb200_ctx* c, double* bytes, double* flops);
+void ks_free(pdeb200_ctx* c);
+
+int32_t kseg_setup(pdeb200_ctx* c);
+int32_t kseg_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum);
+int32_t kseg_cost(const pdeb200_ctx* c, double* bytes, double* flops);
+void kseg_free(pdeb200_ctx* c);
+
+int32_t ns_setup(pdeb200_ctx* c);
+int32_t ns_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum);
+int32_t ns_featurize_reset(pdeb200_ctx* c, const uint8_t* d_mask);
+int32_t ns_cost(const pdeb200_ctx* c, double* bytes, double* flops);
+void ns_free(pdeb200_ctx* c);
+
+void agent_free(pdeb200_ctx* c);
+
+}  // namespace pdeb200

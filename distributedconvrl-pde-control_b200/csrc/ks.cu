@@ -1,0 +1,175 @@
+// KS back-end: spectral constant tables + launch dispatch for ks_step_kernel.
+#include <cmath>
+#include <vector>
+
+#include "ctx.hpp"
+#include "ks_step.cuh"
+
+namespace pdeb200 {
+
+namespace {
+
+struct Fact { int n, n1, n2; };
+// N = N1*N2 four-step factorizations with generated in-register DFTs for both factors.
+const Fact kFacts[] = {{64, 8, 8},     {128, 8, 16},   {192, 12, 16}, {240, 15, 16},
+                       {256, 16, 16},  {320, 16, 20},  {384, 16, 24}, {512, 16, 32},
+                       {600, 24, 25},  {1024, 32, 32}};
+
+template <typename T>
+int32_t upload(pdeb200_ctx* c, void** dst, const std::vector<T>& v) {
+    PDEB_CUDA(c, cudaMalloc(dst, v.size() * sizeof(T)));
+    PDEB_CUDA(c, cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return PDEB200_OK;
+}
+
+template <typename T>
+int32_t setup_t(pdeb200_ctx* c) {
+    using C = typename V2<T>::type;
+    const pdeb200_config& g = c->cfg;
+    const int N = g.nx, N1 = c->N1, N2 = c->N2;
+    const long double two_pi = 6.283185307179586476925286766559L;
+    std::vector<C> t12(N), t21(N);
+    for (int k = 0; k < N1; ++k)
+        for (int t = 0; t < N2; ++t) {
+            long double a = -two_pi * (long double)((long long)k * t % N) / N;
+            t12[k * N2 + t] = V2<T>::make((T)cosl(a), (T)sinl(a));
+        }
+    for (int k = 0; k < N2; ++k)
+        for (int t = 0; t < N1; ++t) {
+            long double a = -two_pi * (long double)((long long)k * t % N) / N;
+            t21[k * N1 + t] = V2<T>::make((T)cosl(a), (T)sinl(a));
+        }
+    // KSSetup.jl:115-119 and :131-135, evaluated in Float64 like the reference.
+    const double h = g.dt / g.oversampling, dt2 = h / 2;
+    std::vector<T> c1(N), cN(N), ah(N);
+    for (int i = 0; i < N; ++i) {
+        double kx = (i < N / 2) ? i : (i == N / 2 ? 0 : i - N);
+        double alpha = 2 * M_PI * kx / g.Lx;
+        double L = alpha * alpha - alpha * alpha * alpha * alpha;
+        double Ainv = 1.0 / (1.0 - dt2 * L);
+        double B = 1.0 + dt2 * L;
+        c1[i] = (T)(Ainv * B);
+        cN[i] = (T)(Ainv * (-0.5 * alpha) / ((double)N * (double)N));
+        ah[i] = (T)(Ainv * h);
+    }
+    int32_t rc;
+    if ((rc = upload<C>(c, &c->tw12, t12))) return rc;
+    if ((rc = upload<C>(c, &c->tw21, t21))) return rc;
+    if ((rc = upload<T>(c, &c->c1, c1))) return rc;
+    if ((rc = upload<T>(c, &c->cN, cN))) return rc;
+    if ((rc = upload<T>(c, &c->ainvh, ah))) return rc;
+    if (g.mu != 0.0) {
+        // h * fft(mu * cos(2 + pi + x/(Lx/2))), KSSetup.jl:155 (quirk Q3), naive DFT in long double
+        std::vector<long double> f(N);
+        const double dx = g.Lx / N;
+        for (int n = 0; n < N; ++n) f[n] = g.mu * std::cos(2 + M_PI + (dx * (n + 1)) / (g.Lx / 2));
+        std::vector<C> hm(N);
+        for (int k = 0; k < N; ++k) {
+            long double sr = 0, si = 0;
+            for (int n = 0; n < N; ++n) {
+                long double a = -two_pi * (long double)((long long)k * n % N) / N;
+                sr += f[n] * cosl(a); si += f[n] * sinl(a);
+            }
+            hm[k] = V2<T>::make((T)(h * sr), (T)(h * si));
+        }
+        if ((rc = upload<C>(c, &c->hm, hm))) return rc;
+    }
+    return PDEB200_OK;
+}
+
+template <typename T, int N1, int N2>
+int32_t launch(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum) {
+    using G = KsGeom<N1, N2>;
+    using C = typename V2<T>::type;
+    constexpr int WARPS = (G::TP == 32) ? 2 : 2;
+    constexpr int PAIRS = WARPS * 32 / G::TP;
+    const pdeb200_config& g = c->cfg;
+    KsArgs<T> A;
+    A.n_envs = g.n_envs; A.S = g.oversampling; A.n_steps = n_steps; A.use_actor = use_actor; A.write_p = 1;
+    A.P = make_obs_params<T>(c);
+    A.tw12 = (const C*)c->tw12; A.tw21 = (const C*)c->tw21;
+    A.c1 = (const T*)c->c1; A.cN = (const T*)c->cN; A.ainvh = (const T*)c->ainvh; A.hm = (const C*)c->hm;
+    const double h = g.dt / g.oversampling;
+    A.dt32 = (T)(3 * h / 2); A.dt2 = (T)(h / 2); A.inv_n = (T)(1.0 / G::N); A.n_scale = (T)G::N;
+    A.power = (T)g.agent_power;
+    A.sens = EllTable<T>{c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows};
+    A.actT = EllTable<T>{c->actT.d_idx, (const T*)c->actT.d_w, c->actT.nnz_max, c->actT.n_rows};
+    A.y = (T*)c->y; A.p = (T*)c->p; A.state = (T*)c->state; A.action = (T*)c->action;
+    A.delta_action = (T*)c->delta_action; A.reward = (T*)c->reward; A.sensors_out = (T*)c->sensors;
+    A.done = c->done; A.time = c->time; A.steps = c->steps;
+    A.actions_in = (const T*)actions_dev;
+    A.actor = c->nets[PDEB200_NET_BEHAVIOR_ACTOR].dev(); A.act_limit = (T)act_limit;
+    A.reward_sum = d_rsum;
+    const int n_pairs = (g.n_envs + 1) / 2;
+    const int grid = (n_pairs + PAIRS - 1) / PAIRS;
+    const size_t smem = ks_smem_bytes<T, N1, N2>(PAIRS, g.n_sensors, g.n_actuators);
+    auto kern = ks_step_kernel<T, N1, N2, WARPS>;
+    static thread_local size_t configured[64] = {0};
+    if (smem > configured[c->device & 63]) {
+        PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[c->device & 63] = smem;
+    }
+    kern<<<grid, WARPS * 32, smem, c->stream>>>(A);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
+template <typename T>
+int32_t dispatch(pdeb200_ctx* c, const void* a, int n, int ua, double lim, double* rs) {
+    switch (c->cfg.nx) {
+        case 64:   return launch<T, 8, 8>(c, a, n, ua, lim, rs);
+        case 128:  return launch<T, 8, 16>(c, a, n, ua, lim, rs);
+        case 192:  return launch<T, 12, 16>(c, a, n, ua, lim, rs);
+        case 240:  return launch<T, 15, 16>(c, a, n, ua, lim, rs);
+        case 256:  return launch<T, 16, 16>(c, a, n, ua, lim, rs);
+        case 320:  return launch<T, 16, 20>(c, a, n, ua, lim, rs);
+        case 384:  return launch<T, 16, 24>(c, a, n, ua, lim, rs);
+        case 512:  return launch<T, 16, 32>(c, a, n, ua, lim, rs);
+        case 600:  return launch<T, 24, 25>(c, a, n, ua, lim, rs);
+        case 1024: return launch<T, 32, 32>(c, a, n, ua, lim, rs);
+    }
+    return fail(c, PDEB200_EUNSUPPORTED, "KS: unsupported nx");
+}
+
+}  // namespace
+
+int32_t ks_setup(pdeb200_ctx* c) {
+    c->N1 = 0;
+    for (const Fact& f : kFacts)
+        if (f.n == c->cfg.nx) { c->N1 = f.n1; c->N2 = f.n2; }
+    if (!c->N1)
+        return fail(c, PDEB200_EUNSUPPORTED,
+                    "KS: nx must be one of 64,128,192,240,256,320,384,512,600,1024 (four-step FFT factor table)");
+    if (c->cfg.oversampling < 1) return fail(c, PDEB200_EINVAL, "KS: oversampling must be >= 1");
+    return c->cfg.dtype == PDEB200_F64 ? setup_t<double>(c) : setup_t<float>(c);
+}
+
+int32_t ks_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum) {
+    return c->cfg.dtype == PDEB200_F64 ? dispatch<double>(c, actions_dev, n_steps, use_actor, act_limit, d_rsum)
+                                       : dispatch<float>(c, actions_dev, n_steps, use_actor, act_limit, d_rsum);
+}
+
+// Algorithmic cost of one env step (SURVEY.md 8d / DESIGN.md):
+//   bytes: y in + y out + action in + obs out + reward out + done
+//   flops: (2S+4) real-data FFTs at 2.5 N log2 N + pointwise + sparse bases
+int32_t ks_cost(const pdeb200_ctx* c, double* bytes, double* flops) {
+    const pdeb200_config& g = c->cfg;
+    const double N = g.nx, S = g.oversampling, w = (double)c->esz;
+    if (bytes) *bytes = 2 * N * w + g.n_actuators * (w * c->a_rows + w * c->obs_rows + w) + 1;
+    if (flops) {
+        const double fft = 2.5 * N * std::log2(N);
+        *flops = (2 * S + 4) * fft + S * 24 * (N / 2 + 1) +
+                 2.0 * (c->sens.nnz_max * (double)g.n_sensors + c->actT.nnz_max * N);
+    }
+    return PDEB200_OK;
+}
+
+void ks_free(pdeb200_ctx* c) {
+    for (void** p : {&c->tw12, &c->tw21, &c->c1, &c->cN, &c->ainvh, &c->hm}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+}
+
+}  // namespace pdeb200

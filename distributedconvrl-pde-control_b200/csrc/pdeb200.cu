@@ -1,0 +1,640 @@
+// libpdeb200.so -- C ABI (include/pdeb200.h): context, constants, environment entry points.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "ctx.hpp"
+#include "obs_reward.cuh"
+
+namespace pdeb200 {
+
+thread_local std::string g_last_error;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// featurize(y0, t0) / reset! for problems whose state is the physical field(s) (KS, KSeg).
+// One CTA per environment.  src/PDEenv.jl:183-193 + the `isnothing(env)` branches of featurize.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void reset_phys_kernel(ObsRewardParams<T> P, EllTable<T> sens, int npts, const T* __restrict__ y0,
+                                  int y0_broadcast, const uint8_t* __restrict__ mask, T* y, T* p, int p_elems,
+                                  T* state, T* action, T* action_in, T* delta_action, T* reward, T* sensors_out,
+                                  uint8_t* done, double* time, int* steps, int n_cols, int n_rew) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_y = reinterpret_cast<T*>(smem_raw);                 // [fields][npts]
+    T* s_sens = s_y + (size_t)P.fields * npts;               // [fields][n_sensors]
+    const int env = blockIdx.x;
+    if (mask && !mask[env]) return;
+    const int ye = P.fields * npts;
+    const T* src = y0 + (y0_broadcast ? 0 : (size_t)env * ye);
+    for (int i = threadIdx.x; i < ye; i += blockDim.x) {
+        const T v = src[i];
+        s_y[i] = v;
+        y[(size_t)env * ye + i] = v;
+    }
+    for (int i = threadIdx.x; i < p_elems; i += blockDim.x) p[(size_t)env * p_elems + i] = T(0);
+    __syncthreads();
+    for (int q = threadIdx.x; q < P.fields * P.n_sensors; q += blockDim.x) {
+        const int f = q / P.n_sensors, i = q % P.n_sensors;
+        T acc = T(0);
+        for (int j = 0; j < sens.nnz_max; ++j)
+            acc += s_y[f * npts + sens.idx[j * P.n_sensors + i]] * sens.w[j * P.n_sensors + i];
+        s_sens[q] = acc;
+        if (sensors_out) sensors_out[(size_t)env * P.fields * P.n_sensors + q] = acc;
+    }
+    __syncthreads();
+    auto sv = [&](int f, int i) { return s_sens[f * P.n_sensors + i]; };
+    if (!P.mono) {
+        for (int c = threadIdx.x; c < P.n_act; c += blockDim.x) {
+            const size_t col = (size_t)env * P.n_act + c;
+            (void)assemble_column<T>(P, sv, c, T(0), T(0), action + col * P.a_rows, state + col * P.obs_rows, true);
+        }
+    } else {
+        T* scol = state + (size_t)env * P.obs_rows;
+        for (int i = threadIdx.x; i < P.n_sensors; i += blockDim.x)
+            for (int k = 0; k < P.temporal; ++k) scol[k * P.n_sensors + i] = s_sens[i] * P.obs_scale;
+        for (int k = threadIdx.x; k < P.memory; k += blockDim.x) scol[P.obs_rows - P.memory + k] = T(0);
+    }
+    const int na = P.n_act * P.a_rows;
+    for (int i = threadIdx.x; i < na; i += blockDim.x) {
+        action[(size_t)env * na + i] = T(0);
+        action_in[(size_t)env * na + i] = T(0);
+        delta_action[(size_t)env * na + i] = T(0);
+    }
+    for (int i = threadIdx.x; i < n_rew; i += blockDim.x) reward[(size_t)env * n_rew + i] = T(0);
+    if (threadIdx.x == 0) { done[env] = 0; time[env] = 0.0; steps[env] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Policy forward: actions = clamp(actor(state) [+ noise * act_noise], +-act_limit)
+// src/PDEagent.jl:189, 201-204.  One thread per column.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
+    const uint64_t p = (uint64_t)a * b; *hi = (uint32_t)(p >> 32); return (uint32_t)p;
+}
+// Philox4x32-10 counter RNG (public algorithm, Salmon et al. 2011) -> two standard normals.
+__device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t ctr, float* n0, float* n1) {
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x9E3779B9u, c3 = 0xBB67AE85u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0, h1;
+        const uint32_t l0 = mulhilo(0xD2511F53u, c0, &h0), l1 = mulhilo(0xCD9E8D57u, c2, &h1);
+        const uint32_t n0_ = h1 ^ c1 ^ k0, n2_ = h0 ^ c3 ^ k1;
+        c0 = n0_; c1 = l1; c2 = n2_; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const float u0 = ((float)c0 + 0.5f) * 2.3283064365386963e-10f;
+    const float u1 = ((float)c1 + 0.5f) * 2.3283064365386963e-10f;
+    const float rad = sqrtf(-2.f * logf(u0));
+    float s, co;
+    sincosf(6.283185307179586f * u1, &s, &co);
+    *n0 = rad * co; *n1 = rad * s;
+}
+
+template <typename T>
+__global__ void policy_kernel(NetDev net, int n_columns, int obs_rows, int a_rows, int memory,
+                              const T* __restrict__ state, T* __restrict__ action_in,
+                              const T* __restrict__ noise, int use_rng, uint64_t seed, uint64_t offset,
+                              T act_noise, T act_limit) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= n_columns) return;
+    float x[kFusedActorMaxWidth], h[kFusedActorMaxWidth];
+    for (int r = 0; r < obs_rows; ++r) x[r] = (float)state[(size_t)col * obs_rows + r];
+    mlp_forward_small(net, x, h);
+    const int n_out = net.sizes[net.n_layers];            // == a_rows (conv agent) or n_act (mono)
+    const int noisy = n_out - memory;
+    for (int r = 0; r < n_out; ++r) {
+        T v = (T)x[r];
+        if (r < noisy) {
+            if (noise) v += noise[(size_t)col * noisy + r] * act_noise;
+            else if (use_rng) {
+                float g0, g1;
+                philox_normal2(seed, offset + (uint64_t)col * noisy + r, &g0, &g1);
+                v += (T)g0 * act_noise;
+            }
+        }
+        action_in[(size_t)col * n_out + r] = clamp_t<T>(v, act_limit);
+    }
+}
+
+template <typename T>
+int32_t build_ell(pdeb200_ctx* c, const std::vector<std::vector<std::pair<int, double>>>& rows, EllHost* out) {
+    int nnz = 1;
+    for (auto& r : rows) nnz = std::max(nnz, (int)r.size());
+    const int n = (int)rows.size();
+    std::vector<int> idx((size_t)nnz * n, 0);
+    std::vector<T> w((size_t)nnz * n, T(0));
+    for (int i = 0; i < n; ++i) {
+        const int pad = rows[i].empty() ? 0 : rows[i][0].first;
+        for (int j = 0; j < nnz; ++j) {
+            if (j < (int)rows[i].size()) { idx[(size_t)j * n + i] = rows[i][j].first; w[(size_t)j * n + i] = (T)rows[i][j].second; }
+            else idx[(size_t)j * n + i] = pad;
+        }
+    }
+    if (out->d_idx) cudaFree(out->d_idx);
+    if (out->d_w) cudaFree(out->d_w);
+    PDEB_CUDA(c, cudaMalloc(&out->d_idx, idx.size() * sizeof(int)));
+    PDEB_CUDA(c, cudaMalloc(&out->d_w, w.size() * sizeof(T)));
+    PDEB_CUDA(c, cudaMemcpy(out->d_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    PDEB_CUDA(c, cudaMemcpy(out->d_w, w.data(), w.size() * sizeof(T), cudaMemcpyHostToDevice));
+    out->nnz_max = nnz; out->n_rows = n;
+    return PDEB200_OK;
+}
+
+template <typename T>
+int32_t set_bases_t(pdeb200_ctx* c, const double* sb, const double* ab, const int32_t* a2s, double tol) {
+    const pdeb200_config& g = c->cfg;
+    const int np = c->npts;
+    std::vector<std::vector<std::pair<int, double>>> srows(g.n_sensors), arows(np);
+    std::vector<T> ssum(g.n_sensors);
+    for (int i = 0; i < g.n_sensors; ++i) {
+        double mx = 0, sum = 0;
+        for (int n = 0; n < np; ++n) { mx = std::max(mx, std::fabs(sb[(size_t)i * np + n])); sum += sb[(size_t)i * np + n]; }
+        ssum[i] = (T)sum;
+        for (int n = 0; n < np; ++n) {
+            const double w = sb[(size_t)i * np + n];
+            if (w != 0.0 && std::fabs(w) > tol * mx) srows[i].push_back({n, w});
+        }
+    }
+    for (int i = 0; i < g.n_actuators; ++i) {
+        double mx = 0;
+        for (int n = 0; n < np; ++n) mx = std::max(mx, std::fabs(ab[(size_t)i * np + n]));
+        for (int n = 0; n < np; ++n) {
+            const double w = ab[(size_t)i * np + n];
+            if (w != 0.0 && std::fabs(w) > tol * mx) arows[n].push_back({i, w});   // ascending actuator index
+        }
+    }
+    int32_t rc;
+    if ((rc = build_ell<T>(c, srows, &c->sens))) return rc;
+    if ((rc = build_ell<T>(c, arows, &c->actT))) return rc;
+    std::vector<int> a(g.n_actuators);
+    for (int i = 0; i < g.n_actuators; ++i) {
+        if (a2s[i] < 0 || a2s[i] >= g.n_sensors) return fail(c, PDEB200_EINVAL, "set_bases: a2s out of range (0-based)");
+        a[i] = a2s[i];
+    }
+    PDEB_CUDA(c, cudaMemcpy(c->d_a2s, a.data(), a.size() * sizeof(int), cudaMemcpyHostToDevice));
+    PDEB_CUDA(c, cudaMemcpy(c->d_sens_sum, ssum.data(), ssum.size() * sizeof(T), cudaMemcpyHostToDevice));
+    c->bases_set = true;
+    return PDEB200_OK;
+}
+
+template <typename T>
+int32_t reset_t(pdeb200_ctx* c, const uint8_t* d_mask) {
+    if (c->cfg.problem == PDEB200_NS2D) return ns_featurize_reset(c, d_mask);
+    const size_t smem = ((size_t)c->fields * c->npts + (size_t)c->fields * c->cfg.n_sensors) * sizeof(T);
+    if (smem > 48 * 1024)
+        PDEB_CUDA(c, cudaFuncSetAttribute(reset_phys_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    reset_phys_kernel<T><<<c->cfg.n_envs, 128, smem, c->stream>>>(
+        make_obs_params<T>(c), EllTable<T>{c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows},
+        c->npts, (const T*)c->y0, 0, d_mask, (T*)c->y, (T*)c->p, c->p_elems, (T*)c->state, (T*)c->action,
+        (T*)c->action_in, (T*)c->delta_action, (T*)c->reward, (T*)c->sensors, c->done, c->time, c->steps, c->n_cols,
+        c->n_rew);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
+int32_t do_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum) {
+    if (!c->bases_set) return fail(c, PDEB200_ESTATE, "step: call pdeb200_set_bases first");
+    if (!c->y0_set) return fail(c, PDEB200_ESTATE, "step: call pdeb200_set_y0 + pdeb200_reset first");
+    if (use_actor) {
+        const HostNet& a = c->nets[PDEB200_NET_BEHAVIOR_ACTOR];
+        if (!a.n_layers) return fail(c, PDEB200_ESTATE, "rollout: behavior actor not set");
+        for (int l = 0; l <= a.n_layers; ++l)
+            if (a.sizes[l] > kFusedActorMaxWidth) return fail(c, PDEB200_EUNSUPPORTED, "fused actor: layer wider than 64");
+    }
+    if (c->timing) cudaEventRecord(c->ev0, c->stream);
+    int32_t rc;
+    switch (c->cfg.problem) {
+        case PDEB200_KS: rc = ks_step(c, actions_dev, n_steps, use_actor, act_limit, d_rsum); break;
+        case PDEB200_KSEG1D: rc = kseg_step(c, actions_dev, n_steps, use_actor, act_limit, d_rsum); break;
+        case PDEB200_NS2D: rc = ns_step(c, actions_dev, n_steps, use_actor, act_limit, d_rsum); break;
+        default: rc = fail(c, PDEB200_EINVAL, "bad problem");
+    }
+    if (c->timing) { cudaEventRecord(c->ev1, c->stream); c->timed = true; }
+    return rc;
+}
+
+struct ArrInfo { void* ptr; size_t bytes; };
+ArrInfo arr_info(pdeb200_ctx* c, int which) {
+    const size_t B = c->cfg.n_envs, e = c->esz;
+    switch (which) {
+        case PDEB200_ARR_Y: return {c->y, B * c->y_elems * e};
+        case PDEB200_ARR_Y0: return {c->y0, B * c->y_elems * e};
+        case PDEB200_ARR_P: return {c->p, B * c->p_elems * e};
+        case PDEB200_ARR_STATE: return {c->state, B * c->n_cols * c->obs_rows * e};
+        case PDEB200_ARR_ACTION: return {c->action, B * c->cfg.n_actuators * c->a_rows * e};
+        case PDEB200_ARR_DELTA_ACTION: return {c->delta_action, B * c->cfg.n_actuators * c->a_rows * e};
+        case PDEB200_ARR_REWARD: return {c->reward, B * c->n_rew * e};
+        case PDEB200_ARR_DONE: return {c->done, B};
+        case PDEB200_ARR_TIME: return {c->time, B * sizeof(double)};
+        case PDEB200_ARR_STEPS: return {c->steps, B * sizeof(int)};
+        case PDEB200_ARR_GRADS: return {c->d_grads, (size_t)c->n_grads * sizeof(float)};
+        case PDEB200_ARR_LOSSES: return {c->d_losses, 2 * sizeof(float)};
+        case PDEB200_ARR_SENSORS: return {c->sensors, B * c->fields * c->cfg.n_sensors * e};
+    }
+    return {nullptr, 0};
+}
+
+}  // namespace
+}  // namespace pdeb200
+
+using namespace pdeb200;
+
+extern "C" {
+
+int32_t pdeb200_abi_version(void) { return PDEB200_ABI_VERSION; }
+
+int32_t pdeb200_default_config(int32_t problem, pdeb200_config* cfg) {
+    if (!cfg) return fail(nullptr, PDEB200_EINVAL, "default_config: null cfg");
+    std::memset(cfg, 0, sizeof(*cfg));
+    cfg->struct_size = (int32_t)sizeof(pdeb200_config);
+    cfg->problem = problem; cfg->dtype = PDEB200_F64; cfg->ny = 1; cfg->n_envs = 1;
+    cfg->temporal_steps = 1; cfg->memory_size = 0; cfg->mono = 0; cfg->ifpad = 1;
+    cfg->Ly = 1.0; cfg->t0 = 0.0;
+    switch (problem) {
+        case PDEB200_KS:          // scripts/KS/setup/KSSetup.jl:20-51, 162-184, 201
+            cfg->nx = 240; cfg->Lx = 200.0; cfg->dt = 0.1; cfg->te = 5.0; cfg->oversampling = 30;
+            cfg->window_size = 1; cfg->check_max_value = PDEB200_CHECK_Y; cfg->max_value = 30.0;
+            cfg->agent_power = 7.5; cfg->obs_scale = 1.0 / 30.0; cfg->reward_gain = 6.0; cfg->reward_pow = 1.3;
+            cfg->reward_div = 90.0; cfg->reward_offset = 0.0; cfg->action_punish = 0.002; cfg->delta_action_punish = 0.002;
+            break;
+        case PDEB200_KSEG1D:      // scripts/Keller-Segel/setup/KellerSegelSetup.jl:26-57, 241-263, 276
+            cfg->nx = 100; cfg->Lx = 10.0; cfg->dt = 0.006; cfg->te = 8.0; cfg->oversampling = 8;
+            cfg->window_size = 3; cfg->temporal_steps = 2; cfg->check_max_value = PDEB200_CHECK_Y; cfg->max_value = 20.0;
+            cfg->agent_power = 10.0; cfg->obs_scale = 0.25; cfg->reward_gain = 1.0; cfg->reward_pow = 2.0;
+            cfg->reward_div = 800.0; cfg->reward_offset = 1.0; cfg->action_punish = 0.0; cfg->delta_action_punish = 0.0;
+            break;
+        case PDEB200_NS2D:        // scripts/Fluid/setup/FluidSetup.jl:28-77, 188-217
+            cfg->nx = 128; cfg->ny = 128; cfg->Lx = 1.0; cfg->Ly = 1.0; cfg->dt = 0.02; cfg->te = 6.0;
+            cfg->oversampling = 40; cfg->nu = 0.00005; cfg->window_size = 3; cfg->sensors_per_axis = 16;
+            cfg->check_max_value = PDEB200_CHECK_REWARD; cfg->max_value = 3.0; cfg->agent_power = 70.0;
+            cfg->obs_scale = 1.0 / 70.0; cfg->reward_gain = 1.0; cfg->reward_pow = 1.1; cfg->reward_div = 320.0;
+            cfg->action_punish = 0.002; cfg->delta_action_punish = 0.002;
+            break;
+        default: return fail(nullptr, PDEB200_EINVAL, "default_config: unknown problem");
+    }
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** out) {
+    if (!cfg || !out) return fail(nullptr, PDEB200_EINVAL, "create: null argument");
+    if (cfg->struct_size != (int32_t)sizeof(pdeb200_config))
+        return fail(nullptr, PDEB200_EINVAL, "create: pdeb200_config.struct_size mismatch (ABI)");
+    if (cfg->n_envs < 1 || cfg->nx < 1 || cfg->n_sensors < 1 || cfg->n_actuators < 1 || cfg->window_size < 1 ||
+        cfg->window_size % 2 == 0 || cfg->temporal_steps < 1 || cfg->memory_size < 0)
+        return fail(nullptr, PDEB200_EINVAL, "create: bad sizes (n_envs/nx/n_sensors/n_actuators/window/temporal/memory)");
+    if (cfg->dtype != PDEB200_F32 && cfg->dtype != PDEB200_F64) return fail(nullptr, PDEB200_EINVAL, "create: bad dtype");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, PDEB200_ECUDA, "create: no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, PDEB200_EINVAL, "create: bad device index");
+    pdeb200_ctx* c = new pdeb200_ctx();
+    c->cfg = *cfg; c->device = device;
+    auto bail = [&](int32_t rc) { std::string m = c->err; pdeb200_destroy(c); g_last_error = m; return rc; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(fail(c, PDEB200_ECUDA, "cudaSetDevice failed"));
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    if (prop.major < 10) return bail(fail(c, PDEB200_EUNSUPPORTED, "pdeb200 kernels are built for sm_100a (B200) only"));
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(c, PDEB200_ECUDA, "cudaStreamCreate failed"));
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    c->esz = cfg->dtype == PDEB200_F64 ? 8 : 4;
+    c->a_rows = 1 + cfg->memory_size;
+    switch (cfg->problem) {
+        case PDEB200_KS: c->npts = cfg->nx; c->fields = 1; c->y_elems = c->npts; c->p_elems = c->npts; c->wrows = cfg->window_size; break;
+        case PDEB200_KSEG1D: c->npts = cfg->nx; c->fields = 2; c->y_elems = 2 * c->npts; c->p_elems = c->npts; c->wrows = cfg->window_size; break;
+        case PDEB200_NS2D: c->npts = cfg->nx * cfg->ny; c->fields = 1; c->y_elems = 2 * c->npts; c->p_elems = 2 * c->npts;
+            c->wrows = cfg->window_size * cfg->window_size; break;
+        default: return bail(fail(c, PDEB200_EINVAL, "create: unknown problem"));
+    }
+    if (cfg->mono) {
+        if (cfg->problem != PDEB200_KS) return bail(fail(c, PDEB200_EUNSUPPORTED, "mono (global agent) exists for KS only"));
+        c->n_cols = 1; c->n_rew = 1; c->obs_rows = cfg->n_sensors * cfg->temporal_steps + cfg->memory_size;
+    } else {
+        c->n_cols = cfg->n_actuators; c->n_rew = cfg->n_actuators;
+        c->obs_rows = c->wrows * c->fields * cfg->temporal_steps + cfg->memory_size;
+    }
+    const size_t B = cfg->n_envs, e = c->esz;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (cudaMalloc(p, bytes ? bytes : 16) != cudaSuccess) return false;
+        return cudaMemset(*p, 0, bytes ? bytes : 16) == cudaSuccess;
+    };
+    const size_t nact = B * cfg->n_actuators * c->a_rows;
+    bool ok = alloc(&c->y, B * c->y_elems * e) && alloc(&c->y0, B * c->y_elems * e) && alloc(&c->p, B * c->p_elems * e) &&
+              alloc(&c->state, B * c->n_cols * c->obs_rows * e) && alloc(&c->action, nact * e) &&
+              alloc(&c->action_in, nact * e) && alloc(&c->delta_action, nact * e) && alloc(&c->reward, B * c->n_rew * e) &&
+              alloc(&c->sensors, B * c->fields * cfg->n_sensors * e) && alloc((void**)&c->done, B) &&
+              alloc((void**)&c->time, B * 8) && alloc((void**)&c->steps, B * 4) && alloc((void**)&c->d_mask, B) &&
+              alloc((void**)&c->d_rsum, B * 8) && alloc(&c->d_noise, nact * e) &&
+              alloc((void**)&c->d_a2s, cfg->n_actuators * 4) && alloc(&c->d_sens_sum, cfg->n_sensors * e) &&
+              alloc((void**)&c->d_losses, 8);
+    if (!ok) return bail(fail(c, PDEB200_ECUDA, std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError())));
+    int32_t rc = PDEB200_OK;
+    switch (cfg->problem) {
+        case PDEB200_KS: rc = ks_setup(c); break;
+        case PDEB200_KSEG1D: rc = kseg_setup(c); break;
+        case PDEB200_NS2D: rc = ns_setup(c); break;
+    }
+    if (rc) return bail(rc);
+    *out = c;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_destroy(pdeb200_ctx* c) {
+    if (!c) return PDEB200_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    ks_free(c); kseg_free(c); ns_free(c); agent_free(c);
+    for (void* p : {c->y, c->y0, c->p, c->state, c->action, c->action_in, c->delta_action, c->reward, c->sensors,
+                    (void*)c->done, (void*)c->time, (void*)c->steps, (void*)c->d_mask, (void*)c->d_rsum, c->d_noise,
+                    (void*)c->d_a2s, c->d_sens_sum, (void*)c->sens.d_idx, c->sens.d_w, (void*)c->actT.d_idx, c->actT.d_w,
+                    (void*)c->d_grads, (void*)c->d_losses})
+        if (p) cudaFree(p);
+    for (auto& n : c->nets)
+        for (float* p : {n.d_params, n.d_m, n.d_v})
+            if (p) cudaFree(p);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return PDEB200_OK;
+}
+
+const char* pdeb200_last_error(const pdeb200_ctx* c) { return c ? c->err.c_str() : g_last_error.c_str(); }
+
+int32_t pdeb200_set_stream(pdeb200_ctx* c, void* s) {
+    if (!c) return PDEB200_EINVAL;
+    cudaStreamSynchronize(c->stream);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    if (s) { c->stream = (cudaStream_t)s; c->own_stream = false; }
+    else { PDEB_CUDA(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_synchronize(pdeb200_ctx* c) {
+    if (!c) return PDEB200_EINVAL;
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_set_bases(pdeb200_ctx* c, const double* sb, const double* ab, const int32_t* a2s, double tol) {
+    if (!c || !sb || !ab || !a2s) return fail(c, PDEB200_EINVAL, "set_bases: null argument");
+    cudaSetDevice(c->device);
+    return c->cfg.dtype == PDEB200_F64 ? set_bases_t<double>(c, sb, ab, a2s, tol) : set_bases_t<float>(c, sb, ab, a2s, tol);
+}
+
+int32_t pdeb200_set_y0(pdeb200_ctx* c, const double* y0, int32_t broadcast) {
+    if (!c || !y0) return fail(c, PDEB200_EINVAL, "set_y0: null argument");
+    cudaSetDevice(c->device);
+    const size_t B = c->cfg.n_envs, ye = c->y_elems;
+    std::vector<unsigned char> buf(B * ye * c->esz);
+    for (size_t b = 0; b < B; ++b)
+        for (size_t i = 0; i < ye; ++i) {
+            const double v = y0[(broadcast ? 0 : b * ye) + i];
+            if (c->esz == 8) ((double*)buf.data())[b * ye + i] = v;
+            else ((float*)buf.data())[b * ye + i] = (float)v;
+        }
+    PDEB_CUDA(c, cudaMemcpyAsync(c->y0, buf.data(), buf.size(), cudaMemcpyHostToDevice, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->y0_set = true;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_reset(pdeb200_ctx* c, const uint8_t* mask) {
+    if (!c) return PDEB200_EINVAL;
+    if (!c->bases_set || !c->y0_set) return fail(c, PDEB200_ESTATE, "reset: set_bases and set_y0 first");
+    cudaSetDevice(c->device);
+    const uint8_t* dm = nullptr;
+    if (mask) {
+        PDEB_CUDA(c, cudaMemcpyAsync(c->d_mask, mask, c->cfg.n_envs, cudaMemcpyHostToDevice, c->stream));
+        dm = c->d_mask;
+    }
+    int32_t rc = c->cfg.dtype == PDEB200_F64 ? reset_t<double>(c, dm) : reset_t<float>(c, dm);
+    if (rc) return rc;
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_step_device(pdeb200_ctx* c, const void* actions_dev) {
+    if (!c) return PDEB200_EINVAL;
+    cudaSetDevice(c->device);
+    return do_step(c, actions_dev ? actions_dev : c->action_in, 1, 0, 0.0, nullptr);
+}
+
+int32_t pdeb200_step(pdeb200_ctx* c, const void* actions_host) {
+    if (!c || !actions_host) return fail(c, PDEB200_EINVAL, "step: null argument");
+    cudaSetDevice(c->device);
+    const size_t bytes = (size_t)c->cfg.n_envs * c->cfg.n_actuators * c->a_rows * c->esz;
+    PDEB_CUDA(c, cudaMemcpyAsync(c->action_in, actions_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    int32_t rc = do_step(c, c->action_in, 1, 0, 0.0, nullptr);
+    if (rc) return rc;
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_step_host(pdeb200_ctx* c, const void* actions_host, void* y_out, void* reward_out, void* state_out,
+                          uint8_t* done_out) {
+    if (!c || !actions_host) return fail(c, PDEB200_EINVAL, "step_host: null argument");
+    cudaSetDevice(c->device);
+    const size_t bytes = (size_t)c->cfg.n_envs * c->cfg.n_actuators * c->a_rows * c->esz;
+    PDEB_CUDA(c, cudaMemcpyAsync(c->action_in, actions_host, bytes, cudaMemcpyHostToDevice, c->stream));
+    int32_t rc = do_step(c, c->action_in, 1, 0, 0.0, nullptr);
+    if (rc) return rc;
+    auto back = [&](int which, void* dst) -> cudaError_t {
+        if (!dst) return cudaSuccess;
+        ArrInfo a = arr_info(c, which);
+        return cudaMemcpyAsync(dst, a.ptr, a.bytes, cudaMemcpyDeviceToHost, c->stream);
+    };
+    PDEB_CUDA(c, back(PDEB200_ARR_Y, y_out));
+    PDEB_CUDA(c, back(PDEB200_ARR_REWARD, reward_out));
+    PDEB_CUDA(c, back(PDEB200_ARR_STATE, state_out));
+    PDEB_CUDA(c, back(PDEB200_ARR_DONE, done_out));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_get(pdeb200_ctx* c, int32_t which, void* dst, size_t bytes) {
+    if (!c || !dst) return fail(c, PDEB200_EINVAL, "get: null argument");
+    cudaSetDevice(c->device);
+    ArrInfo a = arr_info(c, which);
+    if (!a.ptr) return fail(c, PDEB200_EINVAL, "get: unknown or unallocated array");
+    if (bytes != a.bytes) return fail(c, PDEB200_EINVAL, "get: size mismatch (expected " + std::to_string(a.bytes) + " bytes)");
+    PDEB_CUDA(c, cudaMemcpyAsync(dst, a.ptr, bytes, cudaMemcpyDeviceToHost, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_set(pdeb200_ctx* c, int32_t which, const void* src, size_t bytes) {
+    if (!c || !src) return fail(c, PDEB200_EINVAL, "set: null argument");
+    cudaSetDevice(c->device);
+    ArrInfo a = arr_info(c, which);
+    if (!a.ptr) return fail(c, PDEB200_EINVAL, "set: unknown or unallocated array");
+    if (bytes != a.bytes) return fail(c, PDEB200_EINVAL, "set: size mismatch (expected " + std::to_string(a.bytes) + " bytes)");
+    PDEB_CUDA(c, cudaMemcpyAsync(a.ptr, src, bytes, cudaMemcpyHostToDevice, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (which == PDEB200_ARR_Y0) c->y0_set = true;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_device_ptr(pdeb200_ctx* c, int32_t which, void** ptr, size_t* bytes) {
+    if (!c || !ptr) return fail(c, PDEB200_EINVAL, "device_ptr: null argument");
+    ArrInfo a = arr_info(c, which);
+    if (!a.ptr) return fail(c, PDEB200_EINVAL, "device_ptr: unknown or unallocated array");
+    *ptr = a.ptr;
+    if (bytes) *bytes = a.bytes;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_obs_rows(const pdeb200_ctx* c) { return c ? c->obs_rows : PDEB200_EINVAL; }
+int32_t pdeb200_obs_cols(const pdeb200_ctx* c) { return c ? c->n_cols : PDEB200_EINVAL; }
+
+// ---- networks -----------------------------------------------------------------------------------
+int32_t pdeb200_net_set(pdeb200_ctx* c, int32_t net, int32_t n_layers, const int32_t* sizes, const int32_t* acts,
+                        const float* params) {
+    if (!c || net < 0 || net > 3 || !sizes || !acts || !params) return fail(c, PDEB200_EINVAL, "net_set: bad argument");
+    if (n_layers < 1 || n_layers > kMaxLayers) return fail(c, PDEB200_EUNSUPPORTED, "net_set: 1..4 Dense layers supported");
+    cudaSetDevice(c->device);
+    HostNet& n = c->nets[net];
+    int total = 0;
+    for (int l = 0; l < n_layers; ++l) {
+        if (sizes[l] < 1 || sizes[l + 1] < 1) return fail(c, PDEB200_EINVAL, "net_set: layer size < 1");
+        n.offs[l] = total;
+        total += sizes[l] * sizes[l + 1] + sizes[l + 1];
+        n.acts[l] = acts[l];
+    }
+    for (int l = 0; l <= n_layers; ++l) n.sizes[l] = sizes[l];
+    if (total != n.n_params || !n.d_params) {
+        for (float** p : {&n.d_params, &n.d_m, &n.d_v}) { if (*p) cudaFree(*p); *p = nullptr; }
+        PDEB_CUDA(c, cudaMalloc(&n.d_params, total * sizeof(float)));
+        PDEB_CUDA(c, cudaMalloc(&n.d_m, total * sizeof(float)));
+        PDEB_CUDA(c, cudaMalloc(&n.d_v, total * sizeof(float)));
+    }
+    n.n_layers = n_layers; n.n_params = total;
+    PDEB_CUDA(c, cudaMemcpyAsync(n.d_params, params, total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    PDEB_CUDA(c, cudaMemsetAsync(n.d_m, 0, total * sizeof(float), c->stream));
+    PDEB_CUDA(c, cudaMemsetAsync(n.d_v, 0, total * sizeof(float), c->stream));
+    n.beta_p[0] = 0.9; n.beta_p[1] = 0.999;
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_net_get(pdeb200_ctx* c, int32_t net, float* params, size_t n_params) {
+    if (!c || net < 0 || net > 3 || !params) return fail(c, PDEB200_EINVAL, "net_get: bad argument");
+    HostNet& n = c->nets[net];
+    if (!n.d_params || (size_t)n.n_params != n_params) return fail(c, PDEB200_EINVAL, "net_get: network unset or size mismatch");
+    cudaSetDevice(c->device);
+    PDEB_CUDA(c, cudaMemcpyAsync(params, n.d_params, n_params * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_net_num_params(const pdeb200_ctx* c, int32_t net) {
+    if (!c || net < 0 || net > 3) return PDEB200_EINVAL;
+    return c->nets[net].n_params;
+}
+
+// ---- policy -------------------------------------------------------------------------------------
+static int32_t policy_launch(pdeb200_ctx* c, const void* d_noise, int use_rng, uint64_t seed, uint64_t offset,
+                             double act_noise, double act_limit) {
+    const HostNet& a = c->nets[PDEB200_NET_BEHAVIOR_ACTOR];
+    if (!a.n_layers) return fail(c, PDEB200_ESTATE, "policy_act: behavior actor not set");
+    const int n_out = a.sizes[a.n_layers];
+    const int expect_out = c->cfg.mono ? c->cfg.n_actuators * c->a_rows : c->a_rows;
+    if (a.sizes[0] != c->obs_rows || n_out != expect_out)
+        return fail(c, PDEB200_EINVAL, "policy_act: actor in/out sizes do not match the env's state/action spaces");
+    for (int l = 0; l <= a.n_layers; ++l)
+        if (a.sizes[l] > kFusedActorMaxWidth) return fail(c, PDEB200_EUNSUPPORTED, "policy_act: layer wider than 64");
+    const int ncol = c->cfg.n_envs * c->n_cols;
+    const int mem = c->cfg.mono ? 0 : c->cfg.memory_size;
+    const int tpb = 128, grid = (ncol + tpb - 1) / tpb;
+    if (c->cfg.dtype == PDEB200_F64)
+        policy_kernel<double><<<grid, tpb, 0, c->stream>>>(a.dev(), ncol, c->obs_rows, c->a_rows, mem, (const double*)c->state,
+                                                           (double*)c->action_in, (const double*)d_noise, use_rng, seed, offset,
+                                                           act_noise, act_limit);
+    else
+        policy_kernel<float><<<grid, tpb, 0, c->stream>>>(a.dev(), ncol, c->obs_rows, c->a_rows, mem, (const float*)c->state,
+                                                          (float*)c->action_in, (const float*)d_noise, use_rng, seed, offset,
+                                                          (float)act_noise, (float)act_limit);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_policy_act(pdeb200_ctx* c, const double* noise_host, double act_noise, double act_limit) {
+    if (!c) return PDEB200_EINVAL;
+    cudaSetDevice(c->device);
+    const void* dn = nullptr;
+    std::vector<float> tmp;
+    if (noise_host) {
+        const int n_out = c->cfg.mono ? c->cfg.n_actuators * c->a_rows : c->a_rows;
+        const int noisy = n_out - (c->cfg.mono ? 0 : c->cfg.memory_size);
+        const size_t n = (size_t)c->cfg.n_envs * c->n_cols * noisy;
+        if (c->esz == 8) PDEB_CUDA(c, cudaMemcpyAsync(c->d_noise, noise_host, n * 8, cudaMemcpyHostToDevice, c->stream));
+        else {
+            tmp.resize(n);
+            for (size_t i = 0; i < n; ++i) tmp[i] = (float)noise_host[i];
+            PDEB_CUDA(c, cudaMemcpyAsync(c->d_noise, tmp.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+        }
+        dn = c->d_noise;
+    }
+    int32_t rc = policy_launch(c, dn, 0, 0, 0, act_noise, act_limit);
+    if (rc) return rc;
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_policy_act_rng(pdeb200_ctx* c, uint64_t seed, uint64_t offset, double act_noise, double act_limit) {
+    if (!c) return PDEB200_EINVAL;
+    cudaSetDevice(c->device);
+    return policy_launch(c, nullptr, 1, seed, offset, act_noise, act_limit);
+}
+
+int32_t pdeb200_rollout(pdeb200_ctx* c, int32_t n_steps, double act_limit, double* reward_sum_out) {
+    if (!c || n_steps < 1) return fail(c, PDEB200_EINVAL, "rollout: bad argument");
+    cudaSetDevice(c->device);
+    double* rs = nullptr;
+    if (reward_sum_out) {
+        PDEB_CUDA(c, cudaMemsetAsync(c->d_rsum, 0, (size_t)c->cfg.n_envs * 8, c->stream));
+        rs = c->d_rsum;
+    }
+    int32_t rc = do_step(c, nullptr, n_steps, 1, act_limit, rs);
+    if (rc) return rc;
+    if (reward_sum_out) {
+        PDEB_CUDA(c, cudaMemcpyAsync(reward_sum_out, c->d_rsum, (size_t)c->cfg.n_envs * 8, cudaMemcpyDeviceToHost, c->stream));
+        PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return PDEB200_OK;
+}
+
+// ---- introspection ------------------------------------------------------------------------------
+int64_t pdeb200_launch_count(const pdeb200_ctx* c) { return c ? c->launches : 0; }
+
+int32_t pdeb200_enable_step_timing(pdeb200_ctx* c, int32_t on) {
+    if (!c) return PDEB200_EINVAL;
+    c->timing = on != 0; c->timed = false;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_last_step_ms(pdeb200_ctx* c, float* ms) {
+    if (!c || !ms) return PDEB200_EINVAL;
+    if (!c->timed) return fail(c, PDEB200_ESTATE, "last_step_ms: timing not enabled or no step yet");
+    PDEB_CUDA(c, cudaEventSynchronize(c->ev1));
+    PDEB_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_step_cost(const pdeb200_ctx* c, double* bytes, double* flops) {
+    if (!c) return PDEB200_EINVAL;
+    switch (c->cfg.problem) {
+        case PDEB200_KS: return ks_cost(c, bytes, flops);
+        case PDEB200_KSEG1D: return kseg_cost(c, bytes, flops);
+        case PDEB200_NS2D: return ns_cost(c, bytes, flops);
+    }
+    return PDEB200_EINVAL;
+}
+
+}  // extern "C"

@@ -1,0 +1,2 @@
+"""Setup builders mirroring the reference's scripts/*/setup/*Setup.jl files."""
+from .ks import KSSetup  # noqa: F401

@@ -1,0 +1,217 @@
+/*
+ * pdeb200.h -- C ABI of the B200-native batched PDE-control hot path.
+ *
+ * Drop-in boundary for janstenner/DistributedConvRL-PDE-Control: each entry
+ * point replaces one closure / method of the reference's plugin interface and is
+ * what a Julia `ccall` (or, in this repository, Python `ctypes`) binds.  Plain C,
+ * no exceptions across the boundary, no torch types.  Reference citations are
+ * relative to the reference repository root.
+ *
+ *   reference interface                                   replaced by
+ *   ----------------------------------------------------  -----------------------------
+ *   PDEenv(...) constructor        src/PDEenv.jl:64-170    pdeb200_create + set_bases + set_y0 + reset
+ *   RLBase.reset!(env)             src/PDEenv.jl:183-193   pdeb200_reset
+ *   (env::PDEenv)(action)          src/PDEenv.jl:195-241   pdeb200_step / pdeb200_step_device
+ *     prepare_action               scripts/KS/setup/KSSetup.jl:231-245 (KSeg :318-332, Fluid :247-261)
+ *     do_step                      KSSetup.jl:130-160; KellerSegelSetup.jl:213-239; fluid_rk4.jl:122-229 + FluidSetup.jl:163-172
+ *     reward_function              KSSetup.jl:162-184; KellerSegelSetup.jl:241-263; FluidSetup.jl:188-202
+ *     featurize                    KSSetup.jl:190-229; KellerSegelSetup.jl:265-316; FluidSetup.jl:204-245
+ *   env.y / env.p / env.state / env.reward / env.done ...  pdeb200_get / pdeb200_device_ptr
+ *   CustomNeuralNetworkApproximator(model, optimizer)
+ *                                  src/custom_nna.jl:7-27  pdeb200_net_set / pdeb200_net_get
+ *   (policy::CustomDDPGPolicy)(env) src/PDEagent.jl:175-209 pdeb200_policy_act
+ *   policy loop in plot_heat        src/plotting.jl:55-73   pdeb200_rollout (fused actor + env step, K steps / launch)
+ *   trajectory update! overloads   src/PDEagent.jl:237-314 pdeb200_traj_push_pre / _post / _episode_end / _pop_tail
+ *   pde_sample / pde_fetch!        src/PDEagent.jl:317-340 pdeb200_sample
+ *   update!(policy, batch)         src/PDEagent.jl:363-418 pdeb200_ddpg_grads + pdeb200_ddpg_apply (allreduce between)
+ *
+ * Conventions
+ *   - every call returns int32 status: 0 = OK, negative = error; the message is
+ *     available from pdeb200_last_error(ctx) (or pdeb200_last_error(NULL) for
+ *     create failures);
+ *   - host pointers are borrowed for the duration of the call only;
+ *   - calls are synchronous for the caller unless the name ends in _async /
+ *     _device (those enqueue on the context's stream and return);
+ *   - a context is not thread-safe; one Julia task / Python thread drives it;
+ *   - array layouts are exactly the memory of the reference's column-major Julia
+ *     arrays with the environment batch folded into the actuator (column) axis:
+ *       y       Julia (nx, B)  [KS]  (2, nx, B) [KSeg]  complex (ny, nx, B) [NS]   -> env-major contiguous
+ *       state   Julia (ns, n_act*B)      -> [B][n_act][ns]
+ *       action  Julia (1+mem, n_act*B)   -> [B][n_act][1+mem]
+ *       reward  Julia (n_act*B,)         -> [B][n_act]
+ *     Element type of y/p/state/action/reward is the context dtype (f32 or f64);
+ *     networks and the replay buffer are always f32 (src/PDEagent.jl:112-117).
+ */
+#ifndef PDEB200_H
+#define PDEB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDEB200_ABI_VERSION 1
+
+typedef struct pdeb200_ctx pdeb200_ctx;
+
+enum { PDEB200_OK = 0, PDEB200_EINVAL = -1, PDEB200_ECUDA = -2, PDEB200_EUNSUPPORTED = -3, PDEB200_ESTATE = -4 };
+enum { PDEB200_F32 = 0, PDEB200_F64 = 1 };
+enum { PDEB200_KS = 0, PDEB200_KSEG1D = 1, PDEB200_NS2D = 2 };
+enum { PDEB200_CHECK_NONE = 0, PDEB200_CHECK_Y = 1, PDEB200_CHECK_REWARD = 2 };   /* src/PDEenv.jl:226-240 */
+enum { PDEB200_ACT_IDENTITY = 0, PDEB200_ACT_RELU = 1, PDEB200_ACT_TANH = 2 };
+enum { PDEB200_NET_BEHAVIOR_ACTOR = 0, PDEB200_NET_BEHAVIOR_CRITIC = 1, PDEB200_NET_TARGET_ACTOR = 2, PDEB200_NET_TARGET_CRITIC = 3 };
+
+/* arrays addressable through pdeb200_get / pdeb200_set / pdeb200_device_ptr */
+enum {
+    PDEB200_ARR_Y = 0,            /* env.y                                   dtype   */
+    PDEB200_ARR_P = 1,            /* env.p (actuation field)                 dtype   */
+    PDEB200_ARR_STATE = 2,        /* env.state  [B][n_act][ns]               dtype   */
+    PDEB200_ARR_ACTION = 3,       /* env.action [B][n_act][1+mem]            dtype   */
+    PDEB200_ARR_DELTA_ACTION = 4, /* env.delta_action                        dtype   */
+    PDEB200_ARR_REWARD = 5,       /* env.reward [B][n_rew]                   dtype   */
+    PDEB200_ARR_DONE = 6,         /* env.done   [B]                          uint8   */
+    PDEB200_ARR_TIME = 7,         /* env.time   [B]                          float64 */
+    PDEB200_ARR_STEPS = 8,        /* env.steps  [B]                          int32   */
+    PDEB200_ARR_Y0 = 9,           /* env.y0                                  dtype   */
+    PDEB200_ARR_GRADS = 10,       /* flat [critic | actor] gradient (+ tail) float32 */
+    PDEB200_ARR_LOSSES = 11,      /* {critic_loss, actor_loss}               float32 */
+    PDEB200_ARR_SENSORS = 12      /* raw sensor dots [B][fields][n_sensors]  dtype   */
+};
+
+typedef struct pdeb200_config {
+    int32_t struct_size;          /* = sizeof(pdeb200_config), ABI check                       */
+    int32_t problem;              /* PDEB200_KS / KSEG1D / NS2D                                */
+    int32_t dtype;                /* PDEB200_F32 / F64: arithmetic type of the PDE path        */
+    int32_t nx, ny;               /* grid; ny = 1 for 1-D problems                             */
+    int32_t n_envs;               /* B, independent environments on this GPU                   */
+    int32_t n_sensors;            /* length(sensor_positions)                                  */
+    int32_t n_actuators;          /* length(actuator_positions)                                */
+    int32_t window_size;          /* KSSetup.jl:46 ; 2-D problems use window_size^2 rows       */
+    int32_t temporal_steps;       /* KSSetup.jl:43                                             */
+    int32_t memory_size;          /* KSSetup.jl:39                                             */
+    int32_t oversampling;         /* substeps per env step (KS: CNAB2, KSeg/NS: RK4)           */
+    int32_t check_max_value;      /* PDEB200_CHECK_*                                           */
+    int32_t mono;                 /* 1 = global-agent variant (KSglobalSetup.jl): one column   */
+    int32_t sensors_per_axis;     /* NS2D: sensor lattice side (FluidSetup.jl:61)              */
+    int32_t ifpad;                /* NS2D: 3/2-rule de-aliasing (FluidSetup.jl:101)            */
+    double Lx, Ly;                /* domain                                                    */
+    double dt, te, t0;            /* env step, episode end, start                              */
+    double mu;                    /* KS inhomogeneous forcing amplitude (KSSetup.jl:155)       */
+    double nu;                    /* NS viscosity (FluidSetup.jl:28)                           */
+    double agent_power;           /* KSSetup.jl:51                                             */
+    double max_value;             /* divergence guard (PDEenv.jl:226-237)                      */
+    double obs_scale;             /* sensor value = <y,g> * obs_scale  (1/30, 1/4, 1/70)       */
+    double reward_gain;           /* r = -|gain*(<y,g> - offset*sum(g))|^pow / div             */
+    double reward_pow;            /*     - action_punish a^2 - delta_action_punish da^2        */
+    double reward_div;
+    double reward_offset;
+    double action_punish;
+    double delta_action_punish;
+} pdeb200_config;
+
+/* ---- lifecycle -------------------------------------------------------------------------- */
+int32_t pdeb200_abi_version(void);
+/* Fills the problem-specific reward/obs constants of the reference setup file for `problem`. */
+int32_t pdeb200_default_config(int32_t problem, pdeb200_config* cfg);
+int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** out);
+int32_t pdeb200_destroy(pdeb200_ctx* ctx);
+const char* pdeb200_last_error(const pdeb200_ctx* ctx);
+/* Use an externally owned cudaStream_t (e.g. torch's current stream); NULL = own stream. */
+int32_t pdeb200_set_stream(pdeb200_ctx* ctx, void* cuda_stream);
+int32_t pdeb200_synchronize(pdeb200_ctx* ctx);
+
+/* ---- constants -------------------------------------------------------------------------- */
+/* gaussians / gaussians_actuators of the setup files, as dense float64 row-major
+ * [n_sensors][npts] and [n_actuators][npts] (npts = nx*ny; NS: Julia's (nx,ny) column-major
+ * flattening), a2s = actuators_to_sensors, 0-based.  Entries with |w| <= drop_tol*max|w|
+ * are dropped when the banded/sparse device tables are built (0 keeps every non-zero). */
+int32_t pdeb200_set_bases(pdeb200_ctx* ctx, const double* sensor_basis, const double* actuator_basis,
+                          const int32_t* a2s, double drop_tol);
+/* y0 (env.y0): float64 host array, either one environment (broadcast = 1) or [B][...] */
+int32_t pdeb200_set_y0(pdeb200_ctx* ctx, const double* y0, int32_t broadcast);
+
+/* ---- environment ------------------------------------------------------------------------ */
+/* RLBase.reset!(env) for the masked environments (mask == NULL: all). */
+int32_t pdeb200_reset(pdeb200_ctx* ctx, const uint8_t* mask);
+/* env(action): actions is a HOST array [B][n_act][1+mem] of the context dtype.
+ * Copies it to the device, runs the fused step, leaves results on the device. */
+int32_t pdeb200_step(pdeb200_ctx* ctx, const void* actions_host);
+/* same with a DEVICE action buffer; NULL = the context's own action buffer (as
+ * written by pdeb200_policy_act).  Enqueues and returns. */
+int32_t pdeb200_step_device(pdeb200_ctx* ctx, const void* actions_dev);
+/* Convenience for the drop-in closures: step + copy back y/reward/state/done in one call.
+ * Any output pointer may be NULL. */
+int32_t pdeb200_step_host(pdeb200_ctx* ctx, const void* actions_host, void* y_out, void* reward_out,
+                          void* state_out, uint8_t* done_out);
+int32_t pdeb200_get(pdeb200_ctx* ctx, int32_t which, void* host_dst, size_t bytes);
+int32_t pdeb200_set(pdeb200_ctx* ctx, int32_t which, const void* host_src, size_t bytes);
+int32_t pdeb200_device_ptr(pdeb200_ctx* ctx, int32_t which, void** ptr, size_t* bytes);
+int32_t pdeb200_obs_rows(const pdeb200_ctx* ctx);      /* ns = size(state_space)[1] */
+int32_t pdeb200_obs_cols(const pdeb200_ctx* ctx);      /* columns per environment   */
+
+/* ---- networks (always float32, Flux Dense layout: W is (out, in) column-major) ---------- */
+/* n_layers Dense layers; sizes[0..n_layers] = in, hidden..., out; activations[n_layers];
+ * params = concatenation over layers of (W column-major (out,in), b).  */
+int32_t pdeb200_net_set(pdeb200_ctx* ctx, int32_t net, int32_t n_layers, const int32_t* sizes,
+                        const int32_t* activations, const float* params);
+int32_t pdeb200_net_get(pdeb200_ctx* ctx, int32_t net, float* params, size_t n_params);
+int32_t pdeb200_net_num_params(const pdeb200_ctx* ctx, int32_t net);
+
+/* ---- policy ----------------------------------------------------------------------------- */
+/* actions = clamp(behavior_actor(state) + noise*act_noise, +-act_limit)   (PDEagent.jl:189-204)
+ * noise_host: NULL (learning = false) or HOST float64 [B][n_cols][na - mem] standard normals
+ * supplied by the caller (the reference draws them from a StableRNG, PDEagent.jl:201).
+ * Result stays in the context's action buffer (ARR_ACTION is updated by the next step). */
+int32_t pdeb200_policy_act(pdeb200_ctx* ctx, const double* noise_host, double act_noise, double act_limit);
+/* Same, with noise generated on the device (Philox, seed/offset) -- the batched-training path. */
+int32_t pdeb200_policy_act_rng(pdeb200_ctx* ctx, uint64_t seed, uint64_t offset, double act_noise, double act_limit);
+/* Fused roll-out: n_steps x { actor forward (no noise) -> env step } in ONE launch with the PDE
+ * state resident on chip (the evaluation loop of src/plotting.jl:55-73, batched).
+ * reward_sum_out: optional HOST float64 [B] = sum over steps of mean_i reward. */
+int32_t pdeb200_rollout(pdeb200_ctx* ctx, int32_t n_steps, double act_limit, double* reward_sum_out);
+
+/* ---- replay buffer (device resident CircularArraySARTTrajectory) ------------------------ */
+int32_t pdeb200_traj_create(pdeb200_ctx* ctx, int64_t capacity);
+int32_t pdeb200_traj_length(const pdeb200_ctx* ctx, int64_t* length);
+int32_t pdeb200_traj_push_pre(pdeb200_ctx* ctx);          /* PreActStage  PDEagent.jl:254-274 */
+int32_t pdeb200_traj_push_post(pdeb200_ctx* ctx);         /* PostActStage PDEagent.jl:276-289 */
+int32_t pdeb200_traj_episode_end(pdeb200_ctx* ctx);       /* PostEpisode  PDEagent.jl:291-314 */
+int32_t pdeb200_traj_pop_tail(pdeb200_ctx* ctx);          /* PreEpisode   PDEagent.jl:237-252 */
+/* batch of `batch` transitions; inds_host (0-based, < length - n_cols_total) or NULL to draw
+ * uniformly on the device from (seed, offset). */
+int32_t pdeb200_sample(pdeb200_ctx* ctx, int32_t batch, const int64_t* inds_host, uint64_t seed, uint64_t offset);
+/* Explicit batch (host float32): s [batch][ns], a [batch][na], r [batch], t [batch] (uint8), s' [batch][ns]. */
+int32_t pdeb200_set_batch(pdeb200_ctx* ctx, int32_t batch, const float* s, const float* a, const float* r,
+                          const uint8_t* t, const float* snext);
+
+/* ---- DDPG update (PDEagent.jl:363-418) -------------------------------------------------- */
+/* Phase 1: target values + critic gradient into ARR_GRADS[0 .. n_critic).
+ * literal_q1 = 1 reproduces the reference's (1,B) x (B,) broadcast in the critic loss
+ * (SURVEY.md quirk Q1); 0 = per-sample TD target.  global_batch = total columns over all ranks. */
+int32_t pdeb200_ddpg_critic_grads(pdeb200_ctx* ctx, double gamma, int32_t literal_q1, int64_t global_batch);
+/* ADAM step on the behavior critic from ARR_GRADS (after the caller's allreduce). */
+int32_t pdeb200_ddpg_critic_apply(pdeb200_ctx* ctx, double lr);
+/* Phase 2: actor gradient through the UPDATED critic into ARR_GRADS[n_critic ..). */
+int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* ctx, int64_t global_batch);
+/* ADAM on the actor, then Polyak on both targets: dest = p*dest + (1-p)*src. */
+int32_t pdeb200_ddpg_actor_apply(pdeb200_ctx* ctx, double lr, double polyak);
+/* Single-GPU convenience: all four phases back to back. */
+int32_t pdeb200_ddpg_update(pdeb200_ctx* ctx, double gamma, double polyak, double lr_actor, double lr_critic,
+                            int32_t literal_q1);
+
+/* ---- introspection ---------------------------------------------------------------------- */
+/* Kernel launches issued by this context since creation (bench.py's gpu_launches). */
+int64_t pdeb200_launch_count(const pdeb200_ctx* ctx);
+/* Time the n most recent env-step kernels took on the device, via CUDA events on the
+ * context's stream (ms); used for the roofline line.  */
+int32_t pdeb200_last_step_ms(pdeb200_ctx* ctx, float* ms);
+int32_t pdeb200_enable_step_timing(pdeb200_ctx* ctx, int32_t on);
+/* Algorithmic HBM bytes and flops of one env step for this configuration. */
+int32_t pdeb200_step_cost(const pdeb200_ctx* ctx, double* hbm_bytes_per_env, double* flops_per_env);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDEB200_H */

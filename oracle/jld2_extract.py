@@ -1,0 +1,180 @@
+#!/usr/bin/env python3
+"""Golden-vector extractor for the reference's shipped JLD2 checkpoints.
+
+TEST INFRASTRUCTURE ONLY (see oracle/README.md).  Run in the build container,
+where /root/reference exists; the output (tests/golden/*.npz) is committed and
+is what travels to the GPU box.
+
+JLD2 is an HDF5 subset.  We do not need the group tree: every numeric array the
+fixtures need is an HDF5 *object header v2* ("OHDR") carrying
+  0x01 dataspace (v2)  -> dims (reversed w.r.t. Julia's column-major dims)
+  0x03 datatype        -> class (1 = IEEE float, 0 = fixed point) and size
+  0x08 layout (v4)     -> class 0 compact (inline bytes) / class 1 contiguous
+and the arrays appear in file order:  hook.rewards, hook.rewards_compare,
+bestNNA (W1, b1, W2, b2), the bestDF columns action[1..T], p[1..T], y[1..T],
+reward[1..T], then currentNNA (W1, b1, W2, b2).
+(PDEhook fields: /root/reference/src/PDEhook.jl:8-31; DataFrame row written at
+PDEhook.jl:51-63.)
+"""
+import re
+import struct
+import sys
+from pathlib import Path
+
+import numpy as np
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
+
+
+def _parse_ohdr(b, off):
+    """Return (dims, dtype, data bytes) for a numeric dataset header, else None."""
+    if b[off:off + 4] != b"OHDR" or b[off + 4] != 2:
+        return None
+    flags = b[off + 5]
+    pos = off + 6
+    if flags & 0x20:
+        pos += 16                      # access/mod/change/birth times
+    if flags & 0x10:
+        pos += 4                       # max compact / min dense attributes
+    szw = 1 << (flags & 3)
+    chunk0 = int.from_bytes(b[pos:pos + szw], "little")
+    pos += szw
+    end = pos + chunk0
+    dims = dtype = data = None
+    while pos + 4 <= end:
+        mtype = b[pos]
+        msize = struct.unpack_from("<H", b, pos + 1)[0]
+        pos += 4
+        if flags & 0x04:
+            pos += 2                   # creation order
+        body = b[pos:pos + msize]
+        if mtype == 0x01 and len(body) >= 4 and body[0] == 2:
+            rank = body[1]
+            dims = [struct.unpack_from("<Q", body, 4 + 8 * i)[0] for i in range(rank)]
+        elif mtype == 0x03 and len(body) >= 8:
+            cls = body[0] & 0x0F
+            size = struct.unpack_from("<I", body, 4)[0]
+            if cls == 1 and size in (4, 8):
+                dtype = np.dtype("<f%d" % size)
+            elif cls == 0 and size in (1, 2, 4, 8):
+                signed = (body[1] >> 3) & 1
+                dtype = np.dtype("<%s%d" % ("i" if signed else "u", size))
+        elif mtype == 0x08 and len(body) >= 2 and body[0] == 4:
+            lclass = body[1]
+            if lclass == 0:
+                n = struct.unpack_from("<H", body, 2)[0]
+                data = body[4:4 + n]
+            elif lclass == 1:
+                addr, n = struct.unpack_from("<QQ", body, 2)
+                if addr != 0xFFFFFFFFFFFFFFFF:
+                    data = b[addr:addr + n]
+        pos += msize
+    if dims is None or dtype is None or data is None:
+        return None
+    count = int(np.prod(dims)) if dims else 1
+    if count * dtype.itemsize != len(data):
+        return None
+    arr = np.frombuffer(data, dtype=dtype).reshape(dims if dims else ())
+    return arr
+
+
+def numeric_arrays(path, float_only=True):
+    """All numeric dataset arrays of a JLD2 file, in file order.
+
+    HDF5 dims are C-order over the same bytes Julia wrote column-major, so the
+    returned array is the *transpose* of the Julia array: a Julia (h, ns) weight
+    matrix comes back as (ns, h).  We transpose back to Julia's shape.
+    """
+    b = Path(path).read_bytes()
+    out = []
+    for m in re.finditer(b"OHDR", b):
+        arr = _parse_ohdr(b, m.start())
+        if arr is None:
+            continue
+        if float_only and arr.dtype.kind != "f":
+            continue
+        out.append((m.start(), np.ascontiguousarray(arr.T)))
+    return out
+
+
+def hook_fixture(path, n_state_rows=None):
+    """Split a hook.jld2 float-array stream into named pieces."""
+    arrs = [a for _, a in numeric_arrays(path)]
+    # rewards, rewards_compare are 1-D float64; NNA weights are float32.
+    i = 0
+    rewards = arrs[i]; i += 1
+    rewards_compare = arrs[i]; i += 1
+    best = arrs[i:i + 4]; i += 4
+    assert all(a.dtype == np.float32 for a in best), [a.dtype for a in best]
+    rest = arrs[i:]
+    # trailing 4 float32 arrays = currentNNA
+    cur = rest[-4:]
+    assert all(a.dtype == np.float32 for a in cur)
+    df = rest[:-4]
+    assert all(a.dtype == np.float64 for a in df), set(a.dtype for a in df)
+    if len(df) % 4 == 1 and df[-1].size == 1:
+        df = df[:-1]                   # trailing scalar = hook.bestreward
+    assert len(df) % 4 == 0, len(df)
+    T = len(df) // 4
+    action = np.stack([a.reshape(-1) for a in df[0:T]])
+    p = np.stack([a.reshape(-1) for a in df[T:2 * T]])
+    y = np.stack(df[2 * T:3 * T])
+    reward = np.stack([a.reshape(-1) for a in df[3 * T:4 * T]])
+    return dict(rewards=rewards, rewards_compare=rewards_compare,
+                best_W1=best[0], best_b1=best[1], best_W2=best[2], best_b2=best[3],
+                cur_W1=cur[0], cur_b1=cur[1], cur_W2=cur[2], cur_b2=cur[3],
+                action=action, p=p, y=y, reward=reward)
+
+
+def main():
+    OUT.mkdir(parents=True, exist_ok=True)
+    jobs = {
+        "ks22_hook": REF / "scripts/KS/KS22/saves/hook.jld2",
+        "ks200_hook": REF / "scripts/KS/KS200/saves/hook.jld2",
+        "ks22_global_hook": REF / "scripts/KS/KS22_global-agent/saves/hook.jld2",
+        "kseg10_16_hook": REF / "scripts/Keller-Segel/Keller-Segel10_16/saves/hook.jld2",
+    }
+    for name, path in jobs.items():
+        fx = hook_fixture(path)
+        T = fx["y"].shape[0]
+        if name.startswith("kseg"):
+            # 1334 rows x (2,100) is 3.5 MB; keep three consecutive windows.
+            keep = np.r_[0:48, 640:664, 1300:1334]
+            for k in ("action", "p", "y", "reward"):
+                fx[k] = fx[k][keep]
+            fx["rows"] = keep.astype(np.int64)
+        else:
+            fx["rows"] = np.arange(T, dtype=np.int64)
+        np.savez_compressed(OUT / (name + ".npz"), **fx)
+        print(name, "T=%d" % T, {k: v.shape for k, v in fx.items()})
+    # actor weights only (no trajectory) for the Fluid cases
+    for tag in ("8", "16", "32"):
+        arrs = [a for _, a in numeric_arrays(REF / f"scripts/Fluid/Fluid_{tag}/saves/hook.jld2")]
+        f32 = [a for a in arrs if a.dtype == np.float32]
+        f64 = [a for a in arrs if a.dtype == np.float64]
+        np.savez_compressed(OUT / f"fluid{tag}_hook.npz", rewards=f64[0],
+                            best_W1=f32[0], best_b1=f32[1], best_W2=f32[2], best_b2=f32[3],
+                            cur_W1=f32[-4], cur_b1=f32[-3], cur_W2=f32[-2], cur_b2=f32[-1])
+        print("fluid" + tag, [a.shape for a in f32])
+    y0 = [a for _, a in numeric_arrays(REF / "scripts/KS/KS22_global-agent/y0.jld2")]
+    np.savez_compressed(OUT / "ks22_global_y0.npz", y0=y0[0])
+    print("y0", y0[0].shape)
+    # KS agent.jld2: the four networks + ADAM moments (small) and a slice of the replay buffer
+    for tag in ("KS22", "KS200"):
+        arrs = numeric_arrays(REF / f"scripts/KS/{tag}/saves/agent.jld2")
+        small = {}
+        big = {}
+        for n, (off, a) in enumerate(arrs):
+            if a.size <= 4096:
+                small["a%03d" % n] = a
+            else:
+                big["a%03d" % n] = a
+        shapes = {k: (v.shape, str(v.dtype)) for k, v in {**small, **big}.items()}
+        print(tag, "agent arrays:", shapes)
+        sl = {k + "_head": v.reshape(v.shape[0] if v.ndim > 1 else 1, -1)[..., :4096] for k, v in big.items()}
+        np.savez_compressed(OUT / f"{tag.lower()}_agent.npz", **small, **sl)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,98 @@
+"""GPU parity: fused actor forward + env step (rollout) vs oracle MLP + oracle env."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+from oracle import ks_oracle as K
+
+pytestmark = pytest.mark.gpu
+
+
+def mlp_ref(chain, x):
+    """Flux Chain of Dense on a (ns, ncols) matrix, float32."""
+    h = x.astype(np.float32)
+    for l in chain.layers:
+        h = l.W @ h + l.b[:, None]
+        if l.act == "relu":
+            h = np.maximum(h, 0)
+        elif l.act == "tanh":
+            h = np.tanh(h)
+    return h
+
+
+def _agent_mod(pkg):
+    import importlib
+    return importlib.import_module(pkg.__name__ + ".agent")
+
+
+@pytest.mark.parametrize("window", [1, 3])
+def test_rollout_matches_stepwise_oracle(pkg, golden, window):
+    A = _agent_mod(pkg)
+    cfg = K.ks256_config(window)
+    setup = pkg.setups.KSSetup.ks256(window_size=window)
+    rng = np.random.default_rng(5)
+    B, n_a = 5, cfg.n_actuators
+    if window == 1:
+        g = golden("ks200_hook")                                   # KS200 bestNNA actor 1->6->1
+        chain = A.Chain(A.Dense(g["best_W1"], g["best_b1"], "relu"), A.Dense(g["best_W2"], g["best_b2"], "tanh"))
+    else:
+        chain = A.create_chain(na=1, ns=3, is_actor=True, rng=rng, nna_scale=0.6, drop_middle_layer=True)
+    y0 = setup.generate_random_init(rng, B)
+    env = setup.make_env(n_envs=B, dtype="f64", y0=y0)
+    A.CustomNeuralNetworkApproximator(env, pkg.lib.NET_BEHAVIOR_ACTOR, chain)
+    steps = 4
+    rsum = env.rollout(steps, act_limit=1.0, reward_sum=True)
+    for b in range(B):
+        ref = K.KSEnv(cfg, y0=y0[b])
+        acc = 0.0
+        for _ in range(steps):
+            a = np.clip(mlp_ref(chain, ref.state).astype(np.float64), -1, 1)
+            ref.step(a)
+            acc += ref.reward.mean()
+        # fp32 actor inside an fp64 PDE: the action differs at 1e-7 relative, and so does everything downstream
+        assert relerr(env.y[:, b], ref.y) < 1e-5
+        assert abs(rsum[b] - acc) < 1e-5 * max(1.0, abs(acc))
+        assert relerr(env.action[0, b * n_a:(b + 1) * n_a], ref.action[0]) < 1e-5
+    assert np.all(env.steps == steps)
+    env.close()
+
+
+def test_policy_act_then_step_equals_rollout(pkg, golden):
+    A = _agent_mod(pkg)
+    g = golden("ks200_hook")
+    chain = A.Chain(A.Dense(g["best_W1"], g["best_b1"], "relu"), A.Dense(g["best_W2"], g["best_b2"], "tanh"))
+    setup = pkg.setups.KSSetup.ks256()
+    rng = np.random.default_rng(9)
+    B = 8
+    y0 = setup.generate_random_init(rng, B)
+    e1 = setup.make_env(n_envs=B, dtype="f64", y0=y0)
+    e2 = setup.make_env(n_envs=B, dtype="f64", y0=y0)
+    for e in (e1, e2):
+        A.CustomNeuralNetworkApproximator(e, pkg.lib.NET_BEHAVIOR_ACTOR, chain)
+    e1.rollout(3)
+    for _ in range(3):
+        e2.policy_act()
+        e2.step_device()
+    e2.synchronize()
+    assert np.array_equal(e1.y, e2.y)
+    assert np.array_equal(e1.reward, e2.reward)
+    assert np.array_equal(e1.state, e2.state)
+    e1.close(); e2.close()
+
+
+def test_policy_noise_and_clamp(pkg):
+    A = _agent_mod(pkg)
+    setup = pkg.setups.KSSetup.ks22()
+    rng = np.random.default_rng(2)
+    B = 3
+    env = setup.make_env(n_envs=B, dtype="f64", y0=setup.generate_random_init(rng, B))
+    chain = A.create_chain(na=1, ns=1, is_actor=True, rng=rng, nna_scale=0.6, drop_middle_layer=True)
+    A.CustomNeuralNetworkApproximator(env, pkg.lib.NET_BEHAVIOR_ACTOR, chain)
+    noise = rng.standard_normal(B * 8)
+    s = env.state
+    env.policy_act(noise=noise, act_noise=1.2, act_limit=1.0)
+    env.step_device(); env.synchronize()
+    expect = np.clip(mlp_ref(chain, s).astype(np.float64) + noise[None, :] * 1.2, -1, 1)
+    assert relerr(env.action, expect) < 1e-6
+    assert np.max(np.abs(env.action)) <= 1.0
+    env.close()
