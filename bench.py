@@ -1,0 +1,340 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: batched KS environment stepping fused with policy inference.
+
+Metric (BASELINE.json): env-steps/s, KS N=256, 8192 batched envs per GPU, oversampling 30,
+fp64 (the reference's precision), actor = the reference's shipped KS200 network (1->6->1).
+One "step" = one fused {actor forward -> prepare_action -> 30 CNAB2 substeps -> reward ->
+featurize -> done} pass over all environments of the rank = ONE kernel launch.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (under torchrun for N>1)
+  python bench.py --impl reference ...                     CPU arm: oracle restatement on all host cores
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how each field is produced.
+"""
+import argparse
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+PKG = "distributedconvrl-pde-control_b200"
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=8192, help="environments per GPU (weak scaling)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--oversampling", type=int, default=30)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(args, n_gpus):
+    return {"workload": "KS 1D N=256 (Lx=213.33, dt=0.1, oversampling=%d), %d envs/GPU, 64 sensors/actuators, window 1, "
+                        "fused policy inference (KS200 actor 1-6-1) + env step" % (args.oversampling, args.envs),
+            "envs_per_gpu": args.envs, "global_envs": args.envs * n_gpus, "nx": 256, "oversampling": args.oversampling,
+            "parallelism": "env-sharded x%d (no data-path collective)" % n_gpus,
+            "l2": "flushed between timed iterations (256 MiB write); state 16 MiB/GPU < 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's C restatement of the reference algorithm on the host cores
+# ------------------------------------------------------------------------------------------------
+class CpuOracle:
+    def __init__(self, oversampling):
+        from oracle import ks_oracle as K
+        so = ROOT / "oracle" / "_ref" / "libks_oracle.so"
+        if not so.exists():
+            subprocess.run(["make", "-C", str(ROOT / "oracle"), "-s"], check=True)
+        self.lib = C.CDLL(str(so))
+        self.K = K
+        self.cfg = K.ks256_config(1)
+        self.cfg.oversampling = oversampling
+        env = K.KSEnv(self.cfg)
+        self.g_sens = np.ascontiguousarray(env.g_sens)
+        self.g_act = np.ascontiguousarray(env.g_act)
+        self.a2s = np.ascontiguousarray(np.asarray(self.cfg.actuators_to_sensors) - 1, dtype=np.int32)
+        self.cores = len(os.sched_getaffinity(0))
+
+    def run(self, envs_per_core, n_steps, seed=0):
+        """Advance cores*envs_per_core environments n_steps env steps; one thread per core, each
+        stepping its environments one at a time like the (single-threaded) reference.  Returns seconds."""
+        cfg, K = self.cfg, self.K
+        rng = np.random.default_rng(seed)
+        nx, n_a, n_s = cfg.nx, cfg.n_actuators, cfg.n_sensors
+        slices = []
+        for c in range(self.cores):
+            y = np.stack([K.generate_random_init(cfg, rng.uniform(-1, 1, 8)) for _ in range(envs_per_core)])
+            ap = np.zeros((envs_per_core, n_a))
+            act = rng.uniform(-0.2, 0.2, (n_steps, envs_per_core, n_a))
+            st = np.zeros((envs_per_core, n_a, 1))
+            rw = np.zeros((envs_per_core, n_a))
+            slices.append((y, ap, act, st, rw))
+        d = lambda a: a.ctypes.data_as(C.c_void_p)
+
+        def work(s):
+            y, ap, act, st, rw = s
+            self.lib.ks_oracle_env_steps(
+                C.c_int(nx), C.c_double(cfg.Lx), C.c_double(cfg.dt), C.c_int(cfg.oversampling), C.c_double(cfg.mu),
+                C.c_int(envs_per_core), C.c_int(n_steps), C.c_int(n_s), C.c_int(n_a), C.c_int(1),
+                C.c_double(cfg.agent_power), C.c_double(cfg.max_value), C.c_double(cfg.action_punish),
+                C.c_double(cfg.delta_action_punish), d(self.g_sens), d(self.g_act), d(self.a2s), d(y), d(ap), d(act),
+                d(st), d(rw), C.c_int(1))
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max_workers=self.cores) as ex:
+            list(ex.map(work, slices))
+        return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    orc = CpuOracle(args.oversampling)
+    envs_per_core = 16
+    for _ in range(args.warmup):
+        orc.run(envs_per_core, 1)
+    t = 0.0
+    for i in range(args.steps):
+        t += orc.run(envs_per_core, 1, seed=i + 1)
+    n_env_steps = args.steps * envs_per_core * orc.cores
+    value = n_env_steps / t
+    sample = "%d envs (16 per core) x 1 env step per bench step" % (envs_per_core * orc.cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, args.gpus),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": orc.cores, "kind": "port", "sample": sample,
+                             "note": "C restatement of the reference algorithm (oracle/ks_oracle.c, literal 123 FFTs/"
+                                     "env-step, own mixed-radix DFT), not Julia+FFTW: Julia is not installed"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append([x.strip() for x in ln.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = importlib.import_module(PKG)
+    agent = importlib.import_module(PKG + ".agent")
+    L = pkg.lib
+
+    B = args.envs
+    setup = pkg.setups.KSSetup.ks256(oversampling=args.oversampling)
+    rng = np.random.default_rng(1000 + rank)
+    y0 = setup.generate_random_init(rng, B)
+    env = setup.make_env(n_envs=B, dtype=args.dtype, device=local, y0=y0)
+    gpath = ROOT / "tests" / "golden" / "ks200_hook.npz"
+    g = np.load(gpath)
+    chain = agent.Chain(agent.Dense(g["best_W1"], g["best_b1"], "relu"), agent.Dense(g["best_W2"], g["best_b2"], "tanh"))
+    agent.CustomNeuralNetworkApproximator(env, L.NET_BEHAVIOR_ACTOR, chain)
+    stream = torch.cuda.current_stream()
+    L.check(env._lib.pdeb200_set_stream(env._ctx, C.c_void_p(stream.cuda_stream)), env._ctx)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput: one fused launch per step --------------------------------
+    for _ in range(max(args.warmup, 3)):
+        env.rollout(1)
+    torch.cuda.synchronize()
+    env.reset()
+    launches0 = env.launch_count
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    for i in range(args.steps):
+        flush.zero_()                      # L2 flush, outside the event-timed region
+        ev0[i].record(stream)
+        env.rollout(1)
+        ev1[i].record(stream)
+    barrier()
+    clk = clocks.stop()
+    launches = env.launch_count - launches0
+    kern_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
+    total_ms = float(sum(kern_ms))
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = B * world * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers -----------------------------------
+    # Per step, as the drop-in closures do it: policy(env) returns the action on the host
+    # (PDEagent.jl:198), env(action) takes it from the host, reward/state/done come back for the
+    # agent and the hook.
+    esz = 8 if args.dtype == "f64" else 4
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    n_act = B * env.n_actuators
+    h_act = torch.empty(n_act, dtype=tdt).pin_memory()
+    h_rew = torch.empty(n_act, dtype=tdt).pin_memory()
+    h_state = torch.empty(n_act * env.ns, dtype=tdt).pin_memory()
+    h_done = torch.empty(B, dtype=torch.uint8).pin_memory()
+    lib, ctx = env._lib, env._ctx
+
+    def e2e_step():
+        L.check(lib.pdeb200_policy_act(ctx, None, 0.0, 1.0), ctx)
+        L.check(lib.pdeb200_get(ctx, L.ARR_ACTION_IN, C.c_void_p(h_act.data_ptr()), n_act * esz), ctx)
+        L.check(lib.pdeb200_step_host(ctx, C.c_void_p(h_act.data_ptr()), None, C.c_void_p(h_rew.data_ptr()),
+                                      C.c_void_p(h_state.data_ptr()), C.c_void_p(h_done.data_ptr())), ctx)
+    env.reset()
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / float(t.item())
+    h2d = n_act * esz
+    d2h = n_act * esz + n_act * esz + n_act * env.ns * esz + B
+
+    # ---- roofline of the dominant (only) kernel -------------------------------------------------
+    bytes_env, flops_env = env.step_cost()
+    avg_ms = float(np.mean(kern_ms))
+    peak, peak_src = measured_peak()
+    achieved = bytes_env * B / (avg_ms * 1e-3) / 1e9
+    traffic = None
+    tp = ROOT / "profiles" / "traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("ks_step_%s_S%d" % (args.dtype, args.oversampling))
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "ks_step_kernel<%s,16,16>" % args.dtype,
+                "algorithmic_bytes_per_env_step": bytes_env, "kernel_ms": avg_ms,
+                "note": "at oversampling=30 the step is FP64-pipe/shared-memory bound (arithmetic intensity ~%d flop/B), "
+                        "so the HBM fraction is small by construction; see fp_pipe" % round(flops_env / bytes_env),
+                "fp_pipe": {"algorithmic_flops_per_env_step": flops_env,
+                            "achieved_tflops": flops_env * B / (avg_ms * 1e-3) / 1e12,
+                            "nominal_peak_tflops": 37.0 if args.dtype == "f64" else 75.0,
+                            "frac_of_nominal": flops_env * B / (avg_ms * 1e-3) / 1e12 / (37.0 if args.dtype == "f64" else 75.0)}}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic", "config": config_dict(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        orc = CpuOracle(args.oversampling)
+        orc.run(4, 1)
+        n_steps_cpu = 10
+        per_core = 32
+        secs = orc.run(per_core, n_steps_cpu)
+        line["cpu_baseline"] = {"value": per_core * orc.cores * n_steps_cpu / secs, "unit": UNIT, "cores": orc.cores,
+                                "kind": "port", "sample": "%d envs x %d env steps (same KS N=256 config), one thread per core"
+                                % (per_core * orc.cores, n_steps_cpu)}
+    elif rank == 0:
+        line["cpu_baseline"] = None
+    env.close()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -227,6 +227,7 @@ ArrInfo arr_info(pdeb200_ctx* c, int which) {
         case PDEB200_ARR_P: return {c->p, B * c->p_elems * e};
         case PDEB200_ARR_STATE: return {c->state, B * c->n_cols * c->obs_rows * e};
         case PDEB200_ARR_ACTION: return {c->action, B * c->cfg.n_actuators * c->a_rows * e};
+        case PDEB200_ARR_ACTION_IN: return {c->action_in, B * c->cfg.n_actuators * c->a_rows * e};
         case PDEB200_ARR_DELTA_ACTION: return {c->delta_action, B * c->cfg.n_actuators * c->a_rows * e};
         case PDEB200_ARR_REWARD: return {c->reward, B * c->n_rew * e};
         case PDEB200_ARR_DONE: return {c->done, B};

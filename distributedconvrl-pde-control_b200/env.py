@@ -118,6 +118,7 @@ class PDEenv:
             L.ARR_STATE: (B * self.n_cols * self.ns, self.np_dtype),
             L.ARR_ACTION: (B * self.n_actuators * self.a_rows, self.np_dtype),
             L.ARR_DELTA_ACTION: (B * self.n_actuators * self.a_rows, self.np_dtype),
+            L.ARR_ACTION_IN: (B * self.n_actuators * self.a_rows, self.np_dtype),
             L.ARR_REWARD: (B * self.n_rew, self.np_dtype), L.ARR_DONE: (B, np.uint8),
             L.ARR_TIME: (B, np.float64), L.ARR_STEPS: (B, np.int32),
             L.ARR_SENSORS: (B * (2 if self.problem == L.KSEG1D else 1) * self.n_sensors, self.np_dtype),

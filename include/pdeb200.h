@@ -77,7 +77,8 @@ enum {
     PDEB200_ARR_Y0 = 9,           /* env.y0                                  dtype   */
     PDEB200_ARR_GRADS = 10,       /* flat [critic | actor] gradient (+ tail) float32 */
     PDEB200_ARR_LOSSES = 11,      /* {critic_loss, actor_loss}               float32 */
-    PDEB200_ARR_SENSORS = 12      /* raw sensor dots [B][fields][n_sensors]  dtype   */
+    PDEB200_ARR_SENSORS = 12,     /* raw sensor dots [B][fields][n_sensors]  dtype   */
+    PDEB200_ARR_ACTION_IN = 13    /* staged action of the last policy_act    dtype   */
 };
 
 typedef struct pdeb200_config {
