@@ -211,7 +211,11 @@ def run_ours(args):
     g = np.load(gpath)
     chain = agent.Chain(agent.Dense(g["best_W1"], g["best_b1"], "relu"), agent.Dense(g["best_W2"], g["best_b2"], "tanh"))
     agent.CustomNeuralNetworkApproximator(env, L.NET_BEHAVIOR_ACTOR, chain)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream: the default stream's handle is NULL, which the C ABI reads as
+    # "use the context's own stream"; kernels, flushes and events must share one stream to be timed
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     L.check(env._lib.pdeb200_set_stream(env._ctx, C.c_void_p(stream.cuda_stream)), env._ctx)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 

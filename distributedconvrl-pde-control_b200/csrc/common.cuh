@@ -51,8 +51,8 @@ __device__ __forceinline__ void mlp_forward_small(const NetDev& net, float* x, f
         const float* b = W + ni * no;
         for (int o = 0; o < no; ++o) {
             float acc = 0.f;
-            for (int i = 0; i < ni; ++i) acc = fmaf(__ldg(W + o + no * i), in[i], acc);
-            out[o] = act_apply(net.acts[l], acc + __ldg(b + o));
+            for (int i = 0; i < ni; ++i) acc = fmaf(W[o + no * i], in[i], acc);      // params may live in smem
+            out[o] = act_apply(net.acts[l], acc + b[o]);
         }
         float* tmp = in; in = out; out = tmp;
     }

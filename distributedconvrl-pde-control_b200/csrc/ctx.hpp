@@ -58,7 +58,7 @@ struct pdeb200_ctx {
     void *y = nullptr, *y0 = nullptr, *p = nullptr, *state = nullptr, *action = nullptr, *action_in = nullptr,
          *delta_action = nullptr, *reward = nullptr, *sensors = nullptr;
     uint8_t* done = nullptr; double* time = nullptr; int* steps = nullptr;
-    uint8_t* d_mask = nullptr; double* d_rsum = nullptr; void* d_noise = nullptr;
+    uint8_t* d_mask = nullptr; double* d_rsum = nullptr; void* d_noise = nullptr; void* vmax = nullptr;
 
     // bases
     pdeb200::EllHost sens, actT;
@@ -70,6 +70,7 @@ struct pdeb200_ctx {
 
     // problem-specific opaque state (KSeg / NS translation units)
     void* prob = nullptr;
+    void* prob_p_phys = nullptr;    // NS: physical-space actuation sum before its FFT (owned by ns.cu)
 
     // networks + replay + ddpg
     pdeb200::HostNet nets[4];
@@ -116,20 +117,21 @@ inline ObsRewardParams<T> make_obs_params(const pdeb200_ctx* c) {
     return P;
 }
 
-// problem back-ends (one translation unit each)
+// problem back-ends (one translation unit each).  *_core advances env.y by one env step from (y, p),
+// and writes the raw sensor dots and max|y|; *_sensors computes sensor dots from env.y (reset path).
 int32_t ks_setup(pdeb200_ctx* c);
-int32_t ks_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum);
+int32_t ks_core(pdeb200_ctx* c);
 int32_t ks_cost(const pdeb200_ctx* c, double* bytes, double* flops);
 void ks_free(pdeb200_ctx* c);
 
 int32_t kseg_setup(pdeb200_ctx* c);
-int32_t kseg_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum);
+int32_t kseg_core(pdeb200_ctx* c);
 int32_t kseg_cost(const pdeb200_ctx* c, double* bytes, double* flops);
 void kseg_free(pdeb200_ctx* c);
 
 int32_t ns_setup(pdeb200_ctx* c);
-int32_t ns_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum);
-int32_t ns_featurize_reset(pdeb200_ctx* c, const uint8_t* d_mask);
+int32_t ns_core(pdeb200_ctx* c);
+int32_t ns_sensors(pdeb200_ctx* c, const uint8_t* d_mask);
 int32_t ns_cost(const pdeb200_ctx* c, double* bytes, double* flops);
 void ns_free(pdeb200_ctx* c);
 

@@ -1,0 +1,260 @@
+// Problem-independent kernels on either side of the PDE core kernels.
+//
+//   actuate_kernel : [fused actor forward]      src/PDEagent.jl:189,204
+//                    delta_action / action      src/PDEenv.jl:196-197
+//                    prepare_action             KSSetup.jl:231-245, KellerSegelSetup.jl:318-332,
+//                                               FluidSetup.jl:247-259 (the physical-space sum)
+//   observe_kernel : reward_function, featurize, clock/done   (see obs_reward.cuh, PDEenv.jl:220-240)
+//
+// They run at full occupancy with one thread per column / grid point; the register- and
+// shared-memory-heavy core kernels (ks_step.cuh, ...) only see  (y, p) -> (y', sensor dots, max|y|).
+// One CTA per environment.
+#pragma once
+#include "common.cuh"
+#include "obs_reward.cuh"
+
+namespace pdeb200 {
+
+template <typename T>
+struct ActuateArgs {
+    int n_envs, envs_per_cta;
+    int n_act, a_rows, obs_rows, mono, npts, use_actor;
+    int actor_wmax, actor_np;      // widest layer / parameter count of the actor
+    int stage_table;               // 1: the gather table fits the CTA's shared memory
+    const int* act_idx;            // ELL over grid points: [nnz][npts] actuator index
+    const T* act_w;                //                        [nnz][npts] weight
+    int act_nnz;
+    T power, act_limit;
+    NetDev actor;
+    const T* actions_in;           // [B][n_act][a_rows] (ignored when use_actor)
+    const T* state;                // [B][n_cols][obs_rows]
+    T* action; T* delta_action;    // [B][n_act][a_rows]
+    T* p;                          // [B][npts] physical actuation field
+};
+
+// Shared memory: s_a [E][n_act] T | staged table (w, idx) | actor params | activations [2][wmax][blockDim] f32
+template <typename T>
+__host__ __device__ inline size_t actuate_smem_bytes(int E, int n_act, int npts, int nnz, int stage, int use_actor,
+                                                     int actor_np, int wmax, int block) {
+    size_t b = (size_t)E * n_act * sizeof(T);
+    b = (b + 15) & ~(size_t)15;
+    if (stage) b += (size_t)nnz * npts * (sizeof(T) + sizeof(int));
+    b = (b + 15) & ~(size_t)15;
+    if (use_actor) b += (size_t)actor_np * sizeof(float) + (size_t)2 * wmax * block * sizeof(float);
+    return b;
+}
+
+// MLP forward with per-thread activations held in shared memory ([unit][thread], conflict free) and
+// weights broadcast from shared memory.  Restates Flux Dense: y = act.(W*x .+ b)  (src/PDEagent.jl:18-30).
+// Input in xa[i*BD]; returns the buffer holding the output.
+__device__ __forceinline__ float* mlp_forward_smem(const NetDev& net, const float* params, float* xa, float* xb, int BD) {
+    float* in = xa;
+    float* out = xb;
+    for (int l = 0; l < net.n_layers; ++l) {
+        const int ni = net.sizes[l], no = net.sizes[l + 1];
+        const float* W = params + net.offs[l];
+        const float* b = W + ni * no;
+        for (int o = 0; o < no; ++o) {
+            float acc = 0.f;
+            for (int i = 0; i < ni; ++i) acc = fmaf(W[o + no * i], in[i * BD], acc);
+            out[o * BD] = act_apply(net.acts[l], acc + b[o]);
+        }
+        float* tmp = in; in = out; out = tmp;
+    }
+    return in;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) actuate_kernel(const __grid_constant__ ActuateArgs<T> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int E = A.envs_per_cta, BD = blockDim.x, tid = threadIdx.x;
+    T* s_a = reinterpret_cast<T*>(smem_raw);                       // row 0 of the new actions, [E][n_act]
+    size_t off = ((size_t)E * A.n_act * sizeof(T) + 15) & ~(size_t)15;
+    const size_t ntab = (size_t)A.act_nnz * A.npts;
+    T* s_w = reinterpret_cast<T*>(smem_raw + off);
+    int* s_idx = reinterpret_cast<int*>(s_w + ntab);
+    if (A.stage_table) off += ntab * (sizeof(T) + sizeof(int));
+    off = (off + 15) & ~(size_t)15;
+    float* s_par = reinterpret_cast<float*>(smem_raw + off);
+    float* s_x = s_par + A.actor_np;
+    const int env0 = blockIdx.x * E;
+
+    if (A.stage_table)
+        for (size_t i = tid; i < ntab; i += BD) { s_w[i] = __ldg(A.act_w + i); s_idx[i] = __ldg(A.act_idx + i); }
+    if (A.use_actor) {
+        for (int i = tid; i < A.actor_np; i += BD) s_par[i] = A.actor.params[i];
+        __syncthreads();
+    }
+    if (A.use_actor && A.mono) {
+        // global agent: one column per env with n_act outputs
+        for (int e = tid; e < E; e += BD) {
+            const int env = env0 + e;
+            if (env >= A.n_envs) continue;
+            float* xa = s_x + tid;
+            float* xb = s_x + (size_t)A.actor_wmax * BD + tid;
+            const T* scol = A.state + (size_t)env * A.obs_rows;
+            for (int r = 0; r < A.obs_rows; ++r) xa[r * BD] = (float)scol[r];
+            const float* out = mlp_forward_smem(A.actor, s_par, xa, xb, BD);
+            const size_t abase = (size_t)env * A.n_act;
+            for (int j = 0; j < A.n_act; ++j) {
+                const T v = clamp_t<T>((T)out[j * BD], A.act_limit);
+                A.delta_action[abase + j] = v - A.action[abase + j];
+                A.action[abase + j] = v;
+                s_a[e * A.n_act + j] = v;
+            }
+        }
+    } else {
+        for (int q = tid; q < E * A.n_act; q += BD) {
+            const int e = q / A.n_act, j = q % A.n_act, env = env0 + e;
+            if (env >= A.n_envs) { s_a[q] = T(0); continue; }
+            const size_t col = (size_t)env * A.n_act + j;
+            T* acol = A.action + col * A.a_rows;
+            T* dcol = A.delta_action + col * A.a_rows;
+            if (A.use_actor) {
+                float* xa = s_x + tid;
+                float* xb = s_x + (size_t)A.actor_wmax * BD + tid;
+                const T* scol = A.state + col * A.obs_rows;
+                for (int r = 0; r < A.obs_rows; ++r) xa[r * BD] = (float)scol[r];
+                const float* out = mlp_forward_smem(A.actor, s_par, xa, xb, BD);
+                for (int r = 0; r < A.a_rows; ++r) {
+                    const T v = clamp_t<T>((T)out[r * BD], A.act_limit);
+                    dcol[r] = v - acol[r]; acol[r] = v;
+                    if (r == 0) s_a[q] = v;
+                }
+            } else {
+                const T* icol = A.actions_in + col * A.a_rows;
+                for (int r = 0; r < A.a_rows; ++r) {
+                    const T v = icol[r];
+                    dcol[r] = v - acol[r]; acol[r] = v;
+                    if (r == 0) s_a[q] = v;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    // p[n] = sum_i (power * a_i) * g_i[n], ascending actuator index like the reference loop
+    const int* idxp = A.stage_table ? s_idx : A.act_idx;
+    const T* wp = A.stage_table ? s_w : A.act_w;
+    for (int q = tid; q < E * A.npts; q += BD) {
+        const int e = q / A.npts, n = q % A.npts, env = env0 + e;
+        if (env >= A.n_envs) continue;
+        T acc = T(0);
+        for (int j = 0; j < A.act_nnz; ++j) {
+            const int i = idxp[(size_t)j * A.npts + n];
+            acc += (A.power * s_a[e * A.n_act + i]) * wp[(size_t)j * A.npts + n];
+        }
+        A.p[(size_t)env * A.npts + n] = acc;
+    }
+}
+
+template <typename T>
+struct ObserveArgs {
+    ObsRewardParams<T> P;
+    int fresh;                     // 1: reset!/constructor semantics (no clock advance, zero reward)
+    const uint8_t* mask;           // optional per-env mask (reset)
+    const T* sensors;              // [B][fields][n_sensors] raw dots
+    const T* vmax;                 // [B] max |y| (CHECK_Y)
+    T* state; T* action; T* delta_action; T* action_in; T* reward;
+    uint8_t* done; double* time; int* steps; double* reward_sum;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ ObserveArgs<T> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* s_sens = reinterpret_cast<T*>(smem_raw);                    // [fields][n_sensors]
+    __shared__ T s_red[2][4];
+    const ObsRewardParams<T>& P = A.P;
+    const int env = blockIdx.x;
+    if (A.mask && !A.mask[env]) return;
+    const int nsv = P.fields * P.n_sensors;
+    for (int i = threadIdx.x; i < nsv; i += blockDim.x) s_sens[i] = A.sensors[(size_t)env * nsv + i];
+    __syncthreads();
+    auto sv = [&](int f, int i) { return s_sens[f * P.n_sensors + i]; };
+    const bool fresh = A.fresh != 0;
+    T racc = T(0), rmax = T(0);
+    for (int j = threadIdx.x; j < P.n_act; j += blockDim.x) {
+        const size_t col = (size_t)env * P.n_act + j;
+        T* acol = A.action + col * P.a_rows;
+        T* dcol = A.delta_action + col * P.a_rows;
+        if (fresh)
+            for (int r = 0; r < P.a_rows; ++r) { acol[r] = T(0); dcol[r] = T(0); A.action_in[col * P.a_rows + r] = T(0); }
+        const T a0 = acol[0], d0 = dcol[0];
+        T rj;
+        if (!P.mono) {
+            rj = assemble_column<T>(P, sv, j, a0, d0, acol, A.state + col * P.obs_rows, fresh);
+            A.reward[col] = fresh ? T(0) : rj;
+        } else {
+            const int m = P.a2s[j];
+            const T raw = sv(0, m) - P.r_offset * P.sens_sum[m];
+            const T s = pow_t<T>(fabs(P.r_gain * raw), P.r_pow) / P.r_div;
+            rj = -fabs(s) - P.a_pun * a0 * a0 - P.da_pun * d0 * d0;
+        }
+        racc += rj; rmax = fmax(rmax, fabs(rj));
+    }
+    if (P.mono) {
+        // state = reshape(sensors, (n_sensors, 1)) [+ temporal stacking], KSglobalSetup.jl:222-238
+        T* scol = A.state + (size_t)env * P.obs_rows;
+        if (P.temporal > 1 && !fresh) {
+            __syncthreads();
+            if (threadIdx.x == 0)
+                for (int r = P.obs_rows - P.memory - 1; r >= P.n_sensors; --r) scol[r] = scol[r - P.n_sensors];
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < P.n_sensors; i += blockDim.x) {
+            const T v = s_sens[i] * P.obs_scale;
+            scol[i] = v;
+            if (fresh) for (int k = 1; k < P.temporal; ++k) scol[k * P.n_sensors + i] = v;
+        }
+        for (int k = threadIdx.x; k < P.memory; k += blockDim.x) scol[P.obs_rows - P.memory + k] = T(0);
+    }
+    // block reduction of (sum, max) over the columns
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        racc += __shfl_xor_sync(0xffffffffu, racc, o);
+        rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = racc; s_red[1][threadIdx.x >> 5] = rmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        T sum = T(0), mx = T(0);
+        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) { sum += s_red[0][w]; mx = fmax(mx, s_red[1][w]); }
+        if (fresh) {
+            if (P.mono) A.reward[env] = T(0);
+            A.done[env] = 0; A.time[env] = 0.0; A.steps[env] = 0;
+        } else {
+            const T rmean = sum / T(P.n_act);
+            if (P.mono) { A.reward[env] = rmean; mx = fabs(rmean); }
+            const double tm = A.time[env] + P.dt;                 // env.time += env.dt (Float64, quirk Q7)
+            bool dn = tm >= P.te;
+            if (P.check_max == 1) dn = dn || (A.vmax[env] > P.max_value);
+            else if (P.check_max == 2) dn = dn || (mx > P.max_value);
+            A.done[env] = dn ? 1 : 0;
+            A.time[env] = tm;
+            A.steps[env] += 1;
+            if (A.reward_sum) A.reward_sum[env] += (double)rmean;
+        }
+    }
+}
+
+// Sensor dots straight from physical fields in global memory (reset! / set_state path; the core
+// kernels produce them from on-chip state).  One CTA per environment.
+template <typename T>
+__global__ void __launch_bounds__(128) sensors_phys_kernel(int fields, int npts, int n_sensors, EllTable<T> sens,
+                                                           const uint8_t* __restrict__ mask, const T* __restrict__ y,
+                                                           int interleaved, T* sensors_out, T* vmax_out) {
+    const int env = blockIdx.x;
+    if (mask && !mask[env]) return;
+    const T* ye = y + (size_t)env * fields * npts;
+    for (int q = threadIdx.x; q < fields * n_sensors; q += blockDim.x) {
+        const int f = q / n_sensors, i = q % n_sensors;
+        T acc = T(0);
+        for (int j = 0; j < sens.nnz_max; ++j) {
+            const int n = sens.idx[j * n_sensors + i];
+            acc += (interleaved ? ye[n * fields + f] : ye[f * npts + n]) * sens.w[j * n_sensors + i];
+        }
+        sensors_out[(size_t)env * fields * n_sensors + q] = acc;
+    }
+    if (vmax_out && threadIdx.x == 0) vmax_out[env] = T(0);
+}
+
+}  // namespace pdeb200

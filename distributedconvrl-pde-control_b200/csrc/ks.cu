@@ -1,5 +1,7 @@
 // KS back-end: spectral constant tables + launch dispatch for ks_step_kernel.
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "ctx.hpp"
@@ -77,57 +79,80 @@ int32_t setup_t(pdeb200_ctx* c) {
     return PDEB200_OK;
 }
 
+// Pick the CTA size (warps) and residency so that the grid fills whole waves: with deterministic,
+// equal work per pair the step time is (rounds) x (time of one resident set), so a 1.73-wave grid
+// costs as much as a 2.0-wave one.  cost ~ rounds * resident_pairs; ties go to more resident warps.
 template <typename T, int N1, int N2>
-int32_t launch(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum) {
+void plan(const pdeb200_ctx* c, int n_sm, int* warps_out, int* ctas_per_sm_out) {
+    using G = KsGeom<N1, N2>;
+    constexpr int ppw = 32 / G::TP;
+    const int max_warps = KsMaxWarps<T>::value;
+    const int n_pairs = (c->cfg.n_envs + 1) / 2;
+    static const int forced = [] { const char* e = getenv("PDEB200_KS_WARPS"); return e ? atoi(e) : 0; }();
+    double best = 1e300; int bw = 1, bc = 1;
+    for (int w = 1; w <= max_warps; ++w) {
+        if (forced && w != forced) continue;
+        const size_t smem = ks_smem_bytes<T, N1, N2>(w * ppw) + 1024;
+        int cps = std::min((int)((227 * 1024) / smem), max_warps / w);
+        if (cps < 1) continue;
+        const int ppc = w * ppw;
+        const int n_ctas = (n_pairs + ppc - 1) / ppc;
+        const int per_sm = (n_ctas + n_sm - 1) / n_sm;
+        cps = std::min(cps, per_sm);
+        const int rounds = (per_sm + cps - 1) / cps;
+        // more resident warps hide latency better: mild bonus
+        const double cost = (double)rounds * cps * ppc * (1.0 + 0.02 * (max_warps - cps * w));
+        if (cost < best - 1e-9) { best = cost; bw = w; bc = cps; }
+    }
+    *warps_out = bw; *ctas_per_sm_out = bc;
+}
+
+template <typename T, int N1, int N2>
+int32_t launch(pdeb200_ctx* c) {
     using G = KsGeom<N1, N2>;
     using C = typename V2<T>::type;
-    constexpr int WARPS = (G::TP == 32) ? 2 : 2;
-    constexpr int PAIRS = WARPS * 32 / G::TP;
     const pdeb200_config& g = c->cfg;
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+    int warps, cps;
+    plan<T, N1, N2>(c, n_sm, &warps, &cps);
+    const int PAIRS = warps * 32 / G::TP;
     KsArgs<T> A;
-    A.n_envs = g.n_envs; A.S = g.oversampling; A.n_steps = n_steps; A.use_actor = use_actor; A.write_p = 1;
-    A.P = make_obs_params<T>(c);
+    A.n_envs = g.n_envs; A.S = g.oversampling; A.n_sensors = g.n_sensors;
     A.tw12 = (const C*)c->tw12; A.tw21 = (const C*)c->tw21;
     A.c1 = (const T*)c->c1; A.cN = (const T*)c->cN; A.ainvh = (const T*)c->ainvh; A.hm = (const C*)c->hm;
     const double h = g.dt / g.oversampling;
-    A.dt32 = (T)(3 * h / 2); A.dt2 = (T)(h / 2); A.inv_n = (T)(1.0 / G::N); A.n_scale = (T)G::N;
-    A.power = (T)g.agent_power;
+    A.dt32 = (T)(3 * h / 2); A.dt2 = (T)(h / 2); A.inv_n = (T)(1.0 / G::N);
     A.sens = EllTable<T>{c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows};
-    A.actT = EllTable<T>{c->actT.d_idx, (const T*)c->actT.d_w, c->actT.nnz_max, c->actT.n_rows};
-    A.y = (T*)c->y; A.p = (T*)c->p; A.state = (T*)c->state; A.action = (T*)c->action;
-    A.delta_action = (T*)c->delta_action; A.reward = (T*)c->reward; A.sensors_out = (T*)c->sensors;
-    A.done = c->done; A.time = c->time; A.steps = c->steps;
-    A.actions_in = (const T*)actions_dev;
-    A.actor = c->nets[PDEB200_NET_BEHAVIOR_ACTOR].dev(); A.act_limit = (T)act_limit;
-    A.reward_sum = d_rsum;
+    A.y = (T*)c->y; A.p = (const T*)c->p; A.sensors_out = (T*)c->sensors; A.vmax_out = (T*)c->vmax;
     const int n_pairs = (g.n_envs + 1) / 2;
     const int grid = (n_pairs + PAIRS - 1) / PAIRS;
-    const size_t smem = ks_smem_bytes<T, N1, N2>(PAIRS, g.n_sensors, g.n_actuators);
-    auto kern = ks_step_kernel<T, N1, N2, WARPS>;
+    const size_t smem = ks_smem_bytes<T, N1, N2>(PAIRS);
+    auto kern = ks_step_kernel<T, N1, N2>;
     static thread_local size_t configured[64] = {0};
     if (smem > configured[c->device & 63]) {
         PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[c->device & 63] = smem;
     }
-    kern<<<grid, WARPS * 32, smem, c->stream>>>(A);
+    kern<<<grid, warps * 32, smem, c->stream>>>(A);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
 }
 
 template <typename T>
-int32_t dispatch(pdeb200_ctx* c, const void* a, int n, int ua, double lim, double* rs) {
+int32_t dispatch(pdeb200_ctx* c) {
     switch (c->cfg.nx) {
-        case 64:   return launch<T, 8, 8>(c, a, n, ua, lim, rs);
-        case 128:  return launch<T, 8, 16>(c, a, n, ua, lim, rs);
-        case 192:  return launch<T, 12, 16>(c, a, n, ua, lim, rs);
-        case 240:  return launch<T, 15, 16>(c, a, n, ua, lim, rs);
-        case 256:  return launch<T, 16, 16>(c, a, n, ua, lim, rs);
-        case 320:  return launch<T, 16, 20>(c, a, n, ua, lim, rs);
-        case 384:  return launch<T, 16, 24>(c, a, n, ua, lim, rs);
-        case 512:  return launch<T, 16, 32>(c, a, n, ua, lim, rs);
-        case 600:  return launch<T, 24, 25>(c, a, n, ua, lim, rs);
-        case 1024: return launch<T, 32, 32>(c, a, n, ua, lim, rs);
+        case 64:   return launch<T, 8, 8>(c);
+        case 128:  return launch<T, 8, 16>(c);
+        case 192:  return launch<T, 12, 16>(c);
+        case 240:  return launch<T, 15, 16>(c);
+        case 256:  return launch<T, 16, 16>(c);
+        case 320:  return launch<T, 16, 20>(c);
+        case 384:  return launch<T, 16, 24>(c);
+        case 512:  return launch<T, 16, 32>(c);
+        case 600:  return launch<T, 24, 25>(c);
+        case 1024: return launch<T, 32, 32>(c);
     }
     return fail(c, PDEB200_EUNSUPPORTED, "KS: unsupported nx");
 }
@@ -145,10 +170,7 @@ int32_t ks_setup(pdeb200_ctx* c) {
     return c->cfg.dtype == PDEB200_F64 ? setup_t<double>(c) : setup_t<float>(c);
 }
 
-int32_t ks_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum) {
-    return c->cfg.dtype == PDEB200_F64 ? dispatch<double>(c, actions_dev, n_steps, use_actor, act_limit, d_rsum)
-                                       : dispatch<float>(c, actions_dev, n_steps, use_actor, act_limit, d_rsum);
-}
+int32_t ks_core(pdeb200_ctx* c) { return c->cfg.dtype == PDEB200_F64 ? dispatch<double>(c) : dispatch<float>(c); }
 
 // Algorithmic cost of one env step (SURVEY.md 8d / DESIGN.md):
 //   bytes: y in + y out + action in + obs out + reward out + done

@@ -5,7 +5,7 @@
 #include <vector>
 
 #include "ctx.hpp"
-#include "obs_reward.cuh"
+#include "glue.cuh"
 
 namespace pdeb200 {
 
@@ -13,58 +13,14 @@ thread_local std::string g_last_error;
 
 namespace {
 
-// ------------------------------------------------------------------------------------------------
-// featurize(y0, t0) / reset! for problems whose state is the physical field(s) (KS, KSeg).
-// One CTA per environment.  src/PDEenv.jl:183-193 + the `isnothing(env)` branches of featurize.
-// ------------------------------------------------------------------------------------------------
+// reset!: y = y0, p = prepare_action(action0) = 0 for the masked environments (src/PDEenv.jl:183-193)
 template <typename T>
-__global__ void reset_phys_kernel(ObsRewardParams<T> P, EllTable<T> sens, int npts, const T* __restrict__ y0,
-                                  int y0_broadcast, const uint8_t* __restrict__ mask, T* y, T* p, int p_elems,
-                                  T* state, T* action, T* action_in, T* delta_action, T* reward, T* sensors_out,
-                                  uint8_t* done, double* time, int* steps, int n_cols, int n_rew) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_y = reinterpret_cast<T*>(smem_raw);                 // [fields][npts]
-    T* s_sens = s_y + (size_t)P.fields * npts;               // [fields][n_sensors]
+__global__ void reset_copy_kernel(int y_elems, int p_elems, const uint8_t* __restrict__ mask, const T* __restrict__ y0,
+                                  T* y, T* p) {
     const int env = blockIdx.x;
     if (mask && !mask[env]) return;
-    const int ye = P.fields * npts;
-    const T* src = y0 + (y0_broadcast ? 0 : (size_t)env * ye);
-    for (int i = threadIdx.x; i < ye; i += blockDim.x) {
-        const T v = src[i];
-        s_y[i] = v;
-        y[(size_t)env * ye + i] = v;
-    }
+    for (int i = threadIdx.x; i < y_elems; i += blockDim.x) y[(size_t)env * y_elems + i] = y0[(size_t)env * y_elems + i];
     for (int i = threadIdx.x; i < p_elems; i += blockDim.x) p[(size_t)env * p_elems + i] = T(0);
-    __syncthreads();
-    for (int q = threadIdx.x; q < P.fields * P.n_sensors; q += blockDim.x) {
-        const int f = q / P.n_sensors, i = q % P.n_sensors;
-        T acc = T(0);
-        for (int j = 0; j < sens.nnz_max; ++j)
-            acc += s_y[f * npts + sens.idx[j * P.n_sensors + i]] * sens.w[j * P.n_sensors + i];
-        s_sens[q] = acc;
-        if (sensors_out) sensors_out[(size_t)env * P.fields * P.n_sensors + q] = acc;
-    }
-    __syncthreads();
-    auto sv = [&](int f, int i) { return s_sens[f * P.n_sensors + i]; };
-    if (!P.mono) {
-        for (int c = threadIdx.x; c < P.n_act; c += blockDim.x) {
-            const size_t col = (size_t)env * P.n_act + c;
-            (void)assemble_column<T>(P, sv, c, T(0), T(0), action + col * P.a_rows, state + col * P.obs_rows, true);
-        }
-    } else {
-        T* scol = state + (size_t)env * P.obs_rows;
-        for (int i = threadIdx.x; i < P.n_sensors; i += blockDim.x)
-            for (int k = 0; k < P.temporal; ++k) scol[k * P.n_sensors + i] = s_sens[i] * P.obs_scale;
-        for (int k = threadIdx.x; k < P.memory; k += blockDim.x) scol[P.obs_rows - P.memory + k] = T(0);
-    }
-    const int na = P.n_act * P.a_rows;
-    for (int i = threadIdx.x; i < na; i += blockDim.x) {
-        action[(size_t)env * na + i] = T(0);
-        action_in[(size_t)env * na + i] = T(0);
-        delta_action[(size_t)env * na + i] = T(0);
-    }
-    for (int i = threadIdx.x; i < n_rew; i += blockDim.x) reward[(size_t)env * n_rew + i] = T(0);
-    if (threadIdx.x == 0) { done[env] = 0; time[env] = 0.0; steps[env] = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -182,40 +138,111 @@ int32_t set_bases_t(pdeb200_ctx* c, const double* sb, const double* ab, const in
 }
 
 template <typename T>
-int32_t reset_t(pdeb200_ctx* c, const uint8_t* d_mask) {
-    if (c->cfg.problem == PDEB200_NS2D) return ns_featurize_reset(c, d_mask);
-    const size_t smem = ((size_t)c->fields * c->npts + (size_t)c->fields * c->cfg.n_sensors) * sizeof(T);
+int32_t observe_t(pdeb200_ctx* c, int fresh, const uint8_t* d_mask, double* d_rsum) {
+    ObserveArgs<T> O;
+    O.P = make_obs_params<T>(c);
+    O.fresh = fresh; O.mask = d_mask; O.sensors = (const T*)c->sensors; O.vmax = (const T*)c->vmax;
+    O.state = (T*)c->state; O.action = (T*)c->action; O.delta_action = (T*)c->delta_action; O.action_in = (T*)c->action_in;
+    O.reward = (T*)c->reward; O.done = c->done; O.time = c->time; O.steps = c->steps; O.reward_sum = d_rsum;
+    const size_t smem = (size_t)c->fields * c->cfg.n_sensors * sizeof(T);
     if (smem > 48 * 1024)
-        PDEB_CUDA(c, cudaFuncSetAttribute(reset_phys_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    reset_phys_kernel<T><<<c->cfg.n_envs, 128, smem, c->stream>>>(
-        make_obs_params<T>(c), EllTable<T>{c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows},
-        c->npts, (const T*)c->y0, 0, d_mask, (T*)c->y, (T*)c->p, c->p_elems, (T*)c->state, (T*)c->action,
-        (T*)c->action_in, (T*)c->delta_action, (T*)c->reward, (T*)c->sensors, c->done, c->time, c->steps, c->n_cols,
-        c->n_rew);
+        PDEB_CUDA(c, cudaFuncSetAttribute(observe_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tpb = c->cfg.n_actuators <= 32 ? 32 : (c->cfg.n_actuators <= 64 ? 64 : 128);
+    observe_kernel<T><<<c->cfg.n_envs, tpb, smem, c->stream>>>(O);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
 }
 
+template <typename T>
+int32_t actuate_t(pdeb200_ctx* c, const void* actions_dev, int use_actor, double act_limit) {
+    ActuateArgs<T> A;
+    const HostNet& net = c->nets[PDEB200_NET_BEHAVIOR_ACTOR];
+    A.n_envs = c->cfg.n_envs;
+    A.n_act = c->cfg.n_actuators; A.a_rows = c->a_rows; A.obs_rows = c->obs_rows; A.mono = c->cfg.mono;
+    A.npts = c->npts; A.use_actor = use_actor;
+    A.actor_np = use_actor ? net.n_params : 0;
+    A.actor_wmax = 1;
+    if (use_actor) for (int l = 0; l <= net.n_layers; ++l) A.actor_wmax = std::max(A.actor_wmax, net.sizes[l]);
+    A.act_idx = c->actT.d_idx; A.act_w = (const T*)c->actT.d_w; A.act_nnz = c->actT.nnz_max;
+    A.power = (T)c->cfg.agent_power; A.act_limit = (T)act_limit;
+    A.actor = net.dev();
+    A.actions_in = (const T*)actions_dev; A.state = (const T*)c->state;
+    A.action = (T*)c->action; A.delta_action = (T*)c->delta_action;
+    // NS keeps env.p spectral; its physical-space sum goes to a scratch field owned by the NS back-end
+    A.p = (T*)(c->cfg.problem == PDEB200_NS2D ? c->prob_p_phys : c->p);
+    const int tpb = 256;
+    // several environments per CTA so that the column phase fills the block and the table is staged once
+    int E = std::max(1, std::min(8, tpb / std::max(1, c->cfg.n_actuators)));
+    E = std::min(E, std::max(1, 4096 / std::max(1, c->npts)));
+    A.envs_per_cta = E;
+    const size_t tab = (size_t)A.act_nnz * A.npts * (sizeof(T) + sizeof(int));
+    A.stage_table = tab <= 64 * 1024;
+    const size_t smem = actuate_smem_bytes<T>(E, A.n_act, A.npts, A.act_nnz, A.stage_table, use_actor, A.actor_np,
+                                              A.actor_wmax, tpb);
+    if (smem > 200 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "actuate: actor too large for shared memory");
+    if (smem > 48 * 1024)
+        PDEB_CUDA(c, cudaFuncSetAttribute(actuate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    actuate_kernel<T><<<(c->cfg.n_envs + E - 1) / E, tpb, smem, c->stream>>>(A);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
+template <typename T>
+int32_t reset_t(pdeb200_ctx* c, const uint8_t* d_mask) {
+    reset_copy_kernel<T><<<c->cfg.n_envs, 256, 0, c->stream>>>(c->y_elems, c->p_elems, d_mask, (const T*)c->y0,
+                                                              (T*)c->y, (T*)c->p);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    if (c->cfg.problem == PDEB200_NS2D) {
+        int32_t rc = ns_sensors(c, d_mask);
+        if (rc) return rc;
+    } else {
+        sensors_phys_kernel<T><<<c->cfg.n_envs, 128, 0, c->stream>>>(
+            c->fields, c->npts, c->cfg.n_sensors,
+            EllTable<T>{c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows}, d_mask, (const T*)c->y,
+            c->cfg.problem == PDEB200_KSEG1D ? 1 : 0, (T*)c->sensors, (T*)c->vmax);
+        PDEB_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+    }
+    return observe_t<T>(c, 1, d_mask, nullptr);
+}
+
+int32_t core_step(pdeb200_ctx* c) {
+    switch (c->cfg.problem) {
+        case PDEB200_KS: return ks_core(c);
+        case PDEB200_KSEG1D: return kseg_core(c);
+        case PDEB200_NS2D: return ns_core(c);
+    }
+    return fail(c, PDEB200_EINVAL, "bad problem");
+}
+
+// env(action) for all environments: actuate -> core -> observe, `n_steps` times (n_steps > 1 only with
+// the fused actor).  Everything is enqueued on the context's stream; no host synchronisation.
 int32_t do_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum) {
     if (!c->bases_set) return fail(c, PDEB200_ESTATE, "step: call pdeb200_set_bases first");
     if (!c->y0_set) return fail(c, PDEB200_ESTATE, "step: call pdeb200_set_y0 + pdeb200_reset first");
     if (use_actor) {
         const HostNet& a = c->nets[PDEB200_NET_BEHAVIOR_ACTOR];
         if (!a.n_layers) return fail(c, PDEB200_ESTATE, "rollout: behavior actor not set");
+        const int expect_out = c->cfg.mono ? c->cfg.n_actuators * c->a_rows : c->a_rows;
+        if (a.sizes[0] != c->obs_rows || a.sizes[a.n_layers] != expect_out)
+            return fail(c, PDEB200_EINVAL, "rollout: actor in/out sizes do not match the env's state/action spaces");
         for (int l = 0; l <= a.n_layers; ++l)
             if (a.sizes[l] > kFusedActorMaxWidth) return fail(c, PDEB200_EUNSUPPORTED, "fused actor: layer wider than 64");
     }
+    const bool f64 = c->cfg.dtype == PDEB200_F64;
     if (c->timing) cudaEventRecord(c->ev0, c->stream);
-    int32_t rc;
-    switch (c->cfg.problem) {
-        case PDEB200_KS: rc = ks_step(c, actions_dev, n_steps, use_actor, act_limit, d_rsum); break;
-        case PDEB200_KSEG1D: rc = kseg_step(c, actions_dev, n_steps, use_actor, act_limit, d_rsum); break;
-        case PDEB200_NS2D: rc = ns_step(c, actions_dev, n_steps, use_actor, act_limit, d_rsum); break;
-        default: rc = fail(c, PDEB200_EINVAL, "bad problem");
+    for (int s = 0; s < n_steps; ++s) {
+        int32_t rc = f64 ? actuate_t<double>(c, actions_dev, use_actor, act_limit) : actuate_t<float>(c, actions_dev, use_actor, act_limit);
+        if (rc) return rc;
+        if ((rc = core_step(c))) return rc;
+        rc = f64 ? observe_t<double>(c, 0, nullptr, d_rsum) : observe_t<float>(c, 0, nullptr, d_rsum);
+        if (rc) return rc;
     }
     if (c->timing) { cudaEventRecord(c->ev1, c->stream); c->timed = true; }
-    return rc;
+    return PDEB200_OK;
 }
 
 struct ArrInfo { void* ptr; size_t bytes; };
@@ -330,7 +357,7 @@ int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** 
               alloc(&c->action_in, nact * e) && alloc(&c->delta_action, nact * e) && alloc(&c->reward, B * c->n_rew * e) &&
               alloc(&c->sensors, B * c->fields * cfg->n_sensors * e) && alloc((void**)&c->done, B) &&
               alloc((void**)&c->time, B * 8) && alloc((void**)&c->steps, B * 4) && alloc((void**)&c->d_mask, B) &&
-              alloc((void**)&c->d_rsum, B * 8) && alloc(&c->d_noise, nact * e) &&
+              alloc((void**)&c->d_rsum, B * 8) && alloc(&c->d_noise, nact * e) && alloc(&c->vmax, B * e) &&
               alloc((void**)&c->d_a2s, cfg->n_actuators * 4) && alloc(&c->d_sens_sum, cfg->n_sensors * e) &&
               alloc((void**)&c->d_losses, 8);
     if (!ok) return bail(fail(c, PDEB200_ECUDA, std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError())));
@@ -351,7 +378,7 @@ int32_t pdeb200_destroy(pdeb200_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     ks_free(c); kseg_free(c); ns_free(c); agent_free(c);
     for (void* p : {c->y, c->y0, c->p, c->state, c->action, c->action_in, c->delta_action, c->reward, c->sensors,
-                    (void*)c->done, (void*)c->time, (void*)c->steps, (void*)c->d_mask, (void*)c->d_rsum, c->d_noise,
+                    (void*)c->done, (void*)c->time, (void*)c->steps, (void*)c->d_mask, (void*)c->d_rsum, c->d_noise, c->vmax,
                     (void*)c->d_a2s, c->d_sens_sum, (void*)c->sens.d_idx, c->sens.d_w, (void*)c->actT.d_idx, c->actT.d_w,
                     (void*)c->d_grads, (void*)c->d_losses})
         if (p) cudaFree(p);

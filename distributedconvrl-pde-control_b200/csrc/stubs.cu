@@ -3,14 +3,14 @@
 namespace pdeb200 {
 #ifndef PDEB_HAVE_KSEG
 int32_t kseg_setup(pdeb200_ctx* c) { return fail(c, PDEB200_EUNSUPPORTED, "Keller-Segel back-end not built"); }
-int32_t kseg_step(pdeb200_ctx* c, const void*, int, int, double, double*) { return fail(c, PDEB200_EUNSUPPORTED, "Keller-Segel back-end not built"); }
+int32_t kseg_core(pdeb200_ctx* c) { return fail(c, PDEB200_EUNSUPPORTED, "Keller-Segel back-end not built"); }
 int32_t kseg_cost(const pdeb200_ctx*, double*, double*) { return PDEB200_EUNSUPPORTED; }
 void kseg_free(pdeb200_ctx*) {}
 #endif
 #ifndef PDEB_HAVE_NS
 int32_t ns_setup(pdeb200_ctx* c) { return fail(c, PDEB200_EUNSUPPORTED, "Navier-Stokes back-end not built"); }
-int32_t ns_step(pdeb200_ctx* c, const void*, int, int, double, double*) { return fail(c, PDEB200_EUNSUPPORTED, "Navier-Stokes back-end not built"); }
-int32_t ns_featurize_reset(pdeb200_ctx* c, const uint8_t*) { return fail(c, PDEB200_EUNSUPPORTED, "Navier-Stokes back-end not built"); }
+int32_t ns_core(pdeb200_ctx* c) { return fail(c, PDEB200_EUNSUPPORTED, "Navier-Stokes back-end not built"); }
+int32_t ns_sensors(pdeb200_ctx* c, const uint8_t*) { return fail(c, PDEB200_EUNSUPPORTED, "Navier-Stokes back-end not built"); }
 int32_t ns_cost(const pdeb200_ctx*, double*, double*) { return PDEB200_EUNSUPPORTED; }
 void ns_free(pdeb200_ctx*) {}
 #endif

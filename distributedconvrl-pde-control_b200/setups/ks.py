@@ -85,8 +85,12 @@ class KSSetup:
         y0 = a @ basis
         return y0 * 30 / np.linalg.norm(y0, axis=1, keepdims=True)
 
-    def make_env(self, n_envs=1, dtype="f64", device=0, y0=None, drop_tol=0.0):
-        """initialize_setup(), KSSetup.jl:249-262 -- the PDEenv part."""
+    def make_env(self, n_envs=1, dtype="f64", device=0, y0=None, drop_tol=1e-17):
+        """initialize_setup(), KSSetup.jl:249-262 -- the PDEenv part.
+
+        drop_tol: basis entries below drop_tol * max(row) are not stored in the device's banded tables.
+        1e-17 is below half an ulp of the largest term of each dot product, i.e. lossless in fp64;
+        pass 0.0 to keep every non-zero (including the 1e-300 Gaussian tails the reference carries)."""
         if y0 is None:
             y0 = self.y0_standard()
         y0 = np.asarray(y0, dtype=np.float64)
