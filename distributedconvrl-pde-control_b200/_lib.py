@@ -17,7 +17,7 @@ CHECK_NONE, CHECK_Y, CHECK_REWARD = 0, 1, 2
 ACT_IDENTITY, ACT_RELU, ACT_TANH = 0, 1, 2
 NET_BEHAVIOR_ACTOR, NET_BEHAVIOR_CRITIC, NET_TARGET_ACTOR, NET_TARGET_CRITIC = 0, 1, 2, 3
 (ARR_Y, ARR_P, ARR_STATE, ARR_ACTION, ARR_DELTA_ACTION, ARR_REWARD, ARR_DONE, ARR_TIME, ARR_STEPS, ARR_Y0,
- ARR_GRADS, ARR_LOSSES, ARR_SENSORS, ARR_ACTION_IN) = range(14)
+ ARR_GRADS, ARR_LOSSES, ARR_SENSORS, ARR_ACTION_IN, ARR_STATS) = range(15)
 
 
 class Config(C.Structure):

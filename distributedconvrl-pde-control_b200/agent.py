@@ -90,3 +90,202 @@ class CustomNeuralNetworkApproximator:
         """Base.copyto!(dest, src), custom_nna.jl:26-27"""
         self.model.load_flat(src.sync_from_device().flat())
         self.upload()
+
+
+class ZeroPolicy:
+    """src/PDEagent.jl:420-424"""
+
+    def __call__(self, env):
+        return np.zeros((env.a_rows, env.n_envs * env.n_actuators), dtype=env.np_dtype)
+
+
+class DeviceTrajectory:
+    """CircularArraySARTTrajectory kept on the GPU, with the reference's `update!` overload set
+    (src/PDEagent.jl:237-314).  One transition per actuator column."""
+
+    def __init__(self, env, capacity):
+        self.env = env
+        self.capacity = int(capacity)
+        L.check(env._lib.pdeb200_traj_create(env._ctx, self.capacity), env._ctx)
+
+    def __len__(self):
+        n = C.c_int64()
+        L.check(self.env._lib.pdeb200_traj_length(self.env._ctx, C.byref(n)), self.env._ctx)
+        return n.value
+
+    def pre_episode(self):           # PreEpisodeStage: pop the dummy tail
+        L.check(self.env._lib.pdeb200_traj_pop_tail(self.env._ctx), self.env._ctx)
+
+    def pre_act(self):               # PreActStage: push (s[:, i], a[:, i]) for every column
+        L.check(self.env._lib.pdeb200_traj_push_pre(self.env._ctx), self.env._ctx)
+
+    def post_act(self):              # PostActStage: push r[i], terminal for every column
+        L.check(self.env._lib.pdeb200_traj_push_post(self.env._ctx), self.env._ctx)
+
+    def post_episode(self):          # PostEpisodeStage: push final state + zero action
+        L.check(self.env._lib.pdeb200_traj_episode_end(self.env._ctx), self.env._ctx)
+
+
+class CustomDDPGPolicy:
+    """src/PDEagent.jl:121-209 + the update trigger :342-361 + update! :363-418, over the C ABI.
+
+    Field names follow the Julia struct (y = discount, p = Polyak factor).  `comm` is an optional
+    object with `allreduce_sum_(torch_tensor)` used for the data-parallel gradient exchange
+    (see parallel.py); None = single GPU.
+    """
+
+    def __init__(self, env, *, behavior_actor, behavior_critic, target_actor=None, target_critic=None, y=0.99, p=0.995,
+                 batch_size=3, start_steps=6, start_policy=None, update_after=10, update_freq=1, update_loops=20,
+                 act_limit=1.0, act_noise=1.2, memory_size=0, learning_rate=5e-4, learning_rate_critic=1e-3,
+                 trajectory_length=150_000, literal_q1=True, seed=0, comm=None):
+        self.env = env
+        lib = L
+        self.behavior_actor = CustomNeuralNetworkApproximator(env, lib.NET_BEHAVIOR_ACTOR, behavior_actor, learning_rate)
+        self.behavior_critic = CustomNeuralNetworkApproximator(env, lib.NET_BEHAVIOR_CRITIC, behavior_critic, learning_rate_critic)
+        self.target_actor = CustomNeuralNetworkApproximator(
+            env, lib.NET_TARGET_ACTOR, target_actor if target_actor is not None else behavior_actor.copy(), learning_rate)
+        self.target_critic = CustomNeuralNetworkApproximator(
+            env, lib.NET_TARGET_CRITIC, target_critic if target_critic is not None else behavior_critic.copy(), learning_rate_critic)
+        self.y, self.p, self.batch_size = y, p, batch_size
+        self.start_steps, self.start_policy = start_steps, start_policy or ZeroPolicy()
+        self.update_after, self.update_freq, self.update_loops = update_after, update_freq, update_loops
+        self.act_limit, self.act_noise, self.memory_size = act_limit, act_noise, memory_size
+        self.literal_q1 = literal_q1
+        self.update_step = 0
+        self.seed, self._rng_offset = int(seed), 0
+        self.comm = comm
+        self.trajectory = DeviceTrajectory(env, trajectory_length)
+        self.number_actuators = env.n_envs * env.n_cols       # columns per env step (PDEagent.jl:348-353)
+        self.n_updates = 0
+
+    # -- policy forward (PDEagent.jl:175-209); the action is staged on the device ---------------
+    def __call__(self, env=None, learning=True, noise=None):
+        env = env or self.env
+        if learning:
+            self.update_step += 1
+        if self.update_step <= self.start_steps:
+            a = np.ascontiguousarray(np.asarray(self.start_policy(env), dtype=env.np_dtype).T)
+            env.put(L.ARR_ACTION_IN, a)
+        elif not learning:
+            env.policy_act(None, 0.0, self.act_limit)
+        elif noise is not None:
+            env.policy_act(noise, self.act_noise, self.act_limit)
+        else:
+            n = env.n_envs * env.n_actuators * env.a_rows
+            env.policy_act_rng(self.seed, self._rng_offset, self.act_noise, self.act_limit)
+            self._rng_offset += n
+
+    @property
+    def losses(self):
+        out = np.zeros(2, dtype=np.float32)
+        L.check(self.env._lib.pdeb200_get(self.env._ctx, L.ARR_LOSSES, out.ctypes.data, 8), self.env._ctx)
+        return {"critic_loss": float(out[0]), "actor_loss": float(out[1])}
+
+    # -- update trigger (PDEagent.jl:342-361) -------------------------------------------------------
+    def maybe_update(self):
+        if not (len(self.trajectory) > self.update_after * self.number_actuators):
+            return 0
+        if self.update_step % self.update_freq != 0:
+            return 0
+        for _ in range(self.update_loops):
+            self.sample()
+            self.update()
+        return self.update_loops
+
+    def sample(self, inds=None):
+        lib, ctx = self.env._lib, self.env._ctx
+        if inds is not None:
+            inds = np.ascontiguousarray(inds, dtype=np.int64)
+            L.check(lib.pdeb200_sample(ctx, len(inds), inds.ctypes.data, 0, 0), ctx)
+        else:
+            L.check(lib.pdeb200_sample(ctx, int(self.batch_size), None, self.seed ^ 0x5DEECE66D, self._rng_offset), ctx)
+            self._rng_offset += int(self.batch_size)
+
+    def set_batch(self, s, a, r, t, snext):
+        """Explicit batch in the reference's shapes: s (ns,B), a (na,B), r (B,), t (B,), snext (ns,B)."""
+        f = lambda x: np.ascontiguousarray(np.asarray(x, dtype=np.float32).T)
+        s_, a_, s2 = f(s), f(a), f(snext)
+        r_ = np.ascontiguousarray(r, dtype=np.float32).reshape(-1)
+        t_ = np.ascontiguousarray(t, dtype=np.uint8).reshape(-1)
+        self._explicit_batch = len(r_)
+        L.check(self.env._lib.pdeb200_set_batch(self.env._ctx, len(r_), s_.ctypes.data, a_.ctypes.data, r_.ctypes.data,
+                                                t_.ctypes.data, s2.ctypes.data), self.env._ctx)
+
+    # -- DDPG update (PDEagent.jl:363-418) ------------------------------------------------------------
+    def update(self, local_batch=None):
+        lib, ctx = self.env._lib, self.env._ctx
+        B = int(local_batch or getattr(self, "_explicit_batch", None) or self.batch_size)
+        if self.comm is None or self.comm.world_size == 1:
+            L.check(lib.pdeb200_ddpg_update(ctx, float(self.y), float(self.p), float(self.behavior_actor.learning_rate),
+                                            float(self.behavior_critic.learning_rate), int(self.literal_q1)), ctx)
+        else:
+            comm = self.comm
+            Bg = comm.global_batch(B)
+            n_c = lib.pdeb200_net_num_params(ctx, L.NET_BEHAVIOR_CRITIC)
+            n_a = lib.pdeb200_net_num_params(ctx, L.NET_BEHAVIOR_ACTOR)
+            if self.literal_q1:
+                comm.allreduce_sum_(comm.alias(self.env, L.ARR_STATS, "float64")[:2])     # global sum r (quirk Q1)
+            L.check(lib.pdeb200_ddpg_critic_grads(ctx, float(self.y), int(self.literal_q1), Bg), ctx)
+            g = comm.alias(self.env, L.ARR_GRADS, "float32")
+            comm.allreduce_sum_(g[:n_c])
+            L.check(lib.pdeb200_ddpg_critic_apply(ctx, float(self.behavior_critic.learning_rate)), ctx)
+            L.check(lib.pdeb200_ddpg_actor_grads(ctx, Bg), ctx)
+            comm.allreduce_sum_(g[n_c:n_c + n_a])
+            L.check(lib.pdeb200_ddpg_actor_apply(ctx, float(self.behavior_actor.learning_rate), float(self.p)), ctx)
+        self.n_updates += 1
+
+    def grads(self):
+        n = self.env._lib.pdeb200_net_num_params(self.env._ctx, L.NET_BEHAVIOR_CRITIC) + \
+            self.env._lib.pdeb200_net_num_params(self.env._ctx, L.NET_BEHAVIOR_ACTOR)
+        out = np.empty(n, dtype=np.float32)
+        L.check(self.env._lib.pdeb200_get(self.env._ctx, L.ARR_GRADS, out.ctypes.data, out.nbytes), self.env._ctx)
+        return out
+
+    def post_episode(self):
+        """update!(policy, traj, env, ::PostEpisodeStage): update_step = 0 (PDEagent.jl:215-224)."""
+        self.update_step = 0
+
+
+def create_agent(env, *, rng, nna_scale=1.0, nna_scale_critic=None, drop_middle_layer=False,
+                 drop_middle_layer_critic=None, fun="relu", fun_critic=None, mono=False, **kw):
+    """create_agent, src/PDEagent.jl:58-119: four networks (targets copied from behaviors) + trajectory."""
+    nna_scale_critic = nna_scale if nna_scale_critic is None else nna_scale_critic
+    drop_c = drop_middle_layer if drop_middle_layer_critic is None else drop_middle_layer_critic
+    fun_critic = fun_critic or fun
+    ns = env.ns
+    na = env.n_actuators * env.a_rows if mono else env.a_rows
+    actor = create_chain(na=na, ns=ns, is_actor=True, rng=rng, nna_scale=nna_scale, drop_middle_layer=drop_middle_layer, fun=fun)
+    critic = create_chain(na=na, ns=ns, is_actor=False, rng=rng, nna_scale=nna_scale_critic, drop_middle_layer=drop_c, fun=fun_critic)
+    return CustomDDPGPolicy(env, behavior_actor=actor, behavior_critic=critic, **kw)
+
+
+def run_episode(policy, env, hook=None, learning=True, max_steps=None):
+    """One episode in the stage order of RLCore's `run` (spelled out in the reference at
+    scripts/Fluid/setup/FluidSetup.jl:455-519):  reset! -> PreEpisode -> loop { policy -> PreAct
+    (push s,a; update) -> env(action) -> PostAct (push r,t) } -> PostEpisode (dummy push)."""
+    traj = policy.trajectory
+    env.reset()
+    if learning:
+        traj.pre_episode()
+    if hook is not None:
+        hook.pre_episode(env)
+    steps = 0
+    while True:
+        policy(env, learning=learning)
+        if learning:
+            traj.pre_act()
+            policy.maybe_update()
+        env.step_device()
+        if learning:
+            traj.post_act()
+        if hook is not None:
+            hook.post_act(env)
+        steps += 1
+        if (max_steps is not None and steps >= max_steps) or bool(env.done[0]):
+            break
+    if learning:
+        traj.post_episode()
+        policy.post_episode()
+    if hook is not None:
+        hook.post_episode(env, policy)
+    return steps

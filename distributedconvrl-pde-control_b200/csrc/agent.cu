@@ -1,0 +1,729 @@
+// Agent back-end: device-resident replay trajectory, sampler and the DDPG update.
+//
+// Restates (batched; one replay "transition" = one actuator column, as in the reference):
+//   trajectory update! overloads   /root/reference/src/PDEagent.jl:237-314
+//       on RLCore 0.8.13's CircularArraySARTTrajectory: state/action rings of capacity+1
+//       columns, reward/terminal rings of capacity, each a plain circular buffer
+//   pde_sample / pde_fetch!        PDEagent.jl:317-340   (s' = state[inds + n_columns])
+//   update!(policy, batch)         PDEagent.jl:363-418   (critic step, actor step through the
+//                                                         UPDATED critic, Polyak on both targets)
+//   Flux.Optimise.ADAM             (third-party; eta/beta Float64 applied to Float32 arrays)
+//
+// The networks are tiny (KS: 19 + 561 parameters), so the contraction is far too thin for tensor
+// cores: one CTA processes tiles of 32 samples, thread-per-unit forward, thread-per-(unit,input)
+// gradient accumulation in shared memory, per-CTA partials reduced in fixed order (deterministic).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "ctx.hpp"
+
+namespace pdeb200 {
+
+namespace {
+
+constexpr int TS = 32;                 // samples per tile
+
+struct Ring { int64_t cap = 0, start = 0, len = 0; };
+
+struct Agent {
+    int ns = 0, na = 0;                // rows per state / action column
+    int64_t ncols = 0;                 // columns pushed per env step (= B * n_cols)
+    Ring sa, rt;
+    float *state = nullptr, *action = nullptr, *reward = nullptr;
+    uint8_t* terminal = nullptr;
+    // sampled batch
+    int batch = 0, batch_cap = 0;
+    float *bs = nullptr, *ba = nullptr, *br = nullptr, *bs2 = nullptr;
+    uint8_t* bt = nullptr;
+    int64_t* inds = nullptr;
+    double* stats = nullptr;           // [0] sum r  [1] sum r^2  [2] sum c  [3] sum c^2  [4] sum q(actor)
+    float* partials = nullptr; size_t partials_floats = 0;
+    int n_blocks = 0;
+};
+
+Agent* ag(pdeb200_ctx* c) { return static_cast<Agent*>(c->agent); }
+
+// ---------------------------------------------------------------------------------------------
+// replay kernels
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void push_sa_kernel(int64_t n, int ns, int na, int64_t cap, int64_t pos0, const T* __restrict__ state,
+                               const T* __restrict__ action, int zero_action, float* rstate, float* raction) {
+    const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (col >= n) return;
+    const int64_t dst = (pos0 + col) % cap;
+    for (int r = 0; r < ns; ++r) rstate[dst * ns + r] = (float)state[col * ns + r];
+    for (int r = 0; r < na; ++r) raction[dst * na + r] = zero_action ? 0.f : (float)action[col * na + r];
+}
+
+template <typename T>
+__global__ void push_rt_kernel(int64_t n, int cols_per_env, int64_t cap, int64_t pos0, const T* __restrict__ reward,
+                               const uint8_t* __restrict__ done, float* rreward, uint8_t* rterminal) {
+    const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (col >= n) return;
+    const int64_t dst = (pos0 + col) % cap;
+    rreward[dst] = (float)reward[col];
+    rterminal[dst] = done[col / cols_per_env];
+}
+
+__device__ __forceinline__ uint32_t mulhilo32(uint32_t a, uint32_t b, uint32_t* hi) {
+    const uint64_t p = (uint64_t)a * b; *hi = (uint32_t)(p >> 32); return (uint32_t)p;
+}
+__device__ __forceinline__ uint64_t philox_u64(uint64_t seed, uint64_t ctr) {
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = 0x243F6A88u, c3 = 0x85A308D3u;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t h0, h1;
+        const uint32_t l0 = mulhilo32(0xD2511F53u, c0, &h0), l1 = mulhilo32(0xCD9E8D57u, c2, &h1);
+        const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+        c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return ((uint64_t)c0 << 32) | c1;
+}
+
+// inds ~ U{0 .. range-1} (reference: rand(rng, 1:length(t)-number_actuators, batch_size))
+__global__ void draw_inds_kernel(int n, int64_t range, uint64_t seed, uint64_t offset, int64_t* inds) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t u = philox_u64(seed, offset + i);
+    inds[i] = (int64_t)(((unsigned __int128)u * (unsigned __int128)range) >> 64);
+}
+
+__global__ void fetch_kernel(int n, int ns, int na, int64_t ncols, Ring sa, Ring rt, const int64_t* __restrict__ inds,
+                             const float* __restrict__ rstate, const float* __restrict__ raction,
+                             const float* __restrict__ rreward, const uint8_t* __restrict__ rterminal, float* bs,
+                             float* ba, float* br, uint8_t* bt, float* bs2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t ind = inds[i];
+    const int64_t ps = (sa.start + ind) % sa.cap, ps2 = (sa.start + ind + ncols) % sa.cap, pr = (rt.start + ind) % rt.cap;
+    for (int r = 0; r < ns; ++r) { bs[(size_t)i * ns + r] = rstate[ps * ns + r]; bs2[(size_t)i * ns + r] = rstate[ps2 * ns + r]; }
+    for (int r = 0; r < na; ++r) ba[(size_t)i * na + r] = raction[ps * na + r];
+    br[i] = rreward[pr];
+    bt[i] = rterminal[pr];
+}
+
+// stats[0] = sum r, stats[1] = sum r^2 over the local batch (single CTA, fixed order)
+__global__ void reward_stats_kernel(int n, const float* __restrict__ br, double* stats) {
+    __shared__ double s0[256], s1[256];
+    double a = 0, b = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { const double r = br[i]; a += r; b += r * r; }
+    s0[threadIdx.x] = a; s1[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s0[threadIdx.x] += s0[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { stats[0] = s0[0]; stats[1] = s1[0]; stats[2] = stats[3] = stats[4] = 0.0; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// tile-level MLP pieces (activations in shared memory as [sample][unit])
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_grad(int kind, float out) {
+    if (kind == 1) return out > 0.f ? 1.f : 0.f;         // relu
+    if (kind == 2) return 1.f - out * out;               // tanh
+    return 1.f;
+}
+
+__device__ void layer_forward(const float* __restrict__ W, int ni, int no, int act, const float* in, float* out) {
+    const float* b = W + (size_t)ni * no;
+    for (int k = threadIdx.x; k < no; k += blockDim.x) {
+        float acc[TS];
+#pragma unroll
+        for (int i = 0; i < TS; ++i) acc[i] = 0.f;
+        for (int j = 0; j < ni; ++j) {
+            const float w = W[k + (size_t)no * j];
+#pragma unroll
+            for (int i = 0; i < TS; ++i) acc[i] = fmaf(w, in[i * ni + j], acc[i]);
+        }
+        const float bk = b[k];
+#pragma unroll
+        for (int i = 0; i < TS; ++i) out[i * no + k] = act_apply(act, acc[i] + bk);
+    }
+    __syncthreads();
+}
+
+// whole-network forward; acts[l] = pointer to layer-l activations ([TS][sizes[l]])
+__device__ void net_forward(const NetDev& net, float* const* acts) {
+    for (int l = 0; l < net.n_layers; ++l)
+        layer_forward(net.params + net.offs[l], net.sizes[l], net.sizes[l + 1], net.acts[l], acts[l], acts[l + 1]);
+}
+
+// Backward through the network.  d_out: dLoss/d(output) [TS][n_out] (overwritten).  acc: shared
+// accumulator over the flat parameter vector (or nullptr: no parameter gradients).  d_a/d_b:
+// ping-pong scratch [TS][wmax].  Returns the buffer holding dLoss/d(input) [TS][sizes[0]].
+__device__ float* net_backward(const NetDev& net, float* const* acts, float* d_out, float* d_other, float* acc,
+                               bool want_input_grad) {
+    float* d = d_out;
+    float* dn = d_other;
+    for (int l = net.n_layers - 1; l >= 0; --l) {
+        const int ni = net.sizes[l], no = net.sizes[l + 1];
+        const float* W = net.params + net.offs[l];
+        const float* out = acts[l + 1];
+        const float* in = acts[l];
+        // delta_pre = delta_out * act'(out)
+        if (net.acts[l] != 0) {
+            for (int q = threadIdx.x; q < TS * no; q += blockDim.x) d[q] *= act_grad(net.acts[l], out[q]);
+            __syncthreads();
+        }
+        if (acc) {
+            const int n_pairs = (ni + 1) * no;             // flat index offs + q: W column-major then bias
+            for (int q = threadIdx.x; q < n_pairs; q += blockDim.x) {
+                const int k = q % no, j = q / no;
+                float g = 0.f;
+                if (j < ni) {
+#pragma unroll 8
+                    for (int i = 0; i < TS; ++i) g = fmaf(d[i * no + k], in[i * ni + j], g);
+                } else {
+#pragma unroll 8
+                    for (int i = 0; i < TS; ++i) g += d[i * no + k];
+                }
+                acc[net.offs[l] + q] += g;
+            }
+        }
+        if (l > 0 || want_input_grad) {
+            for (int j = threadIdx.x; j < ni; j += blockDim.x) {
+                float s[TS];
+#pragma unroll
+                for (int i = 0; i < TS; ++i) s[i] = 0.f;
+                for (int k = 0; k < no; ++k) {
+                    const float w = W[k + (size_t)no * j];
+#pragma unroll
+                    for (int i = 0; i < TS; ++i) s[i] = fmaf(w, d[i * no + k], s[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < TS; ++i) dn[i * ni + j] = s[i];
+            }
+        }
+        __syncthreads();
+        float* t = d; d = dn; dn = t;
+    }
+    return d;
+}
+
+struct DdpgArgs {
+    NetDev A, C, At, Ct;
+    int batch, ns, na;
+    const float *s, *a, *r, *s2;
+    const uint8_t* t;
+    float gamma; int literal_q1; double inv_global_batch;
+    const double* stats;            // stats[0] = GLOBAL sum of rewards (after the caller's allreduce)
+    float* partials;                // [gridDim.x][n_acc + 2]
+    int n_acc;                      // parameters accumulated (critic or actor)
+    int wmax;                       // widest activation row over all nets (incl. ns+na)
+};
+
+__device__ __forceinline__ int carve_acts(const NetDev& net, float* base, float** acts) {
+    int off = 0;
+    for (int l = 0; l <= net.n_layers; ++l) { acts[l] = base + off; off += TS * net.sizes[l]; }
+    return off;
+}
+
+// Critic phase: targets from (A_t, C_t), critic loss gradient (PDEagent.jl:385-398).
+__global__ void __launch_bounds__(512) ddpg_critic_kernel(const __grid_constant__ DdpgArgs D) {
+    extern __shared__ __align__(16) float sm[];
+    float* actsC[kMaxLayers + 1];
+    float* actsT[kMaxLayers + 1];
+    int off = carve_acts(D.C, sm, actsC);
+    float* scratch0 = sm + off; off += TS * D.wmax;      // target-net ping-pong / deltas
+    float* scratch1 = sm + off; off += TS * D.wmax;
+    float* tin = sm + off; off += TS * (D.ns + D.na);    // [s'; a'] for the target critic
+    float* tgt = sm + off; off += TS;                    // gamma (1-t) q_t
+    float* acc = sm + off; off += D.n_acc;
+    __shared__ double s_c[2];
+    for (int q = threadIdx.x; q < D.n_acc; q += blockDim.x) acc[q] = 0.f;
+    if (threadIdx.x < 2) s_c[threadIdx.x] = 0.0;
+    const int nin = D.ns + D.na;
+    const float rbar = (float)(D.stats[0] * D.inv_global_batch);
+    const int n_tiles = (D.batch + TS - 1) / TS;
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int i0 = tile * TS;
+        // ---- a' = A_t(s') ------------------------------------------------------------------
+        {
+            int o = 0; float* base = scratch0;           // target actor activations, ping-pong in scratch0/1
+            (void)o;
+            for (int q = threadIdx.x; q < TS * D.ns; q += blockDim.x) {
+                const int i = q / D.ns, r = q % D.ns;
+                const float v = (i0 + i < D.batch) ? D.s2[(size_t)(i0 + i) * D.ns + r] : 0.f;
+                base[q] = v;
+                tin[i * nin + r] = v;
+            }
+            __syncthreads();
+            float* in = scratch0; float* out = scratch1;
+            for (int l = 0; l < D.At.n_layers; ++l) {
+                layer_forward(D.At.params + D.At.offs[l], D.At.sizes[l], D.At.sizes[l + 1], D.At.acts[l], in, out);
+                float* t = in; in = out; out = t;
+            }
+            for (int q = threadIdx.x; q < TS * D.na; q += blockDim.x) tin[(q / D.na) * nin + D.ns + q % D.na] = in[q];
+            __syncthreads();
+        }
+        // ---- q_t = C_t([s'; a']) -------------------------------------------------------------
+        {
+            float* in = tin; float* out = scratch0; float* other = scratch1;
+            for (int l = 0; l < D.Ct.n_layers; ++l) {
+                layer_forward(D.Ct.params + D.Ct.offs[l], D.Ct.sizes[l], D.Ct.sizes[l + 1], D.Ct.acts[l], in, out);
+                in = out; out = (out == scratch0) ? other : scratch0;
+            }
+            for (int i = threadIdx.x; i < TS; i += blockDim.x) {
+                const bool ok = i0 + i < D.batch;
+                tgt[i] = ok ? D.gamma * (1.f - (float)D.t[i0 + i]) * in[i] : 0.f;
+            }
+            __syncthreads();
+        }
+        // ---- q = C([s; a]) with kept activations --------------------------------------------
+        for (int q = threadIdx.x; q < TS * nin; q += blockDim.x) {
+            const int i = q / nin, r = q % nin;
+            float v = 0.f;
+            if (i0 + i < D.batch) v = r < D.ns ? D.s[(size_t)(i0 + i) * D.ns + r] : D.a[(size_t)(i0 + i) * D.na + (r - D.ns)];
+            actsC[0][q] = v;
+        }
+        __syncthreads();
+        net_forward(D.C, actsC);
+        // ---- dLoss/dq ------------------------------------------------------------------------
+        // literal (quirk Q1): loss = mean_{i,j} (r_j + T_i - q_i)^2  =>  dq_i = -(2/B)(rbar + T_i - q_i)
+        // per-sample:         loss = mean_i (r_i + T_i - q_i)^2      =>  dq_i = -(2/B)(r_i  + T_i - q_i)
+        const float* qv = actsC[D.C.n_layers];
+        for (int i = threadIdx.x; i < TS; i += blockDim.x) {
+            float dq = 0.f;
+            if (i0 + i < D.batch) {
+                const float c = tgt[i] - qv[i];
+                const float rr = D.literal_q1 ? rbar : D.r[i0 + i];
+                dq = (float)(-2.0 * D.inv_global_batch) * (rr + c);
+                const double cl = D.literal_q1 ? (double)c : (double)(D.r[i0 + i] + c);
+                atomicAdd(&s_c[0], cl); atomicAdd(&s_c[1], cl * cl);
+            }
+            scratch0[i] = dq;
+        }
+        __syncthreads();
+        net_backward(D.C, actsC, scratch0, scratch1, acc, false);
+        __syncthreads();
+        (void)actsT;
+    }
+    float* out = D.partials + (size_t)blockIdx.x * (D.n_acc + 2);
+    for (int q = threadIdx.x; q < D.n_acc; q += blockDim.x) out[q] = acc[q];
+    if (threadIdx.x == 0) { out[D.n_acc] = (float)s_c[0]; out[D.n_acc + 1] = (float)s_c[1]; }
+}
+
+// Actor phase: gradient of -mean C([s; A(s)]) w.r.t. the actor parameters (PDEagent.jl:402-409).
+__global__ void __launch_bounds__(512) ddpg_actor_kernel(const __grid_constant__ DdpgArgs D) {
+    extern __shared__ __align__(16) float sm[];
+    float* actsC[kMaxLayers + 1];
+    float* actsA[kMaxLayers + 1];
+    int off = carve_acts(D.C, sm, actsC);
+    off += carve_acts(D.A, sm + off, actsA);
+    float* scratch0 = sm + off; off += TS * D.wmax;
+    float* scratch1 = sm + off; off += TS * D.wmax;
+    float* acc = sm + off; off += D.n_acc;
+    __shared__ double s_q;
+    for (int q = threadIdx.x; q < D.n_acc; q += blockDim.x) acc[q] = 0.f;
+    if (threadIdx.x == 0) s_q = 0.0;
+    const int nin = D.ns + D.na;
+    const int n_tiles = (D.batch + TS - 1) / TS;
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int i0 = tile * TS;
+        for (int q = threadIdx.x; q < TS * D.ns; q += blockDim.x) {
+            const int i = q / D.ns, r = q % D.ns;
+            const float v = (i0 + i < D.batch) ? D.s[(size_t)(i0 + i) * D.ns + r] : 0.f;
+            actsA[0][q] = v;
+            actsC[0][i * nin + r] = v;
+        }
+        __syncthreads();
+        net_forward(D.A, actsA);
+        const float* av = actsA[D.A.n_layers];
+        for (int q = threadIdx.x; q < TS * D.na; q += blockDim.x) actsC[0][(q / D.na) * nin + D.ns + q % D.na] = av[q];
+        __syncthreads();
+        net_forward(D.C, actsC);
+        const float* qv = actsC[D.C.n_layers];
+        for (int i = threadIdx.x; i < TS; i += blockDim.x) {
+            const bool ok = i0 + i < D.batch;
+            scratch0[i] = ok ? (float)(-D.inv_global_batch) : 0.f;
+            if (ok) atomicAdd(&s_q, (double)qv[i]);
+        }
+        __syncthreads();
+        float* dx = net_backward(D.C, actsC, scratch0, scratch1, nullptr, true);     // [TS][ns+na]
+        float* da = (dx == scratch0) ? scratch1 : scratch0;
+        for (int q = threadIdx.x; q < TS * D.na; q += blockDim.x) da[q] = dx[(q / D.na) * nin + D.ns + q % D.na];
+        __syncthreads();
+        net_backward(D.A, actsA, da, dx, acc, false);
+        __syncthreads();
+    }
+    float* out = D.partials + (size_t)blockIdx.x * (D.n_acc + 2);
+    for (int q = threadIdx.x; q < D.n_acc; q += blockDim.x) out[q] = acc[q];
+    if (threadIdx.x == 0) { out[D.n_acc] = (float)s_q; out[D.n_acc + 1] = 0.f; }
+}
+
+// grads[q] = sum over CTAs (fixed order); tail sums go to stats
+__global__ void reduce_partials_kernel(int n_blocks, int n_acc, const float* __restrict__ partials, float* grads,
+                                       double* stats, int stat0) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_acc + 2) return;
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += (double)partials[(size_t)b * (n_acc + 2) + q];
+    if (q < n_acc) grads[q] = (float)s;
+    else stats[stat0 + (q - n_acc)] = s;
+}
+
+// Flux ADAM on Float32 arrays with Float64 hyper-parameters; optional Polyak pair (dest = p*dest + (1-p)*src).
+__global__ void adam_kernel(int n, float* x, float* m, float* v, const float* __restrict__ g, double eta, double b1,
+                            double b2, double bp1, double bp2, double eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double gi = g[i];
+    const float mi = (float)(b1 * (double)m[i] + (1.0 - b1) * gi);
+    const float vi = (float)(b2 * (double)v[i] + (1.0 - b2) * gi * gi);
+    m[i] = mi; v[i] = vi;
+    const float delta = (float)((double)mi / (1.0 - bp1) / (sqrt((double)vi / (1.0 - bp2)) + eps) * eta);
+    x[i] -= delta;
+}
+
+__global__ void polyak_kernel(int n, float* dest, const float* __restrict__ src, float p) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    dest[i] = p * dest[i] + (1.f - p) * src[i];
+}
+
+// critic_loss / actor_loss (PDEagent.jl:393-396, 403-407) from the reduced sums
+__global__ void losses_kernel(const double* stats, double n_global, int literal, int which, float* losses) {
+    if (which == 0) {
+        // literal: mean_{ij} (r_j + c_i)^2 = sum c^2/B + 2 sum c sum r / B^2 + sum r^2 / B ; per-sample: sum c'^2 / B
+        const double B = n_global;
+        losses[0] = (float)(literal ? stats[3] / B + 2.0 * stats[2] * stats[0] / (B * B) + stats[1] / B : stats[3] / B);
+    } else {
+        losses[1] = (float)(-stats[4] / n_global);
+    }
+}
+
+int32_t ensure_partials(pdeb200_ctx* c, int n_blocks, int n_acc) {
+    Agent* a = ag(c);
+    const size_t need = (size_t)n_blocks * (n_acc + 2);
+    if (need > a->partials_floats) {
+        if (a->partials) cudaFree(a->partials);
+        PDEB_CUDA(c, cudaMalloc(&a->partials, need * sizeof(float)));
+        a->partials_floats = need;
+    }
+    return PDEB200_OK;
+}
+
+int32_t ensure_agent(pdeb200_ctx* c) {
+    if (c->agent) return PDEB200_OK;
+    Agent* a = new Agent();
+    a->ns = c->obs_rows;
+    a->na = c->cfg.mono ? c->cfg.n_actuators * c->a_rows : c->a_rows;
+    a->ncols = (int64_t)c->cfg.n_envs * c->n_cols;
+    c->agent = a;
+    PDEB_CUDA(c, cudaMalloc(&a->stats, 8 * sizeof(double)));
+    PDEB_CUDA(c, cudaMemset(a->stats, 0, 8 * sizeof(double)));
+    return PDEB200_OK;
+}
+
+int32_t ensure_batch(pdeb200_ctx* c, int batch) {
+    Agent* a = ag(c);
+    if (batch > a->batch_cap) {
+        for (void* p : {(void*)a->bs, (void*)a->ba, (void*)a->br, (void*)a->bs2, (void*)a->bt, (void*)a->inds})
+            if (p) cudaFree(p);
+        PDEB_CUDA(c, cudaMalloc(&a->bs, (size_t)batch * a->ns * 4));
+        PDEB_CUDA(c, cudaMalloc(&a->bs2, (size_t)batch * a->ns * 4));
+        PDEB_CUDA(c, cudaMalloc(&a->ba, (size_t)batch * a->na * 4));
+        PDEB_CUDA(c, cudaMalloc(&a->br, (size_t)batch * 4));
+        PDEB_CUDA(c, cudaMalloc(&a->bt, (size_t)batch));
+        PDEB_CUDA(c, cudaMalloc(&a->inds, (size_t)batch * 8));
+        a->batch_cap = batch;
+    }
+    a->batch = batch;
+    return PDEB200_OK;
+}
+
+int32_t check_nets(pdeb200_ctx* c) {
+    Agent* a = ag(c);
+    for (int i = 0; i < 4; ++i)
+        if (!c->nets[i].n_layers) return fail(c, PDEB200_ESTATE, "ddpg: all four networks must be set (pdeb200_net_set)");
+    const HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+    if (A.sizes[0] != a->ns || A.sizes[A.n_layers] != a->na) return fail(c, PDEB200_EINVAL, "ddpg: actor shape != (ns -> na)");
+    if (C.sizes[0] != a->ns + a->na || C.sizes[C.n_layers] != 1) return fail(c, PDEB200_EINVAL, "ddpg: critic shape != (ns+na -> 1)");
+    if (c->nets[PDEB200_NET_TARGET_ACTOR].n_params != A.n_params || c->nets[PDEB200_NET_TARGET_CRITIC].n_params != C.n_params)
+        return fail(c, PDEB200_EINVAL, "ddpg: target networks must have the behavior networks' shapes");
+    const int want = C.n_params + A.n_params;
+    if (c->n_grads != want) {
+        if (c->d_grads) cudaFree(c->d_grads);
+        PDEB_CUDA(c, cudaMalloc(&c->d_grads, (size_t)want * sizeof(float)));
+        PDEB_CUDA(c, cudaMemset(c->d_grads, 0, (size_t)want * sizeof(float)));
+        c->n_grads = want;
+    }
+    return PDEB200_OK;
+}
+
+int net_wmax(const HostNet& n) { int w = 0; for (int l = 0; l <= n.n_layers; ++l) w = std::max(w, n.sizes[l]); return w; }
+int net_act_floats(const HostNet& n) { int s = 0; for (int l = 0; l <= n.n_layers; ++l) s += TS * n.sizes[l]; return s; }
+
+DdpgArgs make_args(pdeb200_ctx* c, double gamma, int literal, int64_t global_batch) {
+    Agent* a = ag(c);
+    DdpgArgs D;
+    D.A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR].dev(); D.C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC].dev();
+    D.At = c->nets[PDEB200_NET_TARGET_ACTOR].dev(); D.Ct = c->nets[PDEB200_NET_TARGET_CRITIC].dev();
+    D.batch = a->batch; D.ns = a->ns; D.na = a->na;
+    D.s = a->bs; D.a = a->ba; D.r = a->br; D.s2 = a->bs2; D.t = a->bt;
+    D.gamma = (float)gamma; D.literal_q1 = literal; D.inv_global_batch = 1.0 / (double)global_batch;
+    D.stats = a->stats; D.partials = nullptr; D.n_acc = 0;
+    D.wmax = std::max({net_wmax(c->nets[0]), net_wmax(c->nets[1]), a->ns + a->na});
+    return D;
+}
+
+int block_threads(int wmax, int n_acc) {
+    int t = std::max(64, ((std::max(wmax, std::min(n_acc, 512)) + 31) / 32) * 32);
+    return std::min(t, 512);
+}
+
+}  // namespace
+
+double* agent_stats(pdeb200_ctx* c) { return c->agent ? ag(c)->stats : nullptr; }
+
+void agent_free(pdeb200_ctx* c) {
+    Agent* a = ag(c);
+    if (!a) return;
+    for (void* p : {(void*)a->state, (void*)a->action, (void*)a->reward, (void*)a->terminal, (void*)a->bs, (void*)a->ba,
+                    (void*)a->br, (void*)a->bs2, (void*)a->bt, (void*)a->inds, (void*)a->stats, (void*)a->partials})
+        if (p) cudaFree(p);
+    delete a;
+    c->agent = nullptr;
+}
+
+}  // namespace pdeb200
+
+using namespace pdeb200;
+
+extern "C" {
+
+int32_t pdeb200_traj_create(pdeb200_ctx* c, int64_t capacity) {
+    if (!c || capacity < 1) return fail(c, PDEB200_EINVAL, "traj_create: bad argument");
+    cudaSetDevice(c->device);
+    int32_t rc = ensure_agent(c);
+    if (rc) return rc;
+    Agent* a = ag(c);
+    if (capacity < 2 * a->ncols) return fail(c, PDEB200_EINVAL, "traj_create: capacity must hold at least two env steps of columns");
+    for (void* p : {(void*)a->state, (void*)a->action, (void*)a->reward, (void*)a->terminal})
+        if (p) cudaFree(p);
+    a->sa = Ring{capacity + 1, 0, 0};
+    a->rt = Ring{capacity, 0, 0};
+    PDEB_CUDA(c, cudaMalloc(&a->state, (size_t)(capacity + 1) * a->ns * 4));
+    PDEB_CUDA(c, cudaMalloc(&a->action, (size_t)(capacity + 1) * a->na * 4));
+    PDEB_CUDA(c, cudaMalloc(&a->reward, (size_t)capacity * 4));
+    PDEB_CUDA(c, cudaMalloc(&a->terminal, (size_t)capacity));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_traj_length(const pdeb200_ctx* c, int64_t* length) {
+    if (!c || !length || !c->agent) return fail(c, PDEB200_ESTATE, "traj_length: no trajectory");
+    *length = static_cast<Agent*>(c->agent)->rt.len;
+    return PDEB200_OK;
+}
+
+static void ring_advance(Ring& r, int64_t n) {
+    const int64_t over = std::max<int64_t>(0, r.len + n - r.cap);
+    r.len = std::min(r.cap, r.len + n);
+    r.start = (r.start + over) % r.cap;
+}
+
+static int32_t push_sa(pdeb200_ctx* c, int zero_action) {
+    Agent* a = ag(c);
+    if (!a || !a->state) return fail(c, PDEB200_ESTATE, "trajectory not created");
+    const int64_t n = a->ncols, pos0 = (a->sa.start + a->sa.len) % a->sa.cap;
+    const int tpb = 128; const int grid = (int)((n + tpb - 1) / tpb);
+    if (c->cfg.dtype == PDEB200_F64)
+        push_sa_kernel<double><<<grid, tpb, 0, c->stream>>>(n, a->ns, a->na, a->sa.cap, pos0, (const double*)c->state,
+                                                            (const double*)c->action_in, zero_action, a->state, a->action);
+    else
+        push_sa_kernel<float><<<grid, tpb, 0, c->stream>>>(n, a->ns, a->na, a->sa.cap, pos0, (const float*)c->state,
+                                                           (const float*)c->action_in, zero_action, a->state, a->action);
+    PDEB_CUDA(c, cudaGetLastError());
+    ring_advance(a->sa, n);
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
+/* PreActStage: push (state[:, i], action[:, i]) for every column.  The action pushed is the one the
+ * policy just produced (the staged action buffer), exactly what `agent(PRE_ACT_STAGE, env, action)` gets. */
+int32_t pdeb200_traj_push_pre(pdeb200_ctx* c) {
+    if (!c) return PDEB200_EINVAL;
+    cudaSetDevice(c->device);
+    return push_sa(c, 0);
+}
+
+int32_t pdeb200_traj_episode_end(pdeb200_ctx* c) {
+    if (!c) return PDEB200_EINVAL;
+    cudaSetDevice(c->device);
+    return push_sa(c, 1);
+}
+
+int32_t pdeb200_traj_push_post(pdeb200_ctx* c) {
+    if (!c) return PDEB200_EINVAL;
+    cudaSetDevice(c->device);
+    Agent* a = ag(c);
+    if (!a || !a->reward) return fail(c, PDEB200_ESTATE, "trajectory not created");
+    const int64_t n = a->ncols, pos0 = (a->rt.start + a->rt.len) % a->rt.cap;
+    const int tpb = 128; const int grid = (int)((n + tpb - 1) / tpb);
+    if (c->cfg.dtype == PDEB200_F64)
+        push_rt_kernel<double><<<grid, tpb, 0, c->stream>>>(n, c->n_cols, a->rt.cap, pos0, (const double*)c->reward, c->done,
+                                                            a->reward, a->terminal);
+    else
+        push_rt_kernel<float><<<grid, tpb, 0, c->stream>>>(n, c->n_cols, a->rt.cap, pos0, (const float*)c->reward, c->done,
+                                                           a->reward, a->terminal);
+    PDEB_CUDA(c, cudaGetLastError());
+    ring_advance(a->rt, n);
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_traj_pop_tail(pdeb200_ctx* c) {
+    if (!c) return PDEB200_EINVAL;
+    Agent* a = ag(c);
+    if (!a || !a->state) return fail(c, PDEB200_ESTATE, "trajectory not created");
+    if (a->rt.len > 0) a->sa.len = std::max<int64_t>(0, a->sa.len - a->ncols);       // PDEagent.jl:243-251
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_sample(pdeb200_ctx* c, int32_t batch, const int64_t* inds_host, uint64_t seed, uint64_t offset) {
+    if (!c || batch < 1) return fail(c, PDEB200_EINVAL, "sample: bad argument");
+    cudaSetDevice(c->device);
+    Agent* a = ag(c);
+    if (!a || !a->state) return fail(c, PDEB200_ESTATE, "sample: trajectory not created");
+    const int64_t range = a->rt.len - a->ncols;
+    if (range < 1) return fail(c, PDEB200_ESTATE, "sample: trajectory shorter than one env step of columns");
+    int32_t rc = ensure_batch(c, batch);
+    if (rc) return rc;
+    const int tpb = 128, grid = (batch + tpb - 1) / tpb;
+    if (inds_host) {
+        for (int i = 0; i < batch; ++i)
+            if (inds_host[i] < 0 || inds_host[i] >= range) return fail(c, PDEB200_EINVAL, "sample: index out of range");
+        PDEB_CUDA(c, cudaMemcpyAsync(a->inds, inds_host, (size_t)batch * 8, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        draw_inds_kernel<<<grid, tpb, 0, c->stream>>>(batch, range, seed, offset, a->inds);
+    }
+    fetch_kernel<<<grid, tpb, 0, c->stream>>>(batch, a->ns, a->na, a->ncols, a->sa, a->rt, a->inds, a->state, a->action,
+                                              a->reward, a->terminal, a->bs, a->ba, a->br, a->bt, a->bs2);
+    reward_stats_kernel<<<1, 256, 0, c->stream>>>(batch, a->br, a->stats);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 3;
+    if (inds_host) PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_set_batch(pdeb200_ctx* c, int32_t batch, const float* s, const float* a_, const float* r, const uint8_t* t,
+                          const float* s2) {
+    if (!c || batch < 1 || !s || !a_ || !r || !t || !s2) return fail(c, PDEB200_EINVAL, "set_batch: bad argument");
+    cudaSetDevice(c->device);
+    int32_t rc = ensure_agent(c);
+    if (rc) return rc;
+    if ((rc = ensure_batch(c, batch))) return rc;
+    Agent* a = ag(c);
+    PDEB_CUDA(c, cudaMemcpyAsync(a->bs, s, (size_t)batch * a->ns * 4, cudaMemcpyHostToDevice, c->stream));
+    PDEB_CUDA(c, cudaMemcpyAsync(a->ba, a_, (size_t)batch * a->na * 4, cudaMemcpyHostToDevice, c->stream));
+    PDEB_CUDA(c, cudaMemcpyAsync(a->br, r, (size_t)batch * 4, cudaMemcpyHostToDevice, c->stream));
+    PDEB_CUDA(c, cudaMemcpyAsync(a->bt, t, (size_t)batch, cudaMemcpyHostToDevice, c->stream));
+    PDEB_CUDA(c, cudaMemcpyAsync(a->bs2, s2, (size_t)batch * a->ns * 4, cudaMemcpyHostToDevice, c->stream));
+    reward_stats_kernel<<<1, 256, 0, c->stream>>>(batch, a->br, a->stats);
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_ddpg_critic_grads(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch) {
+    if (!c) return PDEB200_EINVAL;
+    cudaSetDevice(c->device);
+    Agent* a = ag(c);
+    if (!a || !a->batch) return fail(c, PDEB200_ESTATE, "ddpg: no batch (pdeb200_sample / pdeb200_set_batch first)");
+    int32_t rc = check_nets(c);
+    if (rc) return rc;
+    if (global_batch < a->batch) return fail(c, PDEB200_EINVAL, "ddpg: global_batch < local batch");
+    const HostNet& C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+    DdpgArgs D = make_args(c, gamma, literal_q1, global_batch);
+    D.n_acc = C.n_params;
+    const int n_tiles = (a->batch + TS - 1) / TS;
+    const int n_blocks = std::min(n_tiles, 2 * 148);
+    if ((rc = ensure_partials(c, n_blocks, D.n_acc))) return rc;
+    D.partials = a->partials;
+    const size_t smem = ((size_t)net_act_floats(C) + 2 * (size_t)TS * D.wmax + (size_t)TS * (a->ns + a->na) + TS + D.n_acc) * 4;
+    if (smem > 220 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "ddpg: critic too large for the shared-memory CUDA-core path");
+    PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tpb = block_threads(D.wmax, D.n_acc);
+    ddpg_critic_kernel<<<n_blocks, tpb, smem, c->stream>>>(D);
+    reduce_partials_kernel<<<(D.n_acc + 2 + 127) / 128, 128, 0, c->stream>>>(n_blocks, D.n_acc, a->partials, c->d_grads, a->stats, 2);
+    losses_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)global_batch, literal_q1, 0, c->d_losses);
+    PDEB_CUDA(c, cudaGetLastError());
+    a->n_blocks = n_blocks;
+    c->launches += 3;
+    return PDEB200_OK;
+}
+
+static int32_t adam_apply(pdeb200_ctx* c, HostNet& n, const float* g, double lr) {
+    adam_kernel<<<(n.n_params + 127) / 128, 128, 0, c->stream>>>(n.n_params, n.d_params, n.d_m, n.d_v, g, lr, 0.9, 0.999,
+                                                                  n.beta_p[0], n.beta_p[1], 1e-8);
+    PDEB_CUDA(c, cudaGetLastError());
+    n.beta_p[0] *= 0.9; n.beta_p[1] *= 0.999;
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_ddpg_critic_apply(pdeb200_ctx* c, double lr) {
+    if (!c || !c->d_grads) return fail(c, PDEB200_ESTATE, "ddpg: no gradients");
+    cudaSetDevice(c->device);
+    return adam_apply(c, c->nets[PDEB200_NET_BEHAVIOR_CRITIC], c->d_grads, lr);
+}
+
+int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* c, int64_t global_batch) {
+    if (!c) return PDEB200_EINVAL;
+    cudaSetDevice(c->device);
+    Agent* a = ag(c);
+    if (!a || !a->batch) return fail(c, PDEB200_ESTATE, "ddpg: no batch");
+    int32_t rc = check_nets(c);
+    if (rc) return rc;
+    const HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+    DdpgArgs D = make_args(c, 0.0, 0, global_batch);
+    D.n_acc = A.n_params;
+    const int n_tiles = (a->batch + TS - 1) / TS;
+    const int n_blocks = std::min(n_tiles, 2 * 148);
+    if ((rc = ensure_partials(c, n_blocks, D.n_acc))) return rc;
+    D.partials = a->partials;
+    const size_t smem = ((size_t)net_act_floats(C) + net_act_floats(A) + 2 * (size_t)TS * D.wmax + D.n_acc) * 4;
+    if (smem > 220 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "ddpg: networks too large for the shared-memory CUDA-core path");
+    PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tpb = block_threads(D.wmax, D.n_acc);
+    ddpg_actor_kernel<<<n_blocks, tpb, smem, c->stream>>>(D);
+    reduce_partials_kernel<<<(D.n_acc + 2 + 127) / 128, 128, 0, c->stream>>>(n_blocks, D.n_acc, a->partials,
+                                                                              c->d_grads + C.n_params, a->stats, 4);
+    losses_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)global_batch, 0, 1, c->d_losses);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 3;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_ddpg_actor_apply(pdeb200_ctx* c, double lr, double polyak) {
+    if (!c || !c->d_grads) return fail(c, PDEB200_ESTATE, "ddpg: no gradients");
+    cudaSetDevice(c->device);
+    HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+    HostNet &At = c->nets[PDEB200_NET_TARGET_ACTOR], &Ct = c->nets[PDEB200_NET_TARGET_CRITIC];
+    int32_t rc = adam_apply(c, A, c->d_grads + C.n_params, lr);
+    if (rc) return rc;
+    polyak_kernel<<<(A.n_params + 127) / 128, 128, 0, c->stream>>>(A.n_params, At.d_params, A.d_params, (float)polyak);
+    polyak_kernel<<<(C.n_params + 127) / 128, 128, 0, c->stream>>>(C.n_params, Ct.d_params, C.d_params, (float)polyak);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_ddpg_update(pdeb200_ctx* c, double gamma, double polyak, double lr_actor, double lr_critic, int32_t literal_q1) {
+    if (!c || !c->agent) return fail(c, PDEB200_ESTATE, "ddpg_update: no batch");
+    const int64_t B = ag(c)->batch;
+    int32_t rc;
+    if ((rc = pdeb200_ddpg_critic_grads(c, gamma, literal_q1, B))) return rc;
+    if ((rc = pdeb200_ddpg_critic_apply(c, lr_critic))) return rc;
+    if ((rc = pdeb200_ddpg_actor_grads(c, B))) return rc;
+    return pdeb200_ddpg_actor_apply(c, lr_actor, polyak);
+}
+
+}  // extern "C"

@@ -136,5 +136,6 @@ int32_t ns_cost(const pdeb200_ctx* c, double* bytes, double* flops);
 void ns_free(pdeb200_ctx* c);
 
 void agent_free(pdeb200_ctx* c);
+double* agent_stats(pdeb200_ctx* c);   // 8 doubles, or nullptr before the first batch
 
 }  // namespace pdeb200

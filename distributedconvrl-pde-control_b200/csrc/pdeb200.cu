@@ -262,6 +262,7 @@ ArrInfo arr_info(pdeb200_ctx* c, int which) {
         case PDEB200_ARR_STEPS: return {c->steps, B * sizeof(int)};
         case PDEB200_ARR_GRADS: return {c->d_grads, (size_t)c->n_grads * sizeof(float)};
         case PDEB200_ARR_LOSSES: return {c->d_losses, 2 * sizeof(float)};
+        case PDEB200_ARR_STATS: return {agent_stats(c), 8 * sizeof(double)};
         case PDEB200_ARR_SENSORS: return {c->sensors, B * c->fields * c->cfg.n_sensors * e};
     }
     return {nullptr, 0};

@@ -16,6 +16,7 @@ void ns_free(pdeb200_ctx*) {}
 #endif
 #ifndef PDEB_HAVE_AGENT
 void agent_free(pdeb200_ctx*) {}
+double* agent_stats(pdeb200_ctx*) { return nullptr; }
 #endif
 }  // namespace pdeb200
 #ifndef PDEB_HAVE_AGENT

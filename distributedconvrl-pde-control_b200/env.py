@@ -66,6 +66,7 @@ class PDEenv:
         self.cfg = cfg
         self.np_dtype = _np_dtype(cfg.dtype)
         L.check(lib.pdeb200_create(C.byref(cfg), int(device), C.byref(self._ctx)))
+        self.device_index = int(device)
         self.n_envs = cfg.n_envs
         self.n_actuators = cfg.n_actuators
         self.n_sensors = cfg.n_sensors

@@ -78,7 +78,8 @@ enum {
     PDEB200_ARR_GRADS = 10,       /* flat [critic | actor] gradient (+ tail) float32 */
     PDEB200_ARR_LOSSES = 11,      /* {critic_loss, actor_loss}               float32 */
     PDEB200_ARR_SENSORS = 12,     /* raw sensor dots [B][fields][n_sensors]  dtype   */
-    PDEB200_ARR_ACTION_IN = 13    /* staged action of the last policy_act    dtype   */
+    PDEB200_ARR_ACTION_IN = 13,   /* staged action of the last policy_act    dtype   */
+    PDEB200_ARR_STATS = 14        /* batch sums {sum r, sum r^2, ...}        float64[8] (data-parallel r-bar, quirk Q1) */
 };
 
 typedef struct pdeb200_config {
