@@ -46,7 +46,8 @@ def _defines():
 def _compile(src, verbose):
     obj = OBJ / (src.stem + ".o")
     newest = max(src.stat().st_mtime, _deps_mtime(), Path(__file__).stat().st_mtime)
-    if obj.exists() and obj.stat().st_mtime >= newest:
+    # stubs.cu depends on WHICH back-ends exist (the -D set), not only on file times: always rebuild it
+    if obj.exists() and obj.stat().st_mtime >= newest and src.stem != "stubs":
         return obj, False
     cmd = ["nvcc", *NVCC_FLAGS, *_defines(), "-c", str(src), "-o", str(obj)]
     if verbose:

@@ -292,7 +292,7 @@ int32_t pdeb200_default_config(int32_t problem, pdeb200_config* cfg) {
             cfg->reward_div = 90.0; cfg->reward_offset = 0.0; cfg->action_punish = 0.002; cfg->delta_action_punish = 0.002;
             break;
         case PDEB200_KSEG1D:      // scripts/Keller-Segel/setup/KellerSegelSetup.jl:26-57, 241-263, 276
-            cfg->nx = 100; cfg->Lx = 10.0; cfg->dt = 0.006; cfg->te = 8.0; cfg->oversampling = 8;
+            cfg->nx = 100; cfg->Lx = 10.0; cfg->dt = 0.006; cfg->te = 8.0; cfg->oversampling = 40;
             cfg->window_size = 3; cfg->temporal_steps = 2; cfg->check_max_value = PDEB200_CHECK_Y; cfg->max_value = 20.0;
             cfg->agent_power = 10.0; cfg->obs_scale = 0.25; cfg->reward_gain = 1.0; cfg->reward_pow = 2.0;
             cfg->reward_div = 800.0; cfg->reward_offset = 1.0; cfg->action_punish = 0.0; cfg->delta_action_punish = 0.0;

@@ -1,2 +1,3 @@
 """Setup builders mirroring the reference's scripts/*/setup/*Setup.jl files."""
 from .ks import KSSetup  # noqa: F401
+from .kseg import KellerSegelSetup  # noqa: F401

@@ -1,0 +1,57 @@
+"""Keller-Segel setup: what scripts/Keller-Segel/setup/KellerSegelSetup.jl does around the hot path."""
+import numpy as np
+
+from .. import _lib as L
+from ..env import PDEenv
+
+
+def prepare_rectangles(nx, sensor_positions, half_window_size=2):
+    """KellerSegelSetup.jl:112-126 (1-based positions; non-wrapping 5-point boxes)."""
+    out = np.zeros((len(sensor_positions), nx))
+    for i, pos in enumerate(sensor_positions):
+        out[i, pos - half_window_size - 1:pos + half_window_size] = 1.0
+    return out
+
+
+class KellerSegelSetup:
+    """Globals of scripts/Keller-Segel/Keller-Segel10_16/Keller-Segel10_16.jl + KellerSegelSetup.jl:26-57."""
+
+    def __init__(self, Lx=10.0, nx=100, sensor_positions=None, actuators_to_sensors=None, te=8.0, dt=0.006,
+                 rk4_substeps=40, window_size=3, temporal_steps=2, memory_size=0, action_punish=0.0,
+                 delta_action_punish=0.0, agent_power=10.0, max_value=20.0):
+        self.Lx, self.nx = float(Lx), int(nx)
+        self.sensor_positions = np.arange(3, nx + 1, 5) if sensor_positions is None else np.asarray(sensor_positions)
+        self.actuators_to_sensors = np.arange(3, 19) if actuators_to_sensors is None else np.asarray(actuators_to_sensors)
+        self.te, self.dt, self.rk4_substeps = te, dt, rk4_substeps
+        self.window_size, self.temporal_steps, self.memory_size = window_size, temporal_steps, memory_size
+        self.action_punish, self.delta_action_punish = action_punish, delta_action_punish
+        self.agent_power, self.max_value = agent_power, max_value
+        self.gaussians = prepare_rectangles(self.nx, self.sensor_positions, 2)          # :128
+        self.gaussians_actuators = self.gaussians[self.actuators_to_sensors - 1]        # :129
+
+    def y0_standard(self):
+        """y0_2D_standard, KellerSegelSetup.jl:60-61"""
+        return np.vstack([np.ones(self.nx), 1.01 * np.ones(self.nx)])
+
+    def generate_random_init(self, rng, n=1):
+        """KellerSegelSetup.jl:373-384, batched -> (n, 2, nx)"""
+        ns = int(np.ceil(self.Lx / 3))
+        a = rng.uniform(-1, 1, size=(n, 2 * ns))
+        a /= np.linalg.norm(a, axis=1, keepdims=True)
+        x = (self.Lx / self.nx) * np.arange(1, self.nx + 1)
+        basis = np.sin(np.arange(1, ns + 1)[:, None] * x[None, :] / (2 * np.pi * (self.Lx / 22)))
+        y0 = np.ones((n, 2, self.nx))
+        y0[:, 0] += a[:, :ns] @ basis
+        y0[:, 1] += a[:, ns:] @ basis
+        return y0
+
+    def make_env(self, n_envs=1, dtype="f64", device=0, y0=None):
+        y0 = self.y0_standard() if y0 is None else np.asarray(y0, dtype=np.float64)
+        if y0.ndim == 3:                      # (B, 2, nx) -> reference shape (2, nx, B)
+            y0 = y0.transpose(1, 2, 0)
+        return PDEenv(problem=L.KSEG1D, n_envs=n_envs, dtype=dtype, device=device, sensor_basis=self.gaussians,
+                      actuator_basis=self.gaussians_actuators, actuators_to_sensors=self.actuators_to_sensors, y0=y0,
+                      nx=self.nx, ny=1, Lx=self.Lx, dt=self.dt, te=self.te, oversampling=self.rk4_substeps,
+                      max_value=self.max_value, window_size=self.window_size, temporal_steps=self.temporal_steps,
+                      memory_size=self.memory_size, action_punish=self.action_punish,
+                      delta_action_punish=self.delta_action_punish, agent_power=self.agent_power, check_max_value="y")
