@@ -1,0 +1,143 @@
+# B200PDE.jl -- reference-side binding of libpdeb200.so (include/pdeb200.h).
+#
+# Drop-in for the hot path of DistributedConvRL-PDE-Control: the four closures a setup file hands to
+# `PDEenv(...)` (src/PDEenv.jl:31-35, called in order at :195-241) are replaced by thin `ccall`
+# wrappers; `PDEenv`, `PDEagent`, `PDEhook`, `run(agent, env, ...)` stay unchanged.
+#
+# NOTE: Julia is not installed in the build image, so this file has been syntax-reviewed only; the same
+# entry points are exercised through Python ctypes in tests/ (the C ABI is language neutral).
+module B200PDE
+
+const LIB = get(ENV, "PDEB200_LIB", joinpath(@__DIR__, "..", "distributedconvrl-pde-control_b200", "libpdeb200.so"))
+
+const KS, KSEG1D, NS2D = Int32(0), Int32(1), Int32(2)
+const F32, F64 = Int32(0), Int32(1)
+const ARR_Y, ARR_P, ARR_STATE, ARR_ACTION, ARR_DELTA_ACTION, ARR_REWARD, ARR_DONE, ARR_TIME, ARR_STEPS =
+    Int32.(0:8)
+
+# struct pdeb200_config (field order and types must match include/pdeb200.h)
+Base.@kwdef mutable struct Config
+    struct_size::Int32 = 0
+    problem::Int32 = KS
+    dtype::Int32 = F64
+    nx::Int32 = 0; ny::Int32 = 1
+    n_envs::Int32 = 1
+    n_sensors::Int32 = 0; n_actuators::Int32 = 0
+    window_size::Int32 = 1; temporal_steps::Int32 = 1; memory_size::Int32 = 0
+    oversampling::Int32 = 1
+    check_max_value::Int32 = 1
+    mono::Int32 = 0
+    sensors_per_axis::Int32 = 0
+    ifpad::Int32 = 1
+    Lx::Float64 = 0; Ly::Float64 = 1
+    dt::Float64 = 0; te::Float64 = 0; t0::Float64 = 0
+    mu::Float64 = 0; nu::Float64 = 0
+    agent_power::Float64 = 0; max_value::Float64 = 0
+    obs_scale::Float64 = 0
+    reward_gain::Float64 = 0; reward_pow::Float64 = 0; reward_div::Float64 = 0; reward_offset::Float64 = 0
+    action_punish::Float64 = 0; delta_action_punish::Float64 = 0
+end
+
+struct Ctx
+    ptr::Ptr{Cvoid}
+end
+
+function check(rc::Int32, ctx::Ptr{Cvoid} = C_NULL)
+    rc == 0 && return nothing
+    msg = unsafe_string(ccall((:pdeb200_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx))
+    error("pdeb200 error $rc: $msg")
+end
+
+function default_config(problem::Int32)
+    cfg = Ref(Config())
+    check(ccall((:pdeb200_default_config, LIB), Int32, (Int32, Ref{Config}), problem, cfg))
+    cfg[]
+end
+
+function create(cfg::Config; device::Integer = 0)
+    cfg.struct_size = Int32(sizeof(Config))
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:pdeb200_create, LIB), Int32, (Ref{Config}, Int32, Ref{Ptr{Cvoid}}), Ref(cfg), Int32(device), out))
+    Ctx(out[])
+end
+
+destroy(c::Ctx) = ccall((:pdeb200_destroy, LIB), Int32, (Ptr{Cvoid},), c.ptr)
+
+# gaussians / gaussians_actuators are Vector{Vector{Float64}} in the setup files: hcat them so that the
+# memory is row-major [n][nx] as the C ABI expects.  a2s is 1-based in Julia, 0-based in C.
+function set_bases(c::Ctx, gaussians, gaussians_actuators, actuators_to_sensors; drop_tol = 1e-17)
+    sb = reduce(hcat, gaussians); ab = reduce(hcat, gaussians_actuators)      # (nx, n): column-major == [n][nx]
+    a2s = Int32.(actuators_to_sensors .- 1)
+    check(ccall((:pdeb200_set_bases, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Float64),
+                c.ptr, sb, ab, a2s, drop_tol), c.ptr)
+end
+
+set_y0(c::Ctx, y0::Array{Float64}; broadcast = true) =
+    check(ccall((:pdeb200_set_y0, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), c.ptr, y0, Int32(broadcast)), c.ptr)
+
+reset!(c::Ctx) = check(ccall((:pdeb200_reset, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), c.ptr, C_NULL), c.ptr)
+
+# env(action): one call = prepare_action + do_step + reward_function + featurize + clock for all envs
+function step!(c::Ctx, action::Matrix{Float64}, y::Array{Float64}, reward::Vector{Float64}, state::Matrix{Float64},
+               done::Vector{UInt8})
+    check(ccall((:pdeb200_step_host, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}),
+                c.ptr, action, y, reward, state, done), c.ptr)
+end
+
+get!(c::Ctx, which::Int32, dst::Array) =
+    check(ccall((:pdeb200_get, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Csize_t), c.ptr, which, dst, sizeof(dst)), c.ptr)
+
+# ---- closures for PDEenv(...) -------------------------------------------------------------------
+# In scripts/KS/setup/KSSetup.jl, `initialize_setup()` (:249-262) becomes
+#
+#   ctx = B200PDE.create(cfg); B200PDE.set_bases(ctx, gaussians, gaussians_actuators, actuators_to_sensors)
+#   B200PDE.set_y0(ctx, y0_1D_standard); B200PDE.reset!(ctx)
+#   closures = B200PDE.make_closures(ctx, nx, n_act * n_envs, ns)
+#   env = PDEenv(do_step = closures.do_step, reward_function = closures.reward_function,
+#                featurize = closures.featurize, prepare_action = closures.prepare_action, ...)
+#
+# PDEenv calls prepare_action -> do_step -> reward_function -> featurize (src/PDEenv.jl:199,217,220,222).
+# The fused step runs inside `do_step`; the other three return what that launch already produced.
+function make_closures(c::Ctx, nx::Int, ncols::Int, ns::Int, n_envs::Int = 1)
+    y = zeros(nx, n_envs); reward = zeros(ncols); state = zeros(ns, ncols); done = zeros(UInt8, n_envs)
+    p = zeros(nx, n_envs)
+    prepare_action = function (action0 = nothing, t0 = nothing; env = nothing)
+        isnothing(env) || B200PDE.get!(c, ARR_P, p)     # after the step; before it p is the reset value
+        p
+    end
+    do_step = function (env)
+        step!(c, Matrix{Float64}(env.action), y, reward, state, done)
+        B200PDE.get!(c, ARR_P, p); env.p = copy(p)
+        copy(y)
+    end
+    reward_function = env -> copy(reward)
+    featurize = function (y0 = nothing, t0 = nothing; env = nothing)
+        isnothing(env) && B200PDE.get!(c, ARR_STATE, state)   # constructor / reset!: state of y0
+        copy(state)
+    end
+    (; do_step, reward_function, featurize, prepare_action)
+end
+
+# ---- CustomNeuralNetworkApproximator on the device (src/custom_nna.jl) ----------------------------
+# Flux models stay the host-side source of truth (save()/load() keep working, KSSetup.jl:378-402):
+# push their parameters with net_set!, pull them back with net_get! before saving.
+function net_set!(c::Ctx, net::Int32, sizes::Vector{Int32}, acts::Vector{Int32}, flat::Vector{Float32})
+    check(ccall((:pdeb200_net_set, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Float32}),
+                c.ptr, net, Int32(length(acts)), sizes, acts, flat), c.ptr)
+end
+net_get!(c::Ctx, net::Int32, flat::Vector{Float32}) =
+    check(ccall((:pdeb200_net_get, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float32}, Csize_t), c.ptr, net, flat, length(flat)), c.ptr)
+
+# Flux.Chain of Dense -> flat vector in the C ABI's order (per layer: W column-major, then b)
+flatten(chain) = reduce(vcat, [vcat(vec(l.weight), l.bias) for l in chain.layers])
+
+policy_act!(c::Ctx; act_noise = 0.0, act_limit = 1.0, noise = nothing) =
+    check(ccall((:pdeb200_policy_act, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64),
+                c.ptr, isnothing(noise) ? C_NULL : noise, act_noise, act_limit), c.ptr)
+
+ddpg_update!(c::Ctx; γ = 0.99, p = 0.995, lr_actor = 5e-4, lr_critic = 1e-3, literal_q1 = true) =
+    check(ccall((:pdeb200_ddpg_update, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Float64, Int32),
+                c.ptr, γ, p, lr_actor, lr_critic, Int32(literal_q1)), c.ptr)
+
+end # module
