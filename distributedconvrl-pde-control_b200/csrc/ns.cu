@@ -1,0 +1,620 @@
+// Navier-Stokes back-end: 2-D incompressible flow in vorticity form, pseudo-spectral, fixed-step RK4.
+//
+// Restates (batched over environments; y = omega_hat, the spectral vorticity, like the reference):
+//   rk4 / rhs / advection / pad / chop   src/fluid_rk4.jl:122-229
+//   do_step (RK4 x oversampling)          scripts/Fluid/setup/FluidSetup.jl:163-172
+//   prepare_action's fft(p)               FluidSetup.jl:247-261   (the physical sum is actuate_kernel's)
+//   real(ifft(env.y)) + sensor dots       FluidSetup.jl:189-197, 205-217
+//
+// One rhs evaluation = three kernels; the 3/2-rule work arrays never exist as full 2-D complex arrays:
+//   A  ns_ypass_inv : per (env, kx >= 0 column): the four spectra  u_hat = i ky psi_hat, v_hat = -i kx psi_hat,
+//                     i kx omega_hat, i ky omega_hat  are formed on the fly from omega_hat, zero-padded along ky and
+//                     inverse-transformed along y.  Only the kx >= 0 half is needed because every field is REAL in
+//                     physical space: real(ifft2(X)) == ifft2(X_h), X_h[k] = (P[k] + conj(P[-k]))/2 with P = pad(X).
+//                     X_h is evaluated literally (both k and -k are read), so arbitrary complex input -- including
+//                     the non-Hermitian Nyquist row/column that pad()/chop() create -- is treated like the reference.
+//   B  ns_xpass     : per pair of y-lines: Hermitian extension along kx, two complex inverse FFTs give (u + i v) and
+//                     (omega_x + i omega_y), the product -u omega_x - v omega_y of two lines is packed into ONE
+//                     complex forward FFT along x and split again; only kx in [0, N/2] is kept (chop).
+//   C  ns_ypass_fwd : per (env, kx column): forward FFT along y, chop along ky, scale 1.5*1.5, and the RK4 stage
+//                     update for column kx and (by conjugate symmetry of the FFT of a real field) column -kx:
+//                     k = -nu k^2 f + nonlin + p_hat;  stage combinations of rk4().
+// Arrays are env-major, Julia column-major inside an environment: y[env][i (kx)][j (ky)] complex.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "ctx.hpp"
+#include "fft_pass.cuh"
+#include "glue.cuh"
+
+namespace pdeb200 {
+
+namespace {
+
+template <int P1, int P2> struct NsGeom {
+    static constexpr int NP = P1 * P2;
+    static constexpr int RMAX = P1 > P2 ? P1 : P2;
+    static constexpr int SA = P2 * PassStride<P2, P1>::value;      // inverse pass <P2, P1>
+    static constexpr int SB = P1 * PassStride<P1, P2>::value;      // forward pass <P1, P2>
+    static constexpr int XB0 = (SA > SB ? SA : SB) > NP ? (SA > SB ? SA : SB) : NP;
+    static constexpr int XB = ((XB0 + 7) / 8) * 8 + 1;             // == 1 (mod 8): conflict-free 8-column tiles
+};
+
+constexpr int kColsPerCta = 8;      // warps per CTA = spectral columns (A, C) / line pairs (B) per CTA
+
+struct NsProb {
+    int N = 0, NP = 0, NH = 0, NHP = 0, chunk = 0;
+    int n1 = 0, n2 = 0, p1 = 0, p2 = 0;
+    void *tw_inv = nullptr, *tw_fwd = nullptr, *tw_n = nullptr;
+    void *kx = nullptr, *ky = nullptr;
+    void *fst = nullptr, *acc = nullptr, *W = nullptr, *Q = nullptr;
+    void *p_phys = nullptr, *om_phys = nullptr, *tmpc = nullptr;
+};
+
+template <typename T>
+struct NsArgs {
+    using C = typename V2<T>::type;
+    int N, NH, NHP, stage;
+    const C* tw_inv; const C* tw_fwd;
+    const T* kx; const T* ky;
+    const C* fin;              // stage input (y at stage 1, fst afterwards)
+    C* y; C* fst; C* acc;
+    const C* phat;
+    C* W;                      // [env][4][NP][NHP]
+    C* Q;                      // [env][NP][NHP]
+    T nu, dt, scale;
+};
+
+// padded index -> index in the unpadded array, or -1 if pad() leaves that entry zero (fluid_rk4.jl:205-208)
+__device__ __forceinline__ int unpad_idx(int kp, int NP, int N) {
+    const int s = kp <= NP / 2 ? kp : kp - NP;
+    if (s > N / 2 || s <= -(N / 2)) return -1;
+    return s < 0 ? s + N : s;
+}
+
+// the four spectra of advection() (fluid_rk4.jl:152-161) from one entry w = omega_hat[j, i]
+template <typename T>
+__device__ __forceinline__ typename V2<T>::type field_value(int f, typename V2<T>::type w, T kyv, T kxv, bool origin) {
+    if (f < 2) {
+        const T k2 = kyv * kyv + kxv * kxv;
+        typename V2<T>::type psi = origin ? V2<T>::make(T(0), T(0)) : V2<T>::make(w.x / k2, w.y / k2);
+        if (f == 0) return V2<T>::make(-kyv * psi.y, kyv * psi.x);        // u_hat =  i ky psi_hat
+        return V2<T>::make(kxv * psi.y, -kxv * psi.x);                    // v_hat = -i kx psi_hat
+    }
+    if (f == 2) return V2<T>::make(-kxv * w.y, kxv * w.x);                // i kx omega_hat
+    return V2<T>::make(-kyv * w.y, kyv * w.x);                            // i ky omega_hat
+}
+
+template <typename T> struct NsMinCtas { static constexpr int value = sizeof(T) == 8 ? 1 : 2; };
+
+// ---- A: inverse transform along y of the four padded, Hermitian-symmetrised spectra ---------------------
+template <typename T, int P1, int P2>
+__global__ void __launch_bounds__(kColsPerCta * 32, NsMinCtas<T>::value)
+ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
+    using G = NsGeom<P1, P2>;
+    using C = typename V2<T>::type;
+    constexpr int NP = G::NP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = A.N;
+    C* s_tw = reinterpret_cast<C*>(smem_raw);
+    C* s_xb0 = s_tw + NP;
+    C* s_col0 = s_xb0 + kColsPerCta * G::XB;
+    T* s_ky = reinterpret_cast<T*>(s_col0 + kColsPerCta * 2 * N);
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+    const int env = blockIdx.y, a0 = blockIdx.x * kColsPerCta, a = a0 + w;
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) s_tw[i] = A.tw_inv[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_ky[i] = A.ky[i];
+    C* xb = s_xb0 + w * G::XB;
+    C* colA = s_col0 + (size_t)w * 2 * N;
+    C* colB = colA + N;
+    const bool live = a < A.NH;
+    const int ib = (N - a) % N;                                   // column of -kx in the unpadded array
+    const bool xpartner = unpad_idx((NP - a) % NP, NP, N) >= 0;   // pad() keeps (-kx) ?
+    T kxa = T(0), kxb = T(0);
+    if (live) {
+        const C* src = A.fin + (size_t)env * N * N;
+        for (int j = t; j < N; j += 32) { colA[j] = src[(size_t)a * N + j]; colB[j] = src[(size_t)ib * N + j]; }
+        kxa = A.kx[a]; kxb = A.kx[ib];
+    }
+    __syncthreads();
+    for (int f = 0; f < 4; ++f) {
+        if (live) {
+            T zr[G::RMAX], zi[G::RMAX];
+            if (t < P1) {
+#pragma unroll
+                for (int r = 0; r < P2; ++r) {
+                    const int kyp = t + P1 * r;
+                    const int j1 = unpad_idx(kyp, NP, N);
+                    const int j2 = xpartner ? unpad_idx((NP - kyp) % NP, NP, N) : -1;
+                    C x1 = V2<T>::make(T(0), T(0)), x2 = x1;
+                    if (j1 >= 0) x1 = field_value<T>(f, colA[j1], s_ky[j1], kxa, j1 == 0 && a == 0);
+                    if (j2 >= 0) x2 = field_value<T>(f, colB[j2], s_ky[j2], kxb, j2 == 0 && ib == 0);
+                    zr[r] = T(0.5) * (x1.x + x2.x);
+                    zi[r] = T(0.5) * (x1.y - x2.y);
+                }
+            }
+            fft_pass<T, P2, P1, +1>(zr, zi, xb, s_tw, t);
+            if (t < P2) {
+#pragma unroll
+                for (int r = 0; r < P1; ++r) xb[t + P2 * r] = V2<T>::make(zr[r], zi[r]);
+            }
+        }
+        __syncthreads();
+        C* dst = A.W + ((size_t)(env * 4 + f) * NP) * A.NHP + a0;
+        for (int idx = threadIdx.x; idx < NP * kColsPerCta; idx += blockDim.x) {
+            const int c = idx % kColsPerCta, y = idx / kColsPerCta;
+            if (a0 + c < A.NH) dst[(size_t)y * A.NHP + c] = s_xb0[c * G::XB + y];
+        }
+        __syncthreads();
+    }
+}
+
+// ---- B: x transforms, the quadratic term, forward x transform (two y-lines per warp) ---------------------
+template <typename T, int P1, int P2>
+__global__ void __launch_bounds__(kColsPerCta * 32, NsMinCtas<T>::value)
+ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
+    using G = NsGeom<P1, P2>;
+    using C = typename V2<T>::type;
+    constexpr int NP = G::NP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = A.N;
+    C* s_twi = reinterpret_cast<C*>(smem_raw);
+    C* s_twf = s_twi + NP;
+    C* s_xb0 = s_twf + NP;
+    C* s_uv0 = s_xb0 + kColsPerCta * G::XB;
+    T* s_q0 = reinterpret_cast<T*>(s_uv0 + kColsPerCta * NP);
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+    const int env = blockIdx.y;
+    const int y0 = (blockIdx.x * kColsPerCta + w) * 2;
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) { s_twi[i] = A.tw_inv[i]; s_twf[i] = A.tw_fwd[i]; }
+    __syncthreads();
+    if (y0 >= NP) return;
+    C* xb = s_xb0 + w * G::XB;
+    C* uv = s_uv0 + (size_t)w * NP;
+    T* q1 = s_q0 + (size_t)w * NP;
+    T zr[G::RMAX], zi[G::RMAX];
+#pragma unroll 1
+    for (int L = 0; L < 2; ++L) {
+        const int y = y0 + L;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {        // h = 0: (u, v);  h = 1: (omega_x, omega_y)
+            const C* Wa = A.W + ((size_t)(env * 4 + 2 * h) * NP + y) * A.NHP;
+            const C* Wb = Wa + (size_t)NP * A.NHP;
+            if (t < P1) {
+#pragma unroll
+                for (int r = 0; r < P2; ++r) {
+                    const int kxp = t + P1 * r;
+                    const int s = kxp <= NP / 2 ? kxp : kxp - NP;
+                    const int a = s < 0 ? -s : s;
+                    T re = T(0), im = T(0);
+                    if (a <= N / 2) {
+                        C U = __ldg(Wa + a), V = __ldg(Wb + a);
+                        if (s < 0) { U.y = -U.y; V.y = -V.y; }          // G(y, -kx) = conj(G(y, kx))
+                        re = U.x - V.y; im = U.y + V.x;                  // U + i V
+                    }
+                    zr[r] = re; zi[r] = im;
+                }
+            }
+            fft_pass<T, P2, P1, +1>(zr, zi, xb, s_twi, t);
+            if (t < P2) {
+                if (h == 0) {
+#pragma unroll
+                    for (int r = 0; r < P1; ++r) uv[t + P2 * r] = V2<T>::make(zr[r], zi[r]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < P1; ++r) {
+                        const int x = t + P2 * r;
+                        const C g = uv[x];
+                        const T q = -(g.x * zr[r] + g.y * zi[r]) * A.scale;   // -u w_x - v w_y  (fluid_rk4.jl:175)
+                        if (L == 0) q1[x] = q;
+                        else { zr[r] = q1[x]; zi[r] = q; }
+                    }
+                }
+            }
+        }
+    }
+    fft_pass<T, P1, P2, -1>(zr, zi, xb, s_twf, t);
+    if (t < P1) {
+#pragma unroll
+        for (int r = 0; r < P2; ++r) xb[t + P1 * r] = V2<T>::make(zr[r], zi[r]);
+    }
+    __syncwarp();
+    C* Qa = A.Q + ((size_t)env * NP + y0) * A.NHP;
+    C* Qb = Qa + A.NHP;
+    for (int a = t; a < A.NH; a += 32) {
+        const C za = xb[a], zb = xb[(NP - a) % NP];
+        Qa[a] = V2<T>::make(T(0.5) * (za.x + zb.x), T(0.5) * (za.y - zb.y));
+        Qb[a] = V2<T>::make(T(0.5) * (za.y + zb.y), T(-0.5) * (za.x - zb.x));
+    }
+}
+
+// ---- C: forward transform along y, chop, RK4 stage update ---------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void rk_update(const NsArgs<T>& A, size_t idx, T k2, typename V2<T>::type nl) {
+    using C = typename V2<T>::type;
+    const C fs = A.fin[idx];
+    const C ph = A.phat[idx];
+    // rhs = lin + advection + p,  lin = -nu * (kx2ky2 .* omghat)     (fluid_rk4.jl:138-142)
+    const T kr = (-A.nu * (k2 * fs.x) + nl.x) + ph.x;
+    const T ki = (-A.nu * (k2 * fs.y) + nl.y) + ph.y;
+    if (A.stage == 1) {
+        A.acc[idx] = V2<T>::make(kr, ki);
+        A.fst[idx] = V2<T>::make(fs.x + (T(0.5) * A.dt) * kr, fs.y + (T(0.5) * A.dt) * ki);
+    } else if (A.stage == 4) {
+        const C f0 = A.y[idx], ac = A.acc[idx];
+        A.y[idx] = V2<T>::make(f0.x + (A.dt / T(6)) * (ac.x + kr), f0.y + (A.dt / T(6)) * (ac.y + ki));
+    } else {
+        const C f0 = A.y[idx], ac = A.acc[idx];
+        A.acc[idx] = V2<T>::make(ac.x + T(2) * kr, ac.y + T(2) * ki);
+        const T c = A.stage == 2 ? T(0.5) * A.dt : A.dt;
+        A.fst[idx] = V2<T>::make(f0.x + c * kr, f0.y + c * ki);
+    }
+}
+
+template <typename T, int P1, int P2>
+__global__ void __launch_bounds__(kColsPerCta * 32, NsMinCtas<T>::value)
+ns_ypass_fwd_kernel(const __grid_constant__ NsArgs<T> A) {
+    using G = NsGeom<P1, P2>;
+    using C = typename V2<T>::type;
+    constexpr int NP = G::NP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int N = A.N;
+    C* s_tw = reinterpret_cast<C*>(smem_raw);
+    C* s_xb0 = s_tw + NP;
+    T* s_ky = reinterpret_cast<T*>(s_xb0 + kColsPerCta * G::XB);
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+    const int env = blockIdx.y, a0 = blockIdx.x * kColsPerCta, a = a0 + w;
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) s_tw[i] = A.tw_fwd[i];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_ky[i] = A.ky[i];
+    const C* src = A.Q + ((size_t)env * NP) * A.NHP + a0;
+    for (int idx = threadIdx.x; idx < NP * kColsPerCta; idx += blockDim.x) {
+        const int c = idx % kColsPerCta, y = idx / kColsPerCta;
+        if (a0 + c < A.NH) s_xb0[c * G::XB + y] = src[(size_t)y * A.NHP + c];
+    }
+    __syncthreads();
+    if (a >= A.NH) return;
+    C* xb = s_xb0 + w * G::XB;
+    T zr[G::RMAX], zi[G::RMAX];
+    if (t < P2) {
+#pragma unroll
+        for (int r = 0; r < P1; ++r) { const C v = xb[t + P2 * r]; zr[r] = v.x; zi[r] = v.y; }
+    }
+    __syncwarp();
+    fft_pass<T, P1, P2, -1>(zr, zi, xb, s_tw, t);
+    if (t < P1) {
+#pragma unroll
+        for (int r = 0; r < P2; ++r) xb[t + P1 * r] = V2<T>::make(zr[r], zi[r]);
+    }
+    __syncwarp();
+    const int ib = (N - a) % N;
+    const bool two = ib != a;
+    const T kxa = A.kx[a], kxb = A.kx[ib];
+    const size_t base = (size_t)env * N * N;
+    for (int j = t; j < N; j += 32) {
+        const int s = j <= N / 2 ? j : j - N;                    // chop: rows (-N/2, N/2]   (fluid_rk4.jl:224-227)
+        const int kyp = s < 0 ? s + NP : s;
+        const T kyv = s_ky[j];
+        rk_update<T>(A, base + (size_t)a * N + j, kyv * kyv + kxa * kxa, xb[kyp]);
+        if (two) {
+            // F[ky, -kx] = conj(F[-ky, kx]) for the FFT of a real field (includes the +N/2 Nyquist row,
+            // whose partner is the -N/2 row of the padded transform)
+            C v = xb[(NP - kyp) % NP];
+            v.y = -v.y;
+            rk_update<T>(A, base + (size_t)ib * N + j, kyv * kyv + kxb * kxb, v);
+        }
+    }
+}
+
+// ---- generic batched line FFT for the N x N transforms of featurize / prepare_action ----------------------
+// One warp per line.  Element e of line l of environment b sits at  b*env_stride + l*line_stride + e*elem_stride.
+template <typename T, int N1, int N2, int SIGN>
+__global__ void __launch_bounds__(256) ns_lines_kernel(const void* __restrict__ in, void* __restrict__ out,
+                                                       const typename V2<T>::type* __restrict__ tw, int in_real,
+                                                       int out_real, T out_scale, int n_lines, long long line_stride,
+                                                       long long elem_stride, long long env_stride) {
+    using C = typename V2<T>::type;
+    constexpr int N = N1 * N2;
+    constexpr int XB = N1 * PassStride<N1, N2>::value;
+    __shared__ C s_tw[N];
+    __shared__ C s_xb[8][XB];
+    for (int i = threadIdx.x; i < N; i += blockDim.x) s_tw[i] = tw[i];
+    __syncthreads();
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+    const int line = blockIdx.x * 8 + w;
+    if (line >= n_lines) return;
+    const long long base = (long long)blockIdx.y * env_stride + (long long)line * line_stride;
+    constexpr int RMAX = N1 > N2 ? N1 : N2;
+    T zr[RMAX], zi[RMAX];
+    if (t < N2) {
+#pragma unroll
+        for (int r = 0; r < N1; ++r) {
+            const long long o = base + (long long)(t + N2 * r) * elem_stride;
+            if (in_real) { zr[r] = reinterpret_cast<const T*>(in)[o]; zi[r] = T(0); }
+            else { const C v = reinterpret_cast<const C*>(in)[o]; zr[r] = v.x; zi[r] = v.y; }
+        }
+    }
+    fft_pass<T, N1, N2, SIGN>(zr, zi, s_xb[w], s_tw, t);
+    if (t < N1) {
+#pragma unroll
+        for (int r = 0; r < N2; ++r) {
+            const long long o = base + (long long)(t + N1 * r) * elem_stride;
+            if (out_real) reinterpret_cast<T*>(out)[o] = zr[r] * out_scale;
+            else reinterpret_cast<C*>(out)[o] = V2<T>::make(zr[r] * out_scale, zi[r] * out_scale);
+        }
+    }
+}
+
+// max |omega_hat| per environment (PDEenv.jl:227 with check_max_value = "y"; quirk Q6)
+template <typename T>
+__global__ void __launch_bounds__(256) ns_vmax_kernel(const typename V2<T>::type* __restrict__ y, int n, T* vmax) {
+    __shared__ T s[8];
+    const typename V2<T>::type* ye = y + (size_t)blockIdx.x * n;
+    T m = T(0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, hypot(ye[i].x, ye[i].y));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int i = 1; i < 8; ++i) m = fmax(m, s[i]); vmax[blockIdx.x] = m; }
+}
+
+struct Fact { int n, n1, n2; };
+const Fact kFacts[] = {{64, 8, 8}, {96, 8, 12}, {128, 8, 16}, {192, 12, 16}, {256, 16, 16}, {384, 16, 24}};
+
+inline NsProb* prob(const pdeb200_ctx* c) { return static_cast<NsProb*>(c->prob); }
+
+template <typename T>
+int32_t upload(pdeb200_ctx* c, void** dst, const std::vector<T>& v) {
+    PDEB_CUDA(c, cudaMalloc(dst, v.size() * sizeof(T)));
+    PDEB_CUDA(c, cudaMemcpy(*dst, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return PDEB200_OK;
+}
+
+// table for fft_pass<T, P, Q, .>: tw[n*P + t] = exp(-2 pi i n t / (P Q)), n < Q, t < P
+template <typename T>
+std::vector<typename V2<T>::type> twiddles(int P, int Q) {
+    const long double two_pi = 6.283185307179586476925286766559L;
+    const int N = P * Q;
+    std::vector<typename V2<T>::type> tw((size_t)N);
+    for (int n = 0; n < Q; ++n)
+        for (int t = 0; t < P; ++t) {
+            const long double a = -two_pi * (long double)((long long)n * t % N) / N;
+            tw[(size_t)n * P + t] = V2<T>::make((T)cosl(a), (T)sinl(a));
+        }
+    return tw;
+}
+
+template <typename T>
+int32_t setup_t(pdeb200_ctx* c) {
+    using C = typename V2<T>::type;
+    NsProb* P = prob(c);
+    const pdeb200_config& g = c->cfg;
+    const int N = P->N;
+    int32_t rc;
+    if ((rc = upload<C>(c, &P->tw_inv, twiddles<T>(P->p2, P->p1)))) return rc;    // fft_pass<P2, P1>
+    if ((rc = upload<C>(c, &P->tw_fwd, twiddles<T>(P->p1, P->p2)))) return rc;    // fft_pass<P1, P2>
+    if ((rc = upload<C>(c, &P->tw_n, twiddles<T>(P->n1, P->n2)))) return rc;      // fft_pass<N1, N2>
+    // kx = [0:(nx/2); (-nx/2+1):(-1)] / Lx * 2pi  (Nyquist kept, positive side; FluidSetup.jl:106-107)
+    std::vector<T> kx(N), ky(N);
+    for (int i = 0; i < N; ++i) {
+        const double s = i <= N / 2 ? i : i - N;
+        kx[i] = (T)(s / g.Lx * 2 * M_PI);
+        ky[i] = (T)(s / g.Ly * 2 * M_PI);
+    }
+    if ((rc = upload<T>(c, &P->kx, kx))) return rc;
+    if ((rc = upload<T>(c, &P->ky, ky))) return rc;
+    const size_t B = g.n_envs, nn = (size_t)N * N;
+    PDEB_CUDA(c, cudaMalloc(&P->fst, B * nn * sizeof(C)));
+    PDEB_CUDA(c, cudaMalloc(&P->acc, B * nn * sizeof(C)));
+    PDEB_CUDA(c, cudaMalloc(&P->tmpc, B * nn * sizeof(C)));
+    PDEB_CUDA(c, cudaMalloc(&P->p_phys, B * nn * sizeof(T)));
+    PDEB_CUDA(c, cudaMalloc(&P->om_phys, B * nn * sizeof(T)));
+    PDEB_CUDA(c, cudaMemset(P->p_phys, 0, B * nn * sizeof(T)));
+    PDEB_CUDA(c, cudaMalloc(&P->W, (size_t)P->chunk * 4 * P->NP * P->NHP * sizeof(C)));
+    PDEB_CUDA(c, cudaMalloc(&P->Q, (size_t)P->chunk * P->NP * P->NHP * sizeof(C)));
+    c->prob_p_phys = P->p_phys;
+    return PDEB200_OK;
+}
+
+template <typename T, int P1, int P2>
+size_t smem_a(int N) {
+    using G = NsGeom<P1, P2>; using C = typename V2<T>::type;
+    return ((size_t)G::NP + kColsPerCta * G::XB + kColsPerCta * 2 * N) * sizeof(C) + (size_t)N * sizeof(T);
+}
+template <typename T, int P1, int P2>
+size_t smem_b() {
+    using G = NsGeom<P1, P2>; using C = typename V2<T>::type;
+    return ((size_t)2 * G::NP + kColsPerCta * G::XB + kColsPerCta * G::NP) * sizeof(C) + (size_t)kColsPerCta * G::NP * sizeof(T);
+}
+template <typename T, int P1, int P2>
+size_t smem_c(int N) {
+    using G = NsGeom<P1, P2>; using C = typename V2<T>::type;
+    return ((size_t)G::NP + kColsPerCta * G::XB) * sizeof(C) + (size_t)N * sizeof(T);
+}
+
+template <typename K>
+int32_t set_smem(pdeb200_ctx* c, K kern, size_t bytes) {
+    if (bytes > 227 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "NS: shared-memory budget exceeded");
+    PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return PDEB200_OK;
+}
+
+// RK4 x oversampling for all environments (FluidSetup.jl:163-172), in chunks of `chunk` environments so that
+// the work arrays W and Q of a chunk can stay in L2 between the three kernels of a stage.
+template <typename T, int P1, int P2>
+int32_t rk4_t(pdeb200_ctx* c) {
+    using C = typename V2<T>::type;
+    NsProb* P = prob(c);
+    const pdeb200_config& g = c->cfg;
+    const int N = P->N, NP = P->NP;
+    const size_t nn = (size_t)N * N;
+    auto kA = ns_ypass_inv_kernel<T, P1, P2>;
+    auto kB = ns_xpass_kernel<T, P1, P2>;
+    auto kC = ns_ypass_fwd_kernel<T, P1, P2>;
+    const size_t sa = smem_a<T, P1, P2>(N), sb = smem_b<T, P1, P2>(), sc = smem_c<T, P1, P2>(N);
+    int32_t rc;
+    if ((rc = set_smem(c, kA, sa)) || (rc = set_smem(c, kB, sb)) || (rc = set_smem(c, kC, sc))) return rc;
+    NsArgs<T> A;
+    A.N = N; A.NH = P->NH; A.NHP = P->NHP;
+    A.tw_inv = (const C*)P->tw_inv; A.tw_fwd = (const C*)P->tw_fwd;
+    A.kx = (const T*)P->kx; A.ky = (const T*)P->ky;
+    A.W = (C*)P->W; A.Q = (C*)P->Q;
+    A.nu = (T)g.nu; A.dt = (T)(g.dt / g.oversampling);
+    // ifft normalisation of the two factors (1/NP^2 each) and the 1.5*1.5 of fluid_rk4.jl:178
+    const double np2 = (double)NP * NP;
+    A.scale = (T)((g.ifpad ? 2.25 : 1.0) / (np2 * np2));
+    const int col_groups = (P->NH + kColsPerCta - 1) / kColsPerCta;
+    const int line_groups = (NP / 2 + kColsPerCta - 1) / kColsPerCta;
+    for (int e0 = 0; e0 < g.n_envs; e0 += P->chunk) {
+        const int ne = std::min(P->chunk, g.n_envs - e0);
+        A.y = (C*)c->y + (size_t)e0 * nn; A.fst = (C*)P->fst + (size_t)e0 * nn; A.acc = (C*)P->acc + (size_t)e0 * nn;
+        A.phat = (const C*)c->p + (size_t)e0 * nn;
+        for (int s = 0; s < g.oversampling; ++s)
+            for (int stage = 1; stage <= 4; ++stage) {
+                A.stage = stage;
+                A.fin = stage == 1 ? A.y : A.fst;
+                kA<<<dim3(col_groups, ne), kColsPerCta * 32, sa, c->stream>>>(A);
+                kB<<<dim3(line_groups, ne), kColsPerCta * 32, sb, c->stream>>>(A);
+                kC<<<dim3(col_groups, ne), kColsPerCta * 32, sc, c->stream>>>(A);
+                c->launches += 3;
+            }
+    }
+    PDEB_CUDA(c, cudaGetLastError());
+    return PDEB200_OK;
+}
+
+// N x N transform of all environments: pass along j (contiguous), then along i (stride N).
+template <typename T, int N1, int N2, int SIGN>
+int32_t fft2_t(pdeb200_ctx* c, const void* in, int in_real, void* out, int out_real, double scale) {
+    using C = typename V2<T>::type;
+    NsProb* P = prob(c);
+    const int N = P->N;
+    const long long nn = (long long)N * N;
+    const dim3 grid((N + 7) / 8, c->cfg.n_envs);
+    auto k = ns_lines_kernel<T, N1, N2, SIGN>;
+    k<<<grid, 256, 0, c->stream>>>(in, P->tmpc, (const C*)P->tw_n, in_real, 0, T(1), N, (long long)N, 1LL, nn);
+    k<<<grid, 256, 0, c->stream>>>(P->tmpc, out, (const C*)P->tw_n, 0, out_real, (T)scale, N, 1LL, (long long)N, nn);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    return PDEB200_OK;
+}
+
+template <typename T, int N1, int N2>
+int32_t sensors_t(pdeb200_ctx* c, const uint8_t* d_mask) {
+    NsProb* P = prob(c);
+    const int N = P->N;
+    // y = real(ifft(env.y))   (FluidSetup.jl:189, 206-208)
+    int32_t rc = fft2_t<T, N1, N2, +1>(c, c->y, 0, P->om_phys, 1, 1.0 / ((double)N * N));
+    if (rc) return rc;
+    sensors_phys_kernel<T><<<c->cfg.n_envs, 128, 0, c->stream>>>(
+        1, c->npts, c->cfg.n_sensors, EllTable<T>{c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows},
+        d_mask, (const T*)P->om_phys, 0, (T*)c->sensors, (T*)c->vmax);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    if (c->cfg.check_max_value == PDEB200_CHECK_Y) {
+        ns_vmax_kernel<T><<<c->cfg.n_envs, 256, 0, c->stream>>>((const typename V2<T>::type*)c->y, N * N, (T*)c->vmax);
+        PDEB_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+    }
+    return PDEB200_OK;
+}
+
+template <typename T, int N1, int N2, int P1, int P2>
+int32_t core_t(pdeb200_ctx* c) {
+    NsProb* P = prob(c);
+    // p_hat = fft(p)   (FluidSetup.jl:260); the physical sum was written by actuate_kernel
+    int32_t rc = fft2_t<T, N1, N2, -1>(c, P->p_phys, 1, c->p, 0, 1.0);
+    if (rc) return rc;
+    if ((rc = rk4_t<T, P1, P2>(c))) return rc;
+    return sensors_t<T, N1, N2>(c, nullptr);
+}
+
+template <typename T>
+int32_t core_dispatch(pdeb200_ctx* c) {
+    NsProb* P = prob(c);
+    const int key = P->N * 1000 + P->NP;
+    switch (key) {
+        case 64 * 1000 + 96:   return core_t<T, 8, 8, 8, 12>(c);
+        case 64 * 1000 + 64:   return core_t<T, 8, 8, 8, 8>(c);
+        case 128 * 1000 + 192: return core_t<T, 8, 16, 12, 16>(c);
+        case 128 * 1000 + 128: return core_t<T, 8, 16, 8, 16>(c);
+        case 256 * 1000 + 384: return core_t<T, 16, 16, 16, 24>(c);
+        case 256 * 1000 + 256: return core_t<T, 16, 16, 16, 16>(c);
+    }
+    return fail(c, PDEB200_EUNSUPPORTED, "NS: unsupported grid");
+}
+
+template <typename T>
+int32_t sensors_dispatch(pdeb200_ctx* c, const uint8_t* d_mask) {
+    switch (prob(c)->N) {
+        case 64:  return sensors_t<T, 8, 8>(c, d_mask);
+        case 128: return sensors_t<T, 8, 16>(c, d_mask);
+        case 256: return sensors_t<T, 16, 16>(c, d_mask);
+    }
+    return fail(c, PDEB200_EUNSUPPORTED, "NS: unsupported grid");
+}
+
+}  // namespace
+
+int32_t ns_setup(pdeb200_ctx* c) {
+    const pdeb200_config& g = c->cfg;
+    if (g.nx != g.ny) return fail(c, PDEB200_EUNSUPPORTED, "NS: nx must equal ny (the reference builds kx2ky2 for square grids)");
+    if (g.nx != 64 && g.nx != 128 && g.nx != 256) return fail(c, PDEB200_EUNSUPPORTED, "NS: nx must be 64, 128 or 256");
+    if (g.oversampling < 1) return fail(c, PDEB200_EINVAL, "NS: oversampling must be >= 1");
+    if (g.sensors_per_axis < 1 || g.sensors_per_axis * g.sensors_per_axis != g.n_sensors)
+        return fail(c, PDEB200_EINVAL, "NS: n_sensors must equal sensors_per_axis^2");
+    NsProb* P = new NsProb();
+    c->prob = P;
+    P->N = g.nx;
+    P->NP = g.ifpad ? g.nx * 3 / 2 : g.nx;
+    P->NH = P->N / 2 + 1;
+    P->NHP = (P->NH + 3) / 4 * 4;
+    for (const Fact& f : kFacts) {
+        if (f.n == P->N) { P->n1 = f.n1; P->n2 = f.n2; }
+        if (f.n == P->NP) { P->p1 = f.n1; P->p2 = f.n2; }
+    }
+    const char* e = getenv("PDEB200_NS_CHUNK");
+    P->chunk = e ? std::max(1, atoi(e)) : g.n_envs;
+    P->chunk = std::min(P->chunk, g.n_envs);
+    return g.dtype == PDEB200_F64 ? setup_t<double>(c) : setup_t<float>(c);
+}
+
+int32_t ns_core(pdeb200_ctx* c) {
+    return c->cfg.dtype == PDEB200_F64 ? core_dispatch<double>(c) : core_dispatch<float>(c);
+}
+
+int32_t ns_sensors(pdeb200_ctx* c, const uint8_t* d_mask) {
+    return c->cfg.dtype == PDEB200_F64 ? sensors_dispatch<double>(c, d_mask) : sensors_dispatch<float>(c, d_mask);
+}
+
+// Algorithmic cost of one env step:
+//   bytes: omega_hat in + out (complex), action in, obs + reward out, done
+//   flops: per rhs 4 inverse + 1 forward real-data 2-D FFTs of the padded size at 2.5 n log2 n per real point,
+//          pruned to the non-zero lines, + pointwise work; 4 rhs per RK4 substep
+int32_t ns_cost(const pdeb200_ctx* c, double* bytes, double* flops) {
+    const pdeb200_config& g = c->cfg;
+    const NsProb* P = prob(c);
+    const double N = g.nx, NP = P->NP, w = (double)c->esz;
+    if (bytes) *bytes = 2 * (2 * N * N * w) + g.n_actuators * (w * c->a_rows + w * c->obs_rows + w) + 1;
+    if (flops) {
+        const double cfft = 5 * NP * std::log2(NP);                      // one complex line
+        const double nh = N / 2 + 1;
+        const double per_rhs = 4 * nh * cfft + (NP / 2) * 5 * cfft + nh * cfft + 40 * N * N + 6 * NP * NP;
+        *flops = 4.0 * g.oversampling * per_rhs + 2 * 2 * N * cfft * 2;
+    }
+    return PDEB200_OK;
+}
+
+void ns_free(pdeb200_ctx* c) {
+    NsProb* P = prob(c);
+    if (!P) return;
+    for (void* p : {P->tw_inv, P->tw_fwd, P->tw_n, P->kx, P->ky, P->fst, P->acc, P->W, P->Q, P->p_phys, P->om_phys, P->tmpc})
+        if (p) cudaFree(p);
+    delete P;
+    c->prob = nullptr;
+    c->prob_p_phys = nullptr;
+}
+
+}  // namespace pdeb200

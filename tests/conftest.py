@@ -48,6 +48,7 @@ def golden():
 
 
 def relerr(a, b):
-    a = np.asarray(a, dtype=np.float64)
-    b = np.asarray(b, dtype=np.float64)
+    a, b = np.asarray(a), np.asarray(b)
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a, b = a.astype(dt), b.astype(dt)
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
