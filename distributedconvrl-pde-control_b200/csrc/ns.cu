@@ -90,6 +90,10 @@ __device__ __forceinline__ typename V2<T>::type field_value(int f, typename V2<T
 template <typename T> struct NsMinCtas { static constexpr int value = sizeof(T) == 8 ? 1 : 2; };
 
 // ---- A: inverse transform along y of the four padded, Hermitian-symmetrised spectra ---------------------
+// Input staging is branch-free and uses all 32 lanes: a CTA-wide table maps each padded row to the unpadded
+// rows of its two contributions (k and -k), the column pair (kx, -kx) sits in shared memory, and the two
+// psi-based fields reuse the columns after an in-place division by k^2 (one division per entry, like the
+// reference's `psihat = omghat ./ kx2ky2`).
 template <typename T, int P1, int P2>
 __global__ void __launch_bounds__(kColsPerCta * 32, NsMinCtas<T>::value)
 ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
@@ -102,9 +106,13 @@ ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
     C* s_xb0 = s_tw + NP;
     C* s_col0 = s_xb0 + kColsPerCta * G::XB;
     T* s_ky = reinterpret_cast<T*>(s_col0 + kColsPerCta * 2 * N);
+    short2* s_tab = reinterpret_cast<short2*>(s_ky + N);
     const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
     const int env = blockIdx.y, a0 = blockIdx.x * kColsPerCta, a = a0 + w;
-    for (int i = threadIdx.x; i < NP; i += blockDim.x) s_tw[i] = A.tw_inv[i];
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) {
+        s_tw[i] = A.tw_inv[i];
+        s_tab[i] = make_short2((short)unpad_idx(i, NP, N), (short)unpad_idx((NP - i) % NP, NP, N));
+    }
     for (int i = threadIdx.x; i < N; i += blockDim.x) s_ky[i] = A.ky[i];
     C* xb = s_xb0 + w * G::XB;
     C* colA = s_col0 + (size_t)w * 2 * N;
@@ -119,22 +127,41 @@ ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
         kxa = A.kx[a]; kxb = A.kx[ib];
     }
     __syncthreads();
-    for (int f = 0; f < 4; ++f) {
+#pragma unroll 1
+    for (int fi = 0; fi < 4; ++fi) {
+        const int f = (fi + 2) & 3;              // omega-based fields (2, 3) first, then psi-based (0, 1)
         if (live) {
+            if (fi == 2) {
+                // psi_hat = omega_hat ./ kx2ky2, psi_hat[1,1] = 0   (fluid_rk4.jl:152-153)
+                for (int j = t; j < N; j += 32) {
+                    const T kyv = s_ky[j];
+                    const T ka = kyv * kyv + kxa * kxa, kb = kyv * kyv + kxb * kxb;
+                    const C ca = colA[j], cb = colB[j];
+                    colA[j] = (j == 0 && a == 0) ? V2<T>::make(T(0), T(0)) : V2<T>::make(ca.x / ka, ca.y / ka);
+                    colB[j] = (j == 0 && ib == 0) ? V2<T>::make(T(0), T(0)) : V2<T>::make(cb.x / kb, cb.y / kb);
+                }
+                __syncwarp();
+            }
+            // multiplier i*m: u = i ky psi, v = -i kx psi, w_x = i kx omega, w_y = i ky omega
+            const bool kytype = (f == 0 || f == 3);
+            const T mxa = f == 1 ? -kxa : kxa, mxb = f == 1 ? -kxb : kxb;
+            for (int kyp = t; kyp < NP; kyp += 32) {
+                const short2 jj = s_tab[kyp];
+                const int j1 = jj.x, j2 = xpartner ? (int)jj.y : -1;
+                const int i1 = j1 < 0 ? 0 : j1, i2 = j2 < 0 ? 0 : j2;
+                const C c1 = colA[i1], c2 = colB[i2];
+                T m1 = kytype ? s_ky[i1] : mxa, m2 = kytype ? s_ky[i2] : mxb;
+                m1 = j1 < 0 ? T(0) : m1; m2 = j2 < 0 ? T(0) : m2;
+                // X_h = (X(k) + conj(X(-k))) / 2 with X = i m c
+                xb[kyp] = V2<T>::make(T(0.5) * (-m1 * c1.y - m2 * c2.y), T(0.5) * (m1 * c1.x - m2 * c2.x));
+            }
+            __syncwarp();
             T zr[G::RMAX], zi[G::RMAX];
             if (t < P1) {
 #pragma unroll
-                for (int r = 0; r < P2; ++r) {
-                    const int kyp = t + P1 * r;
-                    const int j1 = unpad_idx(kyp, NP, N);
-                    const int j2 = xpartner ? unpad_idx((NP - kyp) % NP, NP, N) : -1;
-                    C x1 = V2<T>::make(T(0), T(0)), x2 = x1;
-                    if (j1 >= 0) x1 = field_value<T>(f, colA[j1], s_ky[j1], kxa, j1 == 0 && a == 0);
-                    if (j2 >= 0) x2 = field_value<T>(f, colB[j2], s_ky[j2], kxb, j2 == 0 && ib == 0);
-                    zr[r] = T(0.5) * (x1.x + x2.x);
-                    zi[r] = T(0.5) * (x1.y - x2.y);
-                }
+                for (int r = 0; r < P2; ++r) { const C v = xb[t + P1 * r]; zr[r] = v.x; zi[r] = v.y; }
             }
+            __syncwarp();
             fft_pass<T, P2, P1, +1>(zr, zi, xb, s_tw, t);
             if (t < P2) {
 #pragma unroll
@@ -151,7 +178,30 @@ ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
     }
 }
 
+// ---- mbarrier + bulk-copy (TMA, 1-D) helpers ---------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* b) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(b)), "r"(parity) : "memory");
+    }
+}
+
 // ---- B: x transforms, the quadratic term, forward x transform (two y-lines per warp) ---------------------
+// The four half-spectrum lines a warp consumes per y-line are contiguous rows of W: they are staged into
+// shared memory by 1-D bulk copies (cp.async.bulk, completion on a per-warp mbarrier) two phases ahead of
+// their use, so the HBM/L2 latency overlaps the FFT arithmetic of the previous phase.
 template <typename T, int P1, int P2>
 __global__ void __launch_bounds__(kColsPerCta * 32, NsMinCtas<T>::value)
 ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
@@ -159,58 +209,79 @@ ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
     using C = typename V2<T>::type;
     constexpr int NP = G::NP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = A.N;
+    const int N = A.N, NHP = A.NHP;
     C* s_twi = reinterpret_cast<C*>(smem_raw);
     C* s_twf = s_twi + NP;
     C* s_xb0 = s_twf + NP;
     C* s_uv0 = s_xb0 + kColsPerCta * G::XB;
-    T* s_q0 = reinterpret_cast<T*>(s_uv0 + kColsPerCta * NP);
+    C* s_in0 = s_uv0 + kColsPerCta * NP;                              // [warp][slot 2][line 2][NHP]
+    T* s_q0 = reinterpret_cast<T*>(s_in0 + (size_t)kColsPerCta * 4 * NHP);
+    uint64_t* s_bar0 = reinterpret_cast<uint64_t*>(s_q0 + (size_t)kColsPerCta * NP);
     const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
     const int env = blockIdx.y;
     const int y0 = (blockIdx.x * kColsPerCta + w) * 2;
     for (int i = threadIdx.x; i < NP; i += blockDim.x) { s_twi[i] = A.tw_inv[i]; s_twf[i] = A.tw_fwd[i]; }
+    uint64_t* bar = s_bar0 + w * 2;
+    if (t == 0) {
+        mbar_init(bar, 1); mbar_init(bar + 1, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     if (y0 >= NP) return;
     C* xb = s_xb0 + w * G::XB;
     C* uv = s_uv0 + (size_t)w * NP;
+    C* sin = s_in0 + (size_t)w * 4 * NHP;
     T* q1 = s_q0 + (size_t)w * NP;
+    const uint32_t line_bytes = (uint32_t)(NHP * sizeof(C));
+    // phase ph = 2*L + h: y-line y0 + L, fields (2h, 2h + 1); slot = ph & 1
+    auto issue = [&](int ph) {
+        const int L = ph >> 1, h = ph & 1, slot = ph & 1;
+        const C* Wa = A.W + ((size_t)(env * 4 + 2 * h) * NP + (y0 + L)) * NHP;
+        mbar_expect_tx(bar + slot, 2 * line_bytes);
+        bulk_g2s(sin + (size_t)(slot * 2) * NHP, Wa, line_bytes, bar + slot);
+        bulk_g2s(sin + (size_t)(slot * 2 + 1) * NHP, Wa + (size_t)NP * NHP, line_bytes, bar + slot);
+    };
+    if (t == 0) { issue(0); issue(1); }
     T zr[G::RMAX], zi[G::RMAX];
 #pragma unroll 1
-    for (int L = 0; L < 2; ++L) {
-        const int y = y0 + L;
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {        // h = 0: (u, v);  h = 1: (omega_x, omega_y)
-            const C* Wa = A.W + ((size_t)(env * 4 + 2 * h) * NP + y) * A.NHP;
-            const C* Wb = Wa + (size_t)NP * A.NHP;
-            if (t < P1) {
+    for (int ph = 0; ph < 4; ++ph) {
+        const int L = ph >> 1, h = ph & 1, slot = ph & 1;
+        mbar_wait(bar + slot, (uint32_t)(ph >> 1) & 1);
+        const C* Wa = sin + (size_t)(slot * 2) * NHP;
+        const C* Wb = Wa + NHP;
+        if (t < P1) {
 #pragma unroll
-                for (int r = 0; r < P2; ++r) {
-                    const int kxp = t + P1 * r;
-                    const int s = kxp <= NP / 2 ? kxp : kxp - NP;
-                    const int a = s < 0 ? -s : s;
-                    T re = T(0), im = T(0);
-                    if (a <= N / 2) {
-                        C U = __ldg(Wa + a), V = __ldg(Wb + a);
-                        if (s < 0) { U.y = -U.y; V.y = -V.y; }          // G(y, -kx) = conj(G(y, kx))
-                        re = U.x - V.y; im = U.y + V.x;                  // U + i V
-                    }
-                    zr[r] = re; zi[r] = im;
+            for (int r = 0; r < P2; ++r) {
+                const int kxp = t + P1 * r;
+                const int s = kxp <= NP / 2 ? kxp : kxp - NP;
+                const int a = s < 0 ? -s : s;
+                T re = T(0), im = T(0);
+                if (a <= N / 2) {
+                    C U = Wa[a], V = Wb[a];
+                    if (s < 0) { U.y = -U.y; V.y = -V.y; }              // G(y, -kx) = conj(G(y, kx))
+                    re = U.x - V.y; im = U.y + V.x;                      // U + i V
                 }
+                zr[r] = re; zi[r] = im;
             }
-            fft_pass<T, P2, P1, +1>(zr, zi, xb, s_twi, t);
-            if (t < P2) {
-                if (h == 0) {
+        }
+        __syncwarp();                                                    // every lane is done with the slot
+        if (t == 0 && ph + 2 < 4) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(ph + 2);
+        }
+        fft_pass<T, P2, P1, +1>(zr, zi, xb, s_twi, t);
+        if (t < P2) {
+            if (h == 0) {
 #pragma unroll
-                    for (int r = 0; r < P1; ++r) uv[t + P2 * r] = V2<T>::make(zr[r], zi[r]);
-                } else {
+                for (int r = 0; r < P1; ++r) uv[t + P2 * r] = V2<T>::make(zr[r], zi[r]);
+            } else {
 #pragma unroll
-                    for (int r = 0; r < P1; ++r) {
-                        const int x = t + P2 * r;
-                        const C g = uv[x];
-                        const T q = -(g.x * zr[r] + g.y * zi[r]) * A.scale;   // -u w_x - v w_y  (fluid_rk4.jl:175)
-                        if (L == 0) q1[x] = q;
-                        else { zr[r] = q1[x]; zi[r] = q; }
-                    }
+                for (int r = 0; r < P1; ++r) {
+                    const int x = t + P2 * r;
+                    const C g = uv[x];
+                    const T q = -(g.x * zr[r] + g.y * zi[r]) * A.scale;   // -u w_x - v w_y  (fluid_rk4.jl:175)
+                    if (L == 0) q1[x] = q;
+                    else { zr[r] = q1[x]; zi[r] = q; }
                 }
             }
         }
@@ -221,8 +292,8 @@ ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
         for (int r = 0; r < P2; ++r) xb[t + P1 * r] = V2<T>::make(zr[r], zi[r]);
     }
     __syncwarp();
-    C* Qa = A.Q + ((size_t)env * NP + y0) * A.NHP;
-    C* Qb = Qa + A.NHP;
+    C* Qa = A.Q + ((size_t)env * NP + y0) * NHP;
+    C* Qb = Qa + NHP;
     for (int a = t; a < A.NH; a += 32) {
         const C za = xb[a], zb = xb[(NP - a) % NP];
         Qa[a] = V2<T>::make(T(0.5) * (za.x + zb.x), T(0.5) * (za.y - zb.y));
@@ -231,25 +302,33 @@ ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
 }
 
 // ---- C: forward transform along y, chop, RK4 stage update ---------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void rk_update(const NsArgs<T>& A, size_t idx, T k2, typename V2<T>::type nl) {
+// RK4 stage update of U entries at once: all loads are issued before the first store (the arrays may alias
+// from the compiler's point of view, so it cannot do this reordering itself).
+template <typename T, int U>
+__device__ __forceinline__ void rk_update(const NsArgs<T>& A, const size_t* idx, const T* k2, const typename V2<T>::type* nl) {
     using C = typename V2<T>::type;
-    const C fs = A.fin[idx];
-    const C ph = A.phat[idx];
-    // rhs = lin + advection + p,  lin = -nu * (kx2ky2 .* omghat)     (fluid_rk4.jl:138-142)
-    const T kr = (-A.nu * (k2 * fs.x) + nl.x) + ph.x;
-    const T ki = (-A.nu * (k2 * fs.y) + nl.y) + ph.y;
-    if (A.stage == 1) {
-        A.acc[idx] = V2<T>::make(kr, ki);
-        A.fst[idx] = V2<T>::make(fs.x + (T(0.5) * A.dt) * kr, fs.y + (T(0.5) * A.dt) * ki);
-    } else if (A.stage == 4) {
-        const C f0 = A.y[idx], ac = A.acc[idx];
-        A.y[idx] = V2<T>::make(f0.x + (A.dt / T(6)) * (ac.x + kr), f0.y + (A.dt / T(6)) * (ac.y + ki));
-    } else {
-        const C f0 = A.y[idx], ac = A.acc[idx];
-        A.acc[idx] = V2<T>::make(ac.x + T(2) * kr, ac.y + T(2) * ki);
-        const T c = A.stage == 2 ? T(0.5) * A.dt : A.dt;
-        A.fst[idx] = V2<T>::make(f0.x + c * kr, f0.y + c * ki);
+    C fs[U], ph[U], f0[U], ac[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) { fs[u] = A.fin[idx[u]]; ph[u] = A.phat[idx[u]]; }
+    if (A.stage != 1) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) { f0[u] = A.y[idx[u]]; ac[u] = A.acc[idx[u]]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        // rhs = lin + advection + p,  lin = -nu * (kx2ky2 .* omghat)     (fluid_rk4.jl:138-142)
+        const T kr = (-A.nu * (k2[u] * fs[u].x) + nl[u].x) + ph[u].x;
+        const T ki = (-A.nu * (k2[u] * fs[u].y) + nl[u].y) + ph[u].y;
+        if (A.stage == 1) {
+            A.acc[idx[u]] = V2<T>::make(kr, ki);
+            A.fst[idx[u]] = V2<T>::make(fs[u].x + (T(0.5) * A.dt) * kr, fs[u].y + (T(0.5) * A.dt) * ki);
+        } else if (A.stage == 4) {
+            A.y[idx[u]] = V2<T>::make(f0[u].x + (A.dt / T(6)) * (ac[u].x + kr), f0[u].y + (A.dt / T(6)) * (ac[u].y + ki));
+        } else {
+            A.acc[idx[u]] = V2<T>::make(ac[u].x + T(2) * kr, ac[u].y + T(2) * ki);
+            const T c = A.stage == 2 ? T(0.5) * A.dt : A.dt;
+            A.fst[idx[u]] = V2<T>::make(f0[u].x + c * kr, f0[u].y + c * ki);
+        }
     }
 }
 
@@ -292,18 +371,24 @@ ns_ypass_fwd_kernel(const __grid_constant__ NsArgs<T> A) {
     const bool two = ib != a;
     const T kxa = A.kx[a], kxb = A.kx[ib];
     const size_t base = (size_t)env * N * N;
-    for (int j = t; j < N; j += 32) {
-        const int s = j <= N / 2 ? j : j - N;                    // chop: rows (-N/2, N/2]   (fluid_rk4.jl:224-227)
-        const int kyp = s < 0 ? s + NP : s;
-        const T kyv = s_ky[j];
-        rk_update<T>(A, base + (size_t)a * N + j, kyv * kyv + kxa * kxa, xb[kyp]);
-        if (two) {
+    constexpr int U = 2;                                          // rows per lane in flight (N / 32 is even)
+    for (int j0 = t; j0 < N; j0 += 32 * U) {
+        size_t idx[2 * U]; T k2[2 * U]; C nl[2 * U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + 32 * u;
+            const int s = j <= N / 2 ? j : j - N;                // chop: rows (-N/2, N/2]   (fluid_rk4.jl:224-227)
+            const int kyp = s < 0 ? s + NP : s;
+            const T kyv = s_ky[j];
+            idx[u] = base + (size_t)a * N + j; k2[u] = kyv * kyv + kxa * kxa; nl[u] = xb[kyp];
             // F[ky, -kx] = conj(F[-ky, kx]) for the FFT of a real field (includes the +N/2 Nyquist row,
             // whose partner is the -N/2 row of the padded transform)
             C v = xb[(NP - kyp) % NP];
             v.y = -v.y;
-            rk_update<T>(A, base + (size_t)ib * N + j, kyv * kyv + kxb * kxb, v);
+            idx[U + u] = base + (size_t)ib * N + j; k2[U + u] = kyv * kyv + kxb * kxb; nl[U + u] = v;
         }
+        if (two) rk_update<T, 2 * U>(A, idx, k2, nl);
+        else rk_update<T, U>(A, idx, k2, nl);
     }
 }
 
@@ -421,12 +506,14 @@ int32_t setup_t(pdeb200_ctx* c) {
 template <typename T, int P1, int P2>
 size_t smem_a(int N) {
     using G = NsGeom<P1, P2>; using C = typename V2<T>::type;
-    return ((size_t)G::NP + kColsPerCta * G::XB + kColsPerCta * 2 * N) * sizeof(C) + (size_t)N * sizeof(T);
+    return ((size_t)G::NP + kColsPerCta * G::XB + kColsPerCta * 2 * N) * sizeof(C) + (size_t)N * sizeof(T) +
+           (size_t)G::NP * sizeof(short2);
 }
 template <typename T, int P1, int P2>
-size_t smem_b() {
+size_t smem_b(int NHP) {
     using G = NsGeom<P1, P2>; using C = typename V2<T>::type;
-    return ((size_t)2 * G::NP + kColsPerCta * G::XB + kColsPerCta * G::NP) * sizeof(C) + (size_t)kColsPerCta * G::NP * sizeof(T);
+    return ((size_t)2 * G::NP + kColsPerCta * G::XB + kColsPerCta * G::NP + (size_t)kColsPerCta * 4 * NHP) * sizeof(C) +
+           (size_t)kColsPerCta * G::NP * sizeof(T) + (size_t)kColsPerCta * 2 * sizeof(uint64_t);
 }
 template <typename T, int P1, int P2>
 size_t smem_c(int N) {
@@ -453,7 +540,7 @@ int32_t rk4_t(pdeb200_ctx* c) {
     auto kA = ns_ypass_inv_kernel<T, P1, P2>;
     auto kB = ns_xpass_kernel<T, P1, P2>;
     auto kC = ns_ypass_fwd_kernel<T, P1, P2>;
-    const size_t sa = smem_a<T, P1, P2>(N), sb = smem_b<T, P1, P2>(), sc = smem_c<T, P1, P2>(N);
+    const size_t sa = smem_a<T, P1, P2>(N), sb = smem_b<T, P1, P2>(P->NHP), sc = smem_c<T, P1, P2>(N);
     int32_t rc;
     if ((rc = set_smem(c, kA, sa)) || (rc = set_smem(c, kB, sb)) || (rc = set_smem(c, kC, sc))) return rc;
     NsArgs<T> A;

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Summarise an .ncu-rep (one kernel launch) into markdown for profiles/.
 
-usage: tools/ncu_summary.py gpurun_out/foo.ncu-rep "title" >> profiles/foo.md
+usage: tools/ncu_summary.py gpurun_out/foo.ncu-rep "title" [launch index] >> profiles/foo.md
 Needs `ncu` on PATH (reading a report needs no GPU)."""
 import collections
 import csv
@@ -32,13 +32,19 @@ RAW_KEYS = [
 ]
 
 
+SKIP = 0
+
+
 def ncu(rep, page):
-    out = subprocess.run(["ncu", "-i", rep, "--page", page, "--csv"], capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", page, "--csv", "--launch-skip", str(SKIP), "--launch-count", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     return list(csv.reader(io.StringIO(out)))
 
 
 def main():
+    global SKIP
     rep, title = sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else sys.argv[1]
+    SKIP = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # which launch of a multi-launch report
     raw = ncu(rep, "raw")
     hdr, units, vals = raw[0], raw[1], raw[-1]
     ix = {h: i for i, h in enumerate(hdr)}
@@ -51,8 +57,14 @@ def main():
     src = ncu(rep, "source")
     if len(src) > 3:
         h = src[1]
-        data = [r for r in src[2:] if len(r) >= len(h)]
         sx = {x: i for i, x in enumerate(h)}
+        data = []
+        for r in src[2:]:
+            if len(r) < len(h):
+                continue
+            if r[sx["# Samples"]] == "# Samples":      # second view (CUDA-C source) of the same launch follows
+                break
+            data.append(r)
         stall_cols = [x for x in h if x.startswith("stall_") and "Not Issued" not in x]
         tot = sum(int(r[sx["# Samples"]] or 0) for r in data) or 1
         st = collections.Counter()
