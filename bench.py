@@ -36,13 +36,16 @@ UNIT = "env-steps/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=8192, help="environments per GPU (weak scaling)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--oversampling", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-shards", type=int, default=4,
+                    help="the e2e leg drives the batch as this many env shards (own context + stream + host thread each) "
+                         "so that one shard's PCIe copies overlap another shard's kernels")
     return ap.parse_args()
 
 
@@ -133,14 +136,37 @@ def run_reference(args):
 # our arm
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock + throttle reasons sampled DURING the timed regions (NVML from a thread, every ~5 ms;
+    `nvidia-smi -lms` as the fallback)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.nvml = index, [], None, None
+        self.sm, self.reasons, self.power, self.stop_flag, self.mx = [], set(), [], False, None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if self.index < len(ids) and ids[self.index].strip().isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -150,11 +176,32 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)) if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for name, bit in self.BITS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
     def _read(self):
         for ln in self.proc.stdout:
             self.rows.append([x.strip() for x in ln.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm),
+                    "power_w_max": max(self.power) if self.power else None, "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -173,7 +220,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def measured_peak():
@@ -242,7 +289,6 @@ def run_ours(args):
         env.rollout(1)
         ev1[i].record(stream)
     barrier()
-    clk = clocks.stop()
     launches = env.launch_count - launches0
     kern_ms = [a.elapsed_time(b) for a, b in zip(ev0, ev1)]
     total_ms = float(sum(kern_ms))
@@ -258,33 +304,63 @@ def run_ours(args):
     # agent and the hook.
     esz = 8 if args.dtype == "f64" else 4
     tdt = torch.float64 if args.dtype == "f64" else torch.float32
-    n_act = B * env.n_actuators
-    h_act = torch.empty(n_act, dtype=tdt).pin_memory()
-    h_rew = torch.empty(n_act, dtype=tdt).pin_memory()
-    h_state = torch.empty(n_act * env.ns, dtype=tdt).pin_memory()
-    h_done = torch.empty(B, dtype=torch.uint8).pin_memory()
-    lib, ctx = env._lib, env._ctx
+    n_sh = max(1, args.e2e_shards)
+    while B % n_sh:
+        n_sh -= 1
+    Bs = B // n_sh
+    env.close()                                   # the e2e shards replace the device-timed context
 
-    def e2e_step():
-        L.check(lib.pdeb200_policy_act(ctx, None, 0.0, 1.0), ctx)
-        L.check(lib.pdeb200_get(ctx, L.ARR_ACTION_IN, C.c_void_p(h_act.data_ptr()), n_act * esz), ctx)
-        L.check(lib.pdeb200_step_host(ctx, C.c_void_p(h_act.data_ptr()), None, C.c_void_p(h_rew.data_ptr()),
-                                      C.c_void_p(h_state.data_ptr()), C.c_void_p(h_done.data_ptr())), ctx)
-    env.reset()
-    for _ in range(3):
-        e2e_step()
+    class Shard:
+        def __init__(self, k):
+            self.env = setup.make_env(n_envs=Bs, dtype=args.dtype, device=local, y0=y0[k * Bs:(k + 1) * Bs])
+            agent.CustomNeuralNetworkApproximator(self.env, L.NET_BEHAVIOR_ACTOR, chain.copy())
+            self.n_act = Bs * self.env.n_actuators
+            self.h_act = torch.empty(self.n_act, dtype=tdt).pin_memory()
+            self.h_rew = torch.empty(self.n_act, dtype=tdt).pin_memory()
+            self.h_state = torch.empty(self.n_act * self.env.ns, dtype=tdt).pin_memory()
+            self.h_done = torch.empty(Bs, dtype=torch.uint8).pin_memory()
+
+        def step(self):
+            lib, ctx = self.env._lib, self.env._ctx
+            L.check(lib.pdeb200_policy_act(ctx, None, 0.0, 1.0), ctx)
+            L.check(lib.pdeb200_get(ctx, L.ARR_ACTION_IN, C.c_void_p(self.h_act.data_ptr()), self.n_act * esz), ctx)
+            L.check(lib.pdeb200_step_host(ctx, C.c_void_p(self.h_act.data_ptr()), None, C.c_void_p(self.h_rew.data_ptr()),
+                                          C.c_void_p(self.h_state.data_ptr()), C.c_void_p(self.h_done.data_ptr())), ctx)
+
+    shards = [Shard(k) for k in range(n_sh)]
+    e2e_launches0 = sum(sh.env.launch_count for sh in shards)
+
+    def drive(n):
+        # ctypes releases the GIL inside each C-ABI call, so the shard threads really overlap
+        def loop(sh):
+            for _ in range(n):
+                sh.step()
+        if n_sh == 1:
+            loop(shards[0])
+            return
+        ths = [threading.Thread(target=loop, args=(sh,)) for sh in shards]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+
+    drive(3)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
+    drive(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = B * world * args.steps / float(t.item())
+    n_act = B * shards[0].env.n_actuators
+    ns_rows = shards[0].env.ns
     h2d = n_act * esz
-    d2h = n_act * esz + n_act * esz + n_act * env.ns * esz + B
+    d2h = n_act * esz + n_act * esz + n_act * ns_rows * esz + B
+    e2e_launches = sum(sh.env.launch_count for sh in shards) - e2e_launches0
+    env = shards[0].env                             # step_cost below is per environment
 
     # ---- roofline of the dominant (only) kernel -------------------------------------------------
     bytes_env, flops_env = env.step_cost()
@@ -311,7 +387,10 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config_dict(args, world),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "shards": n_sh, "launches": int(e2e_launches),
+                    "call_sequence": "per shard and step: pdeb200_policy_act -> pdeb200_get(ACTION_IN) [D2H] -> "
+                                     "pdeb200_step_host [H2D action; D2H reward, state, done], pinned host buffers"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -325,7 +404,8 @@ def run_ours(args):
                                 % (per_core * orc.cores, n_steps_cpu)}
     elif rank == 0:
         line["cpu_baseline"] = None
-    env.close()
+    for sh in shards:
+        sh.env.close()
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

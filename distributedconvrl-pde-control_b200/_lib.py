@@ -12,7 +12,7 @@ LIB_PATH = PKG / "libpdeb200.so"
 
 OK = 0
 F32, F64 = 0, 1
-KS, KSEG1D, NS2D = 0, 1, 2
+KS, KSEG1D, NS2D, KSEG2D = 0, 1, 2, 3
 CHECK_NONE, CHECK_Y, CHECK_REWARD = 0, 1, 2
 ACT_IDENTITY, ACT_RELU, ACT_TANH = 0, 1, 2
 NET_BEHAVIOR_ACTOR, NET_BEHAVIOR_CRITIC, NET_TARGET_ACTOR, NET_TARGET_CRITIC = 0, 1, 2, 3

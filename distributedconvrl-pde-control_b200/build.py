@@ -36,6 +36,8 @@ def _defines():
     d = []
     if "kseg" in names:
         d.append("-DPDEB_HAVE_KSEG")
+    if "kseg2d" in names:
+        d.append("-DPDEB_HAVE_KSEG2D")
     if "ns" in names:
         d.append("-DPDEB_HAVE_NS")
     if "agent" in names:

@@ -108,7 +108,8 @@ inline ObsRewardParams<T> make_obs_params(const pdeb200_ctx* c) {
     const pdeb200_config& g = c->cfg;
     P.n_sensors = g.n_sensors; P.n_act = g.n_actuators; P.fields = c->fields;
     P.window = g.window_size; P.temporal = g.temporal_steps; P.memory = g.memory_size; P.a_rows = c->a_rows;
-    P.obs_rows = c->obs_rows; P.mono = g.mono; P.spa = (g.problem == PDEB200_NS2D) ? g.sensors_per_axis : 0;
+    P.obs_rows = c->obs_rows; P.mono = g.mono;
+    P.spa = (g.problem == PDEB200_NS2D || g.problem == PDEB200_KSEG2D) ? g.sensors_per_axis : 0;
     P.check_max = g.check_max_value;
     P.obs_scale = (T)g.obs_scale; P.r_gain = (T)g.reward_gain; P.r_pow = (T)g.reward_pow; P.r_div = (T)g.reward_div;
     P.r_offset = (T)g.reward_offset; P.a_pun = (T)g.action_punish; P.da_pun = (T)g.delta_action_punish;
@@ -128,6 +129,10 @@ int32_t kseg_setup(pdeb200_ctx* c);
 int32_t kseg_core(pdeb200_ctx* c);
 int32_t kseg_cost(const pdeb200_ctx* c, double* bytes, double* flops);
 void kseg_free(pdeb200_ctx* c);
+
+int32_t kseg2d_setup(pdeb200_ctx* c);
+int32_t kseg2d_core(pdeb200_ctx* c);
+int32_t kseg2d_cost(const pdeb200_ctx* c, double* bytes, double* flops);
 
 int32_t ns_setup(pdeb200_ctx* c);
 int32_t ns_core(pdeb200_ctx* c);

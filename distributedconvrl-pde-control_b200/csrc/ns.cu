@@ -74,19 +74,6 @@ __device__ __forceinline__ int unpad_idx(int kp, int NP, int N) {
     return s < 0 ? s + N : s;
 }
 
-// the four spectra of advection() (fluid_rk4.jl:152-161) from one entry w = omega_hat[j, i]
-template <typename T>
-__device__ __forceinline__ typename V2<T>::type field_value(int f, typename V2<T>::type w, T kyv, T kxv, bool origin) {
-    if (f < 2) {
-        const T k2 = kyv * kyv + kxv * kxv;
-        typename V2<T>::type psi = origin ? V2<T>::make(T(0), T(0)) : V2<T>::make(w.x / k2, w.y / k2);
-        if (f == 0) return V2<T>::make(-kyv * psi.y, kyv * psi.x);        // u_hat =  i ky psi_hat
-        return V2<T>::make(kxv * psi.y, -kxv * psi.x);                    // v_hat = -i kx psi_hat
-    }
-    if (f == 2) return V2<T>::make(-kxv * w.y, kxv * w.x);                // i kx omega_hat
-    return V2<T>::make(-kyv * w.y, kyv * w.x);                            // i ky omega_hat
-}
-
 template <typename T> struct NsMinCtas { static constexpr int value = sizeof(T) == 8 ? 1 : 2; };
 
 // ---- A: inverse transform along y of the four padded, Hermitian-symmetrised spectra ---------------------
@@ -333,7 +320,7 @@ __device__ __forceinline__ void rk_update(const NsArgs<T>& A, const size_t* idx,
 }
 
 template <typename T, int P1, int P2>
-__global__ void __launch_bounds__(kColsPerCta * 32, NsMinCtas<T>::value)
+__global__ void __launch_bounds__(kColsPerCta * 32, 2 * NsMinCtas<T>::value)     // load-latency bound: 2+ CTAs/SM
 ns_ypass_fwd_kernel(const __grid_constant__ NsArgs<T> A) {
     using G = NsGeom<P1, P2>;
     using C = typename V2<T>::type;

@@ -202,7 +202,7 @@ int32_t reset_t(pdeb200_ctx* c, const uint8_t* d_mask) {
         sensors_phys_kernel<T><<<c->cfg.n_envs, 128, 0, c->stream>>>(
             c->fields, c->npts, c->cfg.n_sensors,
             EllTable<T>{c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows}, d_mask, (const T*)c->y,
-            c->cfg.problem == PDEB200_KSEG1D ? 1 : 0, (T*)c->sensors, (T*)c->vmax);
+            (c->cfg.problem == PDEB200_KSEG1D || c->cfg.problem == PDEB200_KSEG2D) ? 1 : 0, (T*)c->sensors, (T*)c->vmax);
         PDEB_CUDA(c, cudaGetLastError());
         c->launches += 1;
     }
@@ -214,6 +214,7 @@ int32_t core_step(pdeb200_ctx* c) {
         case PDEB200_KS: return ks_core(c);
         case PDEB200_KSEG1D: return kseg_core(c);
         case PDEB200_NS2D: return ns_core(c);
+        case PDEB200_KSEG2D: return kseg2d_core(c);
     }
     return fail(c, PDEB200_EINVAL, "bad problem");
 }
@@ -304,6 +305,13 @@ int32_t pdeb200_default_config(int32_t problem, pdeb200_config* cfg) {
             cfg->obs_scale = 1.0 / 70.0; cfg->reward_gain = 1.0; cfg->reward_pow = 1.1; cfg->reward_div = 320.0;
             cfg->action_punish = 0.002; cfg->delta_action_punish = 0.002;
             break;
+        case PDEB200_KSEG2D:      // 2-D generalisation of the Keller-Segel setup (BASELINE config 3)
+            cfg->nx = 128; cfg->ny = 128; cfg->Lx = 12.8; cfg->Ly = 12.8; cfg->dt = 0.006; cfg->te = 8.0; cfg->oversampling = 40;
+            cfg->window_size = 3; cfg->temporal_steps = 2; cfg->sensors_per_axis = 16;
+            cfg->check_max_value = PDEB200_CHECK_Y; cfg->max_value = 20.0;
+            cfg->agent_power = 10.0; cfg->obs_scale = 1.0 / 20.0; cfg->reward_gain = 1.0; cfg->reward_pow = 2.0;
+            cfg->reward_div = 20000.0; cfg->reward_offset = 1.0; cfg->action_punish = 0.0; cfg->delta_action_punish = 0.0;
+            break;
         default: return fail(nullptr, PDEB200_EINVAL, "default_config: unknown problem");
     }
     return PDEB200_OK;
@@ -338,6 +346,8 @@ int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** 
         case PDEB200_KSEG1D: c->npts = cfg->nx; c->fields = 2; c->y_elems = 2 * c->npts; c->p_elems = c->npts; c->wrows = cfg->window_size; break;
         case PDEB200_NS2D: c->npts = cfg->nx * cfg->ny; c->fields = 1; c->y_elems = 2 * c->npts; c->p_elems = 2 * c->npts;
             c->wrows = cfg->window_size * cfg->window_size; break;
+        case PDEB200_KSEG2D: c->npts = cfg->nx * cfg->ny; c->fields = 2; c->y_elems = 2 * c->npts; c->p_elems = c->npts;
+            c->wrows = cfg->window_size * cfg->window_size; break;
         default: return bail(fail(c, PDEB200_EINVAL, "create: unknown problem"));
     }
     if (cfg->mono) {
@@ -367,6 +377,7 @@ int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** 
         case PDEB200_KS: rc = ks_setup(c); break;
         case PDEB200_KSEG1D: rc = kseg_setup(c); break;
         case PDEB200_NS2D: rc = ns_setup(c); break;
+        case PDEB200_KSEG2D: rc = kseg2d_setup(c); break;
     }
     if (rc) return bail(rc);
     *out = c;
@@ -662,6 +673,7 @@ int32_t pdeb200_step_cost(const pdeb200_ctx* c, double* bytes, double* flops) {
         case PDEB200_KS: return ks_cost(c, bytes, flops);
         case PDEB200_KSEG1D: return kseg_cost(c, bytes, flops);
         case PDEB200_NS2D: return ns_cost(c, bytes, flops);
+        case PDEB200_KSEG2D: return kseg2d_cost(c, bytes, flops);
     }
     return PDEB200_EINVAL;
 }

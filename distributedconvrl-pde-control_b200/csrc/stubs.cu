@@ -7,6 +7,11 @@ int32_t kseg_core(pdeb200_ctx* c) { return fail(c, PDEB200_EUNSUPPORTED, "Keller
 int32_t kseg_cost(const pdeb200_ctx*, double*, double*) { return PDEB200_EUNSUPPORTED; }
 void kseg_free(pdeb200_ctx*) {}
 #endif
+#ifndef PDEB_HAVE_KSEG2D
+int32_t kseg2d_setup(pdeb200_ctx* c) { return fail(c, PDEB200_EUNSUPPORTED, "Keller-Segel 2-D back-end not built"); }
+int32_t kseg2d_core(pdeb200_ctx* c) { return fail(c, PDEB200_EUNSUPPORTED, "Keller-Segel 2-D back-end not built"); }
+int32_t kseg2d_cost(const pdeb200_ctx*, double*, double*) { return PDEB200_EUNSUPPORTED; }
+#endif
 #ifndef PDEB_HAVE_NS
 int32_t ns_setup(pdeb200_ctx* c) { return fail(c, PDEB200_EUNSUPPORTED, "Navier-Stokes back-end not built"); }
 int32_t ns_core(pdeb200_ctx* c) { return fail(c, PDEB200_EUNSUPPORTED, "Navier-Stokes back-end not built"); }

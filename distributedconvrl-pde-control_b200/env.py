@@ -8,7 +8,7 @@ is folded into the actuator (column) axis exactly as SURVEY.md 8b prescribes, so
 every array has the reference's Julia shape with `n_act*B` columns:
 
     env.state   (ns, n_act*B)        env.action  (1+mem, n_act*B)
-    env.reward  (n_act*B,)           env.y       (nx, B) | (2, nx, B) | complex (ny, nx, B)
+    env.reward  (n_act*B,)           env.y       (nx, B) | (2, nx, B) | (2, nx, ny, B) | complex (ny, nx, B)
 
 (returned as numpy views whose memory is the Julia column-major layout).
 """
@@ -27,7 +27,7 @@ class PDEenv:
     """Batched PDE environment.  Mirrors `PDEenv(; ...)` (PDEenv.jl:64-170).
 
     Parameters (keyword, reference names where they exist)
-      problem            L.KS | L.KSEG1D | L.NS2D
+      problem            L.KS | L.KSEG1D | L.KSEG2D | L.NS2D
       n_envs             B independent environments (reference: 1)
       dtype              "f64" | "f32" arithmetic of the PDE path
       sensor_basis       `gaussians`            (n_sensors, npts) float64
@@ -86,6 +86,8 @@ class PDEenv:
             self._y_shape = (cfg.nx,)
         elif problem == L.KSEG1D:
             self._y_shape = (2, cfg.nx)
+        elif problem == L.KSEG2D:
+            self._y_shape = (cfg.ny, cfg.nx, 2)      # Julia (2, nx, ny): memory [iy][ix][field]
         else:
             self._y_shape = (cfg.nx, cfg.ny, 2)      # Julia complex (ny, nx): memory [col i][row j][re,im]
         self.problem = problem
@@ -122,7 +124,7 @@ class PDEenv:
             L.ARR_ACTION_IN: (B * self.n_actuators * self.a_rows, self.np_dtype),
             L.ARR_REWARD: (B * self.n_rew, self.np_dtype), L.ARR_DONE: (B, np.uint8),
             L.ARR_TIME: (B, np.float64), L.ARR_STEPS: (B, np.int32),
-            L.ARR_SENSORS: (B * (2 if self.problem == L.KSEG1D else 1) * self.n_sensors, self.np_dtype),
+            L.ARR_SENSORS: (B * (2 if self.problem in (L.KSEG1D, L.KSEG2D) else 1) * self.n_sensors, self.np_dtype),
         }[which]
 
     def get(self, which):
@@ -151,6 +153,8 @@ class PDEenv:
         if self.problem == L.KSEG1D:
             # Julia (2, nx) column-major => memory [x][field]
             return flat.reshape(B, self.cfg.nx, 2).transpose(2, 1, 0)          # (2, nx, B)
+        if self.problem == L.KSEG2D:
+            return flat.reshape(B, self.cfg.ny, self.cfg.nx, 2).transpose(3, 2, 1, 0)     # (2, nx, ny, B)
         z = flat.reshape(B, self.cfg.nx, self.cfg.ny, 2)
         return (z[..., 0] + 1j * z[..., 1]).transpose(2, 1, 0)                # (ny, nx, B)
 
@@ -219,6 +223,12 @@ class PDEenv:
                 return np.ascontiguousarray(y.T, dtype=np.float64), True
             if y.shape == base + (B,):
                 return np.ascontiguousarray(y.transpose(2, 1, 0), dtype=np.float64), False
+        elif self.problem == L.KSEG2D:
+            base = (2, self.cfg.nx, self.cfg.ny)
+            if y.shape == base:
+                return np.ascontiguousarray(y.transpose(2, 1, 0), dtype=np.float64), True
+            if y.shape == base + (B,):
+                return np.ascontiguousarray(y.transpose(3, 2, 1, 0), dtype=np.float64), False
         else:
             base = (self.cfg.ny, self.cfg.nx)
             if y.shape == base:

@@ -35,7 +35,7 @@
  *   - a context is not thread-safe; one Julia task / Python thread drives it;
  *   - array layouts are exactly the memory of the reference's column-major Julia
  *     arrays with the environment batch folded into the actuator (column) axis:
- *       y       Julia (nx, B)  [KS]  (2, nx, B) [KSeg]  complex (ny, nx, B) [NS]   -> env-major contiguous
+ *       y       Julia (nx, B)  [KS]  (2, nx, B) [KSeg]  (2, nx, ny, B) [KSeg 2-D]  complex (ny, nx, B) [NS]   -> env-major contiguous
  *       state   Julia (ns, n_act*B)      -> [B][n_act][ns]
  *       action  Julia (1+mem, n_act*B)   -> [B][n_act][1+mem]
  *       reward  Julia (n_act*B,)         -> [B][n_act]
@@ -58,7 +58,7 @@ typedef struct pdeb200_ctx pdeb200_ctx;
 
 enum { PDEB200_OK = 0, PDEB200_EINVAL = -1, PDEB200_ECUDA = -2, PDEB200_EUNSUPPORTED = -3, PDEB200_ESTATE = -4 };
 enum { PDEB200_F32 = 0, PDEB200_F64 = 1 };
-enum { PDEB200_KS = 0, PDEB200_KSEG1D = 1, PDEB200_NS2D = 2 };
+enum { PDEB200_KS = 0, PDEB200_KSEG1D = 1, PDEB200_NS2D = 2, PDEB200_KSEG2D = 3 };
 enum { PDEB200_CHECK_NONE = 0, PDEB200_CHECK_Y = 1, PDEB200_CHECK_REWARD = 2 };   /* src/PDEenv.jl:226-240 */
 enum { PDEB200_ACT_IDENTITY = 0, PDEB200_ACT_RELU = 1, PDEB200_ACT_TANH = 2 };
 enum { PDEB200_NET_BEHAVIOR_ACTOR = 0, PDEB200_NET_BEHAVIOR_CRITIC = 1, PDEB200_NET_TARGET_ACTOR = 2, PDEB200_NET_TARGET_CRITIC = 3 };
@@ -84,7 +84,7 @@ enum {
 
 typedef struct pdeb200_config {
     int32_t struct_size;          /* = sizeof(pdeb200_config), ABI check                       */
-    int32_t problem;              /* PDEB200_KS / KSEG1D / NS2D                                */
+    int32_t problem;              /* PDEB200_KS / KSEG1D / NS2D / KSEG2D                       */
     int32_t dtype;                /* PDEB200_F32 / F64: arithmetic type of the PDE path        */
     int32_t nx, ny;               /* grid; ny = 1 for 1-D problems                             */
     int32_t n_envs;               /* B, independent environments on this GPU                   */
@@ -96,7 +96,7 @@ typedef struct pdeb200_config {
     int32_t oversampling;         /* substeps per env step (KS: CNAB2, KSeg/NS: RK4)           */
     int32_t check_max_value;      /* PDEB200_CHECK_*                                           */
     int32_t mono;                 /* 1 = global-agent variant (KSglobalSetup.jl): one column   */
-    int32_t sensors_per_axis;     /* NS2D: sensor lattice side (FluidSetup.jl:61)              */
+    int32_t sensors_per_axis;     /* NS2D, KSEG2D: sensor lattice side (FluidSetup.jl:61)      */
     int32_t ifpad;                /* NS2D: 3/2-rule de-aliasing (FluidSetup.jl:101)            */
     double Lx, Ly;                /* domain                                                    */
     double dt, te, t0;            /* env step, episode end, start                              */
