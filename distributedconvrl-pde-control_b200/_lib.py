@@ -59,6 +59,9 @@ _PROTOS = {
     "pdeb200_net_set": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdeb200_net_get": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]),
     "pdeb200_net_num_params": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "pdeb200_net_forward": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),
+    "pdeb200_net_forward_device": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                               C.c_int32, C.POINTER(C.c_int32)]),
     "pdeb200_policy_act": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_double, C.c_double]),
     "pdeb200_policy_act_rng": (C.c_int32, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_double]),
     "pdeb200_rollout": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double, C.c_void_p]),

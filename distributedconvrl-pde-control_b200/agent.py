@@ -86,6 +86,17 @@ class CustomNeuralNetworkApproximator:
         self.model.load_flat(flat)
         return self.model
 
+    def __call__(self, x, path=0, return_info=False):
+        """(app)(x) = app.model(x), custom_nna.jl:13: x is (rows, n_cols); returns (out, n_cols) float32.
+        path: 0 auto, 1 CUDA cores only, 2 tensor cores where possible."""
+        x = np.asarray(x, dtype=np.float32)
+        xm = np.ascontiguousarray(x.T)
+        y = np.empty((xm.shape[0], self.model.sizes[-1]), dtype=np.float32)
+        used = C.c_int32(0)
+        L.check(self.env._lib.pdeb200_net_forward(self.env._ctx, self.net_id, xm.shape[0], xm.ctypes.data, y.ctypes.data,
+                                                  int(path), C.byref(used)), self.env._ctx)
+        return (y.T, used.value) if return_info else y.T
+
     def copyto(self, src):
         """Base.copyto!(dest, src), custom_nna.jl:26-27"""
         self.model.load_flat(src.sync_from_device().flat())

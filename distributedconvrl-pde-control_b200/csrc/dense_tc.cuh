@@ -1,0 +1,217 @@
+// Dense layer on the 5th-generation tensor cores:  Y[M x N] = act(X[M x K] * Wt[N x K]^T + b)   (fp32 in / out)
+//
+// The weight-shared per-actuator networks of the reference (Flux Chain of Dense applied to a (ns, n_columns)
+// matrix, src/PDEagent.jl:18-44, src/custom_nna.jl:13) are a 1x1 convolution over the column axis, i.e. a GEMM
+// with M = n_columns (up to envs x actuators ~ 5e5).  For the shipped networks the contraction is far too thin
+// (K <= 13) and the CUDA-core kernels are used; this kernel serves the dense case `drop_middle_layer = false`
+// (hidden x hidden layers, 140..340 wide).
+//
+// Numerics: the networks are Float32 and parity is asserted at 1e-5, which a plain TF32 product (10-bit mantissa)
+// misses.  Operands are therefore split on the fly, x = hi + lo with hi = x truncated to TF32, and three
+// tcgen05.mma (hi*hi, hi*lo, lo*hi) accumulate into the same fp32 TMEM tile ("3xTF32": relative error ~2^-21).
+//
+// Structure (one 128 x 128 output tile per CTA, 5 warps):
+//   warps 0-3  producers: coalesced 16-byte global loads -> hi/lo split in registers -> st.shared into the
+//              K-major SWIZZLE_128B canonical layout (the split needs the data in registers, hence no TMA here);
+//              3-stage ring, full/empty mbarriers; afterwards the same warps run the epilogue
+//              (tcgen05.ld 32 lanes x 32 columns -> bias + activation -> global stores).
+//   warp 4     TMEM allocation; one elected lane issues tcgen05.mma (M = 128, N = 128, K = 8 per instruction,
+//              kind::tf32, both operands K-major from shared-memory descriptors) and tcgen05.commit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pdeb200 {
+namespace tc {
+
+constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
+constexpr int TILE_BYTES = BM * BK * 4;                    // 16 KB: 128 rows x 128 B
+constexpr int STAGE_BYTES = 4 * TILE_BYTES;                // A_hi, A_lo, B_hi, B_lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int N_PRODUCERS = 128;
+
+struct DenseArgs {
+    const float* X; long long ldx;     // [M][K] row-major, ldx % 4 == 0
+    const float* Wt; long long ldw;    // [N][K] row-major (K-major), ldw % 4 == 0
+    const float* bias;                 // [N] or nullptr
+    float* Y; long long ldy;           // [M][N] row-major
+    int M, N, K;                       // K % 4 == 0
+    int act;                           // 0 identity, 1 relu, 2 tanh
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    }
+}
+
+// K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart (SBO), 16-byte chunk c of
+// row r stored at chunk (c ^ (r & 7)).  Descriptor fields as in cute::UMMA::SmemDescriptor (sm_100).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3FFF);           // start address
+    d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset
+    d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    return d;
+}
+
+// instruction descriptor, kind::tf32: D = F32, A = B = TF32, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+__device__ __forceinline__ uint32_t instr_desc() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a, uint64_t b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+        ::"r"(d_tmem), "l"(a), "l"(b), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+__device__ __forceinline__ float act_f(int kind, float v) {
+    if (kind == 1) return v > 0.f ? v : 0.f;
+    if (kind == 2) return tanhf(v);
+    return v;
+}
+
+// split a float4 into TF32-representable hi and the remainder lo
+__device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
+    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
+    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+}
+
+__device__ __forceinline__ void load_tile(const float* __restrict__ src, long long ld, int row0, int n_rows, int k0, int K,
+                                          unsigned char* hi_tile, unsigned char* lo_tile, int tid) {
+    float4 v[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int q = it * N_PRODUCERS + tid, row = q >> 3, c = q & 7;
+        const int gr = row0 + row, gk = k0 + c * 4;
+        v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (gr < n_rows && gk < K) v[it] = __ldg(reinterpret_cast<const float4*>(src + (long long)gr * ld + gk));
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int q = it * N_PRODUCERS + tid, row = q >> 3, c = q & 7;
+        const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+        float4 hi, lo;
+        split4(v[it], hi, lo);
+        *reinterpret_cast<float4*>(hi_tile + off) = hi;
+        *reinterpret_cast<float4*>(lo_tile + off) = lo;
+    }
+}
+
+__global__ void __launch_bounds__(160, 1) dense_tc_kernel(const __grid_constant__ DenseArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    const uint32_t raw = s32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B atoms need 1024-byte alignment
+    unsigned char* tiles = smem_raw + (base - raw);
+    const uint32_t bars = base + STAGES * STAGE_BYTES;              // full[STAGES], empty[STAGES], tmem_full, tmem slot
+    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tmem_full = bars + 16 * STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tiles + STAGES * STAGE_BYTES + 16 * STAGES + 8);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int KB = (A.K + BK - 1) / BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { bar_init(full0 + 8 * s, N_PRODUCERS); bar_init(empty0 + 8 * s, 1); }
+        bar_init(tmem_full, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        // ===== producers =====
+        const int tid = threadIdx.x;
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % STAGES;
+            bar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
+            unsigned char* st = tiles + s * STAGE_BYTES;
+            load_tile(A.X, A.ldx, m0, A.M, kb * BK, A.K, st, st + TILE_BYTES, tid);
+            load_tile(A.Wt, A.ldw, n0, A.N, kb * BK, A.K, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
+            bar_arrive(full0 + 8 * s);
+        }
+        // ===== epilogue: this warp owns TMEM lanes [32 warp, 32 warp + 32) = output rows =====
+        bar_wait(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + warp * 32 + lane;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (row < A.M) {
+                float* yrow = A.Y + (long long)row * A.ldy;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int n = n0 + c0 + j;
+                    if (n < A.N) yrow[n] = act_f(A.act, __uint_as_float(r[j]) + (A.bias ? __ldg(A.bias + n) : 0.f));
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    } else {
+        // ===== MMA issuer =====
+        const uint32_t idesc = instr_desc();
+        for (int kb = 0; kb < KB; ++kb) {
+            const int s = kb % STAGES;
+            bar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < BK / 8; ++k) {
+                    // advancing 8 tf32 (32 bytes) inside the 128-byte swizzle atom = +2 in the encoded start address
+                    const uint64_t ahi = smem_desc(st + k * 32), alo = smem_desc(st + TILE_BYTES + k * 32);
+                    const uint64_t bhi = smem_desc(st + 2 * TILE_BYTES + k * 32), blo = smem_desc(st + 3 * TILE_BYTES + k * 32);
+                    mma_tf32(tmem, alo, bhi, idesc, (kb | k) != 0);      // small terms first
+                    mma_tf32(tmem, ahi, blo, idesc, 1);
+                    mma_tf32(tmem, ahi, bhi, idesc, 1);
+                }
+                // commit: arrives on the barrier when the MMAs above have finished reading the stage
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s) : "memory");
+                if (kb == KB - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tmem_full) : "memory");
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (warp == 4) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
+    }
+}
+
+}  // namespace tc
+}  // namespace pdeb200

@@ -19,6 +19,7 @@
  *   env.y / env.p / env.state / env.reward / env.done ...  pdeb200_get / pdeb200_device_ptr
  *   CustomNeuralNetworkApproximator(model, optimizer)
  *                                  src/custom_nna.jl:7-27  pdeb200_net_set / pdeb200_net_get
+ *   (app::CustomNeuralNetworkApproximator)(x)   custom_nna.jl:13  pdeb200_net_forward
  *   (policy::CustomDDPGPolicy)(env) src/PDEagent.jl:175-209 pdeb200_policy_act
  *   policy loop in plot_heat        src/plotting.jl:55-73   pdeb200_rollout (fused actor + env step, K steps / launch)
  *   trajectory update! overloads   src/PDEagent.jl:237-314 pdeb200_traj_push_pre / _post / _episode_end / _pop_tail
@@ -160,6 +161,17 @@ int32_t pdeb200_net_set(pdeb200_ctx* ctx, int32_t net, int32_t n_layers, const i
                         const int32_t* activations, const float* params);
 int32_t pdeb200_net_get(pdeb200_ctx* ctx, int32_t net, float* params, size_t n_params);
 int32_t pdeb200_net_num_params(const pdeb200_ctx* ctx, int32_t net);
+
+/* The approximator call  y = model(x)  on a (rows, n_cols) matrix (src/custom_nna.jl:13): x_host is float32
+ * [n_cols][in] (Julia column-major (in, n_cols)), y_host float32 [n_cols][out].  Dense layers (in, out >= 32) run
+ * on the tensor cores (tcgen05, 3xTF32, fp32-accurate); thin layers on CUDA cores.  path: 0 = auto, 1 = CUDA cores
+ * only, 2 = tensor cores wherever the layout allows.  n_tensor_layers (optional) receives how many layers used them. */
+int32_t pdeb200_net_forward(pdeb200_ctx* ctx, int32_t net, int32_t n_cols, const float* x_host, float* y_host, int32_t path,
+                            int32_t* n_tensor_layers);
+/* same on DEVICE buffers with leading dimensions (floats); ldx must be a multiple of 4 for the tensor-core path and
+ * the padding columns [in, ldx) must be zero. */
+int32_t pdeb200_net_forward_device(pdeb200_ctx* ctx, int32_t net, int32_t n_cols, const float* x_dev, int64_t ldx, float* y_dev,
+                                   int64_t ldy, int32_t path, int32_t* n_tensor_layers);
 
 /* ---- policy ----------------------------------------------------------------------------- */
 /* actions = clamp(behavior_actor(state) + noise*act_noise, +-act_limit)   (PDEagent.jl:189-204)
