@@ -73,6 +73,7 @@ _PROTOS = {
     "pdeb200_traj_pop_tail": (C.c_int32, [C.c_void_p]),
     "pdeb200_sample": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_uint64, C.c_uint64]),
     "pdeb200_set_batch": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdeb200_ddpg_set_path": (C.c_int32, [C.c_void_p, C.c_int32]),
     "pdeb200_ddpg_critic_grads": (C.c_int32, [C.c_void_p, C.c_double, C.c_int32, C.c_int64]),
     "pdeb200_ddpg_critic_apply": (C.c_int32, [C.c_void_p, C.c_double]),
     "pdeb200_ddpg_actor_grads": (C.c_int32, [C.c_void_p, C.c_int64]),

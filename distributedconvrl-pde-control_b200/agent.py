@@ -245,6 +245,10 @@ class CustomDDPGPolicy:
             L.check(lib.pdeb200_ddpg_actor_apply(ctx, float(self.behavior_actor.learning_rate), float(self.p)), ctx)
         self.n_updates += 1
 
+    def set_update_path(self, path):
+        """0 auto, 1 layer-wise CUDA cores, 2 layer-wise tensor cores, 3 layer-wise auto (pdeb200_ddpg_set_path)."""
+        L.check(self.env._lib.pdeb200_ddpg_set_path(self.env._ctx, int(path)), self.env._ctx)
+
     def grads(self):
         n = self.env._lib.pdeb200_net_num_params(self.env._ctx, L.NET_BEHAVIOR_CRITIC) + \
             self.env._lib.pdeb200_net_num_params(self.env._ctx, L.NET_BEHAVIOR_ACTOR)

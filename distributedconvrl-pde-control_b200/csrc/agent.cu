@@ -40,6 +40,9 @@ struct Agent {
     double* stats = nullptr;           // [0] sum r  [1] sum r^2  [2] sum c  [3] sum c^2  [4] sum q(actor)
     float* partials = nullptr; size_t partials_floats = 0;
     int n_blocks = 0;
+    float* arena = nullptr; size_t arena_cap = 0, arena_used = 0;   // activations of the layer-wise (wide network) path
+    int force_wide = 0;                // 1: always use the layer-wise path (tests / measurements)
+    int wide_path = 0;                 // layer dispatch there: 0 auto, 1 CUDA cores only, 2 tensor cores wherever possible
 };
 
 Agent* ag(pdeb200_ctx* c) { return static_cast<Agent*>(c->agent); }
@@ -479,6 +482,242 @@ int block_threads(int wmax, int n_acc) {
     return std::min(t, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Layer-wise DDPG update for networks that do not fit the shared-memory kernels above (wide critics with the
+// middle layer, `drop_middle_layer = false`): activations live in global memory, every Dense layer is a GEMM --
+// forward, input gradient and weight gradient on the tensor cores when the layer is dense (nn_ops.cu /
+// dense_tc.cuh), CUDA-core kernels for the thin input / output layers.  Same arithmetic as update!
+// (PDEagent.jl:363-418), same flat gradient layout, fixed-order reductions.
+// ---------------------------------------------------------------------------------------------
+inline int pad4i(int n) { return (n + 3) / 4 * 4; }
+
+struct Acts { float* out[kMaxLayers + 1]; long long ld[kMaxLayers + 1]; };
+
+float* arena_take(Agent* a, size_t n) {
+    n = (n + 63) / 64 * 64;
+    if (a->arena_used + n > a->arena_cap) return nullptr;
+    float* p = a->arena + a->arena_used;
+    a->arena_used += n;
+    return p;
+}
+
+int32_t arena_reserve(pdeb200_ctx* c, size_t floats) {
+    Agent* a = ag(c);
+    a->arena_used = 0;
+    if (floats <= a->arena_cap) return PDEB200_OK;
+    if (a->arena) cudaFree(a->arena);
+    a->arena = nullptr; a->arena_cap = 0;
+    PDEB_CUDA(c, cudaMalloc(&a->arena, floats * sizeof(float)));
+    PDEB_CUDA(c, cudaMemsetAsync(a->arena, 0, floats * sizeof(float), c->stream));
+    a->arena_cap = floats;
+    return PDEB200_OK;
+}
+
+// X[m] = [s[m]; a[m]; 0-pad]
+__global__ void concat_kernel(int M, int ns, int na, int ld, const float* __restrict__ s, const float* __restrict__ a, int lda,
+                              float* __restrict__ X) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= (long long)M * ld) return;
+    const int m = (int)(q / ld), r = (int)(q % ld);
+    X[q] = r < ns ? s[(size_t)m * ns + r] : (r < ns + na ? a[(size_t)m * lda + (r - ns)] : 0.f);
+}
+
+__global__ void copy_pad_kernel(int M, int n, int ld, const float* __restrict__ src, float* __restrict__ dst) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= (long long)M * ld) return;
+    const int m = (int)(q / ld), r = (int)(q % ld);
+    dst[q] = r < n ? src[(size_t)m * n + r] : 0.f;
+}
+
+// dq and the loss sums of the critic phase (single CTA: fixed summation order)
+__global__ void __launch_bounds__(1024) critic_dq_kernel(int B, const float* __restrict__ q, long long ldq, const float* __restrict__ qt,
+                                                         long long ldqt, const float* __restrict__ r, const uint8_t* __restrict__ t,
+                                                         float gamma, int literal, double inv_gb, double* stats, float* dq,
+                                                         long long lddq) {
+    __shared__ double s0[1024], s1[1024];
+    const float rbar = (float)(stats[0] * inv_gb);
+    double a = 0, b = 0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) {
+        const float cc = gamma * (1.f - (float)t[i]) * qt[(long long)i * ldqt] - q[(long long)i * ldq];
+        const float rr = literal ? rbar : r[i];
+        dq[(long long)i * lddq] = (float)(-2.0 * inv_gb) * (rr + cc);
+        const double cl = literal ? (double)cc : (double)(r[i] + cc);
+        a += cl; b += cl * cl;
+    }
+    s0[threadIdx.x] = a; s1[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s0[threadIdx.x] += s0[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { stats[2] = s0[0]; stats[3] = s1[0]; }
+}
+
+__global__ void __launch_bounds__(1024) actor_dq_kernel(int B, const float* __restrict__ q, long long ldq, double inv_gb, double* stats,
+                                                        float* dq, long long lddq) {
+    __shared__ double s0[1024];
+    double a = 0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) { a += (double)q[(long long)i * ldq]; dq[(long long)i * lddq] = (float)(-inv_gb); }
+    s0[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s0[threadIdx.x] += s0[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { stats[4] = s0[0]; stats[5] = 0.0; }
+}
+
+// d[m][n] *= act'(out[m][n])
+__global__ void act_grad_mul_kernel(long long M, int N, int act, const float* __restrict__ out, long long ldo, float* d, long long ldd) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= M * N) return;
+    const long long m = q / N; const int n = (int)(q % N);
+    d[m * ldd + n] *= act_grad(act, out[m * ldo + n]);
+}
+
+void zero_pad(pdeb200_ctx* c, long long M, int n, long long ld, float* X);
+
+int32_t wide_forward(pdeb200_ctx* c, const HostNet& net, int M, float* x, long long ldx, Acts* A) {
+    Agent* a = ag(c);
+    A->out[0] = x; A->ld[0] = ldx;
+    for (int l = 0; l < net.n_layers; ++l) {
+        const int no = net.sizes[l + 1];
+        A->ld[l + 1] = pad4i(no);
+        A->out[l + 1] = arena_take(a, (size_t)M * A->ld[l + 1]);          // arena is zero-filled: padding columns stay 0
+        if (!A->out[l + 1]) return fail(c, PDEB200_ECUDA, "ddpg (layer-wise path): activation arena exhausted");
+        int32_t rc = dense_layer(c, M, net.sizes[l], no, A->out[l], A->ld[l], net.d_params + net.offs[l], net.acts[l],
+                                 A->out[l + 1], A->ld[l + 1], a->wide_path, nullptr);
+        if (rc) return rc;
+        zero_pad(c, M, no, A->ld[l + 1], A->out[l + 1]);
+    }
+    return PDEB200_OK;
+}
+
+// d: dLoss/d(output) [M][ld of the output]; overwritten.  gflat: flat parameter gradient or nullptr.
+// Returns dLoss/d(input) in *d_in (arena buffer, ld = pad4(sizes[0])) when want_input.
+int32_t wide_backward(pdeb200_ctx* c, const HostNet& net, int M, const Acts& A, float* d, long long ldd, float* gflat,
+                      bool want_input, float** d_in, long long* ld_in) {
+    Agent* a = ag(c);
+    const int L = net.n_layers;
+    if (net.acts[L - 1] != 0) {
+        const long long tot = (long long)M * net.sizes[L];
+        act_grad_mul_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(M, net.sizes[L], net.acts[L - 1], A.out[L], A.ld[L], d, ldd);
+        c->launches += 1;
+    }
+    for (int l = L - 1; l >= 0; --l) {
+        const int K = net.sizes[l], N = net.sizes[l + 1];
+        const float* W = net.d_params + net.offs[l];
+        int32_t rc;
+        if (gflat && (rc = dense_wgrad(c, M, K, N, d, ldd, A.out[l], A.ld[l], gflat + net.offs[l], gflat + net.offs[l] + (size_t)K * N,
+                                       a->wide_path))) return rc;
+        if (l > 0 || want_input) {
+            const long long ldp = pad4i(K);
+            float* dp = arena_take(a, (size_t)M * ldp);
+            if (!dp) return fail(c, PDEB200_ECUDA, "ddpg (layer-wise path): activation arena exhausted");
+            // delta of the previous layer = (d * W) .* act'(its output)
+            const float* mask = l > 0 && net.acts[l - 1] != 0 ? A.out[l] : nullptr;
+            if ((rc = dense_dgrad(c, M, K, N, d, ldd, W, mask, A.ld[l], l > 0 ? net.acts[l - 1] : 0, dp, ldp, a->wide_path))) return rc;
+            zero_pad(c, M, K, ldp, dp);
+            d = dp; ldd = ldp;
+        }
+    }
+    if (want_input) { *d_in = d; *ld_in = ldd; }
+    PDEB_CUDA(c, cudaGetLastError());
+    return PDEB200_OK;
+}
+
+// activations + deltas of every network for one phase, generously (each buffer is rounded up to 64 floats)
+size_t wide_arena_floats(pdeb200_ctx* c) {
+    Agent* a = ag(c);
+    size_t per_col = 64, n_buf = 8;
+    for (int i = 0; i < 4; ++i)
+        for (int l = 0; l <= c->nets[i].n_layers; ++l) { per_col += 2 * (size_t)pad4i(c->nets[i].sizes[l]); n_buf += 2; }
+    return per_col * (size_t)a->batch + n_buf * 64;
+}
+
+// zero the padding columns [n, ld) of a row-major buffer (they take part in the next GEMM's contraction)
+__global__ void zero_pad_kernel(long long M, int n, int ld, float* X) {
+    const int w = ld - n;
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (w <= 0 || q >= M * w) return;
+    X[(q / w) * ld + n + (q % w)] = 0.f;
+}
+void zero_pad(pdeb200_ctx* c, long long M, int n, long long ld, float* X) {
+    if (ld == n) return;
+    const long long tot = M * (ld - n);
+    zero_pad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c->stream>>>(M, n, (int)ld, X);
+    c->launches += 1;
+}
+
+int32_t wide_critic_grads(pdeb200_ctx* c, double gamma, int literal, int64_t global_batch) {
+    Agent* a = ag(c);
+    const int B = a->batch, ns = a->ns, na = a->na, nin = ns + na, ldin = pad4i(nin);
+    const HostNet &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC], &At = c->nets[PDEB200_NET_TARGET_ACTOR], &Ct = c->nets[PDEB200_NET_TARGET_CRITIC];
+    int32_t rc = arena_reserve(c, wide_arena_floats(c));
+    if (rc) return rc;
+    const unsigned gcat = (unsigned)(((long long)B * ldin + 255) / 256);
+    // a' = A_t(s'), q_t = C_t([s'; a'])
+    Acts acts_at, acts_ct, acts_c;
+    const int lds = pad4i(ns);
+    float* s2p = arena_take(a, (size_t)B * lds);
+    float* x2 = arena_take(a, (size_t)B * ldin);
+    float* x = arena_take(a, (size_t)B * ldin);
+    float* dq = arena_take(a, (size_t)B * 4);
+    if (dq) PDEB_CUDA(c, cudaMemsetAsync(dq, 0, (size_t)B * 4 * sizeof(float), c->stream));
+    if (!s2p || !x2 || !x || !dq) return fail(c, PDEB200_ECUDA, "ddpg (layer-wise path): activation arena exhausted");
+    copy_pad_kernel<<<(unsigned)(((long long)B * lds + 255) / 256), 256, 0, c->stream>>>(B, ns, lds, a->bs2, s2p);
+    if ((rc = wide_forward(c, At, B, s2p, lds, &acts_at))) return rc;
+    concat_kernel<<<gcat, 256, 0, c->stream>>>(B, ns, na, ldin, a->bs2, acts_at.out[At.n_layers], (int)acts_at.ld[At.n_layers], x2);
+    if ((rc = wide_forward(c, Ct, B, x2, ldin, &acts_ct))) return rc;
+    // q = C([s; a]) with kept activations
+    concat_kernel<<<gcat, 256, 0, c->stream>>>(B, ns, na, ldin, a->bs, a->ba, na, x);
+    if ((rc = wide_forward(c, C, B, x, ldin, &acts_c))) return rc;
+    critic_dq_kernel<<<1, 1024, 0, c->stream>>>(B, acts_c.out[C.n_layers], acts_c.ld[C.n_layers], acts_ct.out[Ct.n_layers],
+                                                 acts_ct.ld[Ct.n_layers], a->br, a->bt, (float)gamma, literal, 1.0 / (double)global_batch,
+                                                 a->stats, dq, 4);
+    c->launches += 4;
+    if ((rc = wide_backward(c, C, B, acts_c, dq, 4, c->d_grads, false, nullptr, nullptr))) return rc;
+    losses_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)global_batch, literal, 0, c->d_losses);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
+int32_t wide_actor_grads(pdeb200_ctx* c, int64_t global_batch) {
+    Agent* a = ag(c);
+    const int B = a->batch, ns = a->ns, na = a->na, nin = ns + na, ldin = pad4i(nin);
+    const HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+    int32_t rc = arena_reserve(c, wide_arena_floats(c));
+    if (rc) return rc;
+    Acts acts_a, acts_c;
+    const int lds = pad4i(ns);
+    float* sp = arena_take(a, (size_t)B * lds);
+    float* x = arena_take(a, (size_t)B * ldin);
+    float* dq = arena_take(a, (size_t)B * 4);
+    float* da = arena_take(a, (size_t)B * pad4i(na));
+    if (dq) PDEB_CUDA(c, cudaMemsetAsync(dq, 0, (size_t)B * 4 * sizeof(float), c->stream));
+    if (!sp || !x || !dq || !da) return fail(c, PDEB200_ECUDA, "ddpg (layer-wise path): activation arena exhausted");
+    copy_pad_kernel<<<(unsigned)(((long long)B * lds + 255) / 256), 256, 0, c->stream>>>(B, ns, lds, a->bs, sp);
+    if ((rc = wide_forward(c, A, B, sp, lds, &acts_a))) return rc;
+    concat_kernel<<<(unsigned)(((long long)B * ldin + 255) / 256), 256, 0, c->stream>>>(B, ns, na, ldin, a->bs, acts_a.out[A.n_layers],
+                                                                                        (int)acts_a.ld[A.n_layers], x);
+    if ((rc = wide_forward(c, C, B, x, ldin, &acts_c))) return rc;
+    actor_dq_kernel<<<1, 1024, 0, c->stream>>>(B, acts_c.out[C.n_layers], acts_c.ld[C.n_layers], 1.0 / (double)global_batch, a->stats, dq, 4);
+    c->launches += 3;
+    float* dx = nullptr; long long lddx = 0;
+    if ((rc = wide_backward(c, C, B, acts_c, dq, 4, nullptr, true, &dx, &lddx))) return rc;
+    // dLoss/da = the action rows of dLoss/d[s; a]
+    const int lda = pad4i(na);
+    concat_kernel<<<(unsigned)(((long long)B * lda + 255) / 256), 256, 0, c->stream>>>(B, 0, na, lda, nullptr, dx + ns, (int)lddx, da);
+    c->launches += 1;
+    if ((rc = wide_backward(c, A, B, acts_a, da, lda, c->d_grads + C.n_params, false, nullptr, nullptr))) return rc;
+    losses_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)global_batch, 0, 1, c->d_losses);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
 }  // namespace
 
 double* agent_stats(pdeb200_ctx* c) { return c->agent ? ag(c)->stats : nullptr; }
@@ -487,7 +726,8 @@ void agent_free(pdeb200_ctx* c) {
     Agent* a = ag(c);
     if (!a) return;
     for (void* p : {(void*)a->state, (void*)a->action, (void*)a->reward, (void*)a->terminal, (void*)a->bs, (void*)a->ba,
-                    (void*)a->br, (void*)a->bs2, (void*)a->bt, (void*)a->inds, (void*)a->stats, (void*)a->partials})
+                    (void*)a->br, (void*)a->bs2, (void*)a->bt, (void*)a->inds, (void*)a->stats, (void*)a->partials,
+                    (void*)a->arena})
         if (p) cudaFree(p);
     delete a;
     c->agent = nullptr;
@@ -632,6 +872,15 @@ int32_t pdeb200_set_batch(pdeb200_ctx* c, int32_t batch, const float* s, const f
     return PDEB200_OK;
 }
 
+int32_t pdeb200_ddpg_set_path(pdeb200_ctx* c, int32_t path) {
+    if (!c || path < 0 || path > 3) return fail(c, PDEB200_EINVAL, "ddpg_set_path: bad argument");
+    int32_t rc = ensure_agent(c);
+    if (rc) return rc;
+    ag(c)->force_wide = path != 0;
+    ag(c)->wide_path = path == 3 ? 0 : path;
+    return PDEB200_OK;
+}
+
 int32_t pdeb200_ddpg_critic_grads(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch) {
     if (!c) return PDEB200_EINVAL;
     cudaSetDevice(c->device);
@@ -648,7 +897,7 @@ int32_t pdeb200_ddpg_critic_grads(pdeb200_ctx* c, double gamma, int32_t literal_
     if ((rc = ensure_partials(c, n_blocks, D.n_acc))) return rc;
     D.partials = a->partials;
     const size_t smem = ((size_t)net_act_floats(C) + 2 * (size_t)TS * D.wmax + (size_t)TS * (a->ns + a->na) + TS + D.n_acc) * 4;
-    if (smem > 220 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "ddpg: critic too large for the shared-memory CUDA-core path");
+    if (smem > 220 * 1024 || a->force_wide) return wide_critic_grads(c, gamma, literal_q1, global_batch);   // layer-wise GEMM path
     PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tpb = block_threads(D.wmax, D.n_acc);
     ddpg_critic_kernel<<<n_blocks, tpb, smem, c->stream>>>(D);
@@ -690,7 +939,7 @@ int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* c, int64_t global_batch) {
     if ((rc = ensure_partials(c, n_blocks, D.n_acc))) return rc;
     D.partials = a->partials;
     const size_t smem = ((size_t)net_act_floats(C) + net_act_floats(A) + 2 * (size_t)TS * D.wmax + D.n_acc) * 4;
-    if (smem > 220 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "ddpg: networks too large for the shared-memory CUDA-core path");
+    if (smem > 220 * 1024 || a->force_wide) return wide_actor_grads(c, global_batch);                      // layer-wise GEMM path
     PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tpb = block_threads(D.wmax, D.n_acc);
     ddpg_actor_kernel<<<n_blocks, tpb, smem, c->stream>>>(D);

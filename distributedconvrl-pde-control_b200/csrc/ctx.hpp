@@ -140,6 +140,14 @@ int32_t ns_sensors(pdeb200_ctx* c, const uint8_t* d_mask);
 int32_t ns_cost(const pdeb200_ctx* c, double* bytes, double* flops);
 void ns_free(pdeb200_ctx* c);
 
+// layer-wise network operators (nn_ops.cu): tensor cores for dense layers, CUDA cores for thin ones
+int32_t dense_layer(pdeb200_ctx* c, int M, int K, int N, const float* X, long long ldx, const float* W, int act, float* Y,
+                    long long ldy, int path, int* used_tc);
+int32_t dense_dgrad(pdeb200_ctx* c, int M, int K, int N, const float* dY, long long lddy, const float* W, const float* mask,
+                    long long ldm, int mask_act, float* dX, long long lddx, int path);
+int32_t dense_wgrad(pdeb200_ctx* c, int M, int K, int N, const float* dY, long long lddy, const float* X, long long ldx,
+                    float* gW, float* gb, int path);
+
 void agent_free(pdeb200_ctx* c);
 double* agent_stats(pdeb200_ctx* c);   // 8 doubles, or nullptr before the first batch
 

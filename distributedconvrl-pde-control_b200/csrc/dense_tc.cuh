@@ -31,12 +31,21 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256
 constexpr int N_PRODUCERS = 128;
 
 struct DenseArgs {
-    const float* X; long long ldx;     // [M][K] row-major, ldx % 4 == 0
-    const float* Wt; long long ldw;    // [N][K] row-major (K-major), ldw % 4 == 0
+    // TRANSPOSED = false:  Y[M x N] = epilogue(X[M x K] * Wt[N x K]^T)
+    //   X  [M][K] row-major, ldx % 4 == 0;  Wt [N][K] row-major (K-major), ldw % 4 == 0;  K % 4 == 0
+    // TRANSPOSED = true :  Y_z[M x N] = sum over the z-th slice of the contraction index k of  X[k][M]^T * Wt[k][N]
+    //   (both operands stored with the CONTRACTION index as the row: weight gradients dW = delta^T * input,
+    //    contraction over the batch; split along it over gridDim.z, partial tiles at Y + z * y_split_stride)
+    const float* X; long long ldx;
+    const float* Wt; long long ldw;
     const float* bias;                 // [N] or nullptr
     float* Y; long long ldy;           // [M][N] row-major
-    int M, N, K;                       // K % 4 == 0
-    int act;                           // 0 identity, 1 relu, 2 tanh
+    int M, N, K;
+    int act;                           // 0 identity, 1 relu, 2 tanh  (applied to acc + bias)
+    const float* mask; long long ldm;  // optional: Y *= act'(mask[m][n]) with mask_act (backward through the previous layer)
+    int mask_act;
+    int split_len;                     // TRANSPOSED: contraction elements per z-slice (multiple of BK)
+    long long y_split_stride;
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -114,6 +123,36 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ src, long lo
     }
 }
 
+// Transposing producer: tile row r <-> column (col0 + r) of a row-major array whose ROWS are the contraction index.
+// Thread tid owns tile row tid: 32 coalesced scalar loads (consecutive threads read consecutive addresses), then the
+// row is written as 8 swizzled 16-byte chunks.
+__device__ __forceinline__ void load_tile_t(const float* __restrict__ src, long long ld, int col0, int n_cols, int k0, int k_end,
+                                            unsigned char* hi_tile, unsigned char* lo_tile, int tid) {
+    float v[32];
+    const int gc = col0 + tid;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int gk = k0 + j;
+        v[j] = (gc < n_cols && gk < k_end) ? __ldg(src + (long long)gk * ld + gc) : 0.f;
+    }
+    const int row = tid;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+        float4 hi, lo;
+        split4(make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]), hi, lo);
+        *reinterpret_cast<float4*>(hi_tile + off) = hi;
+        *reinterpret_cast<float4*>(lo_tile + off) = lo;
+    }
+}
+
+__device__ __forceinline__ float act_grad_f(int kind, float out) {
+    if (kind == 1) return out > 0.f ? 1.f : 0.f;
+    if (kind == 2) return 1.f - out * out;
+    return 1.f;
+}
+
+template <bool TRANSPOSED>
 __global__ void __launch_bounds__(160, 1) dense_tc_kernel(const __grid_constant__ DenseArgs A) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = s32(smem_raw);
@@ -124,7 +163,10 @@ __global__ void __launch_bounds__(160, 1) dense_tc_kernel(const __grid_constant_
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tiles + STAGES * STAGE_BYTES + 16 * STAGES + 8);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    const int KB = (A.K + BK - 1) / BK;
+    // contraction range of this CTA
+    const int k_begin = TRANSPOSED ? (int)blockIdx.z * A.split_len : 0;
+    const int k_end = TRANSPOSED ? min(A.K, k_begin + A.split_len) : A.K;
+    const int KB = (k_end - k_begin + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { bar_init(full0 + 8 * s, N_PRODUCERS); bar_init(empty0 + 8 * s, 1); }
@@ -147,15 +189,21 @@ __global__ void __launch_bounds__(160, 1) dense_tc_kernel(const __grid_constant_
             const int s = kb % STAGES;
             bar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
             unsigned char* st = tiles + s * STAGE_BYTES;
-            load_tile(A.X, A.ldx, m0, A.M, kb * BK, A.K, st, st + TILE_BYTES, tid);
-            load_tile(A.Wt, A.ldw, n0, A.N, kb * BK, A.K, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
+            if (TRANSPOSED) {
+                load_tile_t(A.X, A.ldx, m0, A.M, k_begin + kb * BK, k_end, st, st + TILE_BYTES, tid);
+                load_tile_t(A.Wt, A.ldw, n0, A.N, k_begin + kb * BK, k_end, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
+            } else {
+                load_tile(A.X, A.ldx, m0, A.M, kb * BK, A.K, st, st + TILE_BYTES, tid);
+                load_tile(A.Wt, A.ldw, n0, A.N, kb * BK, A.K, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
             bar_arrive(full0 + 8 * s);
         }
         // ===== epilogue: this warp owns TMEM lanes [32 warp, 32 warp + 32) = output rows =====
-        bar_wait(tmem_full, 0);
+        if (KB > 0) bar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int row = m0 + warp * 32 + lane;
+        float* const Yz = A.Y + (TRANSPOSED ? (long long)blockIdx.z * A.y_split_stride : 0);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
             uint32_t r[32];
@@ -171,11 +219,17 @@ __global__ void __launch_bounds__(160, 1) dense_tc_kernel(const __grid_constant_
                 : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             if (row < A.M) {
-                float* yrow = A.Y + (long long)row * A.ldy;
+                float* yrow = Yz + (long long)row * A.ldy;
+                const float* mrow = A.mask ? A.mask + (long long)row * A.ldm : nullptr;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int n = n0 + c0 + j;
-                    if (n < A.N) yrow[n] = act_f(A.act, __uint_as_float(r[j]) + (A.bias ? __ldg(A.bias + n) : 0.f));
+                    if (n < A.N) {
+                        float v = KB > 0 ? __uint_as_float(r[j]) : 0.f;
+                        v = act_f(A.act, v + (A.bias ? __ldg(A.bias + n) : 0.f));
+                        if (mrow) v *= act_grad_f(A.mask_act, mrow[n]);
+                        yrow[n] = v;
+                    }
                 }
             }
         }

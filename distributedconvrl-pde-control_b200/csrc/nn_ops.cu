@@ -73,13 +73,14 @@ int32_t dense_layer(pdeb200_ctx* c, int M, int K, int N, const float* X, long lo
         tc::DenseArgs A;
         A.X = X; A.ldx = ldx; A.Wt = g_scr.wt; A.ldw = ldw; A.bias = bias; A.Y = Y; A.ldy = ldy;
         A.M = M; A.N = N; A.K = ldw; A.act = act;      // padded K columns are zero in Wt; X's are zeroed by the caller
+        A.mask = nullptr; A.ldm = 0; A.mask_act = 0; A.split_len = 0; A.y_split_stride = 0;
         static thread_local bool configured = false;
         if (!configured) {
-            PDEB_CUDA(c, cudaFuncSetAttribute(tc::dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+            PDEB_CUDA(c, cudaFuncSetAttribute(tc::dense_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
             configured = true;
         }
         const dim3 grid((M + tc::BM - 1) / tc::BM, (N + tc::BN - 1) / tc::BN);
-        tc::dense_tc_kernel<<<grid, 160, tc::SMEM_BYTES, c->stream>>>(A);
+        tc::dense_tc_kernel<false><<<grid, 160, tc::SMEM_BYTES, c->stream>>>(A);
         PDEB_CUDA(c, cudaGetLastError());
         c->launches += 2;
         if (used_tc) *used_tc += 1;
@@ -89,6 +90,153 @@ int32_t dense_layer(pdeb200_ctx* c, int M, int K, int N, const float* X, long lo
     dense_thin_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(M, K, N, X, ldx, W, bias, act, Y, ldy);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
+    return PDEB200_OK;
+}
+
+namespace {
+
+// Wp[k][n] = W[n + N*k] with leading dimension ldp >= N (zero padded): the Flux memory of W IS the K-major operand
+// of the input-gradient GEMM; this only fixes its row alignment.
+__global__ void pad_w_kernel(int N, int K, int ldp, const float* __restrict__ W, float* __restrict__ Wp) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * ldp) return;
+    const int k = i / ldp, n = i % ldp;
+    Wp[i] = n < N ? W[n + (size_t)N * k] : 0.f;
+}
+
+__global__ void dgrad_thin_kernel(int M, int K, int N, const float* __restrict__ dY, long long lddy, const float* __restrict__ W,
+                                  const float* __restrict__ mask, long long ldm, int mask_act, float* __restrict__ dX, long long lddx) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= (long long)M * K) return;
+    const int m = (int)(q / K), k = (int)(q % K);
+    const float* d = dY + (long long)m * lddy;
+    const float* w = W + (size_t)N * k;
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) acc = fmaf(__ldg(w + n), d[n], acc);
+    if (mask) acc *= tc::act_grad_f(mask_act, mask[(long long)m * ldm + k]);
+    dX[(long long)m * lddx + k] = acc;
+}
+
+// partial[z][n + N*k] = sum over the z-th slice of m of dY[m][n] * X[m][k]   (thin layers: N*K small)
+__global__ void wgrad_thin_kernel(int M, int K, int N, int slice, const float* __restrict__ dY, long long lddy,
+                                  const float* __restrict__ X, long long ldx, float* __restrict__ partial) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= N * K) return;
+    const int n = q % N, k = q / N;
+    const int m0 = blockIdx.y * slice, m1 = min(M, m0 + slice);
+    float acc = 0.f;
+    for (int m = m0; m < m1; ++m) acc = fmaf(dY[(long long)m * lddy + n], __ldg(X + (long long)m * ldx + k), acc);
+    partial[(size_t)blockIdx.y * N * K + q] = acc;
+}
+
+// partial[z][n] = sum over the z-th slice of m of dY[m][n]
+__global__ void colsum_kernel(int M, int N, int slice, const float* __restrict__ dY, long long lddy, float* __restrict__ partial) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int m0 = blockIdx.y * slice, m1 = min(M, m0 + slice);
+    float acc = 0.f;
+    for (int m = m0; m < m1; ++m) acc += dY[(long long)m * lddy + n];
+    partial[(size_t)blockIdx.y * N + n] = acc;
+}
+
+// out[n + N*k] (transpose = 1: partial tiles are [n][ldp] row-major) or out[q] = sum_z partial[z][...], fixed order
+__global__ void reduce_splits_kernel(int Z, int N, int K, int ldp, int transposed, const float* __restrict__ partial,
+                                     long long zstride, float* __restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= N * K) return;
+    const int n = q % N, k = q / N;
+    const long long src = transposed ? (long long)n * ldp + k : q;
+    double s = 0.0;
+    for (int z = 0; z < Z; ++z) s += (double)partial[z * zstride + src];
+    out[q] = (float)s;
+}
+
+struct GradScratch { float* p = nullptr; size_t cap = 0; float* wp = nullptr; size_t wp_cap = 0; };
+thread_local GradScratch g_gs;
+
+}  // namespace
+
+// dX[M x K] = (dY[M x N] * W) (.*) act'(mask)   -- backward through Dense to its input (Zygote pullback of W*x)
+int32_t dense_dgrad(pdeb200_ctx* c, int M, int K, int N, const float* dY, long long lddy, const float* W, const float* mask,
+                    long long ldm, int mask_act, float* dX, long long lddx, int path) {
+    const bool can_tc = lddy % 4 == 0 && N >= 8;
+    const bool want_tc = path == 2 || (path == 0 && K >= 32 && N >= 32 && M >= 64);
+    if (want_tc && can_tc) {
+        const int ldp = pad4(N);
+        int32_t rc = ensure(c, &g_gs.wp, &g_gs.wp_cap, (size_t)K * ldp);
+        if (rc) return rc;
+        pad_w_kernel<<<(K * ldp + 255) / 256, 256, 0, c->stream>>>(N, K, ldp, W, g_gs.wp);
+        tc::DenseArgs A;
+        A.X = dY; A.ldx = lddy; A.Wt = g_gs.wp; A.ldw = ldp; A.bias = nullptr; A.Y = dX; A.ldy = lddx;
+        A.M = M; A.N = K; A.K = ldp; A.act = 0; A.mask = mask; A.ldm = ldm; A.mask_act = mask_act;
+        A.split_len = 0; A.y_split_stride = 0;
+        static thread_local bool configured = false;
+        if (!configured) {
+            PDEB_CUDA(c, cudaFuncSetAttribute(tc::dense_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+            configured = true;
+        }
+        const dim3 grid((M + tc::BM - 1) / tc::BM, (K + tc::BN - 1) / tc::BN);
+        tc::dense_tc_kernel<false><<<grid, 160, tc::SMEM_BYTES, c->stream>>>(A);
+        PDEB_CUDA(c, cudaGetLastError());
+        c->launches += 2;
+        return PDEB200_OK;
+    }
+    const long long total = (long long)M * K;
+    dgrad_thin_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(M, K, N, dY, lddy, W, mask, ldm, mask_act, dX, lddx);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
+// gW[n + N*k] = sum_m dY[m][n] X[m][k],  gb[n] = sum_m dY[m][n]   (flat Flux order: W column-major (out,in), then b)
+int32_t dense_wgrad(pdeb200_ctx* c, int M, int K, int N, const float* dY, long long lddy, const float* X, long long ldx,
+                    float* gW, float* gb, int path) {
+    const bool want_tc = path == 2 || (path == 0 && K >= 32 && N >= 32 && M >= 256);
+    int32_t rc;
+    {   // one scratch allocation for every partial buffer used below (growing it later would sync the device)
+        const size_t zmax = (size_t)std::max((M + 255) / 256, 128);
+        if ((rc = ensure(c, &g_gs.p, &g_gs.cap, zmax * (size_t)N * pad4(K)))) return rc;
+    }
+    if (want_tc) {
+        const int ldp = pad4(K);
+        const int tiles = ((N + tc::BM - 1) / tc::BM) * ((K + tc::BN - 1) / tc::BN);
+        int Z = std::max(1, std::min((M + 255) / 256, (2 * 148 + tiles - 1) / tiles));
+        const int split_len = ((M + Z - 1) / Z + tc::BK - 1) / tc::BK * tc::BK;
+        Z = (M + split_len - 1) / split_len;
+        const long long zstride = (long long)N * ldp;
+        if ((rc = ensure(c, &g_gs.p, &g_gs.cap, (size_t)Z * zstride))) return rc;
+        tc::DenseArgs A;
+        A.X = dY; A.ldx = lddy; A.Wt = X; A.ldw = ldx; A.bias = nullptr; A.Y = g_gs.p; A.ldy = ldp;
+        A.M = N; A.N = K; A.K = M; A.act = 0; A.mask = nullptr; A.ldm = 0; A.mask_act = 0;
+        A.split_len = split_len; A.y_split_stride = zstride;
+        static thread_local bool configured = false;
+        if (!configured) {
+            PDEB_CUDA(c, cudaFuncSetAttribute(tc::dense_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+            configured = true;
+        }
+        const dim3 grid((N + tc::BM - 1) / tc::BM, (K + tc::BN - 1) / tc::BN, Z);
+        tc::dense_tc_kernel<true><<<grid, 160, tc::SMEM_BYTES, c->stream>>>(A);
+        reduce_splits_kernel<<<(N * K + 255) / 256, 256, 0, c->stream>>>(Z, N, K, ldp, 1, g_gs.p, zstride, gW);
+        PDEB_CUDA(c, cudaGetLastError());
+        c->launches += 2;
+    } else {
+        const int Z = std::max(1, std::min(128, M / 64));
+        const int slice = (M + Z - 1) / Z;
+        if ((rc = ensure(c, &g_gs.p, &g_gs.cap, (size_t)Z * N * K))) return rc;
+        wgrad_thin_kernel<<<dim3((N * K + 127) / 128, Z), 128, 0, c->stream>>>(M, K, N, slice, dY, lddy, X, ldx, g_gs.p);
+        reduce_splits_kernel<<<(N * K + 255) / 256, 256, 0, c->stream>>>(Z, N, K, 0, 0, g_gs.p, (long long)N * K, gW);
+        PDEB_CUDA(c, cudaGetLastError());
+        c->launches += 2;
+    }
+    {
+        const int Z = std::max(1, std::min(128, M / 64));
+        const int slice = (M + Z - 1) / Z;
+        if ((rc = ensure(c, &g_gs.p, &g_gs.cap, (size_t)Z * N))) return rc;
+        colsum_kernel<<<dim3((N + 127) / 128, Z), 128, 0, c->stream>>>(M, N, slice, dY, lddy, g_gs.p);
+        reduce_splits_kernel<<<(N + 255) / 256, 256, 0, c->stream>>>(Z, N, 1, 0, 0, g_gs.p, (long long)N, gb);
+        PDEB_CUDA(c, cudaGetLastError());
+        c->launches += 2;
+    }
     return PDEB200_OK;
 }
 

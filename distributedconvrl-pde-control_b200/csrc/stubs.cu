@@ -35,6 +35,7 @@ int32_t pdeb200_traj_episode_end(pdeb200_ctx* c) { UNSUP(c); }
 int32_t pdeb200_traj_pop_tail(pdeb200_ctx* c) { UNSUP(c); }
 int32_t pdeb200_sample(pdeb200_ctx* c, int32_t, const int64_t*, uint64_t, uint64_t) { UNSUP(c); }
 int32_t pdeb200_set_batch(pdeb200_ctx* c, int32_t, const float*, const float*, const float*, const uint8_t*, const float*) { UNSUP(c); }
+int32_t pdeb200_ddpg_set_path(pdeb200_ctx* c, int32_t) { UNSUP(c); }
 int32_t pdeb200_ddpg_critic_grads(pdeb200_ctx* c, double, int32_t, int64_t) { UNSUP(c); }
 int32_t pdeb200_ddpg_critic_apply(pdeb200_ctx* c, double) { UNSUP(c); }
 int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* c, int64_t) { UNSUP(c); }

@@ -211,6 +211,10 @@ int32_t pdeb200_ddpg_critic_apply(pdeb200_ctx* ctx, double lr);
 int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* ctx, int64_t global_batch);
 /* ADAM on the actor, then Polyak on both targets: dest = p*dest + (1-p)*src. */
 int32_t pdeb200_ddpg_actor_apply(pdeb200_ctx* ctx, double lr, double polyak);
+/* Which kernels run the update: 0 = auto (fused shared-memory kernels when the four networks fit, otherwise the
+ * layer-wise GEMM path: tcgen05 tensor cores for dense layers, CUDA cores for thin ones); 1 = layer-wise, CUDA cores
+ * only; 2 = layer-wise, tensor cores wherever the layout allows; 3 = layer-wise, automatic per-layer choice. */
+int32_t pdeb200_ddpg_set_path(pdeb200_ctx* ctx, int32_t path);
 /* Single-GPU convenience: all four phases back to back. */
 int32_t pdeb200_ddpg_update(pdeb200_ctx* ctx, double gamma, double polyak, double lr_actor, double lr_critic,
                             int32_t literal_q1);

@@ -107,3 +107,52 @@ def test_training_loop_smoke(pkg):
     n2 = pkg.agent.run_episode(pol, env)
     assert n2 == 51 and len(pol.trajectory) == 2 * 51 * B * 8
     env.close()
+
+
+@pytest.mark.parametrize("shape,path", [
+    ("wide_critic_middle", 0),      # does not fit the fused smem kernels -> layer-wise path, tensor cores for 340x340
+    ("wide_critic_middle", 1),      # same, CUDA cores only
+    ("wide_both_middle", 2),        # wide actor too, tensor cores wherever possible
+    ("ks_small", 3),                # shipped-size networks forced through the layer-wise path
+])
+@pytest.mark.parametrize("literal", [True, False])
+def test_layerwise_ddpg_update_matches_oracle(pkg, shape, path, literal):
+    """update! (PDEagent.jl:363-418) for `drop_middle_layer = false` networks: forward, input-gradient and
+    weight-gradient GEMMs (tcgen05 3xTF32 / CUDA cores) vs the oracle; three updates so ADAM state carries."""
+    rng = np.random.default_rng(12)
+    if shape == "wide_critic_middle":
+        ns, ha, hc, mid_a, mid_c, B = 12, 20, 340, False, True, 1500
+        setup = pkg.setups.KSSetup.ks22(window_size=3, temporal_steps=4)
+    elif shape == "wide_both_middle":
+        ns, ha, hc, mid_a, mid_c, B = 12, 96, 140, True, True, 777
+        setup = pkg.setups.KSSetup.ks22(window_size=3, temporal_steps=4)
+    else:
+        ns, ha, hc, mid_a, mid_c, B = 1, 6, 140, False, False, 300
+        setup = pkg.setups.KSSetup.ks22()
+    actor, _ = make_nets(rng, ns, 1, ha, hc, mid_a)
+    _, critic = make_nets(rng, ns, 1, ha, hc, mid_c)
+    env, pol = make_policy(pkg, setup, actor, critic, literal_q1=literal)
+    pol.set_update_path(path)
+    ref = AO.DDPG(actor.copy(), critic.copy())
+    for it in range(3):
+        s, a, r, t, s2 = batch(rng, ns, 1, B)
+        pol.set_batch(s, a, r, t, s2)
+        pol.update()
+        gc, ga = ref.update(s, a, r, t, s2, literal)
+        g = pol.grads()
+        nc = len(AO.flat_grads(gc))
+        # first update: identical weights on both sides -> kernel parity at 2e-5.  Later updates start from weights
+        # that already differ by the ADAM-amplified round-off (see below), so only the trajectory is compared.
+        tol_g = 2e-5 if it == 0 else 1e-3
+        assert relerr(g[:nc], AO.flat_grads(gc)) < tol_g, (it, "critic", relerr(g[:nc], AO.flat_grads(gc)))
+        assert relerr(g[nc:], AO.flat_grads(ga)) < tol_g, (it, "actor", relerr(g[nc:], AO.flat_grads(ga)))
+        # ADAM's m / sqrt(v) is scale free: for the many near-zero gradient entries of a 1e5-parameter network a
+        # summation-order difference of the gradient (checked to 2e-5 of its max above) moves the step by up to
+        # ~lr * O(1e-2), so the weights are compared at 2e-4 of their max here (2e-5 for the small networks above).
+        for dev, orc in ((pol.behavior_critic, ref.C), (pol.behavior_actor, ref.A), (pol.target_critic, ref.Ct),
+                         (pol.target_actor, ref.At)):
+            assert relerr(dev.sync_from_device().flat(), orc.flat()) < 2e-4
+        ls = pol.losses
+        assert abs(ls["critic_loss"] - float(ref.critic_loss)) < 1e-4 * max(1.0, abs(float(ref.critic_loss)))
+        assert abs(ls["actor_loss"] - float(ref.actor_loss)) < 1e-4 * max(1.0, abs(float(ref.actor_loss)))
+    env.close()
