@@ -10,12 +10,12 @@
 // misses.  Operands are therefore split on the fly, x = hi + lo with hi = x truncated to TF32, and three
 // tcgen05.mma (hi*hi, hi*lo, lo*hi) accumulate into the same fp32 TMEM tile ("3xTF32": relative error ~2^-21).
 //
-// Structure (one 128 x 128 output tile per CTA, 5 warps):
-//   warps 0-3  producers: coalesced 16-byte global loads -> hi/lo split in registers -> st.shared into the
+// Structure (one 128 x 128 output tile per CTA, 9 warps):
+//   warps 0-7  producers: coalesced 16-byte global loads -> hi/lo split in registers -> st.shared into the
 //              K-major SWIZZLE_128B canonical layout (the split needs the data in registers, hence no TMA here);
 //              3-stage ring, full/empty mbarriers; afterwards the same warps run the epilogue
 //              (tcgen05.ld 32 lanes x 32 columns -> bias + activation -> global stores).
-//   warp 4     TMEM allocation; one elected lane issues tcgen05.mma (M = 128, N = 128, K = 8 per instruction,
+//   warp 8     TMEM allocation; one elected lane issues tcgen05.mma (M = 128, N = 128, K = 8 per instruction,
 //              kind::tf32, both operands K-major from shared-memory descriptors) and tcgen05.commit.
 #pragma once
 #include <cuda_runtime.h>
@@ -28,7 +28,8 @@ constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
 constexpr int TILE_BYTES = BM * BK * 4;                    // 16 KB: 128 rows x 128 B
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;                // A_hi, A_lo, B_hi, B_lo
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int N_PRODUCERS = 128;
+constexpr int N_PRODUCERS = 256;                           // 8 producer / epilogue warps + 1 MMA warp
+constexpr int N_THREADS = N_PRODUCERS + 32;
 
 struct DenseArgs {
     // TRANSPOSED = false:  Y[M x N] = epilogue(X[M x K] * Wt[N x K]^T)
@@ -104,16 +105,17 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 
 __device__ __forceinline__ void load_tile(const float* __restrict__ src, long long ld, int row0, int n_rows, int k0, int K,
                                           unsigned char* hi_tile, unsigned char* lo_tile, int tid) {
-    float4 v[8];
+    constexpr int ITS = BM * 8 / N_PRODUCERS;
+    float4 v[ITS];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < ITS; ++it) {
         const int q = it * N_PRODUCERS + tid, row = q >> 3, c = q & 7;
         const int gr = row0 + row, gk = k0 + c * 4;
         v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gr < n_rows && gk < K) v[it] = __ldg(reinterpret_cast<const float4*>(src + (long long)gr * ld + gk));
     }
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < ITS; ++it) {
         const int q = it * N_PRODUCERS + tid, row = q >> 3, c = q & 7;
         const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
         float4 hi, lo;
@@ -124,23 +126,24 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ src, long lo
 }
 
 // Transposing producer: tile row r <-> column (col0 + r) of a row-major array whose ROWS are the contraction index.
-// Thread tid owns tile row tid: 32 coalesced scalar loads (consecutive threads read consecutive addresses), then the
-// row is written as 8 swizzled 16-byte chunks.
+// Thread tid owns half of tile row (tid & 127): 16 coalesced scalar loads (consecutive threads read consecutive
+// addresses), then 4 swizzled 16-byte chunks of the row.
 __device__ __forceinline__ void load_tile_t(const float* __restrict__ src, long long ld, int col0, int n_cols, int k0, int k_end,
                                             unsigned char* hi_tile, unsigned char* lo_tile, int tid) {
-    float v[32];
-    const int gc = col0 + tid;
+    float v[16];
+    const int row = tid & 127, half = tid >> 7;
+    const int gc = col0 + row;
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-        const int gk = k0 + j;
+    for (int j = 0; j < 16; ++j) {
+        const int gk = k0 + 16 * half + j;
         v[j] = (gc < n_cols && gk < k_end) ? __ldg(src + (long long)gk * ld + gc) : 0.f;
     }
-    const int row = tid;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int cc = 0; cc < 4; ++cc) {
+        const int c = 4 * half + cc;
         const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
         float4 hi, lo;
-        split4(make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]), hi, lo);
+        split4(make_float4(v[4 * cc], v[4 * cc + 1], v[4 * cc + 2], v[4 * cc + 3]), hi, lo);
         *reinterpret_cast<float4*>(hi_tile + off) = hi;
         *reinterpret_cast<float4*>(lo_tile + off) = lo;
     }
@@ -153,7 +156,7 @@ __device__ __forceinline__ float act_grad_f(int kind, float out) {
 }
 
 template <bool TRANSPOSED>
-__global__ void __launch_bounds__(160, 1) dense_tc_kernel(const __grid_constant__ DenseArgs A) {
+__global__ void __launch_bounds__(N_THREADS, 1) dense_tc_kernel(const __grid_constant__ DenseArgs A) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = s32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B atoms need 1024-byte alignment
@@ -173,7 +176,8 @@ __global__ void __launch_bounds__(160, 1) dense_tc_kernel(const __grid_constant_
         bar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    constexpr int MMA_WARP = N_PRODUCERS / 32;
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "n"(BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(160, 1) dense_tc_kernel(const __grid_constant_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 4) {
+    if (warp < MMA_WARP) {
         // ===== producers =====
         const int tid = threadIdx.x;
         for (int kb = 0; kb < KB; ++kb) {
@@ -199,15 +203,16 @@ __global__ void __launch_bounds__(160, 1) dense_tc_kernel(const __grid_constant_
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
             bar_arrive(full0 + 8 * s);
         }
-        // ===== epilogue: this warp owns TMEM lanes [32 warp, 32 warp + 32) = output rows =====
+        // ===== epilogue: warp w reads TMEM lanes [32 (w & 3), +32) = output rows, column half (w >> 2) =====
         if (KB > 0) bar_wait(tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m0 + warp * 32 + lane;
+        const int lq = warp & 3;
+        const int row = m0 + lq * 32 + lane;
         float* const Yz = A.Y + (TRANSPOSED ? (long long)blockIdx.z * A.y_split_stride : 0);
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
+        for (int c0 = (warp >> 2) * (BN / 2); c0 < (warp >> 2) * (BN / 2) + BN / 2; c0 += 32) {
             uint32_t r[32];
-            const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -261,7 +266,7 @@ __global__ void __launch_bounds__(160, 1) dense_tc_kernel(const __grid_constant_
         }
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
     }

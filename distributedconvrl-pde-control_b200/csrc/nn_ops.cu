@@ -33,6 +33,49 @@ __global__ void dense_thin_kernel(int M, int K, int N, const float* __restrict__
     Y[(long long)m * ldy + n] = tc::act_f(act, acc + b[n]);
 }
 
+// Thin contraction, wide output (e.g. 13 -> 340): four output units per thread, float4 weight loads and stores.
+__global__ void dense_thin4_kernel(int M, int K, int N, const float* __restrict__ X, long long ldx, const float* __restrict__ W,
+                                   const float* __restrict__ b, int act, float* __restrict__ Y, long long ldy) {
+    const int n4 = N >> 2;
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (q >= (long long)M * n4) return;
+    const int m = (int)(q / n4), n = (int)(q % n4) * 4;
+    const float* x = X + (long long)m * ldx;
+    float4 acc = __ldg(reinterpret_cast<const float4*>(b + n));
+    for (int k = 0; k < K; ++k) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(W + n + (size_t)N * k));
+        const float xv = x[k];
+        acc.x = fmaf(w.x, xv, acc.x); acc.y = fmaf(w.y, xv, acc.y); acc.z = fmaf(w.z, xv, acc.z); acc.w = fmaf(w.w, xv, acc.w);
+    }
+    acc.x = tc::act_f(act, acc.x); acc.y = tc::act_f(act, acc.y); acc.z = tc::act_f(act, acc.z); acc.w = tc::act_f(act, acc.w);
+    *reinterpret_cast<float4*>(Y + (long long)m * ldy + n) = acc;
+}
+
+// Narrow heads (N <= 8, e.g. the 340 -> 1 output of the critic): one warp per column, lanes stride over K so the
+// row is read coalesced, shuffle reduction.
+template <int NMAX>
+__global__ void dense_head_kernel(int M, int K, int N, const float* __restrict__ X, long long ldx, const float* __restrict__ W,
+                                  const float* __restrict__ b, int act, float* __restrict__ Y, long long ldy) {
+    const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (m >= M) return;
+    const float* x = X + (long long)m * ldx;
+    float acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+    for (int k = lane; k < K; k += 32) {
+        const float xv = x[k];
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n)
+            if (n < N) acc[n] = fmaf(__ldg(W + n + (size_t)N * k), xv, acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[n] += __shfl_xor_sync(0xffffffffu, acc[n], o);
+    if (lane == 0)
+        for (int n = 0; n < N; ++n) Y[(long long)m * ldy + n] = tc::act_f(act, acc[n] + b[n]);
+}
+
 __global__ void pad_rows_kernel(long long M, int K, int ld, float* X) {       // zero the padding columns [K, ld)
     const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int w = ld - K;
@@ -80,14 +123,22 @@ int32_t dense_layer(pdeb200_ctx* c, int M, int K, int N, const float* X, long lo
             configured = true;
         }
         const dim3 grid((M + tc::BM - 1) / tc::BM, (N + tc::BN - 1) / tc::BN);
-        tc::dense_tc_kernel<false><<<grid, 160, tc::SMEM_BYTES, c->stream>>>(A);
+        tc::dense_tc_kernel<false><<<grid, tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A);
         PDEB_CUDA(c, cudaGetLastError());
         c->launches += 2;
         if (used_tc) *used_tc += 1;
         return PDEB200_OK;
     }
     const long long total = (long long)M * N;
-    dense_thin_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(M, K, N, X, ldx, W, bias, act, Y, ldy);
+    if (N <= 8 && K >= 64) {
+        if (N == 1) dense_head_kernel<1><<<(M + 7) / 8, 256, 0, c->stream>>>(M, K, N, X, ldx, W, bias, act, Y, ldy);
+        else dense_head_kernel<8><<<(M + 7) / 8, 256, 0, c->stream>>>(M, K, N, X, ldx, W, bias, act, Y, ldy);
+    } else if (N % 4 == 0 && ldy % 4 == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0 &&
+               ((size_t)K * N) % 4 == 0) {
+        const long long t4 = total / 4;
+        dense_thin4_kernel<<<(unsigned)((t4 + 255) / 256), 256, 0, c->stream>>>(M, K, N, X, ldx, W, bias, act, Y, ldy);
+    } else
+        dense_thin_kernel<<<(unsigned)((total + 255) / 256), 256, 0, c->stream>>>(M, K, N, X, ldx, W, bias, act, Y, ldy);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
@@ -176,7 +227,7 @@ int32_t dense_dgrad(pdeb200_ctx* c, int M, int K, int N, const float* dY, long l
             configured = true;
         }
         const dim3 grid((M + tc::BM - 1) / tc::BM, (K + tc::BN - 1) / tc::BN);
-        tc::dense_tc_kernel<false><<<grid, 160, tc::SMEM_BYTES, c->stream>>>(A);
+        tc::dense_tc_kernel<false><<<grid, tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A);
         PDEB_CUDA(c, cudaGetLastError());
         c->launches += 2;
         return PDEB200_OK;
@@ -215,7 +266,7 @@ int32_t dense_wgrad(pdeb200_ctx* c, int M, int K, int N, const float* dY, long l
             configured = true;
         }
         const dim3 grid((N + tc::BM - 1) / tc::BM, (K + tc::BN - 1) / tc::BN, Z);
-        tc::dense_tc_kernel<true><<<grid, 160, tc::SMEM_BYTES, c->stream>>>(A);
+        tc::dense_tc_kernel<true><<<grid, tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A);
         reduce_splits_kernel<<<(N * K + 255) / 256, 256, 0, c->stream>>>(Z, N, K, ldp, 1, g_gs.p, zstride, gW);
         PDEB_CUDA(c, cudaGetLastError());
         c->launches += 2;
