@@ -277,6 +277,7 @@ def run_ours(args):
         env.rollout(1)
     torch.cuda.synchronize()
     env.reset()
+    fma_peak = env.measure_fma_peak()            # measured CUDA-core peak of THIS GPU for the compute dtype (TFLOP/s)
     launches0 = env.launch_count
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -379,10 +380,13 @@ def run_ours(args):
                 "algorithmic_bytes_per_env_step": bytes_env, "kernel_ms": avg_ms,
                 "note": "at oversampling=30 the step is FP64-pipe/shared-memory bound (arithmetic intensity ~%d flop/B), "
                         "so the HBM fraction is small by construction; see fp_pipe" % round(flops_env / bytes_env),
+                "binding_roof": "fp_pipe (%s CUDA-core FMA)" % args.dtype,
                 "fp_pipe": {"algorithmic_flops_per_env_step": flops_env,
                             "achieved_tflops": flops_env * B / (avg_ms * 1e-3) / 1e12,
-                            "nominal_peak_tflops": 37.0 if args.dtype == "f64" else 75.0,
-                            "frac_of_nominal": flops_env * B / (avg_ms * 1e-3) / 1e12 / (37.0 if args.dtype == "f64" else 75.0)}}
+                            "measured_peak_tflops": fma_peak,
+                            "peak_source": "pdeb200_measure_fma_peak: FMA micro-kernel on this GPU, same run",
+                            "frac": flops_env * B / (avg_ms * 1e-3) / 1e12 / fma_peak if fma_peak else None,
+                            "nominal_peak_tflops": 37.0 if args.dtype == "f64" else 75.0}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -77,14 +77,13 @@ __global__ void __launch_bounds__(256) actuate_kernel(const __grid_constant__ Ac
     off = (off + 15) & ~(size_t)15;
     float* s_par = reinterpret_cast<float*>(smem_raw + off);
     float* s_x = s_par + A.actor_np;
-    const int env0 = blockIdx.x * E;
-
     if (A.stage_table)
         for (size_t i = tid; i < ntab; i += BD) { s_w[i] = __ldg(A.act_w + i); s_idx[i] = __ldg(A.act_idx + i); }
-    if (A.use_actor) {
+    if (A.use_actor)
         for (int i = tid; i < A.actor_np; i += BD) s_par[i] = A.actor.params[i];
-        __syncthreads();
-    }
+    __syncthreads();
+    // persistent over groups of E environments: the tables above are staged once per CTA
+    for (int env0 = blockIdx.x * E; env0 < A.n_envs; env0 += gridDim.x * E) {
     if (A.use_actor && A.mono) {
         // global agent: one column per env with n_act outputs
         for (int e = tid; e < E; e += BD) {
@@ -144,6 +143,8 @@ __global__ void __launch_bounds__(256) actuate_kernel(const __grid_constant__ Ac
             acc += (A.power * s_a[e * A.n_act + i]) * wp[(size_t)j * A.npts + n];
         }
         A.p[(size_t)env * A.npts + n] = acc;
+    }
+    __syncthreads();                     // s_a / activations are reused by the next group
     }
 }
 

@@ -183,7 +183,15 @@ int32_t actuate_t(pdeb200_ctx* c, const void* actions_dev, int use_actor, double
     if (smem > 200 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "actuate: actor too large for shared memory");
     if (smem > 48 * 1024)
         PDEB_CUDA(c, cudaFuncSetAttribute(actuate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    actuate_kernel<T><<<(c->cfg.n_envs + E - 1) / E, tpb, smem, c->stream>>>(A);
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+    const int groups = (c->cfg.n_envs + E - 1) / E;
+    const int per_sm = std::max(1, std::min(8, (int)((200 * 1024) / std::max<size_t>(smem, 1))));
+    // whole waves of persistent CTAs: every CTA gets the same number of groups when the batch allows it
+    const int resident = n_sm * per_sm;
+    const int rounds = (groups + resident - 1) / resident;
+    const int grid = std::min(groups, (groups + rounds - 1) / rounds);
+    actuate_kernel<T><<<grid, tpb, smem, c->stream>>>(A);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
@@ -244,6 +252,24 @@ int32_t do_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_ac
     }
     if (c->timing) { cudaEventRecord(c->ev1, c->stream); c->timed = true; }
     return PDEB200_OK;
+}
+
+// FMA micro-benchmark: measured CUDA-core peak for the roofline denominators (MEASURED_PEAKS.json has HBM and
+// bf16 tensor numbers only).  8 independent chains per thread, 2 flops per FMA.
+template <typename T>
+__global__ void __launch_bounds__(256) fma_peak_kernel(int iters, T seed, T* out) {
+    T a0 = seed, a1 = seed + T(1), a2 = seed + T(2), a3 = seed + T(3), a4 = seed + T(4), a5 = seed + T(5), a6 = seed + T(6),
+      a7 = seed + T(7);
+    const T m = T(0.999999), c = T(1e-6) * (T)threadIdx.x;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+            a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+        }
+    }
+    const T r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == T(-1)) out[0] = r;                       // never true: keeps the chains alive
 }
 
 struct ArrInfo { void* ptr; size_t bytes; };
@@ -664,6 +690,33 @@ int32_t pdeb200_last_step_ms(pdeb200_ctx* c, float* ms) {
     if (!c->timed) return fail(c, PDEB200_ESTATE, "last_step_ms: timing not enabled or no step yet");
     PDEB_CUDA(c, cudaEventSynchronize(c->ev1));
     PDEB_CUDA(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_measure_fma_peak(pdeb200_ctx* c, int32_t dtype, double* tflops) {
+    if (!c || !tflops) return fail(c, PDEB200_EINVAL, "measure_fma_peak: null argument");
+    cudaSetDevice(c->device);
+    int n_sm = 148;
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
+    const int iters = 4096, grid = n_sm * 8, tpb = 256;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0, c->stream);
+        if (dtype == PDEB200_F64) fma_peak_kernel<double><<<grid, tpb, 0, c->stream>>>(iters, 1.0, (double*)c->vmax);
+        else fma_peak_kernel<float><<<grid, tpb, 0, c->stream>>>(iters, 1.f, (float*)c->vmax);
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double fl = 2.0 * 64.0 * iters * (double)grid * tpb;
+        if (rep > 0 && ms > 0.f) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 4;
+    *tflops = best;
     return PDEB200_OK;
 }
 

@@ -287,6 +287,15 @@ class PDEenv:
         L.check(self._lib.pdeb200_step_cost(self._ctx, C.byref(b), C.byref(f)), self._ctx)
         return b.value, f.value
 
+    def measure_fma_peak(self, dtype=None):
+        """Measured CUDA-core FMA peak (TFLOP/s) for "f32" / "f64" (default: the context dtype)."""
+        dt = self.cfg.dtype if dtype is None else (L.F64 if dtype in ("f64", L.F64) and dtype != L.F32 else L.F32)
+        if dtype == "f32":
+            dt = L.F32
+        out = C.c_double()
+        L.check(self._lib.pdeb200_measure_fma_peak(self._ctx, dt, C.byref(out)), self._ctx)
+        return out.value
+
     @property
     def launch_count(self):
         return int(self._lib.pdeb200_launch_count(self._ctx))

@@ -226,6 +226,9 @@ int64_t pdeb200_launch_count(const pdeb200_ctx* ctx);
  * context's stream (ms); used for the roofline line.  */
 int32_t pdeb200_last_step_ms(pdeb200_ctx* ctx, float* ms);
 int32_t pdeb200_enable_step_timing(pdeb200_ctx* ctx, int32_t on);
+/* Measured CUDA-core FMA peak of this GPU (TFLOP/s, 2 flops per FMA) for dtype PDEB200_F32 / F64: the roofline
+ * denominator of the FP-pipe bound kernels (MEASURED_PEAKS.json only carries HBM and bf16 tensor numbers). */
+int32_t pdeb200_measure_fma_peak(pdeb200_ctx* ctx, int32_t dtype, double* tflops);
 /* Algorithmic HBM bytes and flops of one env step for this configuration. */
 int32_t pdeb200_step_cost(const pdeb200_ctx* ctx, double* hbm_bytes_per_env, double* flops_per_env);
 

@@ -10,7 +10,7 @@ module B200PDE
 
 const LIB = get(ENV, "PDEB200_LIB", joinpath(@__DIR__, "..", "distributedconvrl-pde-control_b200", "libpdeb200.so"))
 
-const KS, KSEG1D, NS2D = Int32(0), Int32(1), Int32(2)
+const KS, KSEG1D, NS2D, KSEG2D = Int32(0), Int32(1), Int32(2), Int32(3)
 const F32, F64 = Int32(0), Int32(1)
 const ARR_Y, ARR_P, ARR_STATE, ARR_ACTION, ARR_DELTA_ACTION, ARR_REWARD, ARR_DONE, ARR_TIME, ARR_STEPS =
     Int32.(0:8)
@@ -139,5 +139,58 @@ policy_act!(c::Ctx; act_noise = 0.0, act_limit = 1.0, noise = nothing) =
 ddpg_update!(c::Ctx; γ = 0.99, p = 0.995, lr_actor = 5e-4, lr_critic = 1e-3, literal_q1 = true) =
     check(ccall((:pdeb200_ddpg_update, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Float64, Int32),
                 c.ptr, γ, p, lr_actor, lr_critic, Int32(literal_q1)), c.ptr)
+
+# (app::CustomNeuralNetworkApproximator)(x), src/custom_nna.jl:13: x is (rows, n_cols) Float32; dense layers run on
+# the tensor cores (tcgen05, 3xTF32), thin ones on CUDA cores.  path: 0 auto, 1 CUDA cores, 2 tensor cores.
+function net_forward(c::Ctx, net::Int32, x::Matrix{Float32}, n_out::Integer; path = 0)
+    y = Matrix{Float32}(undef, n_out, size(x, 2))
+    used = Ref{Int32}(0)
+    check(ccall((:pdeb200_net_forward, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float32}, Ptr{Float32}, Int32, Ref{Int32}),
+                c.ptr, net, Int32(size(x, 2)), x, y, Int32(path), used), c.ptr)
+    y
+end
+
+# A device-backed approximator with the method set of src/custom_nna.jl:7-27.  `model` (a Flux Chain) stays the
+# host-side source of truth for save()/load(); `sync!` pulls the trained parameters back into it.
+mutable struct DeviceApproximator
+    ctx::Ctx
+    net::Int32
+    model
+    n_out::Int
+end
+(app::DeviceApproximator)(x) = net_forward(app.ctx, app.net, Matrix{Float32}(x), app.n_out)
+function upload!(app::DeviceApproximator, sizes::Vector{Int32}, acts::Vector{Int32})
+    net_set!(app.ctx, app.net, sizes, acts, Vector{Float32}(flatten(app.model)))
+end
+
+# ---- device-resident CircularArraySARTTrajectory (src/PDEagent.jl:237-340) ----------------------------------
+# The trajectory `update!` overloads of PDEagent.jl push one transition per actuator column; with the batch
+# folded into the column axis these become four calls on device buffers.
+traj_create!(c::Ctx, capacity::Integer) =
+    check(ccall((:pdeb200_traj_create, LIB), Int32, (Ptr{Cvoid}, Int64), c.ptr, Int64(capacity)), c.ptr)
+traj_pre_episode!(c::Ctx) = check(ccall((:pdeb200_traj_pop_tail, LIB), Int32, (Ptr{Cvoid},), c.ptr), c.ptr)       # :237-252
+traj_pre_act!(c::Ctx) = check(ccall((:pdeb200_traj_push_pre, LIB), Int32, (Ptr{Cvoid},), c.ptr), c.ptr)           # :254-274
+traj_post_act!(c::Ctx) = check(ccall((:pdeb200_traj_push_post, LIB), Int32, (Ptr{Cvoid},), c.ptr), c.ptr)         # :276-289
+traj_post_episode!(c::Ctx) = check(ccall((:pdeb200_traj_episode_end, LIB), Int32, (Ptr{Cvoid},), c.ptr), c.ptr)   # :291-314
+function traj_length(c::Ctx)
+    n = Ref{Int64}(0)
+    check(ccall((:pdeb200_traj_length, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), c.ptr, n), c.ptr)
+    n[]
+end
+# pde_sample (:317-340): inds ~ U{1 .. length - number_actuators}; s' = state[inds .+ number_actuators]
+sample!(c::Ctx, batch::Integer; seed = 0, offset = 0) =
+    check(ccall((:pdeb200_sample, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, UInt64, UInt64),
+                c.ptr, Int32(batch), C_NULL, UInt64(seed), UInt64(offset)), c.ptr)
+
+# 0 = auto (fused shared-memory kernels / layer-wise GEMM path for wide networks), 1-3 force the layer-wise path
+ddpg_set_path!(c::Ctx, path::Integer) =
+    check(ccall((:pdeb200_ddpg_set_path, LIB), Int32, (Ptr{Cvoid}, Int32), c.ptr, Int32(path)), c.ptr)
+
+# fused evaluation roll-out (src/plotting.jl:55-73): n_steps x { actor forward -> env step } on the device
+function rollout!(c::Ctx, n_steps::Integer, n_envs::Integer; act_limit = 1.0)
+    rs = zeros(Float64, n_envs)
+    check(ccall((:pdeb200_rollout, LIB), Int32, (Ptr{Cvoid}, Int32, Float64, Ptr{Float64}), c.ptr, Int32(n_steps), act_limit, rs), c.ptr)
+    rs
+end
 
 end # module
