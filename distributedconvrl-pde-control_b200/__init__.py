@@ -6,4 +6,5 @@ from . import _lib as lib  # noqa: F401
 from ._lib import PdeB200Error  # noqa: F401
 from .env import PDEenv  # noqa: F401
 from . import setups  # noqa: F401
-from . import agent, parallel  # noqa: F401,E402
+from . import agent, parallel, checkpoint, hook  # noqa: F401,E402
+from .hook import PDEhook  # noqa: F401,E402

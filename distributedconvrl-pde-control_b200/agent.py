@@ -283,7 +283,7 @@ def run_episode(policy, env, hook=None, learning=True, max_steps=None):
     if learning:
         traj.pre_episode()
     if hook is not None:
-        hook.pre_episode(env)
+        hook.pre_episode(env, policy)
     steps = 0
     while True:
         policy(env, learning=learning)

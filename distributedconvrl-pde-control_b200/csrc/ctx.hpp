@@ -78,7 +78,7 @@ struct pdeb200_ctx {
     void* agent = nullptr;
 
     // timing
-    bool timing = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr; bool timed = false;
+    bool timing = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr; bool timed = false;
 };
 
 namespace pdeb200 {

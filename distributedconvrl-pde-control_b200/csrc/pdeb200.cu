@@ -246,7 +246,10 @@ int32_t do_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_ac
     for (int s = 0; s < n_steps; ++s) {
         int32_t rc = f64 ? actuate_t<double>(c, actions_dev, use_actor, act_limit) : actuate_t<float>(c, actions_dev, use_actor, act_limit);
         if (rc) return rc;
+        const bool tc = c->timing && s == n_steps - 1;            // CUDA events around the core (dominant) kernel
+        if (tc) cudaEventRecord(c->evc0, c->stream);
         if ((rc = core_step(c))) return rc;
+        if (tc) cudaEventRecord(c->evc1, c->stream);
         rc = f64 ? observe_t<double>(c, 0, nullptr, d_rsum) : observe_t<float>(c, 0, nullptr, d_rsum);
         if (rc) return rc;
     }
@@ -364,7 +367,7 @@ int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** 
     if (prop.major < 10) return bail(fail(c, PDEB200_EUNSUPPORTED, "pdeb200 kernels are built for sm_100a (B200) only"));
     if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(c, PDEB200_ECUDA, "cudaStreamCreate failed"));
-    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1);
+    cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1); cudaEventCreate(&c->evc0); cudaEventCreate(&c->evc1);
     c->esz = cfg->dtype == PDEB200_F64 ? 8 : 4;
     c->a_rows = 1 + cfg->memory_size;
     switch (cfg->problem) {
@@ -425,6 +428,8 @@ int32_t pdeb200_destroy(pdeb200_ctx* c) {
             if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->evc0) cudaEventDestroy(c->evc0);
+    if (c->evc1) cudaEventDestroy(c->evc1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return PDEB200_OK;
@@ -717,6 +722,14 @@ int32_t pdeb200_measure_fma_peak(pdeb200_ctx* c, int32_t dtype, double* tflops) 
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 4;
     *tflops = best;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_last_core_ms(pdeb200_ctx* c, float* ms) {
+    if (!c || !ms) return PDEB200_EINVAL;
+    if (!c->timed) return fail(c, PDEB200_ESTATE, "last_core_ms: timing not enabled or no step yet");
+    PDEB_CUDA(c, cudaEventSynchronize(c->evc1));
+    PDEB_CUDA(c, cudaEventElapsedTime(ms, c->evc0, c->evc1));
     return PDEB200_OK;
 }
 

@@ -16,86 +16,21 @@ reward[1..T], then currentNNA (W1, b1, W2, b2).
 (PDEhook fields: /root/reference/src/PDEhook.jl:8-31; DataFrame row written at
 PDEhook.jl:51-63.)
 """
-import re
-import struct
 import sys
 from pathlib import Path
 
 import numpy as np
 
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+
 REF = Path("/root/reference")
 OUT = Path(__file__).resolve().parent.parent / "tests" / "golden"
 
 
-def _parse_ohdr(b, off):
-    """Return (dims, dtype, data bytes) for a numeric dataset header, else None."""
-    if b[off:off + 4] != b"OHDR" or b[off + 4] != 2:
-        return None
-    flags = b[off + 5]
-    pos = off + 6
-    if flags & 0x20:
-        pos += 16                      # access/mod/change/birth times
-    if flags & 0x10:
-        pos += 4                       # max compact / min dense attributes
-    szw = 1 << (flags & 3)
-    chunk0 = int.from_bytes(b[pos:pos + szw], "little")
-    pos += szw
-    end = pos + chunk0
-    dims = dtype = data = None
-    while pos + 4 <= end:
-        mtype = b[pos]
-        msize = struct.unpack_from("<H", b, pos + 1)[0]
-        pos += 4
-        if flags & 0x04:
-            pos += 2                   # creation order
-        body = b[pos:pos + msize]
-        if mtype == 0x01 and len(body) >= 4 and body[0] == 2:
-            rank = body[1]
-            dims = [struct.unpack_from("<Q", body, 4 + 8 * i)[0] for i in range(rank)]
-        elif mtype == 0x03 and len(body) >= 8:
-            cls = body[0] & 0x0F
-            size = struct.unpack_from("<I", body, 4)[0]
-            if cls == 1 and size in (4, 8):
-                dtype = np.dtype("<f%d" % size)
-            elif cls == 0 and size in (1, 2, 4, 8):
-                signed = (body[1] >> 3) & 1
-                dtype = np.dtype("<%s%d" % ("i" if signed else "u", size))
-        elif mtype == 0x08 and len(body) >= 2 and body[0] == 4:
-            lclass = body[1]
-            if lclass == 0:
-                n = struct.unpack_from("<H", body, 2)[0]
-                data = body[4:4 + n]
-            elif lclass == 1:
-                addr, n = struct.unpack_from("<QQ", body, 2)
-                if addr != 0xFFFFFFFFFFFFFFFF:
-                    data = b[addr:addr + n]
-        pos += msize
-    if dims is None or dtype is None or data is None:
-        return None
-    count = int(np.prod(dims)) if dims else 1
-    if count * dtype.itemsize != len(data):
-        return None
-    arr = np.frombuffer(data, dtype=dtype).reshape(dims if dims else ())
-    return arr
+import importlib
 
-
-def numeric_arrays(path, float_only=True):
-    """All numeric dataset arrays of a JLD2 file, in file order.
-
-    HDF5 dims are C-order over the same bytes Julia wrote column-major, so the
-    returned array is the *transpose* of the Julia array: a Julia (h, ns) weight
-    matrix comes back as (ns, h).  We transpose back to Julia's shape.
-    """
-    b = Path(path).read_bytes()
-    out = []
-    for m in re.finditer(b"OHDR", b):
-        arr = _parse_ohdr(b, m.start())
-        if arr is None:
-            continue
-        if float_only and arr.dtype.kind != "f":
-            continue
-        out.append((m.start(), np.ascontiguousarray(arr.T)))
-    return out
+_ckpt = importlib.import_module("distributedconvrl-pde-control_b200.checkpoint")
+numeric_arrays = _ckpt.numeric_arrays          # the JLD2 reader lives in the product (checkpoint compatibility)
 
 
 def hook_fixture(path, n_state_rows=None):
