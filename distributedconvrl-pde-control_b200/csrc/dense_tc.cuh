@@ -10,11 +10,13 @@
 // misses.  Operands are therefore split on the fly, x = hi + lo with hi = x truncated to TF32, and three
 // tcgen05.mma (hi*hi, hi*lo, lo*hi) accumulate into the same fp32 TMEM tile ("3xTF32": relative error ~2^-21).
 //
-// Structure (one 128 x 128 output tile per CTA, 9 warps):
+// Structure (one 128 x 128 output tile per CTA, 9 warps; BK = 16 / SWIZZLE_64B with two CTAs per SM was measured
+// and is slower: twice the barrier round trips per tile):
 //   warps 0-7  producers: coalesced 16-byte global loads -> hi/lo split in registers -> st.shared into the
 //              K-major SWIZZLE_128B canonical layout (the split needs the data in registers, hence no TMA here);
-//              3-stage ring, full/empty mbarriers; afterwards the same warps run the epilogue
-//              (tcgen05.ld 32 lanes x 32 columns -> bias + activation -> global stores).
+//              register double-buffered (the next k-block's loads fly while this one is split and stored), 3-stage ring, full/empty mbarriers; afterwards the same warps run the epilogue
+//              (tcgen05.ld 32 lanes x 32 columns -> transpose through the now idle stage memory -> bias + activation
+//              [x act'(mask)] -> coalesced 256-byte row stores).
 //   warp 8     TMEM allocation; one elected lane issues tcgen05.mma (M = 128, N = 128, K = 8 per instruction,
 //              kind::tf32, both operands K-major from shared-memory descriptors) and tcgen05.commit.
 #pragma once
@@ -25,7 +27,10 @@ namespace pdeb200 {
 namespace tc {
 
 constexpr int BM = 128, BN = 128, BK = 32, STAGES = 3;
-constexpr int TILE_BYTES = BM * BK * 4;                    // 16 KB: 128 rows x 128 B
+constexpr int ROW_BYTES = BK * 4;                          // 128 B rows -> SWIZZLE_128B (BK = 16: 64 B rows -> SWIZZLE_64B)
+constexpr int CHUNKS = ROW_BYTES / 16;                     // 16-byte chunks per tile row
+constexpr int ATOM_BYTES = 8 * ROW_BYTES;                  // 8-row swizzle atom = stride between row groups (SBO)
+constexpr int TILE_BYTES = BM * ROW_BYTES;                 // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;                // A_hi, A_lo, B_hi, B_lo
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 constexpr int N_PRODUCERS = 256;                           // 8 producer / epilogue warps + 1 MMA warp
@@ -65,15 +70,22 @@ __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
-// K-major, SWIZZLE_128B canonical layout: rows of 128 B, 8-row groups 1024 B apart (SBO), 16-byte chunk c of
-// row r stored at chunk (c ^ (r & 7)).  Descriptor fields as in cute::UMMA::SmemDescriptor (sm_100).
+// K-major swizzled canonical layout (cute::UMMA K-major "B64" / "B128"): rows of ROW_BYTES, 8-row groups
+// ATOM_BYTES apart (SBO); the 16-byte chunk c of row r is stored at chunk
+//   c ^ ((r >> 1) & 3)  for 64-byte rows  (Swizzle<2,4,3>: address bits [7,9) xor-ed into bits [4,6))
+//   c ^ (r & 7)         for 128-byte rows (Swizzle<3,4,3>).
+// Descriptor fields as in cute::UMMA::SmemDescriptor (sm_100).
+__device__ __forceinline__ int swizzled_offset(int row, int c) {
+    const int x = ROW_BYTES == 64 ? ((row >> 1) & 3) : (row & 7);
+    return (row >> 3) * ATOM_BYTES + (row & 7) * ROW_BYTES + ((c ^ x) << 4);
+}
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
     uint64_t d = 0;
     d |= (uint64_t)((addr >> 4) & 0x3FFF);           // start address
     d |= (uint64_t)1 << 16;                          // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                // stride byte offset
+    d |= (uint64_t)(ATOM_BYTES >> 4) << 32;          // stride byte offset
     d |= (uint64_t)1 << 46;                          // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
+    d |= (uint64_t)(ROW_BYTES == 64 ? 4 : 2) << 61;  // SWIZZLE_64B / SWIZZLE_128B
     return d;
 }
 
@@ -103,21 +115,26 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
     hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
 }
 
-__device__ __forceinline__ void load_tile(const float* __restrict__ src, long long ld, int row0, int n_rows, int k0, int K,
-                                          unsigned char* hi_tile, unsigned char* lo_tile, int tid) {
-    constexpr int ITS = BM * 8 / N_PRODUCERS;
-    float4 v[ITS];
+constexpr int ITS = BM * CHUNKS / N_PRODUCERS;  // 16-byte chunks per producer thread and tile
+constexpr int KT = BK / 2;                      // contraction elements per thread of the transposing producer
+
+// global -> registers (coalesced 16-byte loads); the split + st.shared happens one k-block later (store_tile), so a
+// k-block's loads are in flight while the previous one is converted and the ring slot is awaited
+__device__ __forceinline__ void fetch_tile(const float* __restrict__ src, long long ld, int row0, int n_rows, int k0, int K,
+                                           float4 (&v)[ITS], int tid) {
 #pragma unroll
     for (int it = 0; it < ITS; ++it) {
-        const int q = it * N_PRODUCERS + tid, row = q >> 3, c = q & 7;
+        const int q = it * N_PRODUCERS + tid, row = q / CHUNKS, c = q % CHUNKS;
         const int gr = row0 + row, gk = k0 + c * 4;
         v[it] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gr < n_rows && gk < K) v[it] = __ldg(reinterpret_cast<const float4*>(src + (long long)gr * ld + gk));
     }
+}
+__device__ __forceinline__ void store_tile(const float4 (&v)[ITS], unsigned char* hi_tile, unsigned char* lo_tile, int tid) {
 #pragma unroll
     for (int it = 0; it < ITS; ++it) {
-        const int q = it * N_PRODUCERS + tid, row = q >> 3, c = q & 7;
-        const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+        const int q = it * N_PRODUCERS + tid, row = q / CHUNKS, c = q % CHUNKS;
+        const int off = swizzled_offset(row, c);
         float4 hi, lo;
         split4(v[it], hi, lo);
         *reinterpret_cast<float4*>(hi_tile + off) = hi;
@@ -126,26 +143,53 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ src, long lo
 }
 
 // Transposing producer: tile row r <-> column (col0 + r) of a row-major array whose ROWS are the contraction index.
-// Thread tid owns half of tile row (tid & 127): 16 coalesced scalar loads (consecutive threads read consecutive
-// addresses), then 4 swizzled 16-byte chunks of the row.
-__device__ __forceinline__ void load_tile_t(const float* __restrict__ src, long long ld, int col0, int n_cols, int k0, int k_end,
-                                            unsigned char* hi_tile, unsigned char* lo_tile, int tid) {
-    float v[16];
+// Thread tid owns half of tile row (tid & 127): KT coalesced scalar loads (consecutive threads read consecutive
+// addresses), then KT/4 swizzled 16-byte chunks of the row.
+__device__ __forceinline__ void fetch_tile_t(const float* __restrict__ src, long long ld, int col0, int n_cols, int k0, int k_end,
+                                             float (&v)[KT], int tid) {
     const int row = tid & 127, half = tid >> 7;
     const int gc = col0 + row;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-        const int gk = k0 + 16 * half + j;
+    for (int j = 0; j < KT; ++j) {
+        const int gk = k0 + KT * half + j;
         v[j] = (gc < n_cols && gk < k_end) ? __ldg(src + (long long)gk * ld + gc) : 0.f;
     }
+}
+__device__ __forceinline__ void store_tile_t(const float (&v)[KT], unsigned char* hi_tile, unsigned char* lo_tile, int tid) {
+    const int row = tid & 127, half = tid >> 7;
 #pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-        const int c = 4 * half + cc;
-        const int off = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+    for (int cc = 0; cc < KT / 4; ++cc) {
+        const int c = (KT / 4) * half + cc;
+        const int off = swizzled_offset(row, c);
         float4 hi, lo;
         split4(make_float4(v[4 * cc], v[4 * cc + 1], v[4 * cc + 2], v[4 * cc + 3]), hi, lo);
         *reinterpret_cast<float4*>(hi_tile + off) = hi;
         *reinterpret_cast<float4*>(lo_tile + off) = lo;
+    }
+}
+
+template <bool TRANSPOSED> struct ProducerRegs;
+template <> struct ProducerRegs<false> { float4 a[ITS], b[ITS]; };
+template <> struct ProducerRegs<true> { float a[KT], b[KT]; };
+
+template <bool TRANSPOSED>
+__device__ __forceinline__ void producer_fetch(const DenseArgs& A, int m0, int n0, int k0, int k_end, ProducerRegs<TRANSPOSED>& R, int tid) {
+    if constexpr (TRANSPOSED) {
+        fetch_tile_t(A.X, A.ldx, m0, A.M, k0, k_end, R.a, tid);
+        fetch_tile_t(A.Wt, A.ldw, n0, A.N, k0, k_end, R.b, tid);
+    } else {
+        fetch_tile(A.X, A.ldx, m0, A.M, k0, k_end, R.a, tid);
+        fetch_tile(A.Wt, A.ldw, n0, A.N, k0, k_end, R.b, tid);
+    }
+}
+template <bool TRANSPOSED>
+__device__ __forceinline__ void producer_store(const ProducerRegs<TRANSPOSED>& R, unsigned char* st, int tid) {
+    if constexpr (TRANSPOSED) {
+        store_tile_t(R.a, st, st + TILE_BYTES, tid);
+        store_tile_t(R.b, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
+    } else {
+        store_tile(R.a, st, st + TILE_BYTES, tid);
+        store_tile(R.b, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
     }
 }
 
@@ -189,30 +233,41 @@ __global__ void __launch_bounds__(N_THREADS, 1) dense_tc_kernel(const __grid_con
     if (warp < MMA_WARP) {
         // ===== producers =====
         const int tid = threadIdx.x;
-        for (int kb = 0; kb < KB; ++kb) {
+        // software pipeline over two register sets: the loads of k-block kb + 1 are issued before k-block kb is
+        // converted and stored, so they fly during the split, the st.shared and the wait for the ring slot
+        ProducerRegs<TRANSPOSED> R0, R1;
+        auto commit = [&](int kb, const ProducerRegs<TRANSPOSED>& R) {
             const int s = kb % STAGES;
             bar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
-            unsigned char* st = tiles + s * STAGE_BYTES;
-            if (TRANSPOSED) {
-                load_tile_t(A.X, A.ldx, m0, A.M, k_begin + kb * BK, k_end, st, st + TILE_BYTES, tid);
-                load_tile_t(A.Wt, A.ldw, n0, A.N, k_begin + kb * BK, k_end, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
-            } else {
-                load_tile(A.X, A.ldx, m0, A.M, kb * BK, A.K, st, st + TILE_BYTES, tid);
-                load_tile(A.Wt, A.ldw, n0, A.N, kb * BK, A.K, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
-            }
+            producer_store<TRANSPOSED>(R, tiles + s * STAGE_BYTES, tid);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
             bar_arrive(full0 + 8 * s);
+        };
+        if (KB > 0) producer_fetch<TRANSPOSED>(A, m0, n0, k_begin, k_end, R0, tid);
+        for (int kb = 0; kb < KB; kb += 2) {
+            if (kb + 1 < KB) producer_fetch<TRANSPOSED>(A, m0, n0, k_begin + (kb + 1) * BK, k_end, R1, tid);
+            commit(kb, R0);
+            if (kb + 1 < KB) {
+                if (kb + 2 < KB) producer_fetch<TRANSPOSED>(A, m0, n0, k_begin + (kb + 2) * BK, k_end, R0, tid);
+                commit(kb + 1, R1);
+            }
         }
         // ===== epilogue: warp w reads TMEM lanes [32 (w & 3), +32) = output rows, column half (w >> 2) =====
-        if (KB > 0) bar_wait(tmem_full, 0);
+        // The accumulator arrives one ROW per lane; it is transposed through the (now idle) stage memory so that the
+        // global stores are coalesced: per output row one 256-byte store of the warp's 64 columns.
+        const int lq = warp & 3, ch = warp >> 2;
+        const int ncol = n0 + ch * (BN / 2) + 2 * lane;                  // this lane's two output columns
+        float b0 = 0.f, b1 = 0.f;
+        if (A.bias) { if (ncol < A.N) b0 = __ldg(A.bias + ncol); if (ncol + 1 < A.N) b1 = __ldg(A.bias + ncol + 1); }
+        if (KB > 0) bar_wait(tmem_full, 0);                              // all MMAs done: stages free, accumulator ready
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int lq = warp & 3;
-        const int row = m0 + lq * 32 + lane;
+        constexpr int TP = BN / 2 + 1;                                   // padded row pitch (floats): conflict-free transpose
+        float* tbuf = reinterpret_cast<float*>(tiles) + (size_t)warp * 32 * TP;
         float* const Yz = A.Y + (TRANSPOSED ? (long long)blockIdx.z * A.y_split_stride : 0);
 #pragma unroll 1
-        for (int c0 = (warp >> 2) * (BN / 2); c0 < (warp >> 2) * (BN / 2) + BN / 2; c0 += 32) {
+        for (int cc = 0; cc < BN / 2; cc += 32) {
             uint32_t r[32];
-            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)c0;
+            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * (BN / 2) + cc);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -223,20 +278,24 @@ __global__ void __launch_bounds__(N_THREADS, 1) dense_tc_kernel(const __grid_con
                   "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                 : "r"(taddr) : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < A.M) {
-                float* yrow = Yz + (long long)row * A.ldy;
-                const float* mrow = A.mask ? A.mask + (long long)row * A.ldm : nullptr;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int n = n0 + c0 + j;
-                    if (n < A.N) {
-                        float v = KB > 0 ? __uint_as_float(r[j]) : 0.f;
-                        v = act_f(A.act, v + (A.bias ? __ldg(A.bias + n) : 0.f));
-                        if (mrow) v *= act_grad_f(A.mask_act, mrow[n]);
-                        yrow[n] = v;
-                    }
-                }
+            for (int j = 0; j < 32; ++j) tbuf[lane * TP + cc + j] = KB > 0 ? __uint_as_float(r[j]) : 0.f;
+        }
+        __syncwarp();
+        const bool v0 = ncol < A.N, v1 = ncol + 1 < A.N;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+            const int row = m0 + lq * 32 + rr;
+            if (row >= A.M) break;
+            float x0 = act_f(A.act, tbuf[rr * TP + 2 * lane] + b0), x1 = act_f(A.act, tbuf[rr * TP + 2 * lane + 1] + b1);
+            if (A.mask) {
+                const float* mrow = A.mask + (long long)row * A.ldm + ncol;
+                if (v0) x0 *= act_grad_f(A.mask_act, mrow[0]);
+                if (v1) x1 *= act_grad_f(A.mask_act, mrow[1]);
             }
+            float* y = Yz + (long long)row * A.ldy + ncol;
+            if (v1 && ((reinterpret_cast<uintptr_t>(y) & 7) == 0)) *reinterpret_cast<float2*>(y) = make_float2(x0, x1);
+            else { if (v0) y[0] = x0; if (v1) y[1] = x1; }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     } else {
@@ -250,7 +309,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) dense_tc_kernel(const __grid_con
                 const uint32_t st = base + s * STAGE_BYTES;
 #pragma unroll
                 for (int k = 0; k < BK / 8; ++k) {
-                    // advancing 8 tf32 (32 bytes) inside the 128-byte swizzle atom = +2 in the encoded start address
+                    // advancing 8 tf32 (32 bytes) inside a swizzled row = +2 in the encoded start address
                     const uint64_t ahi = smem_desc(st + k * 32), alo = smem_desc(st + TILE_BYTES + k * 32);
                     const uint64_t bhi = smem_desc(st + 2 * TILE_BYTES + k * 32), blo = smem_desc(st + 3 * TILE_BYTES + k * 32);
                     mma_tf32(tmem, alo, bhi, idesc, (kb | k) != 0);      // small terms first
