@@ -104,17 +104,18 @@ kseg2d_step_kernel(const __grid_constant__ Kseg2dArgs<T> A) {
     for (int s = 0; s < A.S; ++s) {
 #pragma unroll 1
         for (int stage = 1; stage <= 4; ++stage) {
-            const C* B0 = buf0 + cur * slab;
+            // pointer to this strip's first row in the current buffer; the centre row slides down the strip so every
+            // stage state is read three times per point (left, right, below) instead of five
+            const C* Br = buf0 + cur * slab + (r0 + 1) * nx;
             C st[kR];
+            C c = on[0] ? Br[x] : V2<T>::make(T(0), T(0));
+            C u = (grow0 + r0 == 0 || !on[0]) ? c : Br[x - nx];                // edge copy along y (top)
 #pragma unroll
             for (int r = 0; r < kR; ++r) {
                 if (!on[r]) continue;
-                const int lr = r0 + r, g = grow0 + lr;
-                const C c = B0[(lr + 1) * nx + x];
-                const C l = B0[(lr + 1) * nx + xl];
-                const C rt = B0[(lr + 1) * nx + xr];
-                const C u = g == 0 ? c : B0[lr * nx + x];                     // edge copy along y
-                const C d = g == A.ny - 1 ? c : B0[(lr + 2) * nx + x];
+                const C l = Br[xl];
+                const C rt = Br[xr];
+                const C d = (grow0 + r0 + r == A.ny - 1) ? c : Br[x + nx];       // edge copy along y (bottom)
                 // same operation order as the 1-D f (KellerSegelSetup.jl:225-229) per axis
                 const T u1x = (-A.c1x) * l.x + T(0) * c.x + A.c1x * rt.x;
                 const T u2x = A.c2x * l.x + (T(-2) * A.c2x) * c.x + A.c2x * rt.x;
@@ -131,6 +132,7 @@ kseg2d_step_kernel(const __grid_constant__ Kseg2dArgs<T> A) {
                 else if (stage == 2) { acc[r].x += T(2) * ku; acc[r].y += T(2) * kv; st[r] = V2<T>::make(y0[r].x + h2 * ku, y0[r].y + h2 * kv); }
                 else if (stage == 3) { acc[r].x += T(2) * ku; acc[r].y += T(2) * kv; st[r] = V2<T>::make(y0[r].x + h * ku, y0[r].y + h * kv); }
                 else { y0[r].x += h6 * (acc[r].x + ku); y0[r].y += h6 * (acc[r].y + kv); st[r] = y0[r]; }
+                u = c; c = d; Br += nx;
             }
             publish(cur ^ 1, st);
             cluster.sync();
