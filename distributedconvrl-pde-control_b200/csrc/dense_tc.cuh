@@ -12,7 +12,8 @@
 //
 // Structure (one 128 x 128 output tile per CTA, 9 warps; BK = 16 / SWIZZLE_64B with two CTAs per SM was measured
 // and is slower: twice the barrier round trips per tile):
-//   warps 0-7  producers: coalesced 16-byte global loads -> hi/lo split in registers -> st.shared into the
+//   warps 0-7  producers: the weight operand (pre-split hi / lo arrays) comes by TMA (cp.async.bulk.tensor.2d through
+//              SWIZZLE_128B tensor maps); the activation operand: coalesced 16-byte global loads -> hi/lo split in registers -> st.shared into the
 //              K-major SWIZZLE_128B canonical layout (the split needs the data in registers, hence no TMA here);
 //              register double-buffered (the next k-block's loads fly while this one is split and stored), 3-stage ring, full/empty mbarriers; afterwards the same warps run the epilogue
 //              (tcgen05.ld 32 lanes x 32 columns -> transpose through the now idle stage memory -> bias + activation
@@ -20,6 +21,7 @@
 //   warp 8     TMEM allocation; one elected lane issues tcgen05.mma (M = 128, N = 128, K = 8 per instruction,
 //              kind::tf32, both operands K-major from shared-memory descriptors) and tcgen05.commit.
 #pragma once
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -52,6 +54,13 @@ struct DenseArgs {
     int mask_act;
     int split_len;                     // TRANSPOSED: contraction elements per z-slice (multiple of BK)
     long long y_split_stride;
+};
+
+// B_TMA: the second operand (weights) is pre-split in global memory into hi / lo arrays and staged by TMA
+// (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor maps, zero fill outside [N][K]); only the activation operand is
+// register staged.
+struct DenseTmaMaps {
+    CUtensorMap w_hi, w_lo;
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -172,24 +181,24 @@ template <bool TRANSPOSED> struct ProducerRegs;
 template <> struct ProducerRegs<false> { float4 a[ITS], b[ITS]; };
 template <> struct ProducerRegs<true> { float a[KT], b[KT]; };
 
-template <bool TRANSPOSED>
+template <bool TRANSPOSED, bool B_TMA>
 __device__ __forceinline__ void producer_fetch(const DenseArgs& A, int m0, int n0, int k0, int k_end, ProducerRegs<TRANSPOSED>& R, int tid) {
     if constexpr (TRANSPOSED) {
         fetch_tile_t(A.X, A.ldx, m0, A.M, k0, k_end, R.a, tid);
         fetch_tile_t(A.Wt, A.ldw, n0, A.N, k0, k_end, R.b, tid);
     } else {
         fetch_tile(A.X, A.ldx, m0, A.M, k0, k_end, R.a, tid);
-        fetch_tile(A.Wt, A.ldw, n0, A.N, k0, k_end, R.b, tid);
+        if constexpr (!B_TMA) fetch_tile(A.Wt, A.ldw, n0, A.N, k0, k_end, R.b, tid);
     }
 }
-template <bool TRANSPOSED>
+template <bool TRANSPOSED, bool B_TMA>
 __device__ __forceinline__ void producer_store(const ProducerRegs<TRANSPOSED>& R, unsigned char* st, int tid) {
     if constexpr (TRANSPOSED) {
         store_tile_t(R.a, st, st + TILE_BYTES, tid);
         store_tile_t(R.b, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
     } else {
         store_tile(R.a, st, st + TILE_BYTES, tid);
-        store_tile(R.b, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
+        if constexpr (!B_TMA) store_tile(R.b, st + 2 * TILE_BYTES, st + 3 * TILE_BYTES, tid);
     }
 }
 
@@ -199,8 +208,17 @@ __device__ __forceinline__ float act_grad_f(int kind, float out) {
     return 1.f;
 }
 
-template <bool TRANSPOSED>
-__global__ void __launch_bounds__(N_THREADS, 1) dense_tc_kernel(const __grid_constant__ DenseArgs A) {
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+
+template <bool TRANSPOSED, bool B_TMA>
+__global__ void __launch_bounds__(N_THREADS, 1) dense_tc_kernel(const __grid_constant__ DenseArgs A,
+                                                                const __grid_constant__ DenseTmaMaps TM) {
     extern __shared__ unsigned char smem_raw[];
     const uint32_t raw = s32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B atoms need 1024-byte alignment
@@ -216,7 +234,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) dense_tc_kernel(const __grid_con
     const int KB = (k_end - k_begin + BK - 1) / BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { bar_init(full0 + 8 * s, N_PRODUCERS); bar_init(empty0 + 8 * s, 1); }
+        for (int s = 0; s < STAGES; ++s) { bar_init(full0 + 8 * s, N_PRODUCERS + (B_TMA ? 1 : 0)); bar_init(empty0 + 8 * s, 1); }
         bar_init(tmem_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -239,16 +257,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) dense_tc_kernel(const __grid_con
         auto commit = [&](int kb, const ProducerRegs<TRANSPOSED>& R) {
             const int s = kb % STAGES;
             bar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
-            producer_store<TRANSPOSED>(R, tiles + s * STAGE_BYTES, tid);
+            if constexpr (B_TMA) {
+                if (tid == 0) {     // weights: two 128-row x 128-byte boxes (hi, lo) straight into the swizzled stage
+                    bar_expect_tx(full0 + 8 * s, 2 * TILE_BYTES);
+                    tma_load_2d(base + s * STAGE_BYTES + 2 * TILE_BYTES, &TM.w_hi, k_begin + kb * BK, n0, full0 + 8 * s);
+                    tma_load_2d(base + s * STAGE_BYTES + 3 * TILE_BYTES, &TM.w_lo, k_begin + kb * BK, n0, full0 + 8 * s);
+                }
+            }
+            producer_store<TRANSPOSED, B_TMA>(R, tiles + s * STAGE_BYTES, tid);
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
             bar_arrive(full0 + 8 * s);
         };
-        if (KB > 0) producer_fetch<TRANSPOSED>(A, m0, n0, k_begin, k_end, R0, tid);
+        if (KB > 0) producer_fetch<TRANSPOSED, B_TMA>(A, m0, n0, k_begin, k_end, R0, tid);
         for (int kb = 0; kb < KB; kb += 2) {
-            if (kb + 1 < KB) producer_fetch<TRANSPOSED>(A, m0, n0, k_begin + (kb + 1) * BK, k_end, R1, tid);
+            if (kb + 1 < KB) producer_fetch<TRANSPOSED, B_TMA>(A, m0, n0, k_begin + (kb + 1) * BK, k_end, R1, tid);
             commit(kb, R0);
             if (kb + 1 < KB) {
-                if (kb + 2 < KB) producer_fetch<TRANSPOSED>(A, m0, n0, k_begin + (kb + 2) * BK, k_end, R0, tid);
+                if (kb + 2 < KB) producer_fetch<TRANSPOSED, B_TMA>(A, m0, n0, k_begin + (kb + 2) * BK, k_end, R0, tid);
                 commit(kb + 1, R1);
             }
         }

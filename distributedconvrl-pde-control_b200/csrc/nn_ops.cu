@@ -3,6 +3,7 @@
 // layer by layer:  dense layers (in, out >= 32) on the tensor cores (dense_tc.cuh, 3xTF32 tcgen05), thin ones
 // (the K <= 13 input layers and the 1-wide output heads of the shipped networks) on CUDA cores.
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "ctx.hpp"
@@ -13,12 +14,19 @@ namespace {
 
 inline int pad4(int n) { return (n + 3) / 4 * 4; }
 
-// Wt[n][k] = W[n + N*k]  (Flux Dense weight (out, in) column-major -> K-major rows, leading dimension ldw)
-__global__ void transpose_w_kernel(int N, int K, int ldw, const float* __restrict__ W, float* __restrict__ Wt) {
+// Weight operand for the tensor-core kernels, K-major rows with leading dimension ld, split into TF32 hi + remainder lo:
+//   transpose = 1: out[n][k] = W[n + N*k]  (forward:  Flux (out, in) column-major -> rows n, contraction k)
+//   transpose = 0: out[k][n] = W[n + N*k]  (dgrad:    the Flux memory itself, rows k, contraction n; only re-pitched)
+__global__ void split_w_kernel(int N, int K, int ld, int transpose, const float* __restrict__ W, float* __restrict__ hi,
+                               float* __restrict__ lo) {
+    const int rows = transpose ? N : K, cols = transpose ? K : N;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N * ldw) return;
-    const int n = i / ldw, k = i % ldw;
-    Wt[i] = k < K ? W[n + (size_t)N * k] : 0.f;
+    if (i >= rows * ld) return;
+    const int r = i / ld, c = i % ld;
+    float w = 0.f;
+    if (c < cols) w = transpose ? W[r + (size_t)N * c] : W[c + (size_t)N * r];
+    const float h = __uint_as_float(__float_as_uint(w) & 0xFFFFE000u);
+    hi[i] = h; lo[i] = w - h;
 }
 
 // CUDA-core Dense for thin contractions: one thread per (column, output unit), x row in registers via L1.
@@ -90,6 +98,45 @@ struct Scratch {
 };
 thread_local Scratch g_scr;
 
+// cuTensorMapEncodeTiled through the runtime (libcuda is not linked)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+// 2-D fp32 tensor map over a row-major [rows][ld] array: box = BK x 128 (128 bytes x 128 rows), SWIZZLE_128B, zero fill
+int32_t make_weight_map(pdeb200_ctx* c, CUtensorMap* map, float* ptr, int rows, int cols, int ld) {
+    EncodeTiledFn fn = encode_tiled();
+    if (!fn) return fail(c, PDEB200_ECUDA, "dense: cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)tc::BK, (cuuint32_t)tc::BN};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(c, PDEB200_ECUDA, "dense: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return PDEB200_OK;
+}
+
+template <bool T, bool B>
+int32_t configure_tc(pdeb200_ctx* c) {
+    static thread_local bool done = false;
+    if (!done) {
+        PDEB_CUDA(c, cudaFuncSetAttribute(tc::dense_tc_kernel<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+        done = true;
+    }
+    return PDEB200_OK;
+}
+
 int32_t ensure(pdeb200_ctx* c, float** p, size_t* cap, size_t need) {
     if (need <= *cap) return PDEB200_OK;
     if (*p) cudaFree(*p);
@@ -110,20 +157,19 @@ int32_t dense_layer(pdeb200_ctx* c, int M, int K, int N, const float* X, long lo
     if (path == 2 && !can_tc) return fail(c, PDEB200_EUNSUPPORTED, "dense: tensor-core path needs K >= 8 and a 16-byte aligned leading dimension");
     if (want_tc && can_tc) {
         const int ldw = pad4(K);
-        int32_t rc = ensure(c, &g_scr.wt, &g_scr.wt_cap, (size_t)N * ldw);
+        int32_t rc = ensure(c, &g_scr.wt, &g_scr.wt_cap, (size_t)2 * N * ldw);
         if (rc) return rc;
-        transpose_w_kernel<<<(N * ldw + 255) / 256, 256, 0, c->stream>>>(N, K, ldw, W, g_scr.wt);
+        float* whi = g_scr.wt; float* wlo = g_scr.wt + (size_t)N * ldw;
+        split_w_kernel<<<(N * ldw + 255) / 256, 256, 0, c->stream>>>(N, K, ldw, 1, W, whi, wlo);
+        tc::DenseTmaMaps TM;
+        if ((rc = make_weight_map(c, &TM.w_hi, whi, N, ldw, ldw)) || (rc = make_weight_map(c, &TM.w_lo, wlo, N, ldw, ldw))) return rc;
         tc::DenseArgs A;
-        A.X = X; A.ldx = ldx; A.Wt = g_scr.wt; A.ldw = ldw; A.bias = bias; A.Y = Y; A.ldy = ldy;
-        A.M = M; A.N = N; A.K = ldw; A.act = act;      // padded K columns are zero in Wt; X's are zeroed by the caller
+        A.X = X; A.ldx = ldx; A.Wt = whi; A.ldw = ldw; A.bias = bias; A.Y = Y; A.ldy = ldy;
+        A.M = M; A.N = N; A.K = ldw; A.act = act;      // padded K columns are zero in the weights; X's are zeroed by the caller
         A.mask = nullptr; A.ldm = 0; A.mask_act = 0; A.split_len = 0; A.y_split_stride = 0;
-        static thread_local bool configured = false;
-        if (!configured) {
-            PDEB_CUDA(c, cudaFuncSetAttribute(tc::dense_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-            configured = true;
-        }
+        if ((rc = configure_tc<false, true>(c))) return rc;
         const dim3 grid((M + tc::BM - 1) / tc::BM, (N + tc::BN - 1) / tc::BN);
-        tc::dense_tc_kernel<false><<<grid, tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A);
+        tc::dense_tc_kernel<false, true><<<grid, tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A, TM);
         PDEB_CUDA(c, cudaGetLastError());
         c->launches += 2;
         if (used_tc) *used_tc += 1;
@@ -145,15 +191,6 @@ int32_t dense_layer(pdeb200_ctx* c, int M, int K, int N, const float* X, long lo
 }
 
 namespace {
-
-// Wp[k][n] = W[n + N*k] with leading dimension ldp >= N (zero padded): the Flux memory of W IS the K-major operand
-// of the input-gradient GEMM; this only fixes its row alignment.
-__global__ void pad_w_kernel(int N, int K, int ldp, const float* __restrict__ W, float* __restrict__ Wp) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= K * ldp) return;
-    const int k = i / ldp, n = i % ldp;
-    Wp[i] = n < N ? W[n + (size_t)N * k] : 0.f;
-}
 
 __global__ void dgrad_thin_kernel(int M, int K, int N, const float* __restrict__ dY, long long lddy, const float* __restrict__ W,
                                   const float* __restrict__ mask, long long ldm, int mask_act, float* __restrict__ dX, long long lddx) {
@@ -214,20 +251,19 @@ int32_t dense_dgrad(pdeb200_ctx* c, int M, int K, int N, const float* dY, long l
     const bool want_tc = path == 2 || (path == 0 && K >= 32 && N >= 32 && M >= 64);
     if (want_tc && can_tc) {
         const int ldp = pad4(N);
-        int32_t rc = ensure(c, &g_gs.wp, &g_gs.wp_cap, (size_t)K * ldp);
+        int32_t rc = ensure(c, &g_gs.wp, &g_gs.wp_cap, (size_t)2 * K * ldp);
         if (rc) return rc;
-        pad_w_kernel<<<(K * ldp + 255) / 256, 256, 0, c->stream>>>(N, K, ldp, W, g_gs.wp);
+        float* whi = g_gs.wp; float* wlo = g_gs.wp + (size_t)K * ldp;
+        split_w_kernel<<<(K * ldp + 255) / 256, 256, 0, c->stream>>>(N, K, ldp, 0, W, whi, wlo);
+        tc::DenseTmaMaps TM;
+        if ((rc = make_weight_map(c, &TM.w_hi, whi, K, ldp, ldp)) || (rc = make_weight_map(c, &TM.w_lo, wlo, K, ldp, ldp))) return rc;
         tc::DenseArgs A;
-        A.X = dY; A.ldx = lddy; A.Wt = g_gs.wp; A.ldw = ldp; A.bias = nullptr; A.Y = dX; A.ldy = lddx;
+        A.X = dY; A.ldx = lddy; A.Wt = whi; A.ldw = ldp; A.bias = nullptr; A.Y = dX; A.ldy = lddx;
         A.M = M; A.N = K; A.K = ldp; A.act = 0; A.mask = mask; A.ldm = ldm; A.mask_act = mask_act;
         A.split_len = 0; A.y_split_stride = 0;
-        static thread_local bool configured = false;
-        if (!configured) {
-            PDEB_CUDA(c, cudaFuncSetAttribute(tc::dense_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-            configured = true;
-        }
+        if ((rc = configure_tc<false, true>(c))) return rc;
         const dim3 grid((M + tc::BM - 1) / tc::BM, (K + tc::BN - 1) / tc::BN);
-        tc::dense_tc_kernel<false><<<grid, tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A);
+        tc::dense_tc_kernel<false, true><<<grid, tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A, TM);
         PDEB_CUDA(c, cudaGetLastError());
         c->launches += 2;
         return PDEB200_OK;
@@ -260,13 +296,10 @@ int32_t dense_wgrad(pdeb200_ctx* c, int M, int K, int N, const float* dY, long l
         A.X = dY; A.ldx = lddy; A.Wt = X; A.ldw = ldx; A.bias = nullptr; A.Y = g_gs.p; A.ldy = ldp;
         A.M = N; A.N = K; A.K = M; A.act = 0; A.mask = nullptr; A.ldm = 0; A.mask_act = 0;
         A.split_len = split_len; A.y_split_stride = zstride;
-        static thread_local bool configured = false;
-        if (!configured) {
-            PDEB_CUDA(c, cudaFuncSetAttribute(tc::dense_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-            configured = true;
-        }
+        if ((rc = configure_tc<true, false>(c))) return rc;
         const dim3 grid((N + tc::BM - 1) / tc::BM, (K + tc::BN - 1) / tc::BN, Z);
-        tc::dense_tc_kernel<true><<<grid, tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A);
+        tc::DenseTmaMaps TM{};
+        tc::dense_tc_kernel<true, false><<<grid, tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A, TM);
         reduce_splits_kernel<<<(N * K + 255) / 256, 256, 0, c->stream>>>(Z, N, K, ldp, 1, g_gs.p, zstride, gW);
         PDEB_CUDA(c, cudaGetLastError());
         c->launches += 2;
