@@ -33,7 +33,7 @@ def _deps_mtime():
 
 def _defines():
     names = {p.stem for p in sources()}
-    d = []
+    d = [x for x in os.environ.get("PDEB_EXTRA_DEFINES", "").split() if x]
     if "kseg" in names:
         d.append("-DPDEB_HAVE_KSEG")
     if "kseg2d" in names:
