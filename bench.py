@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--oversampling", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-driver", default="native", choices=["native", "python"],
+                    help="host threads of the e2e leg: native std::threads calling the C ABI (libpdeb200_host.so) or Python threads")
     ap.add_argument("--e2e-shards", type=int, default=4,
                     help="the e2e leg drives the batch as this many env shards (own context + stream + host thread each) "
                          "so that one shard's PCIe copies overlap another shard's kernels")
@@ -342,19 +344,44 @@ def run_ours(args):
     shards = [Shard(k) for k in range(n_sh)]
     e2e_launches0 = sum(sh.env.launch_count for sh in shards)
 
+    host_lib = None
+    if args.e2e_driver == "native":
+        hp = ROOT / PKG / "libpdeb200_host.so"
+        if not hp.exists():
+            raise SystemExit("bench.py: %s missing (python __graft_entry__.py build)" % hp)
+        host_lib = C.CDLL(str(hp))
+        host_lib.pdeb200_host_drive.restype = C.c_int32
+        VP = C.c_void_p * n_sh
+        ctxs = VP(*[sh.env._ctx.value for sh in shards])
+        acts = VP(*[sh.h_act.data_ptr() for sh in shards])
+        rews = VP(*[sh.h_rew.data_ptr() for sh in shards])
+        sts = VP(*[sh.h_state.data_ptr() for sh in shards])
+        dns = VP(*[sh.h_done.data_ptr() for sh in shards])
+        nbytes = (C.c_size_t * n_sh)(*[sh.n_act * esz for sh in shards])
+
     def drive(n):
+        if host_lib is not None:
+            # one std::thread per shard, each running policy_act -> get(ACTION_IN) -> step_host through the C ABI
+            secs = C.c_double()
+            rc = host_lib.pdeb200_host_drive(C.c_int32(n_sh), ctxs, C.c_int32(n), acts, nbytes, rews, sts, dns, C.c_double(1.0),
+                                             C.byref(secs))
+            if rc:
+                raise SystemExit("bench.py: e2e driver failed with %d" % rc)
+            return secs.value
         # ctypes releases the GIL inside each C-ABI call, so the shard threads really overlap
         def loop(sh):
             for _ in range(n):
                 sh.step()
+        t_ = time.perf_counter()
         if n_sh == 1:
             loop(shards[0])
-            return
-        ths = [threading.Thread(target=loop, args=(sh,)) for sh in shards]
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
+        else:
+            ths = [threading.Thread(target=loop, args=(sh,)) for sh in shards]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+        return time.perf_counter() - t_
 
     drive(3)
     barrier()
@@ -410,7 +437,7 @@ def run_ours(args):
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "shards": n_sh, "launches": int(e2e_launches),
+                    "shards": n_sh, "launches": int(e2e_launches), "host_threads": args.e2e_driver,
                     "call_sequence": "per shard and step: pdeb200_policy_act -> pdeb200_get(ACTION_IN) [D2H] -> "
                                      "pdeb200_step_host [H2D action; D2H reward, state, done], pinned host buffers"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}

@@ -15,6 +15,7 @@ ROOT = PKG.parent
 CSRC = PKG / "csrc"
 OBJ = ROOT / "build" / "obj"
 LIB = PKG / "libpdeb200.so"
+HOST_LIB = PKG / "libpdeb200_host.so"      # native host-side driver (C ABI only, g++; used by bench.py's e2e leg)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -78,6 +79,13 @@ def build(verbose=False, force=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    host_src = CSRC / "host" / "e2e_driver.cpp"
+    if host_src.exists() and (rebuilt or not HOST_LIB.exists() or HOST_LIB.stat().st_mtime < host_src.stat().st_mtime):
+        cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", str(host_src), "-o", str(HOST_LIB),
+               "-L" + str(PKG), "-l:libpdeb200.so", "-Wl,-rpath,$ORIGIN"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("host driver build failed:\n%s\n%s" % (r.stdout, r.stderr))
     return LIB
 
 

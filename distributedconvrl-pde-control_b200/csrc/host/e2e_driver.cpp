@@ -1,0 +1,39 @@
+// Native host driver for the end-to-end measurement: what a compiled-language host (the reference is Julia: tasks
+// on real threads, no GIL) does with the C ABI.  One std::thread per environment shard runs the drop-in call
+// sequence with HOST buffers, `steps` times:
+//     pdeb200_policy_act            (policy(env): actor forward on the device)
+//     pdeb200_get(ARR_ACTION_IN)    (the action comes back to the host, src/PDEagent.jl:198)
+//     pdeb200_step_host             (env(action): H2D action; kernels; D2H reward, state, done)
+// Only include/pdeb200.h is used; this file is built into libpdeb200_host.so next to libpdeb200.so.
+#include <atomic>
+#include <chrono>
+#include <thread>
+#include <vector>
+
+#include "../../../include/pdeb200.h"
+
+extern "C" int32_t pdeb200_host_drive(int32_t n_shards, pdeb200_ctx** ctxs, int32_t steps, void** h_act, const size_t* act_bytes,
+                                      void** h_reward, void** h_state, uint8_t** h_done, double act_limit, double* seconds_out) {
+    if (n_shards < 1 || !ctxs || steps < 0 || !h_act || !act_bytes || !seconds_out) return PDEB200_EINVAL;
+    std::atomic<int> ready{0}, failed{0};
+    std::atomic<bool> go{false};
+    std::vector<std::thread> th;
+    auto work = [&](int k) {
+        ready.fetch_add(1);
+        while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+        for (int i = 0; i < steps; ++i) {
+            int32_t rc = pdeb200_policy_act(ctxs[k], nullptr, 0.0, act_limit);
+            if (!rc) rc = pdeb200_get(ctxs[k], PDEB200_ARR_ACTION_IN, h_act[k], act_bytes[k]);
+            if (!rc) rc = pdeb200_step_host(ctxs[k], h_act[k], nullptr, h_reward ? h_reward[k] : nullptr, h_state ? h_state[k] : nullptr,
+                                            h_done ? h_done[k] : nullptr);
+            if (rc) { failed.store(rc); return; }
+        }
+    };
+    for (int k = 0; k < n_shards; ++k) th.emplace_back(work, k);
+    while (ready.load() < n_shards) std::this_thread::yield();
+    const auto t0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
+    for (auto& t : th) t.join();
+    *seconds_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return failed.load();
+}
