@@ -134,6 +134,18 @@ __device__ __forceinline__ float act_grad(int kind, float out) {
 
 __device__ void layer_forward(const float* __restrict__ W, int ni, int no, int act, const float* in, float* out) {
     const float* b = W + (size_t)ni * no;
+    if (no * 8 <= (int)blockDim.x) {
+        // narrow layer (e.g. the 140 -> 1 critic head): one thread per (sample, unit) instead of one per unit, so the
+        // contraction over ni is not serialised into a single thread's 32 accumulators
+        for (int q = threadIdx.x; q < TS * no; q += blockDim.x) {
+            const int i = q / no, k = q - i * no;
+            float acc = 0.f;
+            for (int j = 0; j < ni; ++j) acc = fmaf(W[k + (size_t)no * j], in[i * ni + j], acc);
+            out[q] = act_apply(act, acc + b[k]);
+        }
+        __syncthreads();
+        return;
+    }
     for (int k = threadIdx.x; k < no; k += blockDim.x) {
         float acc[TS];
 #pragma unroll
@@ -188,7 +200,15 @@ __device__ float* net_backward(const NetDev& net, float* const* acts, float* d_o
                 acc[net.offs[l] + q] += g;
             }
         }
-        if (l > 0 || want_input_grad) {
+        if ((l > 0 || want_input_grad) && ni * 8 <= (int)blockDim.x) {
+            // few inputs (e.g. the critic's (s, a) layer): one thread per (sample, input)
+            for (int q = threadIdx.x; q < TS * ni; q += blockDim.x) {
+                const int i = q / ni, j = q - i * ni;
+                float sacc = 0.f;
+                for (int k = 0; k < no; ++k) sacc = fmaf(W[k + (size_t)no * j], d[i * no + k], sacc);
+                dn[q] = sacc;
+            }
+        } else if (l > 0 || want_input_grad) {
             for (int j = threadIdx.x; j < ni; j += blockDim.x) {
                 float s[TS];
 #pragma unroll
@@ -370,6 +390,35 @@ __global__ void reduce_partials_kernel(int n_blocks, int n_acc, const float* __r
     for (int b = 0; b < n_blocks; ++b) s += (double)partials[(size_t)b * (n_acc + 2) + q];
     if (q < n_acc) grads[q] = (float)s;
     else stats[stat0 + (q - n_acc)] = s;
+}
+
+// Single-GPU update: partial reduction (fixed order) + ADAM + Polyak of the target in ONE launch (no allreduce sits
+// between them).  Same arithmetic as reduce_partials_kernel -> adam_kernel -> polyak_kernel.
+__global__ void reduce_adam_polyak_kernel(int n_blocks, int n_acc, const float* __restrict__ partials, float* grads, double* stats,
+                                          int stat0, float* x, float* m, float* v, float* target, double eta, double b1, double b2,
+                                          double bp1, double bp2, double eps, float polyak) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n_acc + 2) return;
+    double s = 0.0;
+    for (int b = 0; b < n_blocks; ++b) s += (double)partials[(size_t)b * (n_acc + 2) + q];
+    if (q >= n_acc) { stats[stat0 + (q - n_acc)] = s; return; }
+    const float g = (float)s;
+    grads[q] = g;
+    const double gi = g;
+    const float mi = (float)(b1 * (double)m[q] + (1.0 - b1) * gi);
+    const float vi = (float)(b2 * (double)v[q] + (1.0 - b2) * gi * gi);
+    m[q] = mi; v[q] = vi;
+    const float delta = (float)((double)mi / (1.0 - bp1) / (sqrt((double)vi / (1.0 - bp2)) + eps) * eta);
+    const float xn = x[q] - delta;
+    x[q] = xn;
+    target[q] = polyak * target[q] + (1.f - polyak) * xn;
+}
+
+// both losses from the reduced sums (one launch per update on the fused path)
+__global__ void losses_both_kernel(const double* stats, double n_global, int literal, float* losses) {
+    const double B = n_global;
+    losses[0] = (float)(literal ? stats[3] / B + 2.0 * stats[2] * stats[0] / (B * B) + stats[1] / B : stats[3] / B);
+    losses[1] = (float)(-stats[4] / n_global);
 }
 
 // Flux ADAM on Float32 arrays with Float64 hyper-parameters; optional Polyak pair (dest = p*dest + (1-p)*src).
@@ -881,7 +930,16 @@ int32_t pdeb200_ddpg_set_path(pdeb200_ctx* c, int32_t path) {
     return PDEB200_OK;
 }
 
+static int32_t critic_grads_impl(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch, bool reduce);
+static int32_t actor_grads_impl(pdeb200_ctx* c, int64_t global_batch, bool reduce);
+
 int32_t pdeb200_ddpg_critic_grads(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch) {
+    return critic_grads_impl(c, gamma, literal_q1, global_batch, true);
+}
+
+// reduce = false: leave the per-CTA partials for reduce_adam_polyak_kernel (single-GPU fused path); returns 1 if the
+// layer-wise path ran instead (gradients already reduced in d_grads)
+static int32_t critic_grads_impl(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch, bool reduce) {
     if (!c) return PDEB200_EINVAL;
     cudaSetDevice(c->device);
     Agent* a = ag(c);
@@ -897,15 +955,21 @@ int32_t pdeb200_ddpg_critic_grads(pdeb200_ctx* c, double gamma, int32_t literal_
     if ((rc = ensure_partials(c, n_blocks, D.n_acc))) return rc;
     D.partials = a->partials;
     const size_t smem = ((size_t)net_act_floats(C) + 2 * (size_t)TS * D.wmax + (size_t)TS * (a->ns + a->na) + TS + D.n_acc) * 4;
-    if (smem > 220 * 1024 || a->force_wide) return wide_critic_grads(c, gamma, literal_q1, global_batch);   // layer-wise GEMM path
+    if (smem > 220 * 1024 || a->force_wide) {                                                              // layer-wise GEMM path
+        rc = wide_critic_grads(c, gamma, literal_q1, global_batch);
+        return rc ? rc : (reduce ? PDEB200_OK : 1);
+    }
     PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tpb = block_threads(D.wmax, D.n_acc);
     ddpg_critic_kernel<<<n_blocks, tpb, smem, c->stream>>>(D);
-    reduce_partials_kernel<<<(D.n_acc + 2 + 127) / 128, 128, 0, c->stream>>>(n_blocks, D.n_acc, a->partials, c->d_grads, a->stats, 2);
-    losses_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)global_batch, literal_q1, 0, c->d_losses);
-    PDEB_CUDA(c, cudaGetLastError());
     a->n_blocks = n_blocks;
-    c->launches += 3;
+    c->launches += 1;
+    if (reduce) {
+        reduce_partials_kernel<<<(D.n_acc + 2 + 127) / 128, 128, 0, c->stream>>>(n_blocks, D.n_acc, a->partials, c->d_grads, a->stats, 2);
+        losses_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)global_batch, literal_q1, 0, c->d_losses);
+        c->launches += 2;
+    }
+    PDEB_CUDA(c, cudaGetLastError());
     return PDEB200_OK;
 }
 
@@ -924,7 +988,9 @@ int32_t pdeb200_ddpg_critic_apply(pdeb200_ctx* c, double lr) {
     return adam_apply(c, c->nets[PDEB200_NET_BEHAVIOR_CRITIC], c->d_grads, lr);
 }
 
-int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* c, int64_t global_batch) {
+int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* c, int64_t global_batch) { return actor_grads_impl(c, global_batch, true); }
+
+static int32_t actor_grads_impl(pdeb200_ctx* c, int64_t global_batch, bool reduce) {
     if (!c) return PDEB200_EINVAL;
     cudaSetDevice(c->device);
     Agent* a = ag(c);
@@ -939,15 +1005,22 @@ int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* c, int64_t global_batch) {
     if ((rc = ensure_partials(c, n_blocks, D.n_acc))) return rc;
     D.partials = a->partials;
     const size_t smem = ((size_t)net_act_floats(C) + net_act_floats(A) + 2 * (size_t)TS * D.wmax + D.n_acc) * 4;
-    if (smem > 220 * 1024 || a->force_wide) return wide_actor_grads(c, global_batch);                      // layer-wise GEMM path
+    if (smem > 220 * 1024 || a->force_wide) {                                                              // layer-wise GEMM path
+        rc = wide_actor_grads(c, global_batch);
+        return rc ? rc : (reduce ? PDEB200_OK : 1);
+    }
     PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tpb = block_threads(D.wmax, D.n_acc);
     ddpg_actor_kernel<<<n_blocks, tpb, smem, c->stream>>>(D);
-    reduce_partials_kernel<<<(D.n_acc + 2 + 127) / 128, 128, 0, c->stream>>>(n_blocks, D.n_acc, a->partials,
-                                                                              c->d_grads + C.n_params, a->stats, 4);
-    losses_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)global_batch, 0, 1, c->d_losses);
+    a->n_blocks = n_blocks;
+    c->launches += 1;
+    if (reduce) {
+        reduce_partials_kernel<<<(D.n_acc + 2 + 127) / 128, 128, 0, c->stream>>>(n_blocks, D.n_acc, a->partials,
+                                                                                  c->d_grads + C.n_params, a->stats, 4);
+        losses_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)global_batch, 0, 1, c->d_losses);
+        c->launches += 2;
+    }
     PDEB_CUDA(c, cudaGetLastError());
-    c->launches += 3;
     return PDEB200_OK;
 }
 
@@ -967,12 +1040,34 @@ int32_t pdeb200_ddpg_actor_apply(pdeb200_ctx* c, double lr, double polyak) {
 
 int32_t pdeb200_ddpg_update(pdeb200_ctx* c, double gamma, double polyak, double lr_actor, double lr_critic, int32_t literal_q1) {
     if (!c || !c->agent) return fail(c, PDEB200_ESTATE, "ddpg_update: no batch");
-    const int64_t B = ag(c)->batch;
-    int32_t rc;
-    if ((rc = pdeb200_ddpg_critic_grads(c, gamma, literal_q1, B))) return rc;
-    if ((rc = pdeb200_ddpg_critic_apply(c, lr_critic))) return rc;
-    if ((rc = pdeb200_ddpg_actor_grads(c, B))) return rc;
-    return pdeb200_ddpg_actor_apply(c, lr_actor, polyak);
+    cudaSetDevice(c->device);
+    Agent* a = ag(c);
+    const int64_t B = a->batch;
+    HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+    HostNet &At = c->nets[PDEB200_NET_TARGET_ACTOR], &Ct = c->nets[PDEB200_NET_TARGET_CRITIC];
+    // Fused single-GPU path: {critic kernel, reduce + ADAM + Polyak} {actor kernel, reduce + ADAM + Polyak} {losses}.
+    // The target critic is not read after the critic phase and the behavior critic is not written by the actor phase,
+    // so its Polyak step can run right after its ADAM step (reference order: both at the end, PDEagent.jl:411-417).
+    int32_t rc = critic_grads_impl(c, gamma, literal_q1, B, false);
+    if (rc < 0) return rc;
+    if (rc == 1) {                       // layer-wise path: gradients are already reduced
+        if ((rc = pdeb200_ddpg_critic_apply(c, lr_critic))) return rc;
+        if ((rc = pdeb200_ddpg_actor_grads(c, B))) return rc;
+        return pdeb200_ddpg_actor_apply(c, lr_actor, polyak);
+    }
+    reduce_adam_polyak_kernel<<<(C.n_params + 2 + 127) / 128, 128, 0, c->stream>>>(
+        a->n_blocks, C.n_params, a->partials, c->d_grads, a->stats, 2, C.d_params, C.d_m, C.d_v, Ct.d_params, lr_critic, 0.9, 0.999,
+        C.beta_p[0], C.beta_p[1], 1e-8, (float)polyak);
+    C.beta_p[0] *= 0.9; C.beta_p[1] *= 0.999;
+    if ((rc = actor_grads_impl(c, B, false)) < 0) return rc;
+    reduce_adam_polyak_kernel<<<(A.n_params + 2 + 127) / 128, 128, 0, c->stream>>>(
+        a->n_blocks, A.n_params, a->partials, c->d_grads + C.n_params, a->stats, 4, A.d_params, A.d_m, A.d_v, At.d_params, lr_actor, 0.9,
+        0.999, A.beta_p[0], A.beta_p[1], 1e-8, (float)polyak);
+    A.beta_p[0] *= 0.9; A.beta_p[1] *= 0.999;
+    losses_both_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)B, literal_q1, c->d_losses);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 3;
+    return PDEB200_OK;
 }
 
 }  // extern "C"
