@@ -50,19 +50,59 @@ __device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t ctr, floa
     *n0 = rad * co; *n1 = rad * s;
 }
 
-template <typename T>
-__global__ void policy_kernel(NetDev net, int n_columns, int obs_rows, int a_rows, int memory,
-                              const T* __restrict__ state, T* __restrict__ action_in,
-                              const T* __restrict__ noise, int use_rng, uint64_t seed, uint64_t offset,
-                              T act_noise, T act_limit) {
+// Per-column MLP with the activations in REGISTERS (fully unrolled to the compile-time width W, predicated by the
+// runtime layer sizes); parameters broadcast from shared memory.  W = 0: generic local-memory path (widths <= 64).
+template <int W>
+__device__ __forceinline__ void mlp_forward_reg(const NetDev& net, const float* __restrict__ params, float (&x)[W > 0 ? W : 1]) {
+    float h[W > 0 ? W : 1];
+    for (int l = 0; l < net.n_layers; ++l) {
+        const int ni = net.sizes[l], no = net.sizes[l + 1];
+        const float* Wl = params + net.offs[l];
+        const float* b = Wl + ni * no;
+#pragma unroll
+        for (int o = 0; o < W; ++o) {
+            float acc = 0.f;
+            if (o < no) {
+#pragma unroll
+                for (int i = 0; i < W; ++i)
+                    if (i < ni) acc = fmaf(Wl[o + no * i], x[i], acc);
+                acc = act_apply(net.acts[l], acc + b[o]);
+            }
+            h[o] = acc;
+        }
+#pragma unroll
+        for (int o = 0; o < W; ++o) x[o] = h[o];
+    }
+}
+
+template <typename T, int W>
+__global__ void __launch_bounds__(128) policy_kernel(NetDev net, int n_params, int n_columns, int obs_rows, int a_rows, int memory,
+                                                     const T* __restrict__ state, T* __restrict__ action_in,
+                                                     const T* __restrict__ noise, int use_rng, uint64_t seed, uint64_t offset,
+                                                     T act_noise, T act_limit) {
+    extern __shared__ float s_par[];
+    for (int i = threadIdx.x; i < n_params; i += blockDim.x) s_par[i] = net.params[i];
+    __syncthreads();
     const int col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= n_columns) return;
-    float x[kFusedActorMaxWidth], h[kFusedActorMaxWidth];
-    for (int r = 0; r < obs_rows; ++r) x[r] = (float)state[(size_t)col * obs_rows + r];
-    mlp_forward_small(net, x, h);
+    constexpr int XW = W > 0 ? W : kFusedActorMaxWidth;
+    float x[XW];
     const int n_out = net.sizes[net.n_layers];            // == a_rows (conv agent) or n_act (mono)
+    if constexpr (W > 0) {
+#pragma unroll
+        for (int r = 0; r < W; ++r) x[r] = r < obs_rows ? (float)state[(size_t)col * obs_rows + r] : 0.f;
+        mlp_forward_reg<W>(net, s_par, x);
+    } else {
+        float h[kFusedActorMaxWidth];
+        for (int r = 0; r < obs_rows; ++r) x[r] = (float)state[(size_t)col * obs_rows + r];
+        NetDev n2 = net;
+        n2.params = s_par;
+        mlp_forward_small(n2, x, h);
+    }
     const int noisy = n_out - memory;
-    for (int r = 0; r < n_out; ++r) {
+#pragma unroll
+    for (int r = 0; r < XW; ++r) {
+        if (r >= n_out) break;
         T v = (T)x[r];
         if (r < noisy) {
             if (noise) v += noise[(size_t)col * noisy + r] * act_noise;
@@ -622,14 +662,20 @@ static int32_t policy_launch(pdeb200_ctx* c, const void* d_noise, int use_rng, u
     const int ncol = c->cfg.n_envs * c->n_cols;
     const int mem = c->cfg.mono ? 0 : c->cfg.memory_size;
     const int tpb = 128, grid = (ncol + tpb - 1) / tpb;
-    if (c->cfg.dtype == PDEB200_F64)
-        policy_kernel<double><<<grid, tpb, 0, c->stream>>>(a.dev(), ncol, c->obs_rows, c->a_rows, mem, (const double*)c->state,
-                                                           (double*)c->action_in, (const double*)d_noise, use_rng, seed, offset,
-                                                           act_noise, act_limit);
-    else
-        policy_kernel<float><<<grid, tpb, 0, c->stream>>>(a.dev(), ncol, c->obs_rows, c->a_rows, mem, (const float*)c->state,
-                                                          (float*)c->action_in, (const float*)d_noise, use_rng, seed, offset,
-                                                          (float)act_noise, (float)act_limit);
+    int wmax = 0;
+    for (int l = 0; l <= a.n_layers; ++l) wmax = std::max(wmax, a.sizes[l]);
+    const size_t smem = (size_t)a.n_params * sizeof(float);
+    if (smem > 48 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "policy_act: actor parameters exceed 48 KB of shared memory");
+#define PDEB_POLICY(TT, WW)                                                                                              \
+    policy_kernel<TT, WW><<<grid, tpb, smem, c->stream>>>(a.dev(), a.n_params, ncol, c->obs_rows, c->a_rows, mem,        \
+                                                          (const TT*)c->state, (TT*)c->action_in, (const TT*)d_noise,    \
+                                                          use_rng, seed, offset, (TT)act_noise, (TT)act_limit)
+    if (c->cfg.dtype == PDEB200_F64) {
+        if (wmax <= 8) PDEB_POLICY(double, 8); else if (wmax <= 24) PDEB_POLICY(double, 24); else PDEB_POLICY(double, 0);
+    } else {
+        if (wmax <= 8) PDEB_POLICY(float, 8); else if (wmax <= 24) PDEB_POLICY(float, 24); else PDEB_POLICY(float, 0);
+    }
+#undef PDEB_POLICY
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
