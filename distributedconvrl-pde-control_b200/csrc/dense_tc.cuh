@@ -34,9 +34,11 @@ constexpr int CHUNKS = ROW_BYTES / 16;                     // 16-byte chunks per
 constexpr int ATOM_BYTES = 8 * ROW_BYTES;                  // 8-row swizzle atom = stride between row groups (SBO)
 constexpr int TILE_BYTES = BM * ROW_BYTES;                 // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;                // A_hi, A_lo, B_hi, B_lo
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
-constexpr int N_PRODUCERS = 256;                           // 8 producer / epilogue warps + 1 MMA warp
-constexpr int N_THREADS = N_PRODUCERS + 32;
+constexpr int N_PRODUCERS = 256;                           // 8 producer warps + 1 MMA warp + 4 epilogue warps
+constexpr int N_EPILOGUE = 128;
+constexpr int N_THREADS = N_PRODUCERS + 32 + N_EPILOGUE;
+constexpr int EPI_BYTES = 4 * 32 * 33 * 4 + 128;           // epilogue transpose tiles (+ pad to keep the barriers 8-aligned)
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
 
 struct DenseArgs {
     // TRANSPOSED = false:  Y[M x N] = epilogue(X[M x K] * Wt[N x K]^T)
@@ -216,6 +218,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
 
+// Persistent kernel: one CTA per SM walks the output tiles (tile = blockIdx.x, += gridDim.x; the N tiles of an M tile
+// are neighbours so that the activation tile is shared through L2).  Roles:
+//   warps 0-7   producers (activation operand in registers -> hi/lo split -> swizzled stage; thread 0 also issues the
+//               weight TMA)
+//   warp  8     MMA issuer; the fp32 accumulator is DOUBLE BUFFERED in TMEM (2 x 128 columns): the MMAs of tile i + 1
+//               run while the epilogue warps drain tile i
+//   warps 9-12  epilogue: warp w owns TMEM lanes [32 (w % 4), +32) = 32 output rows; per 32-column chunk
+//               tcgen05.ld -> transpose through a private 32 x 33 shared-memory tile -> bias / activation / act'(mask)
+//               -> 128-byte coalesced row stores
 template <bool TRANSPOSED, bool B_TMA>
 __global__ void __launch_bounds__(N_THREADS, 1) dense_tc_kernel(const __grid_constant__ DenseArgs A,
                                                                 const __grid_constant__ DenseTmaMaps TM) {
@@ -223,24 +234,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) dense_tc_kernel(const __grid_con
     const uint32_t raw = s32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                   // SWIZZLE_128B atoms need 1024-byte alignment
     unsigned char* tiles = smem_raw + (base - raw);
-    const uint32_t bars = base + STAGES * STAGE_BYTES;              // full[STAGES], empty[STAGES], tmem_full, tmem slot
-    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tmem_full = bars + 16 * STAGES;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tiles + STAGES * STAGE_BYTES + 16 * STAGES + 8);
+    float* epi_buf = reinterpret_cast<float*>(tiles + STAGES * STAGE_BYTES);                 // [4 warps][32][33]
+    const uint32_t bars = base + STAGES * STAGE_BYTES + EPI_BYTES;
+    const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tfull0 = bars + 16 * STAGES, tempty0 = tfull0 + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tiles + STAGES * STAGE_BYTES + EPI_BYTES + 16 * STAGES + 32);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
-    // contraction range of this CTA
-    const int k_begin = TRANSPOSED ? (int)blockIdx.z * A.split_len : 0;
-    const int k_end = TRANSPOSED ? min(A.K, k_begin + A.split_len) : A.K;
-    const int KB = (k_end - k_begin + BK - 1) / BK;
+    const int tiles_m = (A.M + BM - 1) / BM, tiles_n = (A.N + BN - 1) / BN;
+    const int n_z = TRANSPOSED ? (A.K + A.split_len - 1) / A.split_len : 1;
+    const int n_tiles = tiles_m * tiles_n * n_z;
+    constexpr int MMA_WARP = N_PRODUCERS / 32;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) { bar_init(full0 + 8 * s, N_PRODUCERS + (B_TMA ? 1 : 0)); bar_init(empty0 + 8 * s, 1); }
-        bar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) { bar_init(tfull0 + 8 * b, 1); bar_init(tempty0 + 8 * b, N_EPILOGUE); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    constexpr int MMA_WARP = N_PRODUCERS / 32;
     if (warp == MMA_WARP) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "n"(BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "n"(2 * BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -248,111 +258,163 @@ __global__ void __launch_bounds__(N_THREADS, 1) dense_tc_kernel(const __grid_con
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem = *tmem_slot;
 
+    // tile -> (m tile, n tile, contraction slice)
+    auto decode = [&](int tile, int& m0, int& n0, int& z, int& k_begin, int& k_end) {
+        const int tn = tile % tiles_n, rest = tile / tiles_n;
+        const int tm = rest % tiles_m;
+        z = rest / tiles_m;
+        m0 = tm * BM; n0 = tn * BN;
+        k_begin = TRANSPOSED ? z * A.split_len : 0;
+        k_end = TRANSPOSED ? min(A.K, k_begin + A.split_len) : A.K;
+    };
+
     if (warp < MMA_WARP) {
         // ===== producers =====
         const int tid = threadIdx.x;
-        // software pipeline over two register sets: the loads of k-block kb + 1 are issued before k-block kb is
-        // converted and stored, so they fly during the split, the st.shared and the wait for the ring slot
         ProducerRegs<TRANSPOSED> R0, R1;
-        auto commit = [&](int kb, const ProducerRegs<TRANSPOSED>& R) {
-            const int s = kb % STAGES;
-            bar_wait(empty0 + 8 * s, ((kb / STAGES) & 1) ^ 1);
-            if constexpr (B_TMA) {
-                if (tid == 0) {     // weights: two 128-row x 128-byte boxes (hi, lo) straight into the swizzled stage
-                    bar_expect_tx(full0 + 8 * s, 2 * TILE_BYTES);
-                    tma_load_2d(base + s * STAGE_BYTES + 2 * TILE_BYTES, &TM.w_hi, k_begin + kb * BK, n0, full0 + 8 * s);
-                    tma_load_2d(base + s * STAGE_BYTES + 3 * TILE_BYTES, &TM.w_lo, k_begin + kb * BK, n0, full0 + 8 * s);
+        int it = 0;                                                     // k-blocks issued so far (ring position)
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            int m0, n0, z, k_begin, k_end;
+            decode(tile, m0, n0, z, k_begin, k_end);
+            const int KB = (k_end - k_begin + BK - 1) / BK;
+            auto commit = [&](int kb, const ProducerRegs<TRANSPOSED>& R) {
+                const int g = it + kb, s = g % STAGES;
+                bar_wait(empty0 + 8 * s, ((g / STAGES) & 1) ^ 1);
+                if constexpr (B_TMA) {
+                    if (tid == 0) {     // weights: two 128-row x 128-byte boxes (hi, lo) straight into the swizzled stage
+                        bar_expect_tx(full0 + 8 * s, 2 * TILE_BYTES);
+                        tma_load_2d(base + s * STAGE_BYTES + 2 * TILE_BYTES, &TM.w_hi, k_begin + kb * BK, n0, full0 + 8 * s);
+                        tma_load_2d(base + s * STAGE_BYTES + 3 * TILE_BYTES, &TM.w_lo, k_begin + kb * BK, n0, full0 + 8 * s);
+                    }
+                }
+                producer_store<TRANSPOSED, B_TMA>(R, tiles + s * STAGE_BYTES, tid);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
+                bar_arrive(full0 + 8 * s);
+            };
+            // software pipeline over two register sets: the loads of k-block kb + 1 fly while kb is split and stored
+            if (KB > 0) producer_fetch<TRANSPOSED, B_TMA>(A, m0, n0, k_begin, k_end, R0, tid);
+            for (int kb = 0; kb < KB; kb += 2) {
+                if (kb + 1 < KB) producer_fetch<TRANSPOSED, B_TMA>(A, m0, n0, k_begin + (kb + 1) * BK, k_end, R1, tid);
+                commit(kb, R0);
+                if (kb + 1 < KB) {
+                    if (kb + 2 < KB) producer_fetch<TRANSPOSED, B_TMA>(A, m0, n0, k_begin + (kb + 2) * BK, k_end, R0, tid);
+                    commit(kb + 1, R1);
                 }
             }
-            producer_store<TRANSPOSED, B_TMA>(R, tiles + s * STAGE_BYTES, tid);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> tensor-core reads
-            bar_arrive(full0 + 8 * s);
-        };
-        if (KB > 0) producer_fetch<TRANSPOSED, B_TMA>(A, m0, n0, k_begin, k_end, R0, tid);
-        for (int kb = 0; kb < KB; kb += 2) {
-            if (kb + 1 < KB) producer_fetch<TRANSPOSED, B_TMA>(A, m0, n0, k_begin + (kb + 1) * BK, k_end, R1, tid);
-            commit(kb, R0);
-            if (kb + 1 < KB) {
-                if (kb + 2 < KB) producer_fetch<TRANSPOSED, B_TMA>(A, m0, n0, k_begin + (kb + 2) * BK, k_end, R0, tid);
-                commit(kb + 1, R1);
-            }
+            it += KB;
         }
-        // ===== epilogue: warp w reads TMEM lanes [32 (w & 3), +32) = output rows, column half (w >> 2) =====
-        // The accumulator arrives one ROW per lane; it is transposed through the (now idle) stage memory so that the
-        // global stores are coalesced: per output row one 256-byte store of the warp's 64 columns.
-        const int lq = warp & 3, ch = warp >> 2;
-        const int ncol = n0 + ch * (BN / 2) + 2 * lane;                  // this lane's two output columns
-        float b0 = 0.f, b1 = 0.f;
-        if (A.bias) { if (ncol < A.N) b0 = __ldg(A.bias + ncol); if (ncol + 1 < A.N) b1 = __ldg(A.bias + ncol + 1); }
-        if (KB > 0) bar_wait(tmem_full, 0);                              // all MMAs done: stages free, accumulator ready
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        constexpr int TP = BN / 2 + 1;                                   // padded row pitch (floats): conflict-free transpose
-        float* tbuf = reinterpret_cast<float*>(tiles) + (size_t)warp * 32 * TP;
-        float* const Yz = A.Y + (TRANSPOSED ? (long long)blockIdx.z * A.y_split_stride : 0);
-#pragma unroll 1
-        for (int cc = 0; cc < BN / 2; cc += 32) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(ch * (BN / 2) + cc);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-                : "r"(taddr) : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; ++j) tbuf[lane * TP + cc + j] = KB > 0 ? __uint_as_float(r[j]) : 0.f;
-        }
-        __syncwarp();
-        const bool v0 = ncol < A.N, v1 = ncol + 1 < A.N;
-#pragma unroll 4
-        for (int rr = 0; rr < 32; ++rr) {
-            const int row = m0 + lq * 32 + rr;
-            if (row >= A.M) break;
-            float x0 = act_f(A.act, tbuf[rr * TP + 2 * lane] + b0), x1 = act_f(A.act, tbuf[rr * TP + 2 * lane + 1] + b1);
-            if (A.mask) {
-                const float* mrow = A.mask + (long long)row * A.ldm + ncol;
-                if (v0) x0 *= act_grad_f(A.mask_act, mrow[0]);
-                if (v1) x1 *= act_grad_f(A.mask_act, mrow[1]);
-            }
-            float* y = Yz + (long long)row * A.ldy + ncol;
-            if (v1 && ((reinterpret_cast<uintptr_t>(y) & 7) == 0)) *reinterpret_cast<float2*>(y) = make_float2(x0, x1);
-            else { if (v0) y[0] = x0; if (v1) y[1] = x1; }
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    } else {
+    } else if (warp == MMA_WARP) {
         // ===== MMA issuer =====
         const uint32_t idesc = instr_desc();
-        for (int kb = 0; kb < KB; ++kb) {
-            const int s = kb % STAGES;
-            bar_wait(full0 + 8 * s, (kb / STAGES) & 1);
+        int it = 0, lt = 0;                                             // ring position, local tile counter
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            int m0, n0, z, k_begin, k_end;
+            decode(tile, m0, n0, z, k_begin, k_end);
+            const int KB = (k_end - k_begin + BK - 1) / BK;
+            const int buf = lt & 1;
+            bar_wait(tempty0 + 8 * buf, ((lt >> 1) & 1) ^ 1);           // epilogue has drained this accumulator
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t st = base + s * STAGE_BYTES;
+            const uint32_t acc = tmem + (uint32_t)(buf * BN);
+            for (int kb = 0; kb < KB; ++kb) {
+                const int g = it + kb, s = g % STAGES;
+                bar_wait(full0 + 8 * s, (g / STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    const uint32_t st = base + s * STAGE_BYTES;
 #pragma unroll
-                for (int k = 0; k < BK / 8; ++k) {
-                    // advancing 8 tf32 (32 bytes) inside a swizzled row = +2 in the encoded start address
-                    const uint64_t ahi = smem_desc(st + k * 32), alo = smem_desc(st + TILE_BYTES + k * 32);
-                    const uint64_t bhi = smem_desc(st + 2 * TILE_BYTES + k * 32), blo = smem_desc(st + 3 * TILE_BYTES + k * 32);
-                    mma_tf32(tmem, alo, bhi, idesc, (kb | k) != 0);      // small terms first
-                    mma_tf32(tmem, ahi, blo, idesc, 1);
-                    mma_tf32(tmem, ahi, bhi, idesc, 1);
+                    for (int k = 0; k < BK / 8; ++k) {
+                        // advancing 8 tf32 (32 bytes) inside a swizzled row = +2 in the encoded start address
+                        const uint64_t ahi = smem_desc(st + k * 32), alo = smem_desc(st + TILE_BYTES + k * 32);
+                        const uint64_t bhi = smem_desc(st + 2 * TILE_BYTES + k * 32), blo = smem_desc(st + 3 * TILE_BYTES + k * 32);
+                        mma_tf32(acc, alo, bhi, idesc, (kb | k) != 0);      // small terms first
+                        mma_tf32(acc, ahi, blo, idesc, 1);
+                        mma_tf32(acc, ahi, bhi, idesc, 1);
+                    }
+                    // commit: arrives on the barrier when the MMAs above have finished reading the stage
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s) : "memory");
                 }
-                // commit: arrives on the barrier when the MMAs above have finished reading the stage
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty0 + 8 * s) : "memory");
-                if (kb == KB - 1)
-                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tmem_full) : "memory");
+                __syncwarp();
             }
+            if (lane == 0)      // accumulator complete (also for an empty contraction slice: nothing pending)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tfull0 + 8 * buf) : "memory");
             __syncwarp();
+            it += KB;
+        }
+    } else {
+        // ===== epilogue warps =====
+        const int lq = warp & 3;                                        // a warp may only touch TMEM lanes [32 (warp % 4), +32)
+        float* tbuf = epi_buf + lq * 32 * 33;
+        int lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            int m0, n0, z, k_begin, k_end;
+            decode(tile, m0, n0, z, k_begin, k_end);
+            const int KB = (k_end - k_begin + BK - 1) / BK;
+            const int buf = lt & 1;
+            float* const Yz = A.Y + (TRANSPOSED ? (long long)z * A.y_split_stride : 0);
+            bar_wait(tfull0 + 8 * buf, (lt >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem + ((uint32_t)(lq * 32) << 16) + (uint32_t)(buf * BN + c0);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                      "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                      "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr) : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c0 + 32 >= BN) {                                     // last chunk read: hand the accumulator back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    bar_arrive(tempty0 + 8 * buf);
+                }
+                if (n0 + c0 >= A.N) continue;                            // whole chunk outside N (warp-uniform)
+                const int n = n0 + c0 + lane;
+                const bool nv = n < A.N;
+                const float bv = (A.bias && nv) ? __ldg(A.bias + n) : 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) tbuf[lane * 33 + j] = KB > 0 ? __uint_as_float(r[j]) : 0.f;
+                __syncwarp();
+                if (A.mask) {
+                    // backward epilogue, 16 rows at a time: the 16 act'(.) inputs are LOADED first (unconditional,
+                    // clamped addresses) and only then consumed -- the pipeline issues in order, so a load followed
+                    // directly by its use would expose one full memory latency per row
+#pragma unroll 1
+                    for (int h = 0; h < 2; ++h) {
+                        float mk[16];
+                        const int nc = nv ? n : 0;
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr) {
+                            const int row = min(m0 + lq * 32 + h * 16 + rr, A.M - 1);
+                            mk[rr] = __ldg(A.mask + (long long)row * A.ldm + nc);
+                        }
+#pragma unroll
+                        for (int rr = 0; rr < 16; ++rr) {
+                            const int row = m0 + lq * 32 + h * 16 + rr;
+                            if (row < A.M && nv)
+                                Yz[(long long)row * A.ldy + n] =
+                                    act_f(A.act, tbuf[(h * 16 + rr) * 33 + lane] + bv) * act_grad_f(A.mask_act, mk[rr]);
+                        }
+                    }
+                } else {
+#pragma unroll 4
+                    for (int rr = 0; rr < 32; ++rr) {
+                        const int row = m0 + lq * 32 + rr;
+                        if (row >= A.M) break;
+                        if (nv) Yz[(long long)row * A.ldy + n] = act_f(A.act, tbuf[rr * 33 + lane] + bv);
+                    }
+                }
+                __syncwarp();
+            }
         }
     }
     __syncthreads();
     if (warp == MMA_WARP) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * BN) : "memory");
     }
 }
 

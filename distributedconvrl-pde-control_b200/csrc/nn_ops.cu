@@ -127,6 +127,12 @@ int32_t make_weight_map(pdeb200_ctx* c, CUtensorMap* map, float* ptr, int rows, 
     return PDEB200_OK;
 }
 
+int sm_count(const pdeb200_ctx* c) {
+    int n = 148;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, c->device);
+    return n;
+}
+
 template <bool T, bool B>
 int32_t configure_tc(pdeb200_ctx* c) {
     static thread_local bool done = false;
@@ -168,8 +174,8 @@ int32_t dense_layer(pdeb200_ctx* c, int M, int K, int N, const float* X, long lo
         A.M = M; A.N = N; A.K = ldw; A.act = act;      // padded K columns are zero in the weights; X's are zeroed by the caller
         A.mask = nullptr; A.ldm = 0; A.mask_act = 0; A.split_len = 0; A.y_split_stride = 0;
         if ((rc = configure_tc<false, true>(c))) return rc;
-        const dim3 grid((M + tc::BM - 1) / tc::BM, (N + tc::BN - 1) / tc::BN);
-        tc::dense_tc_kernel<false, true><<<grid, tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A, TM);
+        const int n_tiles = ((M + tc::BM - 1) / tc::BM) * ((N + tc::BN - 1) / tc::BN);
+        tc::dense_tc_kernel<false, true><<<std::min(n_tiles, sm_count(c)), tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A, TM);
         PDEB_CUDA(c, cudaGetLastError());
         c->launches += 2;
         if (used_tc) *used_tc += 1;
@@ -262,8 +268,8 @@ int32_t dense_dgrad(pdeb200_ctx* c, int M, int K, int N, const float* dY, long l
         A.M = M; A.N = K; A.K = ldp; A.act = 0; A.mask = mask; A.ldm = ldm; A.mask_act = mask_act;
         A.split_len = 0; A.y_split_stride = 0;
         if ((rc = configure_tc<false, true>(c))) return rc;
-        const dim3 grid((M + tc::BM - 1) / tc::BM, (K + tc::BN - 1) / tc::BN);
-        tc::dense_tc_kernel<false, true><<<grid, tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A, TM);
+        const int n_tiles = ((M + tc::BM - 1) / tc::BM) * ((K + tc::BN - 1) / tc::BN);
+        tc::dense_tc_kernel<false, true><<<std::min(n_tiles, sm_count(c)), tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A, TM);
         PDEB_CUDA(c, cudaGetLastError());
         c->launches += 2;
         return PDEB200_OK;
@@ -297,9 +303,9 @@ int32_t dense_wgrad(pdeb200_ctx* c, int M, int K, int N, const float* dY, long l
         A.M = N; A.N = K; A.K = M; A.act = 0; A.mask = nullptr; A.ldm = 0; A.mask_act = 0;
         A.split_len = split_len; A.y_split_stride = zstride;
         if ((rc = configure_tc<true, false>(c))) return rc;
-        const dim3 grid((N + tc::BM - 1) / tc::BM, (K + tc::BN - 1) / tc::BN, Z);
+        const int n_tiles = ((N + tc::BM - 1) / tc::BM) * ((K + tc::BN - 1) / tc::BN) * Z;
         tc::DenseTmaMaps TM{};
-        tc::dense_tc_kernel<true, false><<<grid, tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A, TM);
+        tc::dense_tc_kernel<true, false><<<std::min(n_tiles, sm_count(c)), tc::N_THREADS, tc::SMEM_BYTES, c->stream>>>(A, TM);
         reduce_splits_kernel<<<(N * K + 255) / 256, 256, 0, c->stream>>>(Z, N, K, ldp, 1, g_gs.p, zstride, gW);
         PDEB_CUDA(c, cudaGetLastError());
         c->launches += 2;
