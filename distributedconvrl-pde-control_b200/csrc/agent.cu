@@ -381,13 +381,28 @@ __global__ void __launch_bounds__(512) ddpg_actor_kernel(const __grid_constant__
     if (threadIdx.x == 0) { out[D.n_acc] = (float)s_q; out[D.n_acc + 1] = 0.f; }
 }
 
+// sum_b partials[b * stride + q] in ascending b (fixed order), with the loads issued eight at a time ahead of the adds
+// (the SM issues in order: load / add / load / add would expose one memory latency per term)
+__device__ __forceinline__ double ordered_sum(const float* __restrict__ partials, int n_blocks, size_t stride, int q) {
+    double s = 0.0;
+    int b = 0;
+    for (; b + 8 <= n_blocks; b += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(partials + (size_t)(b + u) * stride + q);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
+    for (; b < n_blocks; ++b) s += (double)__ldg(partials + (size_t)b * stride + q);
+    return s;
+}
+
 // grads[q] = sum over CTAs (fixed order); tail sums go to stats
 __global__ void reduce_partials_kernel(int n_blocks, int n_acc, const float* __restrict__ partials, float* grads,
                                        double* stats, int stat0) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_acc + 2) return;
-    double s = 0.0;
-    for (int b = 0; b < n_blocks; ++b) s += (double)partials[(size_t)b * (n_acc + 2) + q];
+    const double s = ordered_sum(partials, n_blocks, (size_t)(n_acc + 2), q);
     if (q < n_acc) grads[q] = (float)s;
     else stats[stat0 + (q - n_acc)] = s;
 }
@@ -399,8 +414,7 @@ __global__ void reduce_adam_polyak_kernel(int n_blocks, int n_acc, const float* 
                                           double bp1, double bp2, double eps, float polyak) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_acc + 2) return;
-    double s = 0.0;
-    for (int b = 0; b < n_blocks; ++b) s += (double)partials[(size_t)b * (n_acc + 2) + q];
+    const double s = ordered_sum(partials, n_blocks, (size_t)(n_acc + 2), q);
     if (q >= n_acc) { stats[stat0 + (q - n_acc)] = s; return; }
     const float g = (float)s;
     grads[q] = g;

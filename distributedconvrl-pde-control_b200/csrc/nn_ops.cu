@@ -219,7 +219,15 @@ __global__ void wgrad_thin_kernel(int M, int K, int N, int slice, const float* _
     const int n = q % N, k = q / N;
     const int m0 = blockIdx.y * slice, m1 = min(M, m0 + slice);
     float acc = 0.f;
-    for (int m = m0; m < m1; ++m) acc = fmaf(dY[(long long)m * lddy + n], __ldg(X + (long long)m * ldx + k), acc);
+    int m = m0;
+    for (; m + 8 <= m1; m += 8) {             // loads first, FMAs after, ascending m
+        float a[8], b[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { a[u] = __ldg(dY + (long long)(m + u) * lddy + n); b[u] = __ldg(X + (long long)(m + u) * ldx + k); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc = fmaf(a[u], b[u], acc);
+    }
+    for (; m < m1; ++m) acc = fmaf(__ldg(dY + (long long)m * lddy + n), __ldg(X + (long long)m * ldx + k), acc);
     partial[(size_t)blockIdx.y * N * K + q] = acc;
 }
 
@@ -229,7 +237,15 @@ __global__ void colsum_kernel(int M, int N, int slice, const float* __restrict__
     if (n >= N) return;
     const int m0 = blockIdx.y * slice, m1 = min(M, m0 + slice);
     float acc = 0.f;
-    for (int m = m0; m < m1; ++m) acc += dY[(long long)m * lddy + n];
+    int m = m0;
+    for (; m + 8 <= m1; m += 8) {
+        float a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = __ldg(dY + (long long)(m + u) * lddy + n);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += a[u];
+    }
+    for (; m < m1; ++m) acc += __ldg(dY + (long long)m * lddy + n);
     partial[(size_t)blockIdx.y * N + n] = acc;
 }
 
@@ -241,7 +257,15 @@ __global__ void reduce_splits_kernel(int Z, int N, int K, int ldp, int transpose
     const int n = q % N, k = q / N;
     const long long src = transposed ? (long long)n * ldp + k : q;
     double s = 0.0;
-    for (int z = 0; z < Z; ++z) s += (double)partial[z * zstride + src];
+    int z = 0;
+    for (; z + 8 <= Z; z += 8) {              // loads first, adds after (in-order issue), ascending z (fixed order)
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(partial + (long long)(z + u) * zstride + src);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
+    for (; z < Z; ++z) s += (double)__ldg(partial + (long long)z * zstride + src);
     out[q] = (float)s;
 }
 
