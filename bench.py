@@ -56,7 +56,7 @@ def config_dict(args, n_gpus):
                         "fused policy inference (KS200 actor 1-6-1) + env step" % (args.oversampling, args.envs),
             "envs_per_gpu": args.envs, "global_envs": args.envs * n_gpus, "nx": 256, "oversampling": args.oversampling,
             "parallelism": "env-sharded x%d (no data-path collective)" % n_gpus,
-            "l2": "flushed between timed iterations (256 MiB write); state 16 MiB/GPU < 126 MB L2"}
+            "l2": "flushed between timed iterations (256 MiB write, then read back so the evicted-to lines are clean); state 16 MiB/GPU < 126 MB L2"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -267,6 +267,13 @@ def run_ours(args):
     assert stream.cuda_stream != 0
     L.check(env._lib.pdeb200_set_stream(env._ctx, C.c_void_p(stream.cuda_stream)), env._ctx)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush_sink = torch.zeros(1, dtype=torch.int64, device="cuda")
+
+    def flush_l2():
+        # write a buffer larger than L2 (evicts everything), then read it back so that L2 is left holding CLEAN
+        # lines: a timed step should start cold, not pay for writing someone else's dirty 126 MB back to HBM
+        flush.zero_()
+        flush_sink.copy_(flush.view(torch.int64).sum().reshape(1))
 
     def barrier():
         torch.cuda.synchronize()
@@ -287,7 +294,7 @@ def run_ours(args):
     barrier()
     clocks.start()
     for i in range(args.steps):
-        flush.zero_()                      # L2 flush, outside the event-timed region
+        flush_l2()                         # L2 flush, outside the event-timed region
         ev0[i].record(stream)
         env.rollout(1)
         ev1[i].record(stream)
@@ -297,13 +304,17 @@ def run_ours(args):
     total_ms = float(sum(kern_ms))
     # dominant kernel (the KS core kernel) alone: CUDA events recorded around it inside the library, same stream
     L.check(env._lib.pdeb200_enable_step_timing(env._ctx, 1), env._ctx)
-    core_ms = []
+    core_ms, phases = [], []
     for i in range(min(args.steps, 50)):
-        flush.zero_()
+        flush_l2()
         env.rollout(1)
         ms = C.c_float()
         L.check(env._lib.pdeb200_last_core_ms(env._ctx, C.byref(ms)), env._ctx)
         core_ms.append(ms.value)
+        ph = (C.c_float * 3)()
+        L.check(env._lib.pdeb200_last_phase_ms(env._ctx, ph), env._ctx)
+        phases.append([ph[0], ph[1], ph[2]])
+    phases = [float(x) for x in np.mean(np.asarray(phases), axis=0)]
     L.check(env._lib.pdeb200_enable_step_timing(env._ctx, 0), env._ctx)
     core_ms = float(np.mean(core_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
@@ -420,6 +431,7 @@ def run_ours(args):
                 "traffic": traffic, "peak_source": peak_src, "kernel": "ks_step_kernel<%s,16,16>" % args.dtype,
                 "algorithmic_bytes_per_launch": core_bytes_env * B, "kernel_ms": core_ms,
                 "kernel_share_of_step": core_ms / avg_ms,
+                "phase_ms": {"actuate": phases[0], "core": phases[1], "observe": phases[2]},
                 "step": {"algorithmic_bytes_per_env_step": bytes_env, "ms": avg_ms,
                          "achieved_gbs": bytes_env * B / (avg_ms * 1e-3) / 1e9, "frac": bytes_env * B / (avg_ms * 1e-3) / 1e9 / peak},
                 "note": "at oversampling=30 the step is FP64-pipe/shared-memory bound (arithmetic intensity ~%d flop/B), "

@@ -81,6 +81,7 @@ _PROTOS = {
     "pdeb200_ddpg_update": (C.c_int32, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32]),
     "pdeb200_launch_count": (C.c_int64, [C.c_void_p]),
     "pdeb200_last_step_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
+    "pdeb200_last_phase_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
     "pdeb200_last_core_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
     "pdeb200_enable_step_timing": (C.c_int32, [C.c_void_p, C.c_int32]),
     "pdeb200_measure_fma_peak": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),

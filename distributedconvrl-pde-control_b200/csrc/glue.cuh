@@ -82,6 +82,85 @@ __global__ void __launch_bounds__(256) actuate_kernel(const __grid_constant__ Ac
     if (A.use_actor)
         for (int i = tid; i < A.actor_np; i += BD) s_par[i] = A.actor.params[i];
     __syncthreads();
+    // ---- fast path (conv agent, E * n_act <= blockDim, npts <= blockDim, <= 8 taps per grid point, actor width <= 8):
+    // no integer division in the loops, the thread's gather taps and the actor activations live in registers
+    int actor_w = 0;
+    if (A.use_actor) for (int l = 0; l <= A.actor.n_layers; ++l) actor_w = max(actor_w, A.actor.sizes[l]);
+    if (!A.mono && A.stage_table && E * A.n_act <= BD && A.npts <= BD && A.act_nnz <= 8 && actor_w <= 8 && A.a_rows <= 8) {
+        const int ce = tid / A.n_act, cj = tid - ce * A.n_act;            // this thread's column slot (fixed for all groups)
+        const bool col_on = tid < E * A.n_act;
+        int ti[8]; T tw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const bool on = j < A.act_nnz && tid < A.npts;
+            ti[j] = on ? s_idx[j * A.npts + tid] : 0;
+            tw[j] = on ? s_w[j * A.npts + tid] : T(0);
+        }
+        // the column inputs (previous action, observation or given action) of the NEXT group are requested before this
+        // group's gather phase: their cold-L2 latency (~2 us after a flush) then hides behind it instead of heading every group
+        T prev[8], in8[8];
+        auto request = [&](int env0n) {
+            const int envn = env0n + ce;
+            const bool onn = col_on && env0n < A.n_envs && envn < A.n_envs;
+            const size_t coln = (size_t)(onn ? envn : 0) * A.n_act + (onn ? cj : 0);
+            const T* acoln = A.action + coln * A.a_rows;
+            const T* srcn = A.use_actor ? A.state + coln * A.obs_rows : A.actions_in + coln * A.a_rows;
+            const int nin = A.use_actor ? A.obs_rows : A.a_rows;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                prev[r] = (onn && r < A.a_rows) ? acoln[r] : T(0);
+                in8[r] = (onn && r < nin) ? srcn[r] : T(0);
+            }
+        };
+        request(blockIdx.x * E);
+        for (int env0 = blockIdx.x * E; env0 < A.n_envs; env0 += gridDim.x * E) {
+            const int env = env0 + ce;
+            T first = T(0);
+            T v[8];
+            const bool act_on = col_on && env < A.n_envs;
+            if (act_on) {
+                if (A.use_actor) {
+                    // tiny runtime-shaped MLP: activations in shared memory ([unit][thread], conflict free) with plain
+                    // runtime loops -- for a 1-6-1 actor that is ~130 instructions per column; a fully unrolled,
+                    // predicated 8 x 8 register version issues ~500
+                    float* xa = s_x + tid;
+                    float* xh = s_x + (size_t)A.actor_wmax * BD + tid;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r)
+                        if (r < A.obs_rows) xa[r * BD] = (float)in8[r];
+                    const float* out = mlp_forward_smem(A.actor, s_par, xa, xh, BD);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) v[r] = r < A.a_rows ? clamp_t<T>((T)out[r * BD], A.act_limit) : T(0);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) v[r] = in8[r];
+                }
+                const size_t col = (size_t)env * A.n_act + cj;
+                T* acol = A.action + col * A.a_rows;
+                T* dcol = A.delta_action + col * A.a_rows;
+#pragma unroll
+                for (int r = 0; r < 8; ++r)
+                    if (r < A.a_rows) { dcol[r] = v[r] - prev[r]; acol[r] = v[r]; }
+                first = v[0];
+            }
+            request(env0 + gridDim.x * E);
+            if (col_on) s_a[tid] = first;
+            __syncthreads();
+            if (tid < A.npts) {
+                for (int e = 0; e < E; ++e) {
+                    if (env0 + e >= A.n_envs) break;
+                    const T* sa = s_a + e * A.n_act;
+                    T acc = T(0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (j < A.act_nnz) acc += (A.power * sa[ti[j]]) * tw[j];              // ascending actuator index
+                    A.p[(size_t)(env0 + e) * A.npts + tid] = acc;
+                }
+            }
+            __syncthreads();
+        }
+        return;
+    }
     // persistent over groups of E environments: the tables above are staged once per CTA
     for (int env0 = blockIdx.x * E; env0 < A.n_envs; env0 += gridDim.x * E) {
     if (A.use_actor && A.mono) {

@@ -50,60 +50,30 @@ __device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t ctr, floa
     *n0 = rad * co; *n1 = rad * s;
 }
 
-// Per-column MLP with the activations in REGISTERS (fully unrolled to the compile-time width W, predicated by the
-// runtime layer sizes); parameters broadcast from shared memory.  W = 0: generic local-memory path (widths <= 64).
-template <int W>
-__device__ __forceinline__ void mlp_forward_reg(const NetDev& net, const float* __restrict__ params, float (&x)[W > 0 ? W : 1]) {
-    float h[W > 0 ? W : 1];
-    for (int l = 0; l < net.n_layers; ++l) {
-        const int ni = net.sizes[l], no = net.sizes[l + 1];
-        const float* Wl = params + net.offs[l];
-        const float* b = Wl + ni * no;
-#pragma unroll
-        for (int o = 0; o < W; ++o) {
-            float acc = 0.f;
-            if (o < no) {
-#pragma unroll
-                for (int i = 0; i < W; ++i)
-                    if (i < ni) acc = fmaf(Wl[o + no * i], x[i], acc);
-                acc = act_apply(net.acts[l], acc + b[o]);
-            }
-            h[o] = acc;
-        }
-#pragma unroll
-        for (int o = 0; o < W; ++o) x[o] = h[o];
-    }
-}
-
-template <typename T, int W>
-__global__ void __launch_bounds__(128) policy_kernel(NetDev net, int n_params, int n_columns, int obs_rows, int a_rows, int memory,
-                                                     const T* __restrict__ state, T* __restrict__ action_in,
+// Per-column actor forward.  Activations live in shared memory as [unit][thread] (conflict free) and the layers are
+// plain runtime loops: for the tiny runtime-shaped networks of this path (1-6-1 ... 12-20-1) that is ~4x fewer issued
+// instructions than a register version that has to be unrolled (and predicated) to a compile-time maximum width.
+template <typename T>
+__global__ void __launch_bounds__(128) policy_kernel(NetDev net, int n_params, int wmax, int n_columns, int obs_rows, int a_rows,
+                                                     int memory, const T* __restrict__ state, T* __restrict__ action_in,
                                                      const T* __restrict__ noise, int use_rng, uint64_t seed, uint64_t offset,
                                                      T act_noise, T act_limit) {
-    extern __shared__ float s_par[];
-    for (int i = threadIdx.x; i < n_params; i += blockDim.x) s_par[i] = net.params[i];
+    extern __shared__ float s_dyn[];
+    float* s_par = s_dyn;
+    float* s_x = s_dyn + n_params;                                   // [2][wmax][blockDim]
+    const int BD = blockDim.x;
+    for (int i = threadIdx.x; i < n_params; i += BD) s_par[i] = net.params[i];
     __syncthreads();
-    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    const int col = blockIdx.x * BD + threadIdx.x;
     if (col >= n_columns) return;
-    constexpr int XW = W > 0 ? W : kFusedActorMaxWidth;
-    float x[XW];
+    float* xa = s_x + threadIdx.x;
+    float* xh = s_x + (size_t)wmax * BD + threadIdx.x;
+    for (int r = 0; r < obs_rows; ++r) xa[r * BD] = (float)state[(size_t)col * obs_rows + r];
+    const float* out = mlp_forward_smem(net, s_par, xa, xh, BD);
     const int n_out = net.sizes[net.n_layers];            // == a_rows (conv agent) or n_act (mono)
-    if constexpr (W > 0) {
-#pragma unroll
-        for (int r = 0; r < W; ++r) x[r] = r < obs_rows ? (float)state[(size_t)col * obs_rows + r] : 0.f;
-        mlp_forward_reg<W>(net, s_par, x);
-    } else {
-        float h[kFusedActorMaxWidth];
-        for (int r = 0; r < obs_rows; ++r) x[r] = (float)state[(size_t)col * obs_rows + r];
-        NetDev n2 = net;
-        n2.params = s_par;
-        mlp_forward_small(n2, x, h);
-    }
     const int noisy = n_out - memory;
-#pragma unroll
-    for (int r = 0; r < XW; ++r) {
-        if (r >= n_out) break;
-        T v = (T)x[r];
+    for (int r = 0; r < n_out; ++r) {
+        T v = (T)out[r * BD];
         if (r < noisy) {
             if (noise) v += noise[(size_t)col * noisy + r] * act_noise;
             else if (use_rng) {
@@ -662,20 +632,21 @@ static int32_t policy_launch(pdeb200_ctx* c, const void* d_noise, int use_rng, u
     const int ncol = c->cfg.n_envs * c->n_cols;
     const int mem = c->cfg.mono ? 0 : c->cfg.memory_size;
     const int tpb = 128, grid = (ncol + tpb - 1) / tpb;
-    int wmax = 0;
+    int wmax = 1;
     for (int l = 0; l <= a.n_layers; ++l) wmax = std::max(wmax, a.sizes[l]);
-    const size_t smem = (size_t)a.n_params * sizeof(float);
-    if (smem > 48 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "policy_act: actor parameters exceed 48 KB of shared memory");
-#define PDEB_POLICY(TT, WW)                                                                                              \
-    policy_kernel<TT, WW><<<grid, tpb, smem, c->stream>>>(a.dev(), a.n_params, ncol, c->obs_rows, c->a_rows, mem,        \
-                                                          (const TT*)c->state, (TT*)c->action_in, (const TT*)d_noise,    \
-                                                          use_rng, seed, offset, (TT)act_noise, (TT)act_limit)
+    const size_t smem = ((size_t)a.n_params + (size_t)2 * wmax * tpb) * sizeof(float);
+    if (smem > 200 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "policy_act: actor too large for shared memory");
     if (c->cfg.dtype == PDEB200_F64) {
-        if (wmax <= 8) PDEB_POLICY(double, 8); else if (wmax <= 24) PDEB_POLICY(double, 24); else PDEB_POLICY(double, 0);
+        if (smem > 48 * 1024) PDEB_CUDA(c, cudaFuncSetAttribute(policy_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        policy_kernel<double><<<grid, tpb, smem, c->stream>>>(a.dev(), a.n_params, wmax, ncol, c->obs_rows, c->a_rows, mem,
+                                                             (const double*)c->state, (double*)c->action_in, (const double*)d_noise,
+                                                             use_rng, seed, offset, act_noise, act_limit);
     } else {
-        if (wmax <= 8) PDEB_POLICY(float, 8); else if (wmax <= 24) PDEB_POLICY(float, 24); else PDEB_POLICY(float, 0);
+        if (smem > 48 * 1024) PDEB_CUDA(c, cudaFuncSetAttribute(policy_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        policy_kernel<float><<<grid, tpb, smem, c->stream>>>(a.dev(), a.n_params, wmax, ncol, c->obs_rows, c->a_rows, mem,
+                                                            (const float*)c->state, (float*)c->action_in, (const float*)d_noise,
+                                                            use_rng, seed, offset, (float)act_noise, (float)act_limit);
     }
-#undef PDEB_POLICY
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
@@ -768,6 +739,16 @@ int32_t pdeb200_measure_fma_peak(pdeb200_ctx* c, int32_t dtype, double* tflops) 
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 4;
     *tflops = best;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_last_phase_ms(pdeb200_ctx* c, float* ms3) {
+    if (!c || !ms3) return PDEB200_EINVAL;
+    if (!c->timed) return fail(c, PDEB200_ESTATE, "last_phase_ms: timing not enabled or no step yet");
+    PDEB_CUDA(c, cudaEventSynchronize(c->ev1));
+    PDEB_CUDA(c, cudaEventElapsedTime(ms3 + 0, c->ev0, c->evc0));      // actuation (policy + prepare_action)
+    PDEB_CUDA(c, cudaEventElapsedTime(ms3 + 1, c->evc0, c->evc1));     // core (do_step + sensor dots)
+    PDEB_CUDA(c, cudaEventElapsedTime(ms3 + 2, c->evc1, c->ev1));      // observe (reward, featurize, clock)
     return PDEB200_OK;
 }
 
