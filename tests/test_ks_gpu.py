@@ -168,3 +168,56 @@ def test_global_agent_variant(pkg, golden):
     assert relerr(env.y.T, y[1:B + 1]) < 1e-12
     assert relerr(env.reward, r[1:B + 1, 0]) < 1e-11
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_memory_rows_and_temporal_stacking_over_steps(pkg, dtype):
+    """memory_size > 0 (KSSetup.jl:39, 220-226): the action has 1 + memory rows, the state's last `memory` rows are the
+    tail rows of the action; with window 3 x temporal 2 the older block slides down each step."""
+    mem = 2
+    cfg = K.ks256_config(3)
+    cfg.temporal_steps, cfg.memory_size = 2, mem
+    setup = pkg.setups.KSSetup.ks256(window_size=3, temporal_steps=2, memory_size=mem)
+    rng = np.random.default_rng(21)
+    B, n_a = 3, cfg.n_actuators
+    y0 = setup.generate_random_init(rng, B) * 0.3
+    env = setup.make_env(n_envs=B, dtype=dtype, y0=y0)
+    refs = [K.KSEnv(cfg, y0=y0[b]) for b in range(B)]
+    assert env.state.shape == (3 * 2 + mem, B * n_a) and env.action.shape == (1 + mem, B * n_a)
+    tol = TOL[dtype]
+    for step in range(3):
+        a = rng.uniform(-1, 1, (1 + mem, B * n_a))
+        env(a)
+        for b in range(B):
+            refs[b].step(a[:, b * n_a:(b + 1) * n_a])
+            assert relerr(env.y[:, b], refs[b].y) < tol
+            st = env.state[:, b * n_a:(b + 1) * n_a]
+            assert relerr(st, refs[b].state) < 20 * tol, (step, b)
+            assert np.allclose(st[-mem:], a[1:, b * n_a:(b + 1) * n_a], rtol=1e-6, atol=0)        # memory rows = action tail
+            assert np.allclose(env.reward[b * n_a:(b + 1) * n_a], refs[b].reward, rtol=200 * tol, atol=20 * tol)
+    env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("nx", [64, 128, 320, 384, 512, 1024])
+def test_other_grid_sizes_of_the_factor_table(pkg, nx):
+    """Every four-step factorisation the KS back-end advertises (ks.cu kFacts) against the oracle."""
+    n_s = nx // 4
+    cfg = K.KSConfig(Lx=nx * 200.0 / 240, nx=nx, sensor_positions=np.arange(1, nx + 1, 4), actuators_to_sensors=np.arange(1, n_s + 1),
+                     t_samples=nx + 100, oversampling=5)
+    setup = pkg.setups.KSSetup(Lx=cfg.Lx, nx=nx, sensor_positions=cfg.sensor_positions, actuators_to_sensors=cfg.actuators_to_sensors,
+                               t_samples=nx + 100, oversampling=5)
+    rng = np.random.default_rng(nx)
+    B = 3
+    y0 = setup.generate_random_init(rng, B) * 0.2
+    a = rng.uniform(-1, 1, (1, B * n_s))
+    for dtype in ("f64", "f32"):
+        env = setup.make_env(n_envs=B, dtype=dtype, y0=y0)
+        env(a)
+        for b in range(B):
+            ref = K.KSEnv(cfg, y0=y0[b])
+            ref.step(a[:, b * n_s:(b + 1) * n_s])
+            assert relerr(env.y[:, b], ref.y) < TOL[dtype], (nx, dtype, b)
+            assert relerr(env.state[:, b * n_s:(b + 1) * n_s], ref.state) < 20 * TOL[dtype]
+        env.close()
