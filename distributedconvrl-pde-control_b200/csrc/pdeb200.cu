@@ -196,7 +196,10 @@ int32_t actuate_t(pdeb200_ctx* c, const void* actions_dev, int use_actor, double
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
     const int groups = (c->cfg.n_envs + E - 1) / E;
-    const int per_sm = std::max(1, std::min(8, (int)((200 * 1024) / std::max<size_t>(smem, 1))));
+    // CTAs that are really co-resident (registers AND shared memory): a grid one CTA larger than a whole wave costs a
+    // full extra CTA lifetime
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actuate_kernel<T>, tpb, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     // whole waves of persistent CTAs: every CTA gets the same number of groups when the batch allows it
     const int resident = n_sm * per_sm;
     const int rounds = (groups + resident - 1) / resident;
