@@ -457,8 +457,8 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         orc = CpuOracle(args.oversampling)
         orc.run(4, 1)
-        n_steps_cpu = 10
-        per_core = 32
+        n_steps_cpu = 100                # ~10 s of CPU work on 16 cores (contract: a bounded 10-30 s sample)
+        per_core = 128
         secs = orc.run(per_core, n_steps_cpu)
         line["cpu_baseline"] = {"value": per_core * orc.cores * n_steps_cpu / secs, "unit": UNIT, "cores": orc.cores,
                                 "kind": "port", "sample": "%d envs x %d env steps (same KS N=256 config), one thread per core"
