@@ -225,6 +225,31 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+def bind_to_gpu_cpus(index):
+    """Bind this rank to the CPUs NVML reports as local to its GPU (intersected with the cpuset we are allowed):
+    the e2e leg's pinned buffers and driver threads then sit on the GPU's own NUMA node / PCIe root."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = index
+        if vis:
+            ids = [v for v in vis.split(",") if v.strip() != ""]
+            if index < len(ids) and ids[index].strip().isdigit():
+                phys = int(ids[index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        local = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = sorted(local & allowed)
+        if use:
+            os.sched_setaffinity(0, use)
+            return {"gpu_local_cpus": len(local), "bound_to": len(use)}
+        return {"gpu_local_cpus": len(local), "bound_to": 0, "note": "no GPU-local CPU in the allowed cpuset"}
+    except Exception as e:                                   # noqa: BLE001 -- best effort, never fatal
+        return {"error": type(e).__name__}
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -244,6 +269,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_cpus(local)       # pinned host buffers are then first-touched on the GPU's own NUMA node
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -449,7 +475,7 @@ def run_ours(args):
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "shards": n_sh, "launches": int(e2e_launches), "host_threads": args.e2e_driver,
+                    "shards": n_sh, "launches": int(e2e_launches), "host_threads": args.e2e_driver, "cpu_binding": numa,
                     "call_sequence": "per shard and step: pdeb200_policy_act -> pdeb200_get(ACTION_IN) [D2H] -> "
                                      "pdeb200_step_host [H2D action; D2H reward, state, done], pinned host buffers"},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
