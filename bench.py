@@ -113,15 +113,17 @@ def run_reference(args):
     if rank != 0:
         return
     orc = CpuOracle(args.oversampling)
-    envs_per_core = 16
+    # one bench "step" of this arm = a bounded sample: 64 envs per core advanced 4 env steps (large enough that the
+    # thread start-up does not count against the CPU; ~0.15 s per step, a 200-step run stays under a minute)
+    envs_per_core, inner = 64, 4
     for _ in range(args.warmup):
-        orc.run(envs_per_core, 1)
+        orc.run(envs_per_core, inner)
     t = 0.0
     for i in range(args.steps):
-        t += orc.run(envs_per_core, 1, seed=i + 1)
-    n_env_steps = args.steps * envs_per_core * orc.cores
+        t += orc.run(envs_per_core, inner, seed=i + 1)
+    n_env_steps = args.steps * envs_per_core * orc.cores * inner
     value = n_env_steps / t
-    sample = "%d envs (16 per core) x 1 env step per bench step" % (envs_per_core * orc.cores)
+    sample = "%d envs (%d per core) x %d env steps per bench step" % (envs_per_core * orc.cores, envs_per_core, inner)
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
