@@ -227,6 +227,129 @@ __global__ void __launch_bounds__(256) actuate_kernel(const __grid_constant__ Ac
     }
 }
 
+// ---- shape-specialised actuation for the conv agent (one action row per actuator) ------------------------------
+// Same arithmetic as the fast path of actuate_kernel, with the loop shapes known at compile time: NNZ taps per grid
+// point held in registers (fetched straight from the global table, no staging pass), the actor either absent
+// (NIN = 0: actions given), a NIN-NH-1 network evaluated in registers with its parameters hoisted out of the group
+// loop, or of runtime shape through shared memory (NIN = -1).  The actions of a group go through a double-buffered
+// shared line already multiplied by agent_power, so a group costs one barrier and the gather is one shared load and
+// one FMA per tap.  ncu on the generic kernel (profiles/r1_ks_step_f64.md, "actuate"): 1066 warp instructions per
+// warp and group, 29 % of them in the predicated 8-tap gather and 28 % in the runtime-shaped MLP loops.
+template <int NIN, int NH> struct ActorRegs {
+    static constexpr int NP = NIN > 0 ? NIN * NH + NH + NH + 1 : 1;
+};
+
+template <typename T, int NNZ, int NIN, int NH>
+__global__ void __launch_bounds__(256) actuate_conv_kernel(const __grid_constant__ ActuateArgs<T> A) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int E = A.envs_per_cta, tid = threadIdx.x;
+    constexpr int BD = 256;
+    const int ncol = E * A.n_act;                                   // <= BD
+    T* s_a = reinterpret_cast<T*>(smem_raw);                        // [2][ncol]  power * action
+    float* s_par = reinterpret_cast<float*>(smem_raw + (((size_t)2 * ncol * sizeof(T) + 15) & ~(size_t)15));
+    float* s_x = s_par + ((A.actor_np + 3) & ~3);
+
+    const bool pt_on = tid < A.npts;
+    int tb[NNZ]; T tw[NNZ];                                         // byte offset of the tap's actuator in s_a, weight
+#pragma unroll
+    for (int j = 0; j < NNZ; ++j) {
+        const bool on = pt_on && j < A.act_nnz;
+        tb[j] = on ? __ldg(A.act_idx + j * A.npts + tid) * (int)sizeof(T) : 0;
+        tw[j] = on ? __ldg(A.act_w + j * A.npts + tid) : T(0);
+    }
+#pragma unroll
+    for (int j = 1; j < NNZ; ++j) if (j >= A.act_nnz) tb[j] = tb[0];  // padding taps: weight 0 on a tap the point already has
+
+    float w[ActorRegs<NIN, NH>::NP];
+    if (NIN != 0) {
+        for (int i = tid; i < A.actor_np; i += BD) s_par[i] = A.actor.params[i];
+        __syncthreads();
+        if (NIN > 0) {
+            // W0 (NH x NIN, column-major) | b0 | W1 (1 x NH) | b1 are contiguous in the flat parameter vector
+#pragma unroll
+            for (int i = 0; i < ActorRegs<NIN, NH>::NP; ++i) w[i] = s_par[i];
+        }
+    }
+    const int act0 = A.actor.acts[0], act1 = A.actor.acts[1];
+
+    const int ce = tid / A.n_act, cj = tid - ce * A.n_act;          // this thread's column slot (fixed for all groups)
+    const bool col_on = tid < ncol;
+    constexpr int NX = NIN > 0 ? NIN : (NIN < 0 ? 8 : 1);
+    T prev, xin[NX];
+    auto request = [&](int env0n) {
+        const int envn = env0n + ce;
+        const bool onn = col_on && envn < A.n_envs;
+        const size_t coln = onn ? (size_t)envn * A.n_act + cj : 0;
+        prev = onn ? A.action[coln] : T(0);
+        if (NIN == 0) xin[0] = onn ? A.actions_in[coln] : T(0);
+        else {
+            const T* srcn = A.state + coln * A.obs_rows;
+#pragma unroll
+            for (int r = 0; r < NX; ++r) xin[r] = (onn && (NIN > 0 || r < A.obs_rows)) ? srcn[r] : T(0);
+        }
+    };
+    request(blockIdx.x * E);
+    int buf = 0;
+    for (int env0 = blockIdx.x * E; env0 < A.n_envs; env0 += gridDim.x * E, buf ^= 1) {
+        const int env = env0 + ce;
+        T* sa = s_a + buf * ncol;
+        if (col_on) {
+            T v = T(0);
+            if (env < A.n_envs) {
+                if (NIN == 0) v = xin[0];
+                else {
+                    float o;
+                    if (NIN > 0) {
+                        float h[NH > 0 ? NH : 1];
+#pragma unroll
+                        for (int u = 0; u < NH; ++u) {
+                            float acc = 0.f;
+#pragma unroll
+                            for (int i = 0; i < NIN; ++i) acc = fmaf(w[u + NH * i], (float)xin[i], acc);
+                            h[u] = acc + w[NIN * NH + u];
+                        }
+#pragma unroll
+                        for (int u = 0; u < NH; ++u) h[u] = act_apply(act0, h[u]);
+                        float acc = 0.f;
+#pragma unroll
+                        for (int u = 0; u < NH; ++u) acc = fmaf(w[NIN * NH + NH + u], h[u], acc);
+                        o = act_apply(act1, acc + w[NIN * NH + NH + NH]);
+                    } else {
+                        float* xa = s_x + tid;
+                        float* xh = s_x + (size_t)A.actor_wmax * BD + tid;
+#pragma unroll
+                        for (int r = 0; r < NX; ++r)
+                            if (r < A.obs_rows) xa[r * BD] = (float)xin[r];
+                        o = mlp_forward_smem(A.actor, s_par, xa, xh, BD)[0];
+                    }
+                    v = clamp_t<T>((T)o, A.act_limit);
+                }
+                const size_t col = (size_t)env * A.n_act + cj;
+                A.delta_action[col] = v - prev;
+                A.action[col] = v;
+            }
+            sa[tid] = A.power * v;
+        }
+        request(env0 + gridDim.x * E);                  // next group's inputs travel during this group's gather
+        __syncthreads();
+        if (pt_on) {
+            const unsigned char* sab = reinterpret_cast<const unsigned char*>(sa);
+            T* pout = A.p + (size_t)env0 * A.npts + tid;
+            const int ne = min(E, A.n_envs - env0);
+            for (int e = 0; e < ne; ++e) {
+                T a[NNZ];
+#pragma unroll
+                for (int j = 0; j < NNZ; ++j) a[j] = *reinterpret_cast<const T*>(sab + tb[j]);
+                T acc = T(0);
+#pragma unroll
+                for (int j = 0; j < NNZ; ++j) acc = fma(a[j], tw[j], acc);          // ascending actuator index
+                *pout = acc;
+                sab += A.n_act * sizeof(T); pout += A.npts;
+            }
+        }
+    }
+}
+
 template <typename T>
 struct ObserveArgs {
     ObsRewardParams<T> P;

@@ -1,6 +1,7 @@
 // libpdeb200.so -- C ABI (include/pdeb200.h): context, constants, environment entry points.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -164,6 +165,26 @@ int32_t observe_t(pdeb200_ctx* c, int fresh, const uint8_t* d_mask, double* d_rs
     return PDEB200_OK;
 }
 
+template <typename T> using ActuateFn = void (*)(ActuateArgs<T>);
+
+// mode: 0 actions given, 1 / 3: 1-6-1 / 3-6-1 actor in registers, -1: actor of runtime shape through shared memory
+template <typename T, int NNZ>
+ActuateFn<T> conv_kernel_for(int mode) {
+    switch (mode) {
+        case 0: return actuate_conv_kernel<T, NNZ, 0, 0>;
+        case 1: return actuate_conv_kernel<T, NNZ, 1, 6>;
+        case 3: return actuate_conv_kernel<T, NNZ, 3, 6>;
+        default: return actuate_conv_kernel<T, NNZ, -1, 0>;
+    }
+}
+template <typename T>
+ActuateFn<T> conv_kernel_for(int nnz, int mode) {
+    if (nnz <= 2) return conv_kernel_for<T, 2>(mode);
+    if (nnz <= 4) return conv_kernel_for<T, 4>(mode);
+    if (nnz <= 6) return conv_kernel_for<T, 6>(mode);
+    return conv_kernel_for<T, 8>(mode);
+}
+
 template <typename T>
 int32_t actuate_t(pdeb200_ctx* c, const void* actions_dev, int use_actor, double act_limit) {
     ActuateArgs<T> A;
@@ -188,23 +209,36 @@ int32_t actuate_t(pdeb200_ctx* c, const void* actions_dev, int use_actor, double
     A.envs_per_cta = E;
     const size_t tab = (size_t)A.act_nnz * A.npts * (sizeof(T) + sizeof(int));
     A.stage_table = tab <= 64 * 1024;
-    const size_t smem = actuate_smem_bytes<T>(E, A.n_act, A.npts, A.act_nnz, A.stage_table, use_actor, A.actor_np,
-                                              A.actor_wmax, tpb);
+    // the conv agent with one action row per actuator (every shipped KS / Keller-Segel 1-D / NS script) runs the
+    // shape-specialised kernel; everything else (global agent, action memory rows, > 8 taps, > 256 points) the generic one
+    ActuateFn<T> kern = actuate_kernel<T>;
+    size_t smem = actuate_smem_bytes<T>(E, A.n_act, A.npts, A.act_nnz, A.stage_table, use_actor, A.actor_np,
+                                        A.actor_wmax, tpb);
+    static const bool generic_only = [] { const char* e = getenv("PDEB200_ACTUATE_GENERIC"); return e && atoi(e) != 0; }();
+    if (!generic_only && !A.mono && A.a_rows == 1 && E * A.n_act <= tpb && A.npts <= tpb && A.act_nnz <= 8 &&
+        (!use_actor || (A.obs_rows <= 8 && net.sizes[net.n_layers] == 1))) {
+        const bool two = use_actor && net.n_layers == 2 && net.offs[0] == 0 &&
+                         net.offs[1] == net.sizes[0] * net.sizes[1] + net.sizes[1] && net.sizes[1] == 6;
+        const int mode = !use_actor ? 0 : (two && net.sizes[0] == 1) ? 1 : (two && net.sizes[0] == 3) ? 3 : -1;
+        kern = conv_kernel_for<T>(A.act_nnz, mode);
+        smem = (((size_t)2 * E * A.n_act * sizeof(T) + 15) & ~(size_t)15) + (size_t)((A.actor_np + 3) & ~3) * sizeof(float) +
+               (mode == -1 ? (size_t)2 * A.actor_wmax * tpb * sizeof(float) : 0);
+    }
     if (smem > 200 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "actuate: actor too large for shared memory");
     if (smem > 48 * 1024)
-        PDEB_CUDA(c, cudaFuncSetAttribute(actuate_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
     const int groups = (c->cfg.n_envs + E - 1) / E;
     // CTAs that are really co-resident (registers AND shared memory): a grid one CTA larger than a whole wave costs a
     // full extra CTA lifetime
     int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, actuate_kernel<T>, tpb, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, tpb, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
     // whole waves of persistent CTAs: every CTA gets the same number of groups when the batch allows it
     const int resident = n_sm * per_sm;
     const int rounds = (groups + resident - 1) / resident;
     const int grid = std::min(groups, (groups + rounds - 1) / rounds);
-    actuate_kernel<T><<<grid, tpb, smem, c->stream>>>(A);
+    kern<<<grid, tpb, smem, c->stream>>>(A);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
