@@ -353,6 +353,7 @@ __global__ void __launch_bounds__(256) actuate_conv_kernel(const __grid_constant
 template <typename T>
 struct ObserveArgs {
     ObsRewardParams<T> P;
+    int n_envs;
     int fresh;                     // 1: reset!/constructor semantics (no clock advance, zero reward)
     const uint8_t* mask;           // optional per-env mask (reset)
     const T* sensors;              // [B][fields][n_sensors] raw dots
@@ -361,27 +362,35 @@ struct ObserveArgs {
     uint8_t* done; double* time; int* steps; double* reward_sum;
 };
 
+// One WARP per environment: lanes stride over the actuator columns, the sensor dots are read straight from global
+// memory (512 B per environment, L1-resident after the first touch), the per-environment (sum, max) of the column
+// rewards is a shuffle reduction and lane 0 carries the clock / done flag, whose inputs it requested up front.  No
+// shared memory and no CTA barrier: the earlier one-CTA-per-environment version serialised three DRAM round trips
+// (sensors -> barrier -> columns -> barrier -> scalars) per CTA.
 template <typename T>
 __global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ ObserveArgs<T> A) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* s_sens = reinterpret_cast<T*>(smem_raw);                    // [fields][n_sensors]
-    __shared__ T s_red[2][4];
     const ObsRewardParams<T>& P = A.P;
-    const int env = blockIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (env >= A.n_envs) return;
     if (A.mask && !A.mask[env]) return;
-    const int nsv = P.fields * P.n_sensors;
-    for (int i = threadIdx.x; i < nsv; i += blockDim.x) s_sens[i] = A.sensors[(size_t)env * nsv + i];
-    __syncthreads();
-    auto sv = [&](int f, int i) { return s_sens[f * P.n_sensors + i]; };
     const bool fresh = A.fresh != 0;
+    double tm0 = 0.0; T vm = T(0); int st = 0; double rs0 = 0.0;
+    if (lane == 0 && !fresh) {
+        tm0 = A.time[env]; st = A.steps[env];
+        if (P.check_max == 1) vm = A.vmax[env];
+        if (A.reward_sum) rs0 = A.reward_sum[env];
+    }
+    const T* sens = A.sensors + (size_t)env * P.fields * P.n_sensors;
+    auto sv = [&](int f, int i) { return sens[f * P.n_sensors + i]; };
     T racc = T(0), rmax = T(0);
-    for (int j = threadIdx.x; j < P.n_act; j += blockDim.x) {
+    for (int j = lane; j < P.n_act; j += 32) {
         const size_t col = (size_t)env * P.n_act + j;
         T* acol = A.action + col * P.a_rows;
         T* dcol = A.delta_action + col * P.a_rows;
         if (fresh)
             for (int r = 0; r < P.a_rows; ++r) { acol[r] = T(0); dcol[r] = T(0); A.action_in[col * P.a_rows + r] = T(0); }
-        const T a0 = acol[0], d0 = dcol[0];
+        const T a0 = fresh ? T(0) : acol[0], d0 = fresh ? T(0) : dcol[0];
         T rj;
         if (!P.mono) {
             rj = assemble_column<T>(P, sv, j, a0, d0, acol, A.state + col * P.obs_rows, fresh);
@@ -398,43 +407,39 @@ __global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ Ob
         // state = reshape(sensors, (n_sensors, 1)) [+ temporal stacking], KSglobalSetup.jl:222-238
         T* scol = A.state + (size_t)env * P.obs_rows;
         if (P.temporal > 1 && !fresh) {
-            __syncthreads();
-            if (threadIdx.x == 0)
+            if (lane == 0)
                 for (int r = P.obs_rows - P.memory - 1; r >= P.n_sensors; --r) scol[r] = scol[r - P.n_sensors];
-            __syncthreads();
+            __syncwarp();
         }
-        for (int i = threadIdx.x; i < P.n_sensors; i += blockDim.x) {
-            const T v = s_sens[i] * P.obs_scale;
+        for (int i = lane; i < P.n_sensors; i += 32) {
+            const T v = sens[i] * P.obs_scale;
             scol[i] = v;
             if (fresh) for (int k = 1; k < P.temporal; ++k) scol[k * P.n_sensors + i] = v;
         }
-        for (int k = threadIdx.x; k < P.memory; k += blockDim.x) scol[P.obs_rows - P.memory + k] = T(0);
+        for (int k = lane; k < P.memory; k += 32) scol[P.obs_rows - P.memory + k] = T(0);
     }
-    // block reduction of (sum, max) over the columns
+    // (sum, max) over the columns; lanes hold partial sums of columns lane, lane + 32, ...
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         racc += __shfl_xor_sync(0xffffffffu, racc, o);
         rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
     }
-    if ((threadIdx.x & 31) == 0) { s_red[0][threadIdx.x >> 5] = racc; s_red[1][threadIdx.x >> 5] = rmax; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        T sum = T(0), mx = T(0);
-        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) { sum += s_red[0][w]; mx = fmax(mx, s_red[1][w]); }
+    if (lane == 0) {
         if (fresh) {
             if (P.mono) A.reward[env] = T(0);
             A.done[env] = 0; A.time[env] = 0.0; A.steps[env] = 0;
         } else {
-            const T rmean = sum / T(P.n_act);
+            const T rmean = racc / T(P.n_act);
+            T mx = rmax;
             if (P.mono) { A.reward[env] = rmean; mx = fabs(rmean); }
-            const double tm = A.time[env] + P.dt;                 // env.time += env.dt (Float64, quirk Q7)
+            const double tm = tm0 + P.dt;                         // env.time += env.dt (Float64, quirk Q7)
             bool dn = tm >= P.te;
-            if (P.check_max == 1) dn = dn || (A.vmax[env] > P.max_value);
+            if (P.check_max == 1) dn = dn || (vm > P.max_value);
             else if (P.check_max == 2) dn = dn || (mx > P.max_value);
             A.done[env] = dn ? 1 : 0;
             A.time[env] = tm;
-            A.steps[env] += 1;
-            if (A.reward_sum) A.reward_sum[env] += (double)rmean;
+            A.steps[env] = st + 1;
+            if (A.reward_sum) A.reward_sum[env] = rs0 + (double)rmean;
         }
     }
 }

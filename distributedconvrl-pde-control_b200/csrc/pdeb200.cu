@@ -152,14 +152,11 @@ template <typename T>
 int32_t observe_t(pdeb200_ctx* c, int fresh, const uint8_t* d_mask, double* d_rsum) {
     ObserveArgs<T> O;
     O.P = make_obs_params<T>(c);
-    O.fresh = fresh; O.mask = d_mask; O.sensors = (const T*)c->sensors; O.vmax = (const T*)c->vmax;
+    O.n_envs = c->cfg.n_envs; O.fresh = fresh; O.mask = d_mask; O.sensors = (const T*)c->sensors; O.vmax = (const T*)c->vmax;
     O.state = (T*)c->state; O.action = (T*)c->action; O.delta_action = (T*)c->delta_action; O.action_in = (T*)c->action_in;
     O.reward = (T*)c->reward; O.done = c->done; O.time = c->time; O.steps = c->steps; O.reward_sum = d_rsum;
-    const size_t smem = (size_t)c->fields * c->cfg.n_sensors * sizeof(T);
-    if (smem > 48 * 1024)
-        PDEB_CUDA(c, cudaFuncSetAttribute(observe_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tpb = c->cfg.n_actuators <= 32 ? 32 : (c->cfg.n_actuators <= 64 ? 64 : 128);
-    observe_kernel<T><<<c->cfg.n_envs, tpb, smem, c->stream>>>(O);
+    const int tpb = 128;                                          // one warp per environment
+    observe_kernel<T><<<(c->cfg.n_envs + tpb / 32 - 1) / (tpb / 32), tpb, 0, c->stream>>>(O);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
