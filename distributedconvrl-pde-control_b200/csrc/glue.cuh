@@ -240,7 +240,7 @@ template <int NIN, int NH> struct ActorRegs {
 };
 
 template <typename T, int NNZ, int NIN, int NH>
-__global__ void __launch_bounds__(256) actuate_conv_kernel(const __grid_constant__ ActuateArgs<T> A) {
+__global__ void __launch_bounds__(256, 3) actuate_conv_kernel(const __grid_constant__ ActuateArgs<T> A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int E = A.envs_per_cta, tid = threadIdx.x;
     constexpr int BD = 256;
@@ -367,7 +367,9 @@ struct ObserveArgs {
 // rewards is a shuffle reduction and lane 0 carries the clock / done flag, whose inputs it requested up front.  No
 // shared memory and no CTA barrier: the earlier one-CTA-per-environment version serialised three DRAM round trips
 // (sensors -> barrier -> columns -> barrier -> scalars) per CTA.
-template <typename T>
+// PLAIN = the 1-D conv agent without temporal stacking or action memory (one field, window <= n_sensors): the column
+// loop then has no runtime-shaped inner loops and no integer division (every shipped KS script).
+template <typename T, bool PLAIN>
 __global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ ObserveArgs<T> A) {
     const ObsRewardParams<T>& P = A.P;
     const int lane = threadIdx.x & 31;
@@ -392,7 +394,22 @@ __global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ Ob
             for (int r = 0; r < P.a_rows; ++r) { acol[r] = T(0); dcol[r] = T(0); A.action_in[col * P.a_rows + r] = T(0); }
         const T a0 = fresh ? T(0) : acol[0], d0 = fresh ? T(0) : dcol[0];
         T rj;
-        if (!P.mono) {
+        if (PLAIN) {
+            const int m = P.a2s[j], ns = P.n_sensors, h = P.window / 2;
+            const T sm = sens[m];
+            T* scol = A.state + col * P.window;                       // obs_rows == window
+            for (int r = 0; r < P.window; ++r) {
+                int i = m - (r - h);                                  // circshift(v, i)[j] == v[j - i]
+                i = i < 0 ? i + ns : (i >= ns ? i - ns : i);
+                scol[r] = (r == h ? sm : sens[i]) * P.obs_scale;
+            }
+            const T raw = sm - P.r_offset * P.sens_sum[m];
+            T s;
+            if (P.r_pow == T(2)) { const T g = P.r_gain * raw; s = g * g / P.r_div; }
+            else s = pow_t<T>(fabs(P.r_gain * raw), P.r_pow) / P.r_div;
+            rj = -fabs(s) - P.a_pun * a0 * a0 - P.da_pun * d0 * d0;
+            A.reward[col] = fresh ? T(0) : rj;
+        } else if (!P.mono) {
             rj = assemble_column<T>(P, sv, j, a0, d0, acol, A.state + col * P.obs_rows, fresh);
             A.reward[col] = fresh ? T(0) : rj;
         } else {
@@ -403,7 +420,7 @@ __global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ Ob
         }
         racc += rj; rmax = fmax(rmax, fabs(rj));
     }
-    if (P.mono) {
+    if (!PLAIN && P.mono) {
         // state = reshape(sensors, (n_sensors, 1)) [+ temporal stacking], KSglobalSetup.jl:222-238
         T* scol = A.state + (size_t)env * P.obs_rows;
         if (P.temporal > 1 && !fresh) {

@@ -156,7 +156,10 @@ int32_t observe_t(pdeb200_ctx* c, int fresh, const uint8_t* d_mask, double* d_rs
     O.state = (T*)c->state; O.action = (T*)c->action; O.delta_action = (T*)c->delta_action; O.action_in = (T*)c->action_in;
     O.reward = (T*)c->reward; O.done = c->done; O.time = c->time; O.steps = c->steps; O.reward_sum = d_rsum;
     const int tpb = 128;                                          // one warp per environment
-    observe_kernel<T><<<(c->cfg.n_envs + tpb / 32 - 1) / (tpb / 32), tpb, 0, c->stream>>>(O);
+    const bool plain = !O.P.mono && O.P.spa == 0 && O.P.temporal == 1 && O.P.memory == 0 && O.P.fields == 1 &&
+                       O.P.a_rows == 1 && O.P.window <= O.P.n_sensors && O.P.obs_rows == O.P.window;
+    auto kern = plain ? observe_kernel<T, true> : observe_kernel<T, false>;
+    kern<<<(c->cfg.n_envs + tpb / 32 - 1) / (tpb / 32), tpb, 0, c->stream>>>(O);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
