@@ -51,7 +51,7 @@ int32_t setup_t(pdeb200_ctx* c) {
         double Ainv = 1.0 / (1.0 - dt2 * L);
         double B = 1.0 + dt2 * L;
         c1[i] = (T)(Ainv * B);
-        cN[i] = (T)(Ainv * (-0.5 * alpha) / ((double)N * (double)N));
+        cN[i] = (T)(Ainv * (-0.5 * alpha) / ((double)N * (double)N) * (3 * h / 2));   // the 3h/2 of AB2 folded in
         ah[i] = (T)(Ainv * h);
     }
     int32_t rc;
@@ -122,7 +122,7 @@ int32_t launch(pdeb200_ctx* c) {
     A.tw12 = (const C*)c->tw12; A.tw21 = (const C*)c->tw21;
     A.c1 = (const T*)c->c1; A.cN = (const T*)c->cN; A.ainvh = (const T*)c->ainvh; A.hm = (const C*)c->hm;
     const double h = g.dt / g.oversampling;
-    A.dt32 = (T)(3 * h / 2); A.dt2 = (T)(h / 2); A.inv_n = (T)(1.0 / G::N);
+    A.third = (T)((h / 2) / (3 * h / 2)); A.inv_n = (T)(1.0 / G::N);
     A.sens = EllTable<T>{c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows};
     A.y = (T*)c->y; A.p = (const T*)c->p; A.sensors_out = (T*)c->sensors; A.vmax_out = (T*)c->vmax;
     const int n_pairs = (g.n_envs + 1) / 2;

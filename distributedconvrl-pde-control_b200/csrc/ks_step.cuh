@@ -39,10 +39,10 @@ struct KsArgs {
     const C* tw12;                     // [N1][N2]  exp(-2*pi*i*a*b/N)
     const C* tw21;                     // [N2][N1]
     const T* c1;                       // A_inv * B
-    const T* cN;                       // A_inv * (-alpha/2) / N^2
+    const T* cN;                       // A_inv * (-alpha/2) / N^2 * 3h/2
     const T* ainvh;                    // A_inv * h (global, read once per env step)
     const C* hm;                       // h * fft(mu*cos(...)) or nullptr (mu == 0)
-    T dt32, dt2, inv_n;
+    T third, inv_n;                    // (h/2)/(3h/2); 1/N
     EllTable<T> sens;                  // rows: sensors, gather over grid points
     T* y;                              // [B][N] in/out
     const T* p;                        // [B][N] actuation field (physical)
@@ -136,6 +136,10 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
     // Pairs beyond the batch keep running on zeros (they share barriers with live pairs).
 
     T zr[RMAX], zi[RMAX], ur[RMAX], ui[RMAX];
+    // F = A_inv*h*p_hat + h*m_hat of this thread's modes: in registers where the register file allows it (fp64 is
+    // compiled for 255 registers anyway; fp32 keeps it in shared memory to stay at 128)
+    constexpr bool F_REGS = sizeof(T) == 8;
+    T fr[F_REGS ? RMAX : 1], fi[F_REGS ? RMAX : 1];
 
     // ---- load p into z and y into u (physical layout: thread t < N2 holds n = t + N2*r) -----
 #pragma unroll
@@ -170,9 +174,10 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
                 for (int r = 0; r < N2; ++r) {
                     const int k = t + N1 * r;
                     const T ah = __ldg(A.ainvh + k);
-                    T fr = ah * zr[r], fi = ah * zi[r];
-                    if (A.hm) { const C m = A.hm[k]; fr += m.x - m.y; fi += m.x + m.y; }   // m_hat*(1+i)
-                    s_F[k] = V2<T>::make(fr, fi);
+                    T f_r = ah * zr[r], f_i = ah * zi[r];
+                    if (A.hm) { const C m = A.hm[k]; f_r += m.x - m.y; f_i += m.x + m.y; }   // m_hat*(1+i)
+                    if (F_REGS) { fr[r] = f_r; fi[r] = f_i; }
+                    else s_F[k] = V2<T>::make(f_r, f_i);
                 }
             } else if (job == -1) {
 #pragma unroll
@@ -185,13 +190,16 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
                     // reference gets N^n there from fft(y^2) and here from fft(ifft(fft(y))^2): equal
                     // to round-off, one transform fewer.
                     const C z1 = (job == 0) ? V2<T>::make(zr[r], zi[r]) : s_prev[k];
-                    const C f = s_F[k];
+                    T f_r, f_i;
+                    if (F_REGS) { f_r = fr[r]; f_i = fi[r]; }
+                    else { const C f = s_F[k]; f_r = f.x; f_i = f.y; }
                     s_prev[k] = V2<T>::make(zr[r], zi[r]);
-                    const T dr = A.dt32 * zr[r] - A.dt2 * z1.x;
-                    const T di = A.dt32 * zi[r] - A.dt2 * z1.y;
+                    // u = c1*u + i*cn*(3h/2 N^n - h/2 N^{n-1}) + F  with cn32 = cn*3h/2:  u = c1*u + F + i*cn32*(N^n - N^{n-1}/3)
+                    const T tr = fma(-A.third, z1.x, zr[r]);
+                    const T ti = fma(-A.third, z1.y, zi[r]);
                     const T c1 = s_c1[k], cn = s_cN[k];
-                    ur[r] = c1 * ur[r] - cn * di + f.x;              // u = c1*u + i*cn*d + F
-                    ui[r] = c1 * ui[r] + cn * dr + f.y;
+                    ur[r] = fma(-cn, ti, fma(c1, ur[r], f_r));
+                    ui[r] = fma(cn, tr, fma(c1, ui[r], f_i));
                     zr[r] = ur[r]; zi[r] = ui[r];
                 }
             }
