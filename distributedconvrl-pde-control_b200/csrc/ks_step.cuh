@@ -137,8 +137,8 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
 
     T zr[RMAX], zi[RMAX], ur[RMAX], ui[RMAX];
     // F = A_inv*h*p_hat + h*m_hat of this thread's modes: in registers where the register file allows it (fp64 is
-    // compiled for 255 registers anyway; fp32 keeps it in shared memory to stay at 128)
-    constexpr bool F_REGS = sizeof(T) == 8;
+    // compiled for 255 registers anyway; fp32 keeps it in shared memory to stay at 128, N > 256 would only spill)
+    constexpr bool F_REGS = sizeof(T) == 8 && RMAX <= 16;
     T fr[F_REGS ? RMAX : 1], fi[F_REGS ? RMAX : 1];
 
     // ---- load p into z and y into u (physical layout: thread t < N2 holds n = t + N2*r) -----

@@ -54,7 +54,11 @@ __device__ __forceinline__ void atomic_max_nonneg(T* addr, T v) {
     atomicMax(reinterpret_cast<I*>(addr), bits);        // order of non-negative IEEE values == order of their bits
 }
 
-template <typename T>
+// FULL: the BASELINE shape (nx = 128, ny = 128 -> 32 rows per CTA, 8 per strip).  Every point is live, so the
+// per-point predicates disappear, the four RK stages are unrolled (no stage branches inside the row loop) and all
+// shared-memory addresses are "row pointer + immediate"; ncu on the runtime-shaped version showed 40 % integer /
+// 28 % FP64 instructions (profiles/r1_kseg2d.md).
+template <typename T, bool FULL>
 __global__ void __cluster_dims__(kCS, 1, 1) __launch_bounds__(kTX * kStrips, 1)
 kseg2d_step_kernel(const __grid_constant__ Kseg2dArgs<T> A) {
     using C = typename V2<T>::type;
@@ -62,15 +66,15 @@ kseg2d_step_kernel(const __grid_constant__ Kseg2dArgs<T> A) {
     cg::cluster_group cluster = cg::this_cluster();
     const int rank = (int)cluster.block_rank();
     const int env = blockIdx.x / kCS;
-    const int nx = A.nx, rows = A.rows;
+    const int nx = FULL ? kTX : A.nx, rows = FULL ? kStrips * kR : A.rows;
     const int x = threadIdx.x % kTX, strip = threadIdx.x / kTX;
-    const int R = (rows + kStrips - 1) / kStrips;
+    const int R = FULL ? kR : (rows + kStrips - 1) / kStrips;
     const int r0 = strip * R;
     const int slab = (rows + 2) * nx;                     // one buffer: halo row, `rows` rows, halo row
     C* const buf0 = reinterpret_cast<C*>(smem_raw);
     C* const up0 = rank > 0 ? cluster.map_shared_rank(buf0, rank - 1) : nullptr;           // CTA owning the rows above
     C* const dn0 = rank < kCS - 1 ? cluster.map_shared_rank(buf0, rank + 1) : nullptr;     // ... below
-    const bool xon = x < nx;
+    const bool xon = FULL || x < nx;
     const int grow0 = rank * rows;                        // global index of local row 0
 
     C y0[kR], acc[kR];
@@ -80,63 +84,79 @@ kseg2d_step_kernel(const __grid_constant__ Kseg2dArgs<T> A) {
 #pragma unroll
     for (int r = 0; r < kR; ++r) {
         const int lr = r0 + r;
-        on[r] = xon && r < R && lr < rows;
+        on[r] = FULL || (xon && r < R && lr < rows);
         y0[r] = on[r] ? yg[(size_t)(grow0 + lr) * nx + x] : V2<T>::make(T(0), T(0));
         pp[r] = on[r] ? A.p[((size_t)env * A.ny + grow0 + lr) * nx + x] : T(0);
         acc[r] = V2<T>::make(T(0), T(0));
     }
+    // which of this thread's rows touch a neighbour CTA / the domain edge (row index within the strip)
+    const int r_first = 0, r_last = FULL ? kR - 1 : min(R, rows - r0) - 1;
+    const bool push_up = up0 != nullptr && r0 == 0;                       // my first row = their lower halo
+    const bool push_dn = dn0 != nullptr && r0 + r_last == rows - 1;       // my last row = their upper halo
+    const bool top_edge = grow0 + r0 == 0;                                // edge copy along y (top)
+    const bool bot_edge = grow0 + r0 + r_last == A.ny - 1;                // edge copy along y (bottom)
     // publish a stage state: own rows into buf[b], boundary rows into the neighbours' halo rows
     auto publish = [&](int b, const C* st) {
+        C* row = buf0 + b * slab + (r0 + 1) * nx + x;
 #pragma unroll
         for (int r = 0; r < kR; ++r) {
             if (!on[r]) continue;
-            const int lr = r0 + r;
-            buf0[b * slab + (lr + 1) * nx + x] = st[r];
-            if (lr == 0 && up0) up0[b * slab + (rows + 1) * nx + x] = st[r];       // my first row = their lower halo
-            if (lr == rows - 1 && dn0) dn0[b * slab + x] = st[r];                   // my last row = their upper halo
+            row[r * nx] = st[r];
+            if (r == r_first && push_up) up0[b * slab + (rows + 1) * nx + x] = st[r];
+            if (r == r_last && push_dn) dn0[b * slab + x] = st[r];
         }
     };
     publish(0, y0);
     cluster.sync();
     const T h = A.h, h2 = T(0.5) * A.h, h6 = A.h / T(6);
     const int xl = x == 0 ? 0 : x - 1, xr = x >= nx - 1 ? (xon ? x : 0) : x + 1;
+    const T c1x = A.c1x, c2x = A.c2x, c1y = A.c1y, c2y = A.c2y, m2x = T(-2) * A.c2x, m2y = T(-2) * A.c2y;
     int cur = 0;
-    for (int s = 0; s < A.S; ++s) {
-#pragma unroll 1
-        for (int stage = 1; stage <= 4; ++stage) {
-            // pointer to this strip's first row in the current buffer; the centre row slides down the strip so every
-            // stage state is read three times per point (left, right, below) instead of five
-            const C* Br = buf0 + cur * slab + (r0 + 1) * nx;
-            C st[kR];
-            C c = on[0] ? Br[x] : V2<T>::make(T(0), T(0));
-            C u = (grow0 + r0 == 0 || !on[0]) ? c : Br[x - nx];                // edge copy along y (top)
+    // one RK stage over the strip; the centre row slides down the strip so every stage state is read three times
+    // per point (left, right, below) instead of five
+    auto run_stage = [&](const int stage) {
+        const C* Br = buf0 + cur * slab + (r0 + 1) * nx;
+        // the new stage state goes straight into the other buffer (nobody reads it before the cluster barrier below)
+        const int b = cur ^ 1;
+        C* row = buf0 + b * slab + (r0 + 1) * nx + x;
+        C c = on[0] ? Br[x] : V2<T>::make(T(0), T(0));
+        C u = (top_edge || !on[0]) ? c : Br[x - nx];
 #pragma unroll
-            for (int r = 0; r < kR; ++r) {
-                if (!on[r]) continue;
-                const C l = Br[xl];
-                const C rt = Br[xr];
-                const C d = (grow0 + r0 + r == A.ny - 1) ? c : Br[x + nx];       // edge copy along y (bottom)
-                // same operation order as the 1-D f (KellerSegelSetup.jl:225-229) per axis
-                const T u1x = (-A.c1x) * l.x + T(0) * c.x + A.c1x * rt.x;
-                const T u2x = A.c2x * l.x + (T(-2) * A.c2x) * c.x + A.c2x * rt.x;
-                const T v1x = (-A.c1x) * l.y + T(0) * c.y + A.c1x * rt.y;
-                const T v2x = A.c2x * l.y + (T(-2) * A.c2x) * c.y + A.c2x * rt.y;
-                const T u1y = (-A.c1y) * u.x + T(0) * c.x + A.c1y * d.x;
-                const T u2y = A.c2y * u.x + (T(-2) * A.c2y) * c.x + A.c2y * d.x;
-                const T v1y = (-A.c1y) * u.y + T(0) * c.y + A.c1y * d.y;
-                const T v2y = A.c2y * u.y + (T(-2) * A.c2y) * c.y + A.c2y * d.y;
-                const T lapu = u2x + u2y, lapv = v2x + v2y;
-                const T kv = lapv - c.y + c.x + pp[r];
-                const T ku = lapu + c.x - (T(5.6) * u1x * v1x + T(5.6) * u1y * v1y) - T(5.6) * c.x * lapv - c.x * c.x;
-                if (stage == 1) { acc[r] = V2<T>::make(ku, kv); st[r] = V2<T>::make(y0[r].x + h2 * ku, y0[r].y + h2 * kv); }
-                else if (stage == 2) { acc[r].x += T(2) * ku; acc[r].y += T(2) * kv; st[r] = V2<T>::make(y0[r].x + h2 * ku, y0[r].y + h2 * kv); }
-                else if (stage == 3) { acc[r].x += T(2) * ku; acc[r].y += T(2) * kv; st[r] = V2<T>::make(y0[r].x + h * ku, y0[r].y + h * kv); }
-                else { y0[r].x += h6 * (acc[r].x + ku); y0[r].y += h6 * (acc[r].y + kv); st[r] = y0[r]; }
-                u = c; c = d; Br += nx;
-            }
-            publish(cur ^ 1, st);
-            cluster.sync();
-            cur ^= 1;
+        for (int r = 0; r < kR; ++r) {
+            if (!on[r]) continue;
+            const C l = Br[r * nx + xl];
+            const C rt = Br[r * nx + xr];
+            const C d = (r == r_last && bot_edge) ? c : Br[(r + 1) * nx + x];
+            // same operation order as the 1-D f (KellerSegelSetup.jl:225-229) per axis
+            const T u1x = (-c1x) * l.x + T(0) * c.x + c1x * rt.x;
+            const T u2x = c2x * l.x + m2x * c.x + c2x * rt.x;
+            const T v1x = (-c1x) * l.y + T(0) * c.y + c1x * rt.y;
+            const T v2x = c2x * l.y + m2x * c.y + c2x * rt.y;
+            const T u1y = (-c1y) * u.x + T(0) * c.x + c1y * d.x;
+            const T u2y = c2y * u.x + m2y * c.x + c2y * d.x;
+            const T v1y = (-c1y) * u.y + T(0) * c.y + c1y * d.y;
+            const T v2y = c2y * u.y + m2y * c.y + c2y * d.y;
+            const T lapu = u2x + u2y, lapv = v2x + v2y;
+            const T kv = lapv - c.y + c.x + pp[r];
+            const T ku = lapu + c.x - (T(5.6) * u1x * v1x + T(5.6) * u1y * v1y) - T(5.6) * c.x * lapv - c.x * c.x;
+            C st;
+            if (stage == 1) { acc[r] = V2<T>::make(ku, kv); st = V2<T>::make(y0[r].x + h2 * ku, y0[r].y + h2 * kv); }
+            else if (stage == 2) { acc[r].x += T(2) * ku; acc[r].y += T(2) * kv; st = V2<T>::make(y0[r].x + h2 * ku, y0[r].y + h2 * kv); }
+            else if (stage == 3) { acc[r].x += T(2) * ku; acc[r].y += T(2) * kv; st = V2<T>::make(y0[r].x + h * ku, y0[r].y + h * kv); }
+            else { y0[r].x += h6 * (acc[r].x + ku); y0[r].y += h6 * (acc[r].y + kv); st = y0[r]; }
+            row[r * nx] = st;
+            if (r == r_first && push_up) up0[b * slab + (rows + 1) * nx + x] = st;
+            if (r == r_last && push_dn) dn0[b * slab + x] = st;
+            u = c; c = d;
+        }
+        cluster.sync();
+        cur ^= 1;
+    };
+    for (int s = 0; s < A.S; ++s) {
+        if (FULL) { run_stage(1); run_stage(2); run_stage(3); run_stage(4); }
+        else {
+#pragma unroll 1
+            for (int stage = 1; stage <= 4; ++stage) run_stage(stage);
         }
     }
     C* yo = reinterpret_cast<C*>(A.y) + (size_t)env * A.ny * nx;
@@ -159,7 +179,8 @@ int32_t launch(pdeb200_ctx* c) {
     A.c1x = (T)(0.5 / dx); A.c2x = (T)(1.0 / (dx * dx)); A.c1y = (T)(0.5 / dy); A.c2y = (T)(1.0 / (dy * dy));
     A.y = (T*)c->y; A.p = (const T*)c->p; A.vmax_out = (T*)c->vmax;
     const size_t smem = (size_t)2 * (A.rows + 2) * g.nx * 2 * sizeof(T);
-    auto kern = kseg2d_step_kernel<T>;
+    const bool full = g.nx == kTX && g.ny == kCS * kStrips * kR;
+    auto kern = full ? kseg2d_step_kernel<T, true> : kseg2d_step_kernel<T, false>;
     PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PDEB_CUDA(c, cudaMemsetAsync(c->vmax, 0, (size_t)g.n_envs * sizeof(T), c->stream));
     kern<<<g.n_envs * kCS, kTX * kStrips, smem, c->stream>>>(A);
