@@ -7,11 +7,13 @@
 //                     third-party step controller); here the same classical RK4 tableau runs
 //                     `oversampling` fixed substeps per env step (default 40: error vs the exact ODE
 //                     solution ~5e-9, below the reference's own tolerance; tests/test_kseg_*.py).
-// One CTA per environment, one thread per grid point; (u, v) live in registers, the four RK4 stage
+// One thread per grid point, E environments per CTA (E chosen so that E * nx fills whole warps: the reference's
+// nx = 100 would otherwise idle 28 of every 128 lanes); (u, v) live in registers, the four RK4 stage
 // states go through a double-buffered shared-memory line for the neighbour reads; sensor dots and
 // max|y| are produced from the on-chip state like in the KS core kernel.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "ctx.hpp"
 
@@ -20,7 +22,7 @@ namespace {
 
 template <typename T>
 struct KsegArgs {
-    int nx, S, n_sensors;
+    int nx, S, n_sensors, n_envs, E;
     T h, c1, c2;                 // substep, 0.5/dx, 1/dx^2
     EllTable<T> sens;
     T* y;                        // [B][nx][2] (Julia (2,nx) column-major)
@@ -29,6 +31,7 @@ struct KsegArgs {
     T* vmax_out;                 // [B]
 };
 
+// `line` points at the environment's first cell, i is the cell index within the environment
 template <typename T>
 __device__ __forceinline__ void rhs(const typename V2<T>::type* line, int i, int nx, T p, T c1, T c2, T& du, T& dv) {
     using C = typename V2<T>::type;
@@ -43,56 +46,60 @@ __device__ __forceinline__ void rhs(const typename V2<T>::type* line, int i, int
     du = u2 + c.x - T(5.6) * u1 * v1 - T(5.6) * c.x * v2 - c.x * c.x;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(1024) kseg_step_kernel(const __grid_constant__ KsegArgs<T> A) {
+// MAXT = 800: CTAs of <= 25 warps, compiled for two per SM (40 registers); MAXT = 1024: anything larger
+template <typename T, int MAXT>
+__global__ void __launch_bounds__(MAXT) kseg_step_kernel(const __grid_constant__ KsegArgs<T> A) {
     using C = typename V2<T>::type;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nx = A.nx, E = A.E;
     C* line0 = reinterpret_cast<C*>(smem_raw);
-    C* line1 = line0 + A.nx;
-    __shared__ T s_red[32];
-    const int env = blockIdx.x, i = threadIdx.x, nx = A.nx;
-    const bool on = i < nx;
+    C* line1 = line0 + E * nx;
+    __shared__ long long s_max[32];                // bits of max|y| as double, per environment of the CTA
+    const int e = threadIdx.x / nx, i = threadIdx.x - e * nx;
+    const int env = blockIdx.x * E + e;
+    const bool on = e < E && env < A.n_envs;
+    if (threadIdx.x < 32) s_max[threadIdx.x] = 0;
     C* yg = reinterpret_cast<C*>(A.y) + (size_t)env * nx;
     C y = on ? yg[i] : V2<T>::make(T(0), T(0));
     const T p = on ? A.p[(size_t)env * nx + i] : T(0);
     const T h = A.h, h2 = T(0.5) * A.h, h6 = A.h / T(6);
+    C* l0 = line0 + e * nx;
+    C* l1 = line1 + e * nx;
     for (int s = 0; s < A.S; ++s) {
         T k1u, k1v, k2u, k2v, k3u, k3v, k4u, k4v;
-        if (on) line0[i] = y;
+        if (on) l0[i] = y;
         __syncthreads();
-        if (on) { rhs<T>(line0, i, nx, p, A.c1, A.c2, k1u, k1v); line1[i] = V2<T>::make(y.x + h2 * k1u, y.y + h2 * k1v); }
+        if (on) { rhs<T>(l0, i, nx, p, A.c1, A.c2, k1u, k1v); l1[i] = V2<T>::make(y.x + h2 * k1u, y.y + h2 * k1v); }
         __syncthreads();
-        if (on) { rhs<T>(line1, i, nx, p, A.c1, A.c2, k2u, k2v); line0[i] = V2<T>::make(y.x + h2 * k2u, y.y + h2 * k2v); }
+        if (on) { rhs<T>(l1, i, nx, p, A.c1, A.c2, k2u, k2v); l0[i] = V2<T>::make(y.x + h2 * k2u, y.y + h2 * k2v); }
         __syncthreads();
-        if (on) { rhs<T>(line0, i, nx, p, A.c1, A.c2, k3u, k3v); line1[i] = V2<T>::make(y.x + h * k3u, y.y + h * k3v); }
+        if (on) { rhs<T>(l0, i, nx, p, A.c1, A.c2, k3u, k3v); l1[i] = V2<T>::make(y.x + h * k3u, y.y + h * k3v); }
         __syncthreads();
         if (on) {
-            rhs<T>(line1, i, nx, p, A.c1, A.c2, k4u, k4v);
+            rhs<T>(l1, i, nx, p, A.c1, A.c2, k4u, k4v);
             y.x = y.x + h6 * (k1u + T(2) * (k2u + k3u) + k4u);
             y.y = y.y + h6 * (k1v + T(2) * (k2v + k3v) + k4v);
         }
     }
-    if (on) { yg[i] = y; line0[i] = y; }
-    // max |y| over both fields
-    T m = on ? fmax(fabs(y.x), fabs(y.y)) : T(0);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((i & 31) == 0) s_red[i >> 5] = m;
-    __syncthreads();
-    if (i == 0) {
-        T mm = T(0);
-        for (int w = 0; w < (int)(blockDim.x + 31) / 32; ++w) mm = fmax(mm, s_red[w]);
-        A.vmax_out[env] = mm;
+    if (on) {
+        yg[i] = y; l0[i] = y;
+        // max |y| over both fields: non-negative IEEE values order like their bit patterns
+        const double m = (double)fmax(fabs(y.x), fabs(y.y));
+        atomicMax(&s_max[e], __double_as_longlong(m));
     }
+    __syncthreads();
+    if (on && i == 0) A.vmax_out[env] = (T)__longlong_as_double(s_max[e]);
     const int ns = A.n_sensors;
-    for (int q = i; q < 2 * ns; q += blockDim.x) {
-        const int f = q / ns, k = q % ns;
-        T acc = T(0);
-        for (int j = 0; j < A.sens.nnz_max; ++j) {
-            const C v = line0[A.sens.idx[j * ns + k]];
-            acc += (f ? v.y : v.x) * A.sens.w[j * ns + k];
+    if (on) {
+        for (int q = i; q < 2 * ns; q += nx) {
+            const int f = q / ns, k = q % ns;
+            T acc = T(0);
+            for (int j = 0; j < A.sens.nnz_max; ++j) {
+                const C v = l0[A.sens.idx[j * ns + k]];
+                acc += (f ? v.y : v.x) * A.sens.w[j * ns + k];
+            }
+            A.sensors_out[(size_t)env * 2 * ns + q] = acc;
         }
-        A.sensors_out[(size_t)env * 2 * ns + q] = acc;
     }
 }
 
@@ -105,9 +112,25 @@ int32_t launch(pdeb200_ctx* c) {
     A.h = (T)(g.dt / g.oversampling); A.c1 = (T)(0.5 / dx); A.c2 = (T)(1.0 / (dx * dx));
     A.sens = EllTable<T>{c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows};
     A.y = (T*)c->y; A.p = (const T*)c->p; A.sensors_out = (T*)c->sensors; A.vmax_out = (T*)c->vmax;
-    const int tpb = ((g.nx + 31) / 32) * 32;
-    const size_t smem = (size_t)2 * g.nx * 2 * sizeof(T);
-    kseg_step_kernel<T><<<g.n_envs, tpb, smem, c->stream>>>(A);
+    // environments per CTA: fewest idle lanes in the last warp among CTAs of <= 512 threads, ties to the smaller CTA
+    // (nx = 100: E = 5, 500 of 512 lanes; sweep on B200, fp64 / fp32 M env-steps/s: E=1 27.4 / 35.8, 2: 28.7 / 38.3,
+    // 3: 28.5 / 40.6, 4: 25.5 / 39.8, 5: 29.0 / 42.8, 8: 23.6 / 36.5 -- beyond 16 warps the four CTA barriers per
+    // substep cost more than the idle lanes).  PDEB200_KSEG_E overrides for experiments.
+    int E = 1; double best = 2.0;
+    for (int e = 1; e <= 32 && e * g.nx <= 512; ++e) {
+        const int thr = ((e * g.nx + 31) / 32) * 32;
+        const double waste = 1.0 - (double)(e * g.nx) / thr;
+        if (waste < best - 1e-9) { best = waste; E = e; }
+    }
+    static const int forced = [] { const char* e = getenv("PDEB200_KSEG_E"); return e ? atoi(e) : 0; }();
+    if (forced > 0 && forced <= 32 && forced * g.nx <= 1024) E = forced;
+    A.n_envs = g.n_envs; A.E = E;
+    const int tpb = ((E * g.nx + 31) / 32) * 32;
+    const size_t smem = (size_t)2 * E * g.nx * 2 * sizeof(T);
+    auto kern = tpb <= 512 ? kseg_step_kernel<T, 512> : kseg_step_kernel<T, 1024>;
+    if (smem > 48 * 1024)
+        PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(g.n_envs + E - 1) / E, tpb, smem, c->stream>>>(A);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
