@@ -81,14 +81,15 @@ template <typename T> struct NsMinCtas { static constexpr int value = sizeof(T) 
 // rows of its two contributions (k and -k), the column pair (kx, -kx) sits in shared memory, and the two
 // psi-based fields reuse the columns after an in-place division by k^2 (one division per entry, like the
 // reference's `psihat = omghat ./ kx2ky2`).
-template <typename T, int P1, int P2>
+template <typename T, int P1, int P2, int NN>
 __global__ void __launch_bounds__(kColsPerCta * 32, NsMinCtas<T>::value)
 ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
     using G = NsGeom<P1, P2>;
     using C = typename V2<T>::type;
     constexpr int NP = G::NP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = A.N;
+    constexpr int N = NN;                                         // grid size, NH, NHP known at compile time
+    constexpr int NH = NN / 2 + 1, NHP = (NH + 3) / 4 * 4;
     C* s_tw = reinterpret_cast<C*>(smem_raw);
     C* s_xb0 = s_tw + NP;
     C* s_col0 = s_xb0 + kColsPerCta * G::XB;
@@ -104,7 +105,7 @@ ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
     C* xb = s_xb0 + w * G::XB;
     C* colA = s_col0 + (size_t)w * 2 * N;
     C* colB = colA + N;
-    const bool live = a < A.NH;
+    const bool live = a < NH;
     const int ib = (N - a) % N;                                   // column of -kx in the unpadded array
     const bool xpartner = unpad_idx((NP - a) % NP, NP, N) >= 0;   // pad() keeps (-kx) ?
     T kxa = T(0), kxb = T(0);
@@ -132,7 +133,12 @@ ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
             // multiplier i*m: u = i ky psi, v = -i kx psi, w_x = i kx omega, w_y = i ky omega
             const bool kytype = (f == 0 || f == 3);
             const T mxa = f == 1 ? -kxa : kxa, mxb = f == 1 ? -kxb : kxb;
-            for (int kyp = t; kyp < NP; kyp += 32) {
+#pragma unroll
+            for (int kyp0 = 0; kyp0 < NP; kyp0 += 32) {
+                const int kyp = kyp0 + t;
+                if (NP % 32 != 0 && kyp >= NP) break;
+                // 32-row blocks inside N/2 < ky' < NP - N/2 are zero in pad(X) for both k and -k: no loads
+                if (kyp0 > N / 2 && kyp0 + 31 < NP - N / 2) { xb[kyp] = V2<T>::make(T(0), T(0)); continue; }
                 const short2 jj = s_tab[kyp];
                 const int j1 = jj.x, j2 = xpartner ? (int)jj.y : -1;
                 const int i1 = j1 < 0 ? 0 : j1, i2 = j2 < 0 ? 0 : j2;
@@ -156,10 +162,15 @@ ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
             }
         }
         __syncthreads();
-        C* dst = A.W + ((size_t)(env * 4 + f) * NP) * A.NHP + a0;
-        for (int idx = threadIdx.x; idx < NP * kColsPerCta; idx += blockDim.x) {
-            const int c = idx % kColsPerCta, y = idx / kColsPerCta;
-            if (a0 + c < A.NH) dst[(size_t)y * A.NHP + c] = s_xb0[c * G::XB + y];
+        {
+            // 8-column tile store: thread -> (column c, row y), rows advance by 32 per iteration
+            const int c = threadIdx.x % kColsPerCta, y0 = threadIdx.x / kColsPerCta;
+            C* dst = A.W + ((size_t)(env * 4 + f) * NP + y0) * NHP + a0 + c;
+            const C* srow = s_xb0 + c * G::XB + y0;
+            if (a0 + c < NH) {
+#pragma unroll 4
+                for (int y = y0; y < NP; y += 32) { *dst = *srow; dst += (size_t)32 * NHP; srow += 32; }
+            }
         }
         __syncthreads();
     }
@@ -189,14 +200,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 // The four half-spectrum lines a warp consumes per y-line are contiguous rows of W: they are staged into
 // shared memory by 1-D bulk copies (cp.async.bulk, completion on a per-warp mbarrier) two phases ahead of
 // their use, so the HBM/L2 latency overlaps the FFT arithmetic of the previous phase.
-template <typename T, int P1, int P2>
+template <typename T, int P1, int P2, int NN>
 __global__ void __launch_bounds__(kColsPerCta * 32, NsMinCtas<T>::value)
 ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
     using G = NsGeom<P1, P2>;
     using C = typename V2<T>::type;
     constexpr int NP = G::NP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = A.N, NHP = A.NHP;
+    constexpr int N = NN, NH = NN / 2 + 1, NHP = (NH + 3) / 4 * 4;
     C* s_twi = reinterpret_cast<C*>(smem_raw);
     C* s_twf = s_twi + NP;
     C* s_xb0 = s_twf + NP;
@@ -281,7 +292,7 @@ ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
     __syncwarp();
     C* Qa = A.Q + ((size_t)env * NP + y0) * NHP;
     C* Qb = Qa + NHP;
-    for (int a = t; a < A.NH; a += 32) {
+    for (int a = t; a < NH; a += 32) {
         const C za = xb[a], zb = xb[(NP - a) % NP];
         Qa[a] = V2<T>::make(T(0.5) * (za.x + zb.x), T(0.5) * (za.y - zb.y));
         Qb[a] = V2<T>::make(T(0.5) * (za.y + zb.y), T(-0.5) * (za.x - zb.x));
@@ -319,14 +330,14 @@ __device__ __forceinline__ void rk_update(const NsArgs<T>& A, const size_t* idx,
     }
 }
 
-template <typename T, int P1, int P2>
+template <typename T, int P1, int P2, int NN>
 __global__ void __launch_bounds__(kColsPerCta * 32, 2 * NsMinCtas<T>::value)     // load-latency bound: 2+ CTAs/SM
 ns_ypass_fwd_kernel(const __grid_constant__ NsArgs<T> A) {
     using G = NsGeom<P1, P2>;
     using C = typename V2<T>::type;
     constexpr int NP = G::NP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int N = A.N;
+    constexpr int N = NN, NH = NN / 2 + 1, NHP = (NH + 3) / 4 * 4;
     C* s_tw = reinterpret_cast<C*>(smem_raw);
     C* s_xb0 = s_tw + NP;
     T* s_ky = reinterpret_cast<T*>(s_xb0 + kColsPerCta * G::XB);
@@ -334,13 +345,17 @@ ns_ypass_fwd_kernel(const __grid_constant__ NsArgs<T> A) {
     const int env = blockIdx.y, a0 = blockIdx.x * kColsPerCta, a = a0 + w;
     for (int i = threadIdx.x; i < NP; i += blockDim.x) s_tw[i] = A.tw_fwd[i];
     for (int i = threadIdx.x; i < N; i += blockDim.x) s_ky[i] = A.ky[i];
-    const C* src = A.Q + ((size_t)env * NP) * A.NHP + a0;
-    for (int idx = threadIdx.x; idx < NP * kColsPerCta; idx += blockDim.x) {
-        const int c = idx % kColsPerCta, y = idx / kColsPerCta;
-        if (a0 + c < A.NH) s_xb0[c * G::XB + y] = src[(size_t)y * A.NHP + c];
+    {
+        const int c = threadIdx.x % kColsPerCta, y0 = threadIdx.x / kColsPerCta;
+        const C* src = A.Q + ((size_t)env * NP + y0) * NHP + a0 + c;
+        C* srow = s_xb0 + c * G::XB + y0;
+        if (a0 + c < NH) {
+#pragma unroll 4
+            for (int y = y0; y < NP; y += 32) { *srow = *src; src += (size_t)32 * NHP; srow += 32; }
+        }
     }
     __syncthreads();
-    if (a >= A.NH) return;
+    if (a >= NH) return;
     C* xb = s_xb0 + w * G::XB;
     T zr[G::RMAX], zi[G::RMAX];
     if (t < P2) {
@@ -517,16 +532,16 @@ int32_t set_smem(pdeb200_ctx* c, K kern, size_t bytes) {
 
 // RK4 x oversampling for all environments (FluidSetup.jl:163-172), in chunks of `chunk` environments so that
 // the work arrays W and Q of a chunk can stay in L2 between the three kernels of a stage.
-template <typename T, int P1, int P2>
+template <typename T, int P1, int P2, int NN>
 int32_t rk4_t(pdeb200_ctx* c) {
     using C = typename V2<T>::type;
     NsProb* P = prob(c);
     const pdeb200_config& g = c->cfg;
     const int N = P->N, NP = P->NP;
     const size_t nn = (size_t)N * N;
-    auto kA = ns_ypass_inv_kernel<T, P1, P2>;
-    auto kB = ns_xpass_kernel<T, P1, P2>;
-    auto kC = ns_ypass_fwd_kernel<T, P1, P2>;
+    auto kA = ns_ypass_inv_kernel<T, P1, P2, NN>;
+    auto kB = ns_xpass_kernel<T, P1, P2, NN>;
+    auto kC = ns_ypass_fwd_kernel<T, P1, P2, NN>;
     const size_t sa = smem_a<T, P1, P2>(N), sb = smem_b<T, P1, P2>(P->NHP), sc = smem_c<T, P1, P2>(N);
     int32_t rc;
     if ((rc = set_smem(c, kA, sa)) || (rc = set_smem(c, kB, sb)) || (rc = set_smem(c, kC, sc))) return rc;
@@ -601,7 +616,7 @@ int32_t core_t(pdeb200_ctx* c) {
     // p_hat = fft(p)   (FluidSetup.jl:260); the physical sum was written by actuate_kernel
     int32_t rc = fft2_t<T, N1, N2, -1>(c, P->p_phys, 1, c->p, 0, 1.0);
     if (rc) return rc;
-    if ((rc = rk4_t<T, P1, P2>(c))) return rc;
+    if ((rc = rk4_t<T, P1, P2, N1 * N2>(c))) return rc;
     return sensors_t<T, N1, N2>(c, nullptr);
 }
 
