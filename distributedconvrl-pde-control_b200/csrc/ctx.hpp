@@ -67,6 +67,9 @@ struct pdeb200_ctx {
     // KS spectral constants
     int N1 = 0, N2 = 0;
     void *tw12 = nullptr, *tw21 = nullptr, *c1 = nullptr, *cN = nullptr, *ainvh = nullptr, *hm = nullptr;
+    // KS sensor gather: layout permutation of the natural-order state in shared memory and the sensor table's
+    // indices under it (ks.cu::sensor_layout); rebuilt after pdeb200_set_bases
+    int *ks_perm = nullptr, *ks_sens_idx = nullptr; bool ks_layout_dirty = true, ks_layout_on = false;
 
     // problem-specific opaque state (KSeg / NS translation units)
     void* prob = nullptr;

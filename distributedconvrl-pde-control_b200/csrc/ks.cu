@@ -107,6 +107,40 @@ void plan(const pdeb200_ctx* c, int n_sm, int* warps_out, int* ctas_per_sm_out) 
     *warps_out = bw; *ctas_per_sm_out = bc;
 }
 
+// Layout of the natural-order state copy the sensor gather reads (see the epilogue of ks_step_kernel): if the
+// sensors' first taps are equally spaced by `sp` grid points (sp | N), point n goes to plane n % sp, slot n / sp,
+// planes padded by one entry against bank conflicts on the write side; the table's indices are mapped once here.
+template <int N1, int N2>
+int32_t sensor_layout(pdeb200_ctx* c) {
+    using G = KsGeom<N1, N2>;
+    constexpr int N = G::N;
+    c->ks_layout_dirty = false; c->ks_layout_on = false;
+    static const bool off = [] { const char* e = getenv("PDEB200_KS_PLAIN_SENSOR_LAYOUT"); return e && atoi(e) != 0; }();
+    const int ns = c->sens.n_rows, nnz = c->sens.nnz_max;
+    if (off || ns < 2) return PDEB200_OK;
+    std::vector<int> idx((size_t)nnz * ns);
+    PDEB_CUDA(c, cudaMemcpy(idx.data(), c->sens.d_idx, idx.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    // most frequent distance between the first taps of neighbouring sensors (windows that wrap around the periodic
+    // boundary list their taps in a different order; any permutation is CORRECT, the spacing only decides how well
+    // the gather coalesces)
+    std::vector<int> votes(N, 0);
+    for (int i = 0; i + 1 < ns; ++i) votes[((idx[i + 1] - idx[i]) % N + N) % N]++;
+    const int sp = (int)(std::max_element(votes.begin(), votes.end()) - votes.begin());
+    if (sp < 2 || N % sp != 0 || 2 * votes[sp] < ns) return PDEB200_OK;
+    const int slots = N / sp;
+    const int stride = (sp * (slots + 1) <= G::XB) ? slots + 1 : slots;
+    std::vector<int> perm(N);
+    for (int n = 0; n < N; ++n) perm[n] = (n % sp) * stride + n / sp;
+    for (int& v : idx) v = perm[v];
+    if (!c->ks_perm) PDEB_CUDA(c, cudaMalloc(&c->ks_perm, N * sizeof(int)));
+    if (c->ks_sens_idx) { cudaFree(c->ks_sens_idx); c->ks_sens_idx = nullptr; }
+    PDEB_CUDA(c, cudaMalloc(&c->ks_sens_idx, idx.size() * sizeof(int)));
+    PDEB_CUDA(c, cudaMemcpy(c->ks_perm, perm.data(), N * sizeof(int), cudaMemcpyHostToDevice));
+    PDEB_CUDA(c, cudaMemcpy(c->ks_sens_idx, idx.data(), idx.size() * sizeof(int), cudaMemcpyHostToDevice));
+    c->ks_layout_on = true;
+    return PDEB200_OK;
+}
+
 template <typename T, int N1, int N2>
 int32_t launch(pdeb200_ctx* c) {
     using G = KsGeom<N1, N2>;
@@ -123,7 +157,12 @@ int32_t launch(pdeb200_ctx* c) {
     A.c1 = (const T*)c->c1; A.cN = (const T*)c->cN; A.ainvh = (const T*)c->ainvh; A.hm = (const C*)c->hm;
     const double h = g.dt / g.oversampling;
     A.third = (T)((h / 2) / (3 * h / 2)); A.inv_n = (T)(1.0 / G::N);
-    A.sens = EllTable<T>{c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows};
+    if (c->ks_layout_dirty) {
+        int32_t rc = sensor_layout<N1, N2>(c);
+        if (rc) return rc;
+    }
+    A.sens = EllTable<T>{c->ks_layout_on ? c->ks_sens_idx : c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows};
+    A.perm = c->ks_layout_on ? c->ks_perm : nullptr;
     A.y = (T*)c->y; A.p = (const T*)c->p; A.sensors_out = (T*)c->sensors; A.vmax_out = (T*)c->vmax;
     const int n_pairs = (g.n_envs + 1) / 2;
     const int grid = (n_pairs + PAIRS - 1) / PAIRS;
@@ -188,7 +227,7 @@ int32_t ks_cost(const pdeb200_ctx* c, double* bytes, double* flops) {
 }
 
 void ks_free(pdeb200_ctx* c) {
-    for (void** p : {&c->tw12, &c->tw21, &c->c1, &c->cN, &c->ainvh, &c->hm}) {
+    for (void** p : {&c->tw12, &c->tw21, &c->c1, &c->cN, &c->ainvh, &c->hm, (void**)&c->ks_perm, (void**)&c->ks_sens_idx}) {
         if (*p) cudaFree(*p);
         *p = nullptr;
     }

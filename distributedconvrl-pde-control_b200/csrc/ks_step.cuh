@@ -43,7 +43,8 @@ struct KsArgs {
     const T* ainvh;                    // A_inv * h (global, read once per env step)
     const C* hm;                       // h * fft(mu*cos(...)) or nullptr (mu == 0)
     T third, inv_n;                    // (h/2)/(3h/2); 1/N
-    EllTable<T> sens;                  // rows: sensors, gather over grid points
+    EllTable<T> sens;                  // rows: sensors, gather over grid points (indices already under `perm`)
+    const int* perm;                   // position of grid point n in the natural-order shared line, or nullptr (identity)
     T* y;                              // [B][N] in/out
     const T* p;                        // [B][N] actuation field (physical)
     T* sensors_out;                    // [B][n_sensors] raw <y, g_i>
@@ -70,26 +71,6 @@ __host__ __device__ inline size_t ks_smem_bytes(int pairs_per_cta) {
     size_t shared = (size_t)(N1 == N2 ? 1 : 2) * G::N * sizeof(C) + 2 * (size_t)G::N * sizeof(T);
     size_t per_pair = ((size_t)G::XB + 2 * G::N) * sizeof(C);
     return shared + per_pair * pairs_per_cta;
-}
-
-template <typename T>
-struct EllView { const int* idx; const T* w; };
-
-// Cooperative copy of an ELL table into shared memory (falls back to the global table when it
-// does not fit).  Returns pointers usable with plain loads.
-template <typename T>
-__device__ __forceinline__ EllView<T> stage_table(const EllTable<T>& tab, unsigned char* dead, size_t dead_bytes,
-                                                  int tid, int nthreads) {
-    const size_t n = (size_t)tab.nnz_max * tab.n_rows;
-    const size_t need = n * (sizeof(T) + sizeof(int));
-    EllView<T> v{tab.idx, tab.w};
-    if (need <= dead_bytes) {                          // CTA-uniform
-        T* sw = reinterpret_cast<T*>(dead);
-        int* si = reinterpret_cast<int*>(sw + n);
-        for (size_t i = tid; i < n; i += nthreads) { sw[i] = __ldg(tab.w + i); si[i] = __ldg(tab.idx + i); }
-        v.idx = si; v.w = sw;
-    }
-    return v;
 }
 
 // Register budget: fp64 keeps z and u_hat (4*RMAX doubles) in registers, so it is compiled for 8 resident
@@ -205,14 +186,17 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
             }
         }
     }
-    // ---- y = real/imag(ifft(u_hat)); store; keep natural-order copy in xb for the sensors ----
+    // ---- y = real/imag(ifft(u_hat)); store; keep a copy in xb for the sensors.  With equally spaced sensors the
+    // copy is laid out in `spacing` planes (perm) so that, for a given tap, the lanes of a pair read CONSECUTIVE
+    // 16-byte entries: the plain natural order costs 8 wavefronts per half warp and tap (lanes 4 points = 64 B
+    // apart), which ncu showed as ~10 us of shared-memory time per launch at 8192 environments ----
     T vmax_a = T(0), vmax_b = T(0);
     if (t < N2) {
 #pragma unroll
         for (int r = 0; r < N1; ++r) {
             const int n = t + N2 * r;
             const T ya = zr[r] * A.inv_n, yb = zi[r] * A.inv_n;
-            xb[n] = V2<T>::make(ya, yb);
+            xb[A.perm ? __ldg(A.perm + n) : n] = V2<T>::make(ya, yb);
             if (va) A.y[(size_t)ea * N + n] = ya;
             if (vb) A.y[(size_t)eb * N + n] = yb;
             vmax_a = fmax(vmax_a, fabs(ya)); vmax_b = fmax(vmax_b, fabs(yb));
@@ -230,35 +214,46 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
     __syncthreads();                     // PREV / F dead from here
 
     // ---- sensors: raw dots <y, g_i> for both envs (CU sensors per thread in flight) ---------
-    const EllView<T> senv = stage_table<T>(A.sens, dead, dead_bytes, threadIdx.x, NT);
+    const size_t n_tab = (size_t)A.sens.nnz_max * n_s;
+    const bool staged = n_tab * (sizeof(T) + sizeof(int)) <= dead_bytes;       // CTA-uniform
+    T* s_w = reinterpret_cast<T*>(dead);
+    int* s_i = reinterpret_cast<int*>(s_w + n_tab);
+    if (staged)
+        for (size_t i = threadIdx.x; i < n_tab; i += NT) { s_w[i] = __ldg(A.sens.w + i); s_i[i] = __ldg(A.sens.idx + i); }
     __syncthreads();
-    for (int i0 = t; i0 < n_s; i0 += CU * TP) {
-        T sa[CU], sb[CU];
+    // called once with shared-memory and once with global pointers so that the staged case compiles to LDS
+    auto dots = [&](const int* __restrict__ tidx, const T* __restrict__ tw) {
+        for (int i0 = t; i0 < n_s; i0 += CU * TP) {
+            T sa[CU], sb[CU];
 #pragma unroll
-        for (int m = 0; m < CU; ++m) { sa[m] = T(0); sb[m] = T(0); }
-        for (int j = 0; j < A.sens.nnz_max; ++j) {
-            int idx[CU]; T w[CU];
+            for (int m = 0; m < CU; ++m) { sa[m] = T(0); sb[m] = T(0); }
+#pragma unroll 3
+            for (int j = 0; j < A.sens.nnz_max; ++j) {
+                int idx[CU]; T w[CU];
+#pragma unroll
+                for (int m = 0; m < CU; ++m) {
+                    const int i = i0 + m * TP;
+                    idx[m] = i < n_s ? tidx[j * n_s + i] : 0;
+                    w[m] = i < n_s ? tw[j * n_s + i] : T(0);
+                }
+#pragma unroll
+                for (int m = 0; m < CU; ++m) {
+                    const C v = xb[idx[m]];
+                    sa[m] += v.x * w[m]; sb[m] += v.y * w[m];
+                }
+            }
 #pragma unroll
             for (int m = 0; m < CU; ++m) {
                 const int i = i0 + m * TP;
-                idx[m] = i < n_s ? senv.idx[j * n_s + i] : 0;
-                w[m] = i < n_s ? senv.w[j * n_s + i] : T(0);
-            }
-#pragma unroll
-            for (int m = 0; m < CU; ++m) {
-                const C v = xb[idx[m]];
-                sa[m] += v.x * w[m]; sb[m] += v.y * w[m];
+                if (i < n_s) {
+                    if (va) A.sensors_out[(size_t)ea * n_s + i] = sa[m];
+                    if (vb) A.sensors_out[(size_t)eb * n_s + i] = sb[m];
+                }
             }
         }
-#pragma unroll
-        for (int m = 0; m < CU; ++m) {
-            const int i = i0 + m * TP;
-            if (i < n_s) {
-                if (va) A.sensors_out[(size_t)ea * n_s + i] = sa[m];
-                if (vb) A.sensors_out[(size_t)eb * n_s + i] = sb[m];
-            }
-        }
-    }
+    };
+    if (staged) dots(s_i, s_w);
+    else dots(A.sens.idx, A.sens.w);
 }
 
 }  // namespace pdeb200

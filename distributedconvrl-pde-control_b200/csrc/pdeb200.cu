@@ -145,6 +145,7 @@ int32_t set_bases_t(pdeb200_ctx* c, const double* sb, const double* ab, const in
     PDEB_CUDA(c, cudaMemcpy(c->d_a2s, a.data(), a.size() * sizeof(int), cudaMemcpyHostToDevice));
     PDEB_CUDA(c, cudaMemcpy(c->d_sens_sum, ssum.data(), ssum.size() * sizeof(T), cudaMemcpyHostToDevice));
     c->bases_set = true;
+    c->ks_layout_dirty = true;
     return PDEB200_OK;
 }
 
