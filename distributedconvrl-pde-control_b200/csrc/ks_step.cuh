@@ -106,11 +106,6 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
     unsigned char* dead = reinterpret_cast<unsigned char*>(s_prev0);
     const size_t dead_bytes = (size_t)2 * PAIRS * N * sizeof(C);
 
-    for (int i = threadIdx.x; i < N; i += NT) {
-        s_tw12[i] = A.tw12[i];
-        if (N1 != N2) s_tw21[i] = A.tw21[i];
-        s_c1[i] = A.c1[i]; s_cN[i] = A.cN[i];
-    }
 
     const int ea = 2 * pair, eb = 2 * pair + 1;
     const bool va = ea < A.n_envs, vb = eb < A.n_envs;
@@ -131,6 +126,12 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
         zi[r] = (vb && in) ? __ldg(A.p + (size_t)eb * N + n) : T(0);
         ur[r] = (va && in) ? A.y[(size_t)ea * N + n] : T(0);
         ui[r] = (vb && in) ? A.y[(size_t)eb * N + n] : T(0);
+    }
+    // constant tables after the state loads are in flight (the staging stores wait for their own loads)
+    for (int i = threadIdx.x; i < N; i += NT) {
+        s_tw12[i] = A.tw12[i];
+        if (N1 != N2) s_tw21[i] = A.tw21[i];
+        s_c1[i] = A.c1[i]; s_cN[i] = A.cN[i];
     }
     __syncthreads();
 
@@ -190,6 +191,20 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
     // copy is laid out in `spacing` planes (perm) so that, for a given tap, the lanes of a pair read CONSECUTIVE
     // 16-byte entries: the plain natural order costs 8 wavefronts per half warp and tap (lanes 4 points = 64 B
     // apart), which ncu showed as ~10 us of shared-memory time per launch at 8192 environments ----
+    // the sensor table's entries are requested now (u_hat / F registers are dead) and stored into the dead PREV / F
+    // region after the barrier below: their L2 latency hides behind the epilogue instead of heading the sensor phase
+    const size_t n_tab = (size_t)A.sens.nnz_max * n_s;
+    const bool staged = n_tab * (sizeof(T) + sizeof(int)) <= dead_bytes;       // CTA-uniform
+    constexpr int PF = 8;
+    T pf_w[PF]; int pf_i[PF];
+    if (staged) {
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const size_t i = threadIdx.x + (size_t)k * NT;
+            pf_w[k] = i < n_tab ? __ldg(A.sens.w + i) : T(0);
+            pf_i[k] = i < n_tab ? __ldg(A.sens.idx + i) : 0;
+        }
+    }
     T vmax_a = T(0), vmax_b = T(0);
     if (t < N2) {
 #pragma unroll
@@ -214,12 +229,16 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
     __syncthreads();                     // PREV / F dead from here
 
     // ---- sensors: raw dots <y, g_i> for both envs (CU sensors per thread in flight) ---------
-    const size_t n_tab = (size_t)A.sens.nnz_max * n_s;
-    const bool staged = n_tab * (sizeof(T) + sizeof(int)) <= dead_bytes;       // CTA-uniform
     T* s_w = reinterpret_cast<T*>(dead);
     int* s_i = reinterpret_cast<int*>(s_w + n_tab);
-    if (staged)
-        for (size_t i = threadIdx.x; i < n_tab; i += NT) { s_w[i] = __ldg(A.sens.w + i); s_i[i] = __ldg(A.sens.idx + i); }
+    if (staged) {
+#pragma unroll
+        for (int k = 0; k < PF; ++k) {
+            const size_t i = threadIdx.x + (size_t)k * NT;
+            if (i < n_tab) { s_w[i] = pf_w[k]; s_i[i] = pf_i[k]; }
+        }
+        for (size_t i = threadIdx.x + (size_t)PF * NT; i < n_tab; i += NT) { s_w[i] = __ldg(A.sens.w + i); s_i[i] = __ldg(A.sens.idx + i); }
+    }
     __syncthreads();
     // called once with shared-memory and once with global pointers so that the staged case compiles to LDS
     auto dots = [&](const int* __restrict__ tidx, const T* __restrict__ tw) {
