@@ -75,14 +75,17 @@ __device__ __forceinline__ int unpad_idx(int kp, int NP, int N) {
 }
 
 template <typename T> struct NsMinCtas { static constexpr int value = sizeof(T) == 8 ? 1 : 2; };
+// Kernel A is latency bound at one 8-warp CTA per SM (fp64: ~180 registers/thread): 12 columns per CTA is what the
+// register file allows (fp32 runs two 8-warp CTAs per SM instead).
+template <typename T> struct NsColsA { static constexpr int value = sizeof(T) == 8 ? 12 : 8; };
 
 // ---- A: inverse transform along y of the four padded, Hermitian-symmetrised spectra ---------------------
 // Input staging is branch-free and uses all 32 lanes: a CTA-wide table maps each padded row to the unpadded
 // rows of its two contributions (k and -k), the column pair (kx, -kx) sits in shared memory, and the two
 // psi-based fields reuse the columns after an in-place division by k^2 (one division per entry, like the
 // reference's `psihat = omghat ./ kx2ky2`).
-template <typename T, int P1, int P2, int NN>
-__global__ void __launch_bounds__(kColsPerCta * 32, NsMinCtas<T>::value)
+template <typename T, int P1, int P2, int NN, int COLS>
+__global__ void __launch_bounds__(COLS * 32, NsMinCtas<T>::value)
 ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
     using G = NsGeom<P1, P2>;
     using C = typename V2<T>::type;
@@ -92,11 +95,11 @@ ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
     constexpr int NH = NN / 2 + 1, NHP = (NH + 3) / 4 * 4;
     C* s_tw = reinterpret_cast<C*>(smem_raw);
     C* s_xb0 = s_tw + NP;
-    C* s_col0 = s_xb0 + kColsPerCta * G::XB;
-    T* s_ky = reinterpret_cast<T*>(s_col0 + kColsPerCta * 2 * N);
+    C* s_col0 = s_xb0 + COLS * G::XB;
+    T* s_ky = reinterpret_cast<T*>(s_col0 + COLS * 2 * N);
     short2* s_tab = reinterpret_cast<short2*>(s_ky + N);
     const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
-    const int env = blockIdx.y, a0 = blockIdx.x * kColsPerCta, a = a0 + w;
+    const int env = blockIdx.y, a0 = blockIdx.x * COLS, a = a0 + w;
     for (int i = threadIdx.x; i < NP; i += blockDim.x) {
         s_tw[i] = A.tw_inv[i];
         s_tab[i] = make_short2((short)unpad_idx(i, NP, N), (short)unpad_idx((NP - i) % NP, NP, N));
@@ -164,7 +167,7 @@ ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
         __syncthreads();
         {
             // 8-column tile store: thread -> (column c, row y), rows advance by 32 per iteration
-            const int c = threadIdx.x % kColsPerCta, y0 = threadIdx.x / kColsPerCta;
+            const int c = threadIdx.x % COLS, y0 = threadIdx.x / COLS;
             C* dst = A.W + ((size_t)(env * 4 + f) * NP + y0) * NHP + a0 + c;
             const C* srow = s_xb0 + c * G::XB + y0;
             if (a0 + c < NH) {
@@ -508,7 +511,8 @@ int32_t setup_t(pdeb200_ctx* c) {
 template <typename T, int P1, int P2>
 size_t smem_a(int N) {
     using G = NsGeom<P1, P2>; using C = typename V2<T>::type;
-    return ((size_t)G::NP + kColsPerCta * G::XB + kColsPerCta * 2 * N) * sizeof(C) + (size_t)N * sizeof(T) +
+    constexpr int COLS = NsColsA<T>::value;
+    return ((size_t)G::NP + COLS * G::XB + COLS * 2 * N) * sizeof(C) + (size_t)N * sizeof(T) +
            (size_t)G::NP * sizeof(short2);
 }
 template <typename T, int P1, int P2>
@@ -539,7 +543,8 @@ int32_t rk4_t(pdeb200_ctx* c) {
     const pdeb200_config& g = c->cfg;
     const int N = P->N, NP = P->NP;
     const size_t nn = (size_t)N * N;
-    auto kA = ns_ypass_inv_kernel<T, P1, P2, NN>;
+    constexpr int COLS_A = NsColsA<T>::value;
+    auto kA = ns_ypass_inv_kernel<T, P1, P2, NN, COLS_A>;
     auto kB = ns_xpass_kernel<T, P1, P2, NN>;
     auto kC = ns_ypass_fwd_kernel<T, P1, P2, NN>;
     const size_t sa = smem_a<T, P1, P2>(N), sb = smem_b<T, P1, P2>(P->NHP), sc = smem_c<T, P1, P2>(N);
@@ -564,7 +569,7 @@ int32_t rk4_t(pdeb200_ctx* c) {
             for (int stage = 1; stage <= 4; ++stage) {
                 A.stage = stage;
                 A.fin = stage == 1 ? A.y : A.fst;
-                kA<<<dim3(col_groups, ne), kColsPerCta * 32, sa, c->stream>>>(A);
+                kA<<<dim3((P->NH + COLS_A - 1) / COLS_A, ne), COLS_A * 32, sa, c->stream>>>(A);
                 kB<<<dim3(line_groups, ne), kColsPerCta * 32, sb, c->stream>>>(A);
                 kC<<<dim3(col_groups, ne), kColsPerCta * 32, sc, c->stream>>>(A);
                 c->launches += 3;
