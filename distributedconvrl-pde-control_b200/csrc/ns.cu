@@ -78,6 +78,9 @@ template <typename T> struct NsMinCtas { static constexpr int value = sizeof(T) 
 // Kernel A is latency bound at one 8-warp CTA per SM (fp64: ~180 registers/thread): 12 columns per CTA is what the
 // register file allows (fp32 runs two 8-warp CTAs per SM instead).
 template <typename T> struct NsColsA { static constexpr int value = sizeof(T) == 8 ? 12 : 8; };
+// Kernel B: a ninth warp fits 227 KB of shared memory in fp64 (24.2 KB per warp + 12 KB of twiddles) but measured
+// slower (568 -> 554 env-steps/s: 192 line pairs do not divide by 9 and B is the FP64-pipe-bound kernel of the three)
+template <typename T> struct NsColsB { static constexpr int value = 8; };
 
 // ---- A: inverse transform along y of the four padded, Hermitian-symmetrised spectra ---------------------
 // Input staging is branch-free and uses all 32 lanes: a CTA-wide table maps each padded row to the unpadded
@@ -203,8 +206,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 // The four half-spectrum lines a warp consumes per y-line are contiguous rows of W: they are staged into
 // shared memory by 1-D bulk copies (cp.async.bulk, completion on a per-warp mbarrier) two phases ahead of
 // their use, so the HBM/L2 latency overlaps the FFT arithmetic of the previous phase.
-template <typename T, int P1, int P2, int NN>
-__global__ void __launch_bounds__(kColsPerCta * 32, NsMinCtas<T>::value)
+template <typename T, int P1, int P2, int NN, int COLS>
+__global__ void __launch_bounds__(COLS * 32, NsMinCtas<T>::value)
 ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
     using G = NsGeom<P1, P2>;
     using C = typename V2<T>::type;
@@ -214,13 +217,13 @@ ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
     C* s_twi = reinterpret_cast<C*>(smem_raw);
     C* s_twf = s_twi + NP;
     C* s_xb0 = s_twf + NP;
-    C* s_uv0 = s_xb0 + kColsPerCta * G::XB;
-    C* s_in0 = s_uv0 + kColsPerCta * NP;                              // [warp][slot 2][line 2][NHP]
-    T* s_q0 = reinterpret_cast<T*>(s_in0 + (size_t)kColsPerCta * 4 * NHP);
-    uint64_t* s_bar0 = reinterpret_cast<uint64_t*>(s_q0 + (size_t)kColsPerCta * NP);
+    C* s_uv0 = s_xb0 + COLS * G::XB;
+    C* s_in0 = s_uv0 + COLS * NP;                              // [warp][slot 2][line 2][NHP]
+    T* s_q0 = reinterpret_cast<T*>(s_in0 + (size_t)COLS * 4 * NHP);
+    uint64_t* s_bar0 = reinterpret_cast<uint64_t*>(s_q0 + (size_t)COLS * NP);
     const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
     const int env = blockIdx.y;
-    const int y0 = (blockIdx.x * kColsPerCta + w) * 2;
+    const int y0 = (blockIdx.x * COLS + w) * 2;
     for (int i = threadIdx.x; i < NP; i += blockDim.x) { s_twi[i] = A.tw_inv[i]; s_twf[i] = A.tw_fwd[i]; }
     uint64_t* bar = s_bar0 + w * 2;
     if (t == 0) {
@@ -518,8 +521,9 @@ size_t smem_a(int N) {
 template <typename T, int P1, int P2>
 size_t smem_b(int NHP) {
     using G = NsGeom<P1, P2>; using C = typename V2<T>::type;
-    return ((size_t)2 * G::NP + kColsPerCta * G::XB + kColsPerCta * G::NP + (size_t)kColsPerCta * 4 * NHP) * sizeof(C) +
-           (size_t)kColsPerCta * G::NP * sizeof(T) + (size_t)kColsPerCta * 2 * sizeof(uint64_t);
+    constexpr int COLS = NsColsB<T>::value;
+    return ((size_t)2 * G::NP + COLS * G::XB + COLS * G::NP + (size_t)COLS * 4 * NHP) * sizeof(C) +
+           (size_t)COLS * G::NP * sizeof(T) + (size_t)COLS * 2 * sizeof(uint64_t);
 }
 template <typename T, int P1, int P2>
 size_t smem_c(int N) {
@@ -545,7 +549,8 @@ int32_t rk4_t(pdeb200_ctx* c) {
     const size_t nn = (size_t)N * N;
     constexpr int COLS_A = NsColsA<T>::value;
     auto kA = ns_ypass_inv_kernel<T, P1, P2, NN, COLS_A>;
-    auto kB = ns_xpass_kernel<T, P1, P2, NN>;
+    constexpr int COLS_B = NsColsB<T>::value;
+    auto kB = ns_xpass_kernel<T, P1, P2, NN, COLS_B>;
     auto kC = ns_ypass_fwd_kernel<T, P1, P2, NN>;
     const size_t sa = smem_a<T, P1, P2>(N), sb = smem_b<T, P1, P2>(P->NHP), sc = smem_c<T, P1, P2>(N);
     int32_t rc;
@@ -560,7 +565,6 @@ int32_t rk4_t(pdeb200_ctx* c) {
     const double np2 = (double)NP * NP;
     A.scale = (T)((g.ifpad ? 2.25 : 1.0) / (np2 * np2));
     const int col_groups = (P->NH + kColsPerCta - 1) / kColsPerCta;
-    const int line_groups = (NP / 2 + kColsPerCta - 1) / kColsPerCta;
     for (int e0 = 0; e0 < g.n_envs; e0 += P->chunk) {
         const int ne = std::min(P->chunk, g.n_envs - e0);
         A.y = (C*)c->y + (size_t)e0 * nn; A.fst = (C*)P->fst + (size_t)e0 * nn; A.acc = (C*)P->acc + (size_t)e0 * nn;
@@ -570,7 +574,7 @@ int32_t rk4_t(pdeb200_ctx* c) {
                 A.stage = stage;
                 A.fin = stage == 1 ? A.y : A.fst;
                 kA<<<dim3((P->NH + COLS_A - 1) / COLS_A, ne), COLS_A * 32, sa, c->stream>>>(A);
-                kB<<<dim3(line_groups, ne), kColsPerCta * 32, sb, c->stream>>>(A);
+                kB<<<dim3((NP / 2 + COLS_B - 1) / COLS_B, ne), COLS_B * 32, sb, c->stream>>>(A);
                 kC<<<dim3(col_groups, ne), kColsPerCta * 32, sc, c->stream>>>(A);
                 c->launches += 3;
             }
