@@ -77,7 +77,7 @@ __device__ __forceinline__ int unpad_idx(int kp, int NP, int N) {
 template <typename T> struct NsMinCtas { static constexpr int value = sizeof(T) == 8 ? 1 : 2; };
 // Kernel A is latency bound at one 8-warp CTA per SM (fp64: ~180 registers/thread): 12 columns per CTA is what the
 // register file allows (fp32 runs two 8-warp CTAs per SM instead).
-template <typename T> struct NsColsA { static constexpr int value = sizeof(T) == 8 ? 12 : 8; };
+template <typename T> struct NsColsA { static constexpr int value = sizeof(T) == 8 ? 6 : 8; };
 // Kernel B: a ninth warp fits 227 KB of shared memory in fp64 (24.2 KB per warp + 12 KB of twiddles) but measured
 // slower (568 -> 554 env-steps/s: 192 line pairs do not divide by 9 and B is the FP64-pipe-bound kernel of the three)
 template <typename T> struct NsColsB { static constexpr int value = 8; };
@@ -88,7 +88,7 @@ template <typename T> struct NsColsB { static constexpr int value = 8; };
 // psi-based fields reuse the columns after an in-place division by k^2 (one division per entry, like the
 // reference's `psihat = omghat ./ kx2ky2`).
 template <typename T, int P1, int P2, int NN, int COLS>
-__global__ void __launch_bounds__(COLS * 32, NsMinCtas<T>::value)
+__global__ void __launch_bounds__(COLS * 32, (sizeof(T) == 8 && COLS > 6) ? 1 : 2)
 ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
     using G = NsGeom<P1, P2>;
     using C = typename V2<T>::type;
