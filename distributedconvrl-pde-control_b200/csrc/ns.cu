@@ -42,7 +42,6 @@ template <int P1, int P2> struct NsGeom {
     static constexpr int XB = ((XB0 + 7) / 8) * 8 + 1;             // == 1 (mod 8): conflict-free 8-column tiles
 };
 
-constexpr int kColsPerCta = 8;      // warps per CTA = spectral columns (A, C) / line pairs (B) per CTA
 
 struct NsProb {
     int N = 0, NP = 0, NH = 0, NHP = 0, chunk = 0;
@@ -77,10 +76,11 @@ __device__ __forceinline__ int unpad_idx(int kp, int NP, int N) {
 template <typename T> struct NsMinCtas { static constexpr int value = sizeof(T) == 8 ? 1 : 2; };
 // Kernel A is latency bound at one 8-warp CTA per SM (fp64: ~180 registers/thread): 12 columns per CTA is what the
 // register file allows (fp32 runs two 8-warp CTAs per SM instead).
-template <typename T> struct NsColsA { static constexpr int value = sizeof(T) == 8 ? 6 : 8; };
+template <typename T> struct NsColsA { static constexpr int value = 4; };
+template <typename T> struct NsColsC { static constexpr int value = 8; };
 // Kernel B: a ninth warp fits 227 KB of shared memory in fp64 (24.2 KB per warp + 12 KB of twiddles) but measured
 // slower (568 -> 554 env-steps/s: 192 line pairs do not divide by 9 and B is the FP64-pipe-bound kernel of the three)
-template <typename T> struct NsColsB { static constexpr int value = 8; };
+template <typename T> struct NsColsB { static constexpr int value = 4; };
 
 // ---- A: inverse transform along y of the four padded, Hermitian-symmetrised spectra ---------------------
 // Input staging is branch-free and uses all 32 lanes: a CTA-wide table maps each padded row to the unpadded
@@ -88,7 +88,7 @@ template <typename T> struct NsColsB { static constexpr int value = 8; };
 // psi-based fields reuse the columns after an in-place division by k^2 (one division per entry, like the
 // reference's `psihat = omghat ./ kx2ky2`).
 template <typename T, int P1, int P2, int NN, int COLS>
-__global__ void __launch_bounds__(COLS * 32, (sizeof(T) == 8 && COLS > 6) ? 1 : 2)
+__global__ void __launch_bounds__(COLS * 32, (sizeof(T) == 8 ? 1 : 2) * (COLS > 6 ? 1 : (COLS > 4 ? 2 : (COLS > 3 ? 3 : 4))))
 ns_ypass_inv_kernel(const __grid_constant__ NsArgs<T> A) {
     using G = NsGeom<P1, P2>;
     using C = typename V2<T>::type;
@@ -207,7 +207,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
 // shared memory by 1-D bulk copies (cp.async.bulk, completion on a per-warp mbarrier) two phases ahead of
 // their use, so the HBM/L2 latency overlaps the FFT arithmetic of the previous phase.
 template <typename T, int P1, int P2, int NN, int COLS>
-__global__ void __launch_bounds__(COLS * 32, NsMinCtas<T>::value)
+__global__ void __launch_bounds__(COLS * 32, NsMinCtas<T>::value * (8 / COLS))
 ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
     using G = NsGeom<P1, P2>;
     using C = typename V2<T>::type;
@@ -336,8 +336,8 @@ __device__ __forceinline__ void rk_update(const NsArgs<T>& A, const size_t* idx,
     }
 }
 
-template <typename T, int P1, int P2, int NN>
-__global__ void __launch_bounds__(kColsPerCta * 32, 2 * NsMinCtas<T>::value)     // load-latency bound: 2+ CTAs/SM
+template <typename T, int P1, int P2, int NN, int COLS>
+__global__ void __launch_bounds__(COLS * 32, (sizeof(T) == 8 ? 2 : 4) * (8 / COLS))     // load-latency bound: 16+ warps/SM
 ns_ypass_fwd_kernel(const __grid_constant__ NsArgs<T> A) {
     using G = NsGeom<P1, P2>;
     using C = typename V2<T>::type;
@@ -346,13 +346,13 @@ ns_ypass_fwd_kernel(const __grid_constant__ NsArgs<T> A) {
     constexpr int N = NN, NH = NN / 2 + 1, NHP = (NH + 3) / 4 * 4;
     C* s_tw = reinterpret_cast<C*>(smem_raw);
     C* s_xb0 = s_tw + NP;
-    T* s_ky = reinterpret_cast<T*>(s_xb0 + kColsPerCta * G::XB);
+    T* s_ky = reinterpret_cast<T*>(s_xb0 + COLS * G::XB);
     const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
-    const int env = blockIdx.y, a0 = blockIdx.x * kColsPerCta, a = a0 + w;
+    const int env = blockIdx.y, a0 = blockIdx.x * COLS, a = a0 + w;
     for (int i = threadIdx.x; i < NP; i += blockDim.x) s_tw[i] = A.tw_fwd[i];
     for (int i = threadIdx.x; i < N; i += blockDim.x) s_ky[i] = A.ky[i];
     {
-        const int c = threadIdx.x % kColsPerCta, y0 = threadIdx.x / kColsPerCta;
+        const int c = threadIdx.x % COLS, y0 = threadIdx.x / COLS;
         const C* src = A.Q + ((size_t)env * NP + y0) * NHP + a0 + c;
         C* srow = s_xb0 + c * G::XB + y0;
         if (a0 + c < NH) {
@@ -528,7 +528,7 @@ size_t smem_b(int NHP) {
 template <typename T, int P1, int P2>
 size_t smem_c(int N) {
     using G = NsGeom<P1, P2>; using C = typename V2<T>::type;
-    return ((size_t)G::NP + kColsPerCta * G::XB) * sizeof(C) + (size_t)N * sizeof(T);
+    return ((size_t)G::NP + NsColsC<T>::value * G::XB) * sizeof(C) + (size_t)N * sizeof(T);
 }
 
 template <typename K>
@@ -551,7 +551,8 @@ int32_t rk4_t(pdeb200_ctx* c) {
     auto kA = ns_ypass_inv_kernel<T, P1, P2, NN, COLS_A>;
     constexpr int COLS_B = NsColsB<T>::value;
     auto kB = ns_xpass_kernel<T, P1, P2, NN, COLS_B>;
-    auto kC = ns_ypass_fwd_kernel<T, P1, P2, NN>;
+    constexpr int COLS_C = NsColsC<T>::value;
+    auto kC = ns_ypass_fwd_kernel<T, P1, P2, NN, COLS_C>;
     const size_t sa = smem_a<T, P1, P2>(N), sb = smem_b<T, P1, P2>(P->NHP), sc = smem_c<T, P1, P2>(N);
     int32_t rc;
     if ((rc = set_smem(c, kA, sa)) || (rc = set_smem(c, kB, sb)) || (rc = set_smem(c, kC, sc))) return rc;
@@ -564,7 +565,6 @@ int32_t rk4_t(pdeb200_ctx* c) {
     // ifft normalisation of the two factors (1/NP^2 each) and the 1.5*1.5 of fluid_rk4.jl:178
     const double np2 = (double)NP * NP;
     A.scale = (T)((g.ifpad ? 2.25 : 1.0) / (np2 * np2));
-    const int col_groups = (P->NH + kColsPerCta - 1) / kColsPerCta;
     for (int e0 = 0; e0 < g.n_envs; e0 += P->chunk) {
         const int ne = std::min(P->chunk, g.n_envs - e0);
         A.y = (C*)c->y + (size_t)e0 * nn; A.fst = (C*)P->fst + (size_t)e0 * nn; A.acc = (C*)P->acc + (size_t)e0 * nn;
@@ -575,7 +575,7 @@ int32_t rk4_t(pdeb200_ctx* c) {
                 A.fin = stage == 1 ? A.y : A.fst;
                 kA<<<dim3((P->NH + COLS_A - 1) / COLS_A, ne), COLS_A * 32, sa, c->stream>>>(A);
                 kB<<<dim3((NP / 2 + COLS_B - 1) / COLS_B, ne), COLS_B * 32, sb, c->stream>>>(A);
-                kC<<<dim3(col_groups, ne), kColsPerCta * 32, sc, c->stream>>>(A);
+                kC<<<dim3((P->NH + COLS_C - 1) / COLS_C, ne), COLS_C * 32, sc, c->stream>>>(A);
                 c->launches += 3;
             }
     }
