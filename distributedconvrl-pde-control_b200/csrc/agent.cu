@@ -113,7 +113,16 @@ __global__ void fetch_kernel(int n, int ns, int na, int64_t ncols, Ring sa, Ring
 __global__ void reward_stats_kernel(int n, const float* __restrict__ br, double* stats) {
     __shared__ double s0[256], s1[256];
     double a = 0, b = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { const double r = br[i]; a += r; b += r * r; }
+    int i = threadIdx.x;
+    // same per-thread order as a plain strided loop, loads issued 16 at a time
+    for (; i + 15 * (int)blockDim.x < n; i += 16 * blockDim.x) {
+        float v[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) v[u] = br[i + u * blockDim.x];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) { const double r = v[u]; a += r; b += r * r; }
+    }
+    for (; i < n; i += blockDim.x) { const double r = br[i]; a += r; b += r * r; }
     s0[threadIdx.x] = a; s1[threadIdx.x] = b;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {
@@ -381,11 +390,19 @@ __global__ void __launch_bounds__(512) ddpg_actor_kernel(const __grid_constant__
     if (threadIdx.x == 0) { out[D.n_acc] = (float)s_q; out[D.n_acc + 1] = 0.f; }
 }
 
-// sum_b partials[b * stride + q] in ascending b (fixed order), with the loads issued eight at a time ahead of the adds
-// (the SM issues in order: load / add / load / add would expose one memory latency per term)
+// sum_b partials[b * stride + q] in ascending b (fixed order), with the loads issued 32 at a time ahead of the adds
+// (the SM issues in order: load / add / load / add would expose one memory latency per term; with 128 CTA partials
+// batches of 8 were still 16 dependent L2 round trips = 11 of the kernel's 14 us)
 __device__ __forceinline__ double ordered_sum(const float* __restrict__ partials, int n_blocks, size_t stride, int q) {
     double s = 0.0;
     int b = 0;
+    for (; b + 32 <= n_blocks; b += 32) {
+        float v[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] = __ldg(partials + (size_t)(b + u) * stride + q);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) s += (double)v[u];
+    }
     for (; b + 8 <= n_blocks; b += 8) {
         float v[8];
 #pragma unroll
@@ -411,11 +428,22 @@ __global__ void reduce_partials_kernel(int n_blocks, int n_acc, const float* __r
 // between them).  Same arithmetic as reduce_partials_kernel -> adam_kernel -> polyak_kernel.
 __global__ void reduce_adam_polyak_kernel(int n_blocks, int n_acc, const float* __restrict__ partials, float* grads, double* stats,
                                           int stat0, float* x, float* m, float* v, float* target, double eta, double b1, double b2,
-                                          double bp1, double bp2, double eps, float polyak) {
+                                          double bp1, double bp2, double eps, float polyak, float* losses, double n_global,
+                                          int literal) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n_acc + 2) return;
     const double s = ordered_sum(partials, n_blocks, (size_t)(n_acc + 2), q);
-    if (q >= n_acc) { stats[stat0 + (q - n_acc)] = s; return; }
+    if (q >= n_acc) {
+        stats[stat0 + (q - n_acc)] = s;
+        if (losses && q == n_acc) {
+            // actor phase (stat0 == 4): both losses from the reduced sums, like losses_kernel; stats[0..3] were written
+            // by the sampling and critic kernels earlier in the stream
+            const double B = n_global;
+            losses[0] = (float)(literal ? stats[3] / B + 2.0 * stats[2] * stats[0] / (B * B) + stats[1] / B : stats[3] / B);
+            losses[1] = (float)(-s / n_global);
+        }
+        return;
+    }
     const float g = (float)s;
     grads[q] = g;
     const double gi = g;
@@ -426,13 +454,6 @@ __global__ void reduce_adam_polyak_kernel(int n_blocks, int n_acc, const float* 
     const float xn = x[q] - delta;
     x[q] = xn;
     target[q] = polyak * target[q] + (1.f - polyak) * xn;
-}
-
-// both losses from the reduced sums (one launch per update on the fused path)
-__global__ void losses_both_kernel(const double* stats, double n_global, int literal, float* losses) {
-    const double B = n_global;
-    losses[0] = (float)(literal ? stats[3] / B + 2.0 * stats[2] * stats[0] / (B * B) + stats[1] / B : stats[3] / B);
-    losses[1] = (float)(-stats[4] / n_global);
 }
 
 // Flux ADAM on Float32 arrays with Float64 hyper-parameters; optional Polyak pair (dest = p*dest + (1-p)*src).
@@ -1059,7 +1080,7 @@ int32_t pdeb200_ddpg_update(pdeb200_ctx* c, double gamma, double polyak, double 
     const int64_t B = a->batch;
     HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
     HostNet &At = c->nets[PDEB200_NET_TARGET_ACTOR], &Ct = c->nets[PDEB200_NET_TARGET_CRITIC];
-    // Fused single-GPU path: {critic kernel, reduce + ADAM + Polyak} {actor kernel, reduce + ADAM + Polyak} {losses}.
+    // Fused single-GPU path: {critic kernel, reduce + ADAM + Polyak} {actor kernel, reduce + ADAM + Polyak + losses}.
     // The target critic is not read after the critic phase and the behavior critic is not written by the actor phase,
     // so its Polyak step can run right after its ADAM step (reference order: both at the end, PDEagent.jl:411-417).
     int32_t rc = critic_grads_impl(c, gamma, literal_q1, B, false);
@@ -1071,16 +1092,15 @@ int32_t pdeb200_ddpg_update(pdeb200_ctx* c, double gamma, double polyak, double 
     }
     reduce_adam_polyak_kernel<<<(C.n_params + 2 + 127) / 128, 128, 0, c->stream>>>(
         a->n_blocks, C.n_params, a->partials, c->d_grads, a->stats, 2, C.d_params, C.d_m, C.d_v, Ct.d_params, lr_critic, 0.9, 0.999,
-        C.beta_p[0], C.beta_p[1], 1e-8, (float)polyak);
+        C.beta_p[0], C.beta_p[1], 1e-8, (float)polyak, nullptr, 0.0, 0);
     C.beta_p[0] *= 0.9; C.beta_p[1] *= 0.999;
     if ((rc = actor_grads_impl(c, B, false)) < 0) return rc;
     reduce_adam_polyak_kernel<<<(A.n_params + 2 + 127) / 128, 128, 0, c->stream>>>(
         a->n_blocks, A.n_params, a->partials, c->d_grads + C.n_params, a->stats, 4, A.d_params, A.d_m, A.d_v, At.d_params, lr_actor, 0.9,
-        0.999, A.beta_p[0], A.beta_p[1], 1e-8, (float)polyak);
+        0.999, A.beta_p[0], A.beta_p[1], 1e-8, (float)polyak, c->d_losses, (double)B, literal_q1);
     A.beta_p[0] *= 0.9; A.beta_p[1] *= 0.999;
-    losses_both_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)B, literal_q1, c->d_losses);
     PDEB_CUDA(c, cudaGetLastError());
-    c->launches += 3;
+    c->launches += 2;
     return PDEB200_OK;
 }
 
