@@ -259,7 +259,6 @@ __device__ __forceinline__ int carve_acts(const NetDev& net, float* base, float*
 __global__ void __launch_bounds__(512) ddpg_critic_kernel(const __grid_constant__ DdpgArgs D) {
     extern __shared__ __align__(16) float sm[];
     float* actsC[kMaxLayers + 1];
-    float* actsT[kMaxLayers + 1];
     int off = carve_acts(D.C, sm, actsC);
     float* scratch0 = sm + off; off += TS * D.wmax;      // target-net ping-pong / deltas
     float* scratch1 = sm + off; off += TS * D.wmax;
@@ -277,8 +276,7 @@ __global__ void __launch_bounds__(512) ddpg_critic_kernel(const __grid_constant_
         const int i0 = tile * TS;
         // ---- a' = A_t(s') ------------------------------------------------------------------
         {
-            int o = 0; float* base = scratch0;           // target actor activations, ping-pong in scratch0/1
-            (void)o;
+            float* base = scratch0;                      // target actor activations, ping-pong in scratch0/1
             for (int q = threadIdx.x; q < TS * D.ns; q += blockDim.x) {
                 const int i = q / D.ns, r = q % D.ns;
                 const float v = (i0 + i < D.batch) ? D.s2[(size_t)(i0 + i) * D.ns + r] : 0.f;
@@ -334,7 +332,6 @@ __global__ void __launch_bounds__(512) ddpg_critic_kernel(const __grid_constant_
         __syncthreads();
         net_backward(D.C, actsC, scratch0, scratch1, acc, false);
         __syncthreads();
-        (void)actsT;
     }
     float* out = D.partials + (size_t)blockIdx.x * (D.n_acc + 2);
     for (int q = threadIdx.x; q < D.n_acc; q += blockDim.x) out[q] = acc[q];

@@ -39,27 +39,25 @@ __device__ __forceinline__ float act_apply(int kind, float v) {
     return v;
 }
 
-// Per-column MLP forward in registers/local memory (actor widths <= kFusedActorMaxWidth).
-// x: in/out scratch of size kFusedActorMaxWidth (input in x[0..sizes[0])).
+// NIN-NH-1 actor evaluated in registers.  w: the flat parameter vector W0 (NH x NIN, column-major) | b0 | W1 (1 x NH) |
+// b1; same accumulation order as the runtime-shaped loops (ascending input index from 0, bias added last).
 // Restates Flux Dense: y = act.(W*x .+ b)   (src/PDEagent.jl:18-30).
-__device__ __forceinline__ void mlp_forward_small(const NetDev& net, float* x, float* h) {
-    float* in = x;
-    float* out = h;
-    for (int l = 0; l < net.n_layers; ++l) {
-        const int ni = net.sizes[l], no = net.sizes[l + 1];
-        const float* W = net.params + net.offs[l];
-        const float* b = W + ni * no;
-        for (int o = 0; o < no; ++o) {
-            float acc = 0.f;
-            for (int i = 0; i < ni; ++i) acc = fmaf(W[o + no * i], in[i], acc);      // params may live in smem
-            out[o] = act_apply(net.acts[l], acc + b[o]);
-        }
-        float* tmp = in; in = out; out = tmp;
+template <int NIN, int NH>
+__device__ __forceinline__ float actor_two_layer(const float* w, const float* x, int act0, int act1) {
+    float h[NH];
+#pragma unroll
+    for (int u = 0; u < NH; ++u) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < NIN; ++i) acc = fmaf(w[u + NH * i], x[i], acc);
+        h[u] = acc + w[NIN * NH + u];
     }
-    if (in != x) {
-        const int no = net.sizes[net.n_layers];
-        for (int o = 0; o < no; ++o) x[o] = in[o];
-    }
+#pragma unroll
+    for (int u = 0; u < NH; ++u) h[u] = act_apply(act0, h[u]);
+    float acc = 0.f;
+#pragma unroll
+    for (int u = 0; u < NH; ++u) acc = fmaf(w[NIN * NH + NH + u], h[u], acc);
+    return act_apply(act1, acc + w[NIN * NH + NH + NH]);
 }
 
 template <typename T> __device__ __forceinline__ T pow_t(T a, T b);

@@ -300,20 +300,10 @@ __global__ void __launch_bounds__(256, 3) actuate_conv_kernel(const __grid_const
                 else {
                     float o;
                     if (NIN > 0) {
-                        float h[NH > 0 ? NH : 1];
+                        float xf[NIN > 0 ? NIN : 1];
 #pragma unroll
-                        for (int u = 0; u < NH; ++u) {
-                            float acc = 0.f;
-#pragma unroll
-                            for (int i = 0; i < NIN; ++i) acc = fmaf(w[u + NH * i], (float)xin[i], acc);
-                            h[u] = acc + w[NIN * NH + u];
-                        }
-#pragma unroll
-                        for (int u = 0; u < NH; ++u) h[u] = act_apply(act0, h[u]);
-                        float acc = 0.f;
-#pragma unroll
-                        for (int u = 0; u < NH; ++u) acc = fmaf(w[NIN * NH + NH + u], h[u], acc);
-                        o = act_apply(act1, acc + w[NIN * NH + NH + NH]);
+                        for (int i = 0; i < NIN; ++i) xf[i] = (float)xin[i];
+                        o = actor_two_layer<(NIN > 0 ? NIN : 1), (NH > 0 ? NH : 1)>(w, xf, act0, act1);
                     } else {
                         float* xa = s_x + tid;
                         float* xh = s_x + (size_t)A.actor_wmax * BD + tid;

@@ -54,7 +54,8 @@ __device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t ctr, floa
 // Per-column actor forward.  Activations live in shared memory as [unit][thread] (conflict free) and the layers are
 // plain runtime loops: for the tiny runtime-shaped networks of this path (1-6-1 ... 12-20-1) that is ~4x fewer issued
 // instructions than a register version that has to be unrolled (and predicated) to a compile-time maximum width.
-template <typename T>
+// NIN > 0: NIN-NH-1 actor in registers (one output row: the conv agent of every shipped KS script); NIN = -1: runtime shape
+template <typename T, int NIN, int NH>
 __global__ void __launch_bounds__(128) policy_kernel(NetDev net, int n_params, int wmax, int n_columns, int obs_rows, int a_rows,
                                                      int memory, const T* __restrict__ state, T* __restrict__ action_in,
                                                      const T* __restrict__ noise, int use_rng, uint64_t seed, uint64_t offset,
@@ -67,14 +68,28 @@ __global__ void __launch_bounds__(128) policy_kernel(NetDev net, int n_params, i
     __syncthreads();
     const int col = blockIdx.x * BD + threadIdx.x;
     if (col >= n_columns) return;
-    float* xa = s_x + threadIdx.x;
-    float* xh = s_x + (size_t)wmax * BD + threadIdx.x;
-    for (int r = 0; r < obs_rows; ++r) xa[r * BD] = (float)state[(size_t)col * obs_rows + r];
-    const float* out = mlp_forward_smem(net, s_par, xa, xh, BD);
+    float one[1];
+    const float* out = one;
+    int ostride = 1;
+    if (NIN > 0) {
+        constexpr int NP = NIN > 0 ? NIN * NH + 2 * NH + 1 : 1;
+        float w[NP], x[NIN > 0 ? NIN : 1];
+#pragma unroll
+        for (int i = 0; i < NP; ++i) w[i] = s_par[i];
+#pragma unroll
+        for (int r = 0; r < NIN; ++r) x[r] = (float)state[(size_t)col * (NIN > 0 ? NIN : 1) + r];
+        one[0] = actor_two_layer<(NIN > 0 ? NIN : 1), (NH > 0 ? NH : 1)>(w, x, net.acts[0], net.acts[1]);
+    } else {
+        float* xa = s_x + threadIdx.x;
+        float* xh = s_x + (size_t)wmax * BD + threadIdx.x;
+        for (int r = 0; r < obs_rows; ++r) xa[r * BD] = (float)state[(size_t)col * obs_rows + r];
+        out = mlp_forward_smem(net, s_par, xa, xh, BD);
+        ostride = BD;
+    }
     const int n_out = net.sizes[net.n_layers];            // == a_rows (conv agent) or n_act (mono)
     const int noisy = n_out - memory;
     for (int r = 0; r < n_out; ++r) {
-        T v = (T)out[r * BD];
+        T v = (T)out[r * ostride];
         if (r < noisy) {
             if (noise) v += noise[(size_t)col * noisy + r] * act_noise;
             else if (use_rng) {
@@ -674,16 +689,20 @@ static int32_t policy_launch(pdeb200_ctx* c, const void* d_noise, int use_rng, u
     for (int l = 0; l <= a.n_layers; ++l) wmax = std::max(wmax, a.sizes[l]);
     const size_t smem = ((size_t)a.n_params + (size_t)2 * wmax * tpb) * sizeof(float);
     if (smem > 200 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "policy_act: actor too large for shared memory");
+    const bool two = a.n_layers == 2 && a.offs[0] == 0 && a.offs[1] == a.sizes[0] * a.sizes[1] + a.sizes[1] && a.sizes[1] == 6 &&
+                     a.sizes[2] == 1 && c->obs_rows == a.sizes[0];
+    const int mode = (two && a.sizes[0] == 1) ? 1 : (two && a.sizes[0] == 3) ? 3 : -1;
     if (c->cfg.dtype == PDEB200_F64) {
-        if (smem > 48 * 1024) PDEB_CUDA(c, cudaFuncSetAttribute(policy_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        policy_kernel<double><<<grid, tpb, smem, c->stream>>>(a.dev(), a.n_params, wmax, ncol, c->obs_rows, c->a_rows, mem,
-                                                             (const double*)c->state, (double*)c->action_in, (const double*)d_noise,
-                                                             use_rng, seed, offset, act_noise, act_limit);
+        auto kern = mode == 1 ? policy_kernel<double, 1, 6> : mode == 3 ? policy_kernel<double, 3, 6> : policy_kernel<double, -1, 0>;
+        if (smem > 48 * 1024) PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, tpb, smem, c->stream>>>(a.dev(), a.n_params, wmax, ncol, c->obs_rows, c->a_rows, mem, (const double*)c->state,
+                                            (double*)c->action_in, (const double*)d_noise, use_rng, seed, offset, act_noise, act_limit);
     } else {
-        if (smem > 48 * 1024) PDEB_CUDA(c, cudaFuncSetAttribute(policy_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        policy_kernel<float><<<grid, tpb, smem, c->stream>>>(a.dev(), a.n_params, wmax, ncol, c->obs_rows, c->a_rows, mem,
-                                                            (const float*)c->state, (float*)c->action_in, (const float*)d_noise,
-                                                            use_rng, seed, offset, (float)act_noise, (float)act_limit);
+        auto kern = mode == 1 ? policy_kernel<float, 1, 6> : mode == 3 ? policy_kernel<float, 3, 6> : policy_kernel<float, -1, 0>;
+        if (smem > 48 * 1024) PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<grid, tpb, smem, c->stream>>>(a.dev(), a.n_params, wmax, ncol, c->obs_rows, c->a_rows, mem, (const float*)c->state,
+                                            (float*)c->action_in, (const float*)d_noise, use_rng, seed, offset, (float)act_noise,
+                                            (float)act_limit);
     }
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
