@@ -106,6 +106,7 @@ kseg2d_step_kernel(const __grid_constant__ Kseg2dArgs<T> A) {
             if (r == r_last && push_dn) dn0[b * slab + x] = st[r];
         }
     };
+    cluster.sync();              // every CTA of the cluster is running before anyone writes into its shared memory
     publish(0, y0);
     cluster.sync();
     const T h = A.h, h2 = T(0.5) * A.h, h6 = A.h / T(6);
