@@ -53,6 +53,15 @@ def main():
     env(rng.uniform(-1, 1, (1, 3 * env.n_actuators)))
     assert np.isfinite(np.asarray(env.y)).all()
     env.close()
+    # agent: device replay rings (with wrap), sampler, fused DDPG update kernels, ADAM / Polyak
+    setup = pkg.setups.KSSetup.ks22(oversampling=2)
+    B = 3
+    env = setup.make_env(n_envs=B, dtype="f32", y0=setup.generate_random_init(rng, B))
+    pol = A.create_agent(env, rng=rng, nna_scale=0.6, nna_scale_critic=7.0, drop_middle_layer=True, batch_size=40,
+                         start_steps=2, update_after=3, update_loops=2, trajectory_length=600)
+    n = A.run_episode(pol, env)
+    assert n == 51 and np.all(np.isfinite(pol.behavior_actor.sync_from_device().flat()))
+    env.close()
     print("sanitize_smoke: ok")
 
 
