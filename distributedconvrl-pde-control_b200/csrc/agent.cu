@@ -40,6 +40,8 @@ struct Agent {
     double* stats = nullptr;           // [0] sum r  [1] sum r^2  [2] sum c  [3] sum c^2  [4] sum q(actor)
     float* partials = nullptr; size_t partials_floats = 0;
     int n_blocks = 0;
+    double* stat_part = nullptr; int stat_part_cap = 0;   // per-CTA (sum r, sum r^2) of the sampler
+    unsigned int* tickets = nullptr;                     // [0] sampler, [1] critic, [2] actor: "last CTA" counters (self-resetting)
     float* arena = nullptr; size_t arena_cap = 0, arena_used = 0;   // activations of the layer-wise (wide network) path
     int force_wide = 0;                // 1: always use the layer-wise path (tests / measurements)
     int wide_path = 0;                 // layer dispatch there: 0 auto, 1 CUDA cores only, 2 tensor cores wherever possible
@@ -87,26 +89,52 @@ __device__ __forceinline__ uint64_t philox_u64(uint64_t seed, uint64_t ctr) {
     return ((uint64_t)c0 << 32) | c1;
 }
 
-// inds ~ U{0 .. range-1} (reference: rand(rng, 1:length(t)-number_actuators, batch_size))
-__global__ void draw_inds_kernel(int n, int64_t range, uint64_t seed, uint64_t offset, int64_t* inds) {
+// sampled batch: inds ~ U{0 .. range-1} (reference: rand(rng, 1:length(t)-number_actuators, batch_size)), gather,
+// reward statistics
+__global__ void __launch_bounds__(128)
+fetch_kernel(int n, int ns, int na, int64_t ncols, Ring sa, Ring rt, int64_t* inds, int draw, int64_t range, uint64_t seed,
+             uint64_t offset, const float* __restrict__ rstate, const float* __restrict__ raction,
+             const float* __restrict__ rreward, const uint8_t* __restrict__ rterminal, float* bs, float* ba, float* br,
+             uint8_t* bt, float* bs2, double* stat_part, unsigned int* ticket, double* stats) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t u = philox_u64(seed, offset + i);
-    inds[i] = (int64_t)(((unsigned __int128)u * (unsigned __int128)range) >> 64);
-}
-
-__global__ void fetch_kernel(int n, int ns, int na, int64_t ncols, Ring sa, Ring rt, const int64_t* __restrict__ inds,
-                             const float* __restrict__ rstate, const float* __restrict__ raction,
-                             const float* __restrict__ rreward, const uint8_t* __restrict__ rterminal, float* bs,
-                             float* ba, float* br, uint8_t* bt, float* bs2) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int64_t ind = inds[i];
-    const int64_t ps = (sa.start + ind) % sa.cap, ps2 = (sa.start + ind + ncols) % sa.cap, pr = (rt.start + ind) % rt.cap;
-    for (int r = 0; r < ns; ++r) { bs[(size_t)i * ns + r] = rstate[ps * ns + r]; bs2[(size_t)i * ns + r] = rstate[ps2 * ns + r]; }
-    for (int r = 0; r < na; ++r) ba[(size_t)i * na + r] = raction[ps * na + r];
-    br[i] = rreward[pr];
-    bt[i] = rterminal[pr];
+    double r1 = 0.0, r2 = 0.0;
+    if (i < n) {
+        int64_t ind;
+        if (draw) {          // inds ~ U{0 .. range-1}
+            const uint64_t u = philox_u64(seed, offset + i);
+            ind = (int64_t)(((unsigned __int128)u * (unsigned __int128)range) >> 64);
+            inds[i] = ind;
+        } else ind = inds[i];
+        const int64_t ps = (sa.start + ind) % sa.cap, ps2 = (sa.start + ind + ncols) % sa.cap, pr = (rt.start + ind) % rt.cap;
+        for (int r = 0; r < ns; ++r) { bs[(size_t)i * ns + r] = rstate[ps * ns + r]; bs2[(size_t)i * ns + r] = rstate[ps2 * ns + r]; }
+        for (int r = 0; r < na; ++r) ba[(size_t)i * na + r] = raction[ps * na + r];
+        const float rv = rreward[pr];
+        br[i] = rv;
+        bt[i] = rterminal[pr];
+        r1 = rv; r2 = (double)rv * rv;
+    }
+    // stats[0] = sum r, stats[1] = sum r^2 over the local batch, in a fixed order: shuffle tree per warp, warps and
+    // CTAs ascending; the last CTA to finish (ticket counter) adds the per-CTA sums -- no separate launch
+    __shared__ double s_p[2][4];
+    __shared__ bool s_last;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { r1 += __shfl_xor_sync(0xffffffffu, r1, o); r2 += __shfl_xor_sync(0xffffffffu, r2, o); }
+    if ((threadIdx.x & 31) == 0) { s_p[0][threadIdx.x >> 5] = r1; s_p[1][threadIdx.x >> 5] = r2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_p[0][w]; b += s_p[1][w]; }
+        stat_part[2 * blockIdx.x] = a; stat_part[2 * blockIdx.x + 1] = b;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+        if (s_last) {
+            __threadfence();
+            double sa_ = 0.0, sb_ = 0.0;
+            for (unsigned int k = 0; k < gridDim.x; ++k) { sa_ += __ldcg(stat_part + 2 * k); sb_ += __ldcg(stat_part + 2 * k + 1); }
+            stats[0] = sa_; stats[1] = sb_; stats[2] = stats[3] = stats[4] = 0.0;
+            *ticket = 0;
+        }
+    }
 }
 
 // stats[0] = sum r, stats[1] = sum r^2 over the local batch (single CTA, fixed order)
@@ -247,7 +275,16 @@ struct DdpgArgs {
     float* partials;                // [gridDim.x][n_acc + 2]
     int n_acc;                      // parameters accumulated (critic or actor)
     int wmax;                       // widest activation row over all nets (incl. ns+na)
+    // single-GPU fused tail: the last CTA to finish reduces the partials (fixed order) and applies ADAM + Polyak
+    int fuse;
+    unsigned int* ticket;
+    float* grads; double* stats_out; int stat0;
+    float *x, *m, *v, *target;
+    double eta, b1, b2, bp1, bp2, eps; float polyak;
+    float* losses; double n_global; int literal_loss;
 };
+
+__device__ void fused_tail(const DdpgArgs& D);
 
 __device__ __forceinline__ int carve_acts(const NetDev& net, float* base, float** acts) {
     int off = 0;
@@ -336,6 +373,7 @@ __global__ void __launch_bounds__(512) ddpg_critic_kernel(const __grid_constant_
     float* out = D.partials + (size_t)blockIdx.x * (D.n_acc + 2);
     for (int q = threadIdx.x; q < D.n_acc; q += blockDim.x) out[q] = acc[q];
     if (threadIdx.x == 0) { out[D.n_acc] = (float)s_c[0]; out[D.n_acc + 1] = (float)s_c[1]; }
+    if (D.fuse) fused_tail(D);
 }
 
 // Actor phase: gradient of -mean C([s; A(s)]) w.r.t. the actor parameters (PDEagent.jl:402-409).
@@ -385,6 +423,7 @@ __global__ void __launch_bounds__(512) ddpg_actor_kernel(const __grid_constant__
     float* out = D.partials + (size_t)blockIdx.x * (D.n_acc + 2);
     for (int q = threadIdx.x; q < D.n_acc; q += blockDim.x) out[q] = acc[q];
     if (threadIdx.x == 0) { out[D.n_acc] = (float)s_q; out[D.n_acc + 1] = 0.f; }
+    if (D.fuse) fused_tail(D);
 }
 
 // sum_b partials[b * stride + q] in ascending b (fixed order), with the loads issued 32 at a time ahead of the adds
@@ -411,6 +450,59 @@ __device__ __forceinline__ double ordered_sum(const float* __restrict__ partials
     return s;
 }
 
+// Same loads through L2 (the partials were written by other CTAs of the SAME launch: no non-coherent path)
+__device__ __forceinline__ double ordered_sum_cg(const float* partials, int n_blocks, size_t stride, int q) {
+    double s = 0.0;
+    int b = 0;
+    for (; b + 32 <= n_blocks; b += 32) {
+        float v[32];
+#pragma unroll
+        for (int u = 0; u < 32; ++u) v[u] = __ldcg(partials + (size_t)(b + u) * stride + q);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) s += (double)v[u];
+    }
+    for (; b < n_blocks; ++b) s += (double)__ldcg(partials + (size_t)b * stride + q);
+    return s;
+}
+
+// Tail of the fused gradient kernels: every CTA has written its partials; the last one to arrive (ticket counter,
+// self-resetting) does reduce_partials_kernel -> adam_kernel -> polyak_kernel -> losses_kernel in one go: same
+// fixed-order sums, same ADAM / Polyak arithmetic.
+__device__ void fused_tail(const DdpgArgs& D) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(D.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const size_t stride = (size_t)(D.n_acc + 2);
+    for (int q = threadIdx.x; q < D.n_acc + 2; q += blockDim.x) {
+        const double s = ordered_sum_cg(D.partials, (int)gridDim.x, stride, q);
+        if (q >= D.n_acc) {
+            D.stats_out[D.stat0 + (q - D.n_acc)] = s;
+            if (D.losses && q == D.n_acc) {
+                const double B = D.n_global;
+                const double* st = D.stats_out;
+                D.losses[0] = (float)(D.literal_loss ? st[3] / B + 2.0 * st[2] * st[0] / (B * B) + st[1] / B : st[3] / B);
+                D.losses[1] = (float)(-s / D.n_global);
+            }
+            continue;
+        }
+        const float g = (float)s;
+        D.grads[q] = g;
+        const double gi = g;
+        const float mi = (float)(D.b1 * (double)D.m[q] + (1.0 - D.b1) * gi);
+        const float vi = (float)(D.b2 * (double)D.v[q] + (1.0 - D.b2) * gi * gi);
+        D.m[q] = mi; D.v[q] = vi;
+        const float delta = (float)((double)mi / (1.0 - D.bp1) / (sqrt((double)vi / (1.0 - D.bp2)) + D.eps) * D.eta);
+        const float xn = D.x[q] - delta;
+        D.x[q] = xn;
+        D.target[q] = D.polyak * D.target[q] + (1.f - D.polyak) * xn;
+    }
+    if (threadIdx.x == 0) *D.ticket = 0;
+}
+
 // grads[q] = sum over CTAs (fixed order); tail sums go to stats
 __global__ void reduce_partials_kernel(int n_blocks, int n_acc, const float* __restrict__ partials, float* grads,
                                        double* stats, int stat0) {
@@ -419,38 +511,6 @@ __global__ void reduce_partials_kernel(int n_blocks, int n_acc, const float* __r
     const double s = ordered_sum(partials, n_blocks, (size_t)(n_acc + 2), q);
     if (q < n_acc) grads[q] = (float)s;
     else stats[stat0 + (q - n_acc)] = s;
-}
-
-// Single-GPU update: partial reduction (fixed order) + ADAM + Polyak of the target in ONE launch (no allreduce sits
-// between them).  Same arithmetic as reduce_partials_kernel -> adam_kernel -> polyak_kernel.
-__global__ void reduce_adam_polyak_kernel(int n_blocks, int n_acc, const float* __restrict__ partials, float* grads, double* stats,
-                                          int stat0, float* x, float* m, float* v, float* target, double eta, double b1, double b2,
-                                          double bp1, double bp2, double eps, float polyak, float* losses, double n_global,
-                                          int literal) {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n_acc + 2) return;
-    const double s = ordered_sum(partials, n_blocks, (size_t)(n_acc + 2), q);
-    if (q >= n_acc) {
-        stats[stat0 + (q - n_acc)] = s;
-        if (losses && q == n_acc) {
-            // actor phase (stat0 == 4): both losses from the reduced sums, like losses_kernel; stats[0..3] were written
-            // by the sampling and critic kernels earlier in the stream
-            const double B = n_global;
-            losses[0] = (float)(literal ? stats[3] / B + 2.0 * stats[2] * stats[0] / (B * B) + stats[1] / B : stats[3] / B);
-            losses[1] = (float)(-s / n_global);
-        }
-        return;
-    }
-    const float g = (float)s;
-    grads[q] = g;
-    const double gi = g;
-    const float mi = (float)(b1 * (double)m[q] + (1.0 - b1) * gi);
-    const float vi = (float)(b2 * (double)v[q] + (1.0 - b2) * gi * gi);
-    m[q] = mi; v[q] = vi;
-    const float delta = (float)((double)mi / (1.0 - bp1) / (sqrt((double)vi / (1.0 - bp2)) + eps) * eta);
-    const float xn = x[q] - delta;
-    x[q] = xn;
-    target[q] = polyak * target[q] + (1.f - polyak) * xn;
 }
 
 // Flux ADAM on Float32 arrays with Float64 hyper-parameters; optional Polyak pair (dest = p*dest + (1-p)*src).
@@ -519,6 +579,16 @@ int32_t ensure_batch(pdeb200_ctx* c, int batch) {
         PDEB_CUDA(c, cudaMalloc(&a->inds, (size_t)batch * 8));
         a->batch_cap = batch;
     }
+    const int grid = (batch + 127) / 128;
+    if (grid > a->stat_part_cap) {
+        if (a->stat_part) cudaFree(a->stat_part);
+        PDEB_CUDA(c, cudaMalloc(&a->stat_part, (size_t)2 * grid * sizeof(double)));
+        a->stat_part_cap = grid;
+    }
+    if (!a->tickets) {
+        PDEB_CUDA(c, cudaMalloc(&a->tickets, 4 * sizeof(unsigned int)));
+        PDEB_CUDA(c, cudaMemsetAsync(a->tickets, 0, 4 * sizeof(unsigned int), c->stream));
+    }
     a->batch = batch;
     return PDEB200_OK;
 }
@@ -554,6 +624,9 @@ DdpgArgs make_args(pdeb200_ctx* c, double gamma, int literal, int64_t global_bat
     D.s = a->bs; D.a = a->ba; D.r = a->br; D.s2 = a->bs2; D.t = a->bt;
     D.gamma = (float)gamma; D.literal_q1 = literal; D.inv_global_batch = 1.0 / (double)global_batch;
     D.stats = a->stats; D.partials = nullptr; D.n_acc = 0;
+    D.fuse = 0; D.ticket = nullptr; D.grads = nullptr; D.stats_out = a->stats; D.stat0 = 0;
+    D.x = D.m = D.v = D.target = nullptr; D.eta = D.b1 = D.b2 = D.bp1 = D.bp2 = D.eps = 0.0; D.polyak = 0.f;
+    D.losses = nullptr; D.n_global = (double)global_batch; D.literal_loss = literal;
     D.wmax = std::max({net_wmax(c->nets[0]), net_wmax(c->nets[1]), a->ns + a->na});
     return D;
 }
@@ -922,14 +995,13 @@ int32_t pdeb200_sample(pdeb200_ctx* c, int32_t batch, const int64_t* inds_host, 
         for (int i = 0; i < batch; ++i)
             if (inds_host[i] < 0 || inds_host[i] >= range) return fail(c, PDEB200_EINVAL, "sample: index out of range");
         PDEB_CUDA(c, cudaMemcpyAsync(a->inds, inds_host, (size_t)batch * 8, cudaMemcpyHostToDevice, c->stream));
-    } else {
-        draw_inds_kernel<<<grid, tpb, 0, c->stream>>>(batch, range, seed, offset, a->inds);
     }
-    fetch_kernel<<<grid, tpb, 0, c->stream>>>(batch, a->ns, a->na, a->ncols, a->sa, a->rt, a->inds, a->state, a->action,
-                                              a->reward, a->terminal, a->bs, a->ba, a->br, a->bt, a->bs2);
-    reward_stats_kernel<<<1, 256, 0, c->stream>>>(batch, a->br, a->stats);
+    // one launch: index draw (device Philox unless the host supplied indices), gather, reward statistics
+    fetch_kernel<<<grid, tpb, 0, c->stream>>>(batch, a->ns, a->na, a->ncols, a->sa, a->rt, a->inds, inds_host ? 0 : 1, range, seed,
+                                              offset, a->state, a->action, a->reward, a->terminal, a->bs, a->ba, a->br, a->bt,
+                                              a->bs2, a->stat_part, a->tickets, a->stats);
     PDEB_CUDA(c, cudaGetLastError());
-    c->launches += 3;
+    c->launches += 1;
     if (inds_host) PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
     return PDEB200_OK;
 }
@@ -962,16 +1034,20 @@ int32_t pdeb200_ddpg_set_path(pdeb200_ctx* c, int32_t path) {
     return PDEB200_OK;
 }
 
-static int32_t critic_grads_impl(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch, bool reduce);
-static int32_t actor_grads_impl(pdeb200_ctx* c, int64_t global_batch, bool reduce);
+// fused tail of the single-GPU update: learning rate, Polyak factor (lr <= 0: not fused)
+struct FuseTail { double lr = 0.0, polyak = 0.0; int literal = 0; };
+static int32_t critic_grads_impl(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch, bool reduce,
+                                 const FuseTail* ft = nullptr);
+static int32_t actor_grads_impl(pdeb200_ctx* c, int64_t global_batch, bool reduce, const FuseTail* ft = nullptr);
 
 int32_t pdeb200_ddpg_critic_grads(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch) {
     return critic_grads_impl(c, gamma, literal_q1, global_batch, true);
 }
 
-// reduce = false: leave the per-CTA partials for reduce_adam_polyak_kernel (single-GPU fused path); returns 1 if the
+// reduce = false: leave the per-CTA partials unreduced (the fused tail `ft` consumes them); returns 1 if the
 // layer-wise path ran instead (gradients already reduced in d_grads)
-static int32_t critic_grads_impl(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch, bool reduce) {
+static int32_t critic_grads_impl(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch, bool reduce,
+                                 const FuseTail* ft) {
     if (!c) return PDEB200_EINVAL;
     cudaSetDevice(c->device);
     Agent* a = ag(c);
@@ -993,6 +1069,13 @@ static int32_t critic_grads_impl(pdeb200_ctx* c, double gamma, int32_t literal_q
     }
     PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tpb = block_threads(D.wmax, D.n_acc);
+    if (ft) {
+        HostNet& Cw = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+        D.fuse = 1; D.ticket = a->tickets + 1; D.grads = c->d_grads; D.stat0 = 2;
+        D.x = Cw.d_params; D.m = Cw.d_m; D.v = Cw.d_v; D.target = c->nets[PDEB200_NET_TARGET_CRITIC].d_params;
+        D.eta = ft->lr; D.b1 = 0.9; D.b2 = 0.999; D.bp1 = Cw.beta_p[0]; D.bp2 = Cw.beta_p[1]; D.eps = 1e-8; D.polyak = (float)ft->polyak;
+        Cw.beta_p[0] *= 0.9; Cw.beta_p[1] *= 0.999;
+    }
     ddpg_critic_kernel<<<n_blocks, tpb, smem, c->stream>>>(D);
     a->n_blocks = n_blocks;
     c->launches += 1;
@@ -1022,7 +1105,7 @@ int32_t pdeb200_ddpg_critic_apply(pdeb200_ctx* c, double lr) {
 
 int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* c, int64_t global_batch) { return actor_grads_impl(c, global_batch, true); }
 
-static int32_t actor_grads_impl(pdeb200_ctx* c, int64_t global_batch, bool reduce) {
+static int32_t actor_grads_impl(pdeb200_ctx* c, int64_t global_batch, bool reduce, const FuseTail* ft) {
     if (!c) return PDEB200_EINVAL;
     cudaSetDevice(c->device);
     Agent* a = ag(c);
@@ -1043,6 +1126,14 @@ static int32_t actor_grads_impl(pdeb200_ctx* c, int64_t global_batch, bool reduc
     }
     PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tpb = block_threads(D.wmax, D.n_acc);
+    if (ft) {
+        HostNet& Aw = c->nets[PDEB200_NET_BEHAVIOR_ACTOR];
+        D.fuse = 1; D.ticket = a->tickets + 2; D.grads = c->d_grads + C.n_params; D.stat0 = 4;
+        D.x = Aw.d_params; D.m = Aw.d_m; D.v = Aw.d_v; D.target = c->nets[PDEB200_NET_TARGET_ACTOR].d_params;
+        D.eta = ft->lr; D.b1 = 0.9; D.b2 = 0.999; D.bp1 = Aw.beta_p[0]; D.bp2 = Aw.beta_p[1]; D.eps = 1e-8; D.polyak = (float)ft->polyak;
+        D.losses = c->d_losses; D.literal_loss = ft->literal;
+        Aw.beta_p[0] *= 0.9; Aw.beta_p[1] *= 0.999;
+    }
     ddpg_actor_kernel<<<n_blocks, tpb, smem, c->stream>>>(D);
     a->n_blocks = n_blocks;
     c->launches += 1;
@@ -1075,29 +1166,22 @@ int32_t pdeb200_ddpg_update(pdeb200_ctx* c, double gamma, double polyak, double 
     cudaSetDevice(c->device);
     Agent* a = ag(c);
     const int64_t B = a->batch;
-    HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
-    HostNet &At = c->nets[PDEB200_NET_TARGET_ACTOR], &Ct = c->nets[PDEB200_NET_TARGET_CRITIC];
-    // Fused single-GPU path: {critic kernel, reduce + ADAM + Polyak} {actor kernel, reduce + ADAM + Polyak + losses}.
-    // The target critic is not read after the critic phase and the behavior critic is not written by the actor phase,
-    // so its Polyak step can run right after its ADAM step (reference order: both at the end, PDEagent.jl:411-417).
-    int32_t rc = critic_grads_impl(c, gamma, literal_q1, B, false);
+    // Fused single-GPU path: two launches -- {critic gradients; last CTA: reduce + ADAM + Polyak} {actor gradients; last
+    // CTA: reduce + ADAM + Polyak + losses}.  The target critic is not read after the critic phase and the behavior
+    // critic is not written by the actor phase, so its Polyak step can run right after its ADAM step (reference order:
+    // both at the end, PDEagent.jl:411-417).  The layer-wise (wide network) path applies its updates separately.
+    const bool wide = a->force_wide != 0;
+    FuseTail fc; fc.lr = lr_critic; fc.polyak = polyak; fc.literal = literal_q1;
+    FuseTail fa; fa.lr = lr_actor; fa.polyak = polyak; fa.literal = literal_q1;
+    int32_t rc = critic_grads_impl(c, gamma, literal_q1, B, false, wide ? nullptr : &fc);
     if (rc < 0) return rc;
     if (rc == 1) {                       // layer-wise path: gradients are already reduced
         if ((rc = pdeb200_ddpg_critic_apply(c, lr_critic))) return rc;
         if ((rc = pdeb200_ddpg_actor_grads(c, B))) return rc;
         return pdeb200_ddpg_actor_apply(c, lr_actor, polyak);
     }
-    reduce_adam_polyak_kernel<<<(C.n_params + 2 + 127) / 128, 128, 0, c->stream>>>(
-        a->n_blocks, C.n_params, a->partials, c->d_grads, a->stats, 2, C.d_params, C.d_m, C.d_v, Ct.d_params, lr_critic, 0.9, 0.999,
-        C.beta_p[0], C.beta_p[1], 1e-8, (float)polyak, nullptr, 0.0, 0);
-    C.beta_p[0] *= 0.9; C.beta_p[1] *= 0.999;
-    if ((rc = actor_grads_impl(c, B, false)) < 0) return rc;
-    reduce_adam_polyak_kernel<<<(A.n_params + 2 + 127) / 128, 128, 0, c->stream>>>(
-        a->n_blocks, A.n_params, a->partials, c->d_grads + C.n_params, a->stats, 4, A.d_params, A.d_m, A.d_v, At.d_params, lr_actor, 0.9,
-        0.999, A.beta_p[0], A.beta_p[1], 1e-8, (float)polyak, c->d_losses, (double)B, literal_q1);
-    A.beta_p[0] *= 0.9; A.beta_p[1] *= 0.999;
+    if ((rc = actor_grads_impl(c, B, false, &fa)) < 0) return rc;
     PDEB_CUDA(c, cudaGetLastError());
-    c->launches += 2;
     return PDEB200_OK;
 }
 
