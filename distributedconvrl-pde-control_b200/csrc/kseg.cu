@@ -38,9 +38,10 @@ __device__ __forceinline__ void rhs(const typename V2<T>::type* line, int i, int
     const C c = line[i];
     const C l = line[i == 0 ? 0 : i - 1];          // edge copy: left neighbour of the first cell is itself
     const C r = line[i == nx - 1 ? i : i + 1];     // right neighbour of the last cell is itself
-    const T u1 = (-c1) * l.x + T(0) * c.x + c1 * r.x;
+    // the reference's literal "+ 0 * c" term of the first differences adds an exact zero for finite data and is dropped
+    const T u1 = (-c1) * l.x + c1 * r.x;
     const T u2 = c2 * l.x + (T(-2) * c2) * c.x + c2 * r.x;
-    const T v1 = (-c1) * l.y + T(0) * c.y + c1 * r.y;
+    const T v1 = (-c1) * l.y + c1 * r.y;
     const T v2 = c2 * l.y + (T(-2) * c2) * c.y + c2 * r.y;
     dv = v2 - c.y + c.x + p;
     du = u2 + c.x - T(5.6) * u1 * v1 - T(5.6) * c.x * v2 - c.x * c.x;

@@ -128,14 +128,16 @@ kseg2d_step_kernel(const __grid_constant__ Kseg2dArgs<T> A) {
             const C l = Br[r * nx + xl];
             const C rt = Br[r * nx + xr];
             const C d = (r == r_last && bot_edge) ? c : Br[(r + 1) * nx + x];
-            // same operation order as the 1-D f (KellerSegelSetup.jl:225-229) per axis
-            const T u1x = (-c1x) * l.x + T(0) * c.x + c1x * rt.x;
+            // same operation order as the 1-D f (KellerSegelSetup.jl:225-229) per axis; the reference's literal
+            // "+ 0 * centre" term of the first differences is dropped: it adds an exact zero for finite data, and
+            // the compiler may not remove it itself (NaN / inf semantics)
+            const T u1x = (-c1x) * l.x + c1x * rt.x;
             const T u2x = c2x * l.x + m2x * c.x + c2x * rt.x;
-            const T v1x = (-c1x) * l.y + T(0) * c.y + c1x * rt.y;
+            const T v1x = (-c1x) * l.y + c1x * rt.y;
             const T v2x = c2x * l.y + m2x * c.y + c2x * rt.y;
-            const T u1y = (-c1y) * u.x + T(0) * c.x + c1y * d.x;
+            const T u1y = (-c1y) * u.x + c1y * d.x;
             const T u2y = c2y * u.x + m2y * c.x + c2y * d.x;
-            const T v1y = (-c1y) * u.y + T(0) * c.y + c1y * d.y;
+            const T v1y = (-c1y) * u.y + c1y * d.y;
             const T v2y = c2y * u.y + m2y * c.y + c2y * d.y;
             const T lapu = u2x + u2y, lapv = v2x + v2y;
             const T kv = lapv - c.y + c.x + pp[r];
