@@ -7,7 +7,7 @@
 // with the PDE state resident in registers/shared memory across all substeps.  The column-level
 // work on either side (actor, prepare_action sum, reward, observation windows, clock) runs in the
 // full-occupancy kernels of glue.cuh; profiling showed that keeping it inside this register-heavy
-// kernel made it instruction-cache and latency bound (profiles/README.md, r1b/r1c).
+// kernel made it instruction-cache and latency bound (profiles/r1_ks_step_f64.md, r1a-r1c).
 //
 // Mapping (B200-first, not a translation of the reference's FFTW calls):
 //   * Two environments are packed into ONE complex sequence z = u_a + i*u_b.  Every
