@@ -6,9 +6,10 @@
 //                                               FluidSetup.jl:247-259 (the physical-space sum)
 //   observe_kernel : reward_function, featurize, clock/done   (see obs_reward.cuh, PDEenv.jl:220-240)
 //
-// They run at full occupancy with one thread per column / grid point; the register- and
-// shared-memory-heavy core kernels (ks_step.cuh, ...) only see  (y, p) -> (y', sensor dots, max|y|).
-// One CTA per environment.
+// They run at high occupancy with one thread per column / grid point (actuation: persistent CTAs over groups of
+// environments; observation: one warp per environment); the register- and shared-memory-heavy core kernels
+// (ks_step.cuh, ...) only see  (y, p) -> (y', sensor dots, max|y|).  actuate_conv_kernel is the shape-specialised
+// actuation of the conv agent, actuate_kernel the runtime-shaped one; both give bit-identical results.
 #pragma once
 #include "common.cuh"
 #include "obs_reward.cuh"
