@@ -141,6 +141,10 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
     //   job S: only the inverse transform (KSSetup.jl:158)
     for (int job = -2; job <= A.S; ++job) {
         if (job >= 0) {
+            // z = u_hat here, at the top, so that z is not live across the loop's back edge (a copy at the end of the
+            // CNAB2 update kept 4*N2 extra registers loop-carried and cost 64 register moves per substep)
+#pragma unroll
+            for (int r = 0; r < N2; ++r) { zr[r] = ur[r]; zi[r] = ui[r]; }
             fft_pass<T, N2, N1, +1>(zr, zi, xb, s_tw12, t);          // z = N * u  (physical)
             if (job == A.S) break;
 #pragma unroll
@@ -182,7 +186,6 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
                     const T c1 = s_c1[k], cn = s_cN[k];
                     ur[r] = fma(-cn, ti, fma(c1, ur[r], f_r));
                     ui[r] = fma(cn, tr, fma(c1, ui[r], f_i));
-                    zr[r] = ur[r]; zi[r] = ui[r];
                 }
             }
         }
