@@ -3,8 +3,12 @@
 
 Metric (BASELINE.json): env-steps/s, KS N=256, 8192 batched envs per GPU, oversampling 30,
 fp64 (the reference's precision), actor = the reference's shipped KS200 network (1->6->1).
-One "step" = one fused {actor forward -> prepare_action -> 30 CNAB2 substeps -> reward ->
-featurize -> done} pass over all environments of the rank = ONE kernel launch.
+One "step" = one {actor forward -> prepare_action -> 30 CNAB2 substeps -> reward -> featurize -> done} pass
+over all environments of the rank = THREE kernel launches on one stream (actuation, KS core, observation).
+
+The line also carries a `train` record (BASELINE config 5): the KS training loop -- policy with exploration noise,
+replay push, update_loops x {sample, critic, actor} as one CUDA graph with the gradient exchange over NVLink peer
+memory inside the kernels, env step, reward push -- at update_loops 1 and 20, on every N.
 
   python bench.py --gpus N --steps K --warmup W            our arm (under torchrun for N>1)
   python bench.py --impl reference ...                     CPU arm: oracle restatement on all host cores
@@ -43,6 +47,9 @@ def parse():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--oversampling", type=int, default=30)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-loop record (BASELINE config 5)")
+    ap.add_argument("--train-batch", type=int, default=4096, help="DDPG batch (replay columns) per GPU and update")
+    ap.add_argument("--train-steps", type=int, default=30, help="timed loop steps per update_loops setting")
     ap.add_argument("--e2e-driver", default="native", choices=["native", "python"],
                     help="host threads of the e2e leg: native std::threads calling the C ABI (libpdeb200_host.so) or Python threads")
     ap.add_argument("--e2e-shards", type=int, default=4,
@@ -262,6 +269,83 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def train_record(args, pkg, torch, dist, rank, world, local):
+    """BASELINE config 5: KS training loop at `world` GPUs.  One loop step = policy (actor + device Philox noise) ->
+    PreAct push of (s, a) for every column -> update_loops x {sample, critic grads + exchange + ADAM, actor grads +
+    exchange + ADAM + Polyak} (ONE CUDA graph launch; the exchange is the library's peer-memory allreduce inside the
+    gradient kernels) -> env step -> PostAct push of (r, terminal) -> masked reset of diverged environments; the stage
+    order of RLCore's run() (scripts/Fluid/setup/FluidSetup.jl:455-519, src/PDEagent.jl:342-361).  Device events on the
+    context's stream, max over ranks; weights must be bit-identical on every rank afterwards."""
+    A, L, par = pkg.agent, pkg.lib, pkg.parallel
+    B = args.envs
+    setup = pkg.setups.KSSetup.ks256(oversampling=args.oversampling)
+    out = {"workload": "KS N=256 training loop (BASELINE config 5): %d envs/GPU, DDPG batch %d replay columns/GPU per update, "
+                       "actor 1-6-1 / critic 2-140-1 (KSSetup.jl sizes), act_noise 1.2, literal quirk-Q1 loss, %s"
+                       % (B, args.train_batch, args.dtype),
+           "unit": UNIT, "n_gpus": world, "steps": args.train_steps}
+    comm = par.Comm(dist if world > 1 else None)
+    for loops in (1, 20):
+        rng = np.random.default_rng(100 + rank)
+        env = setup.make_env(n_envs=B, dtype=args.dtype, device=local, y0=setup.generate_random_init(rng, B))
+        stream = torch.cuda.current_stream()
+        L.check(env._lib.pdeb200_set_stream(env._ctx, C.c_void_p(stream.cuda_stream)), env._ctx)
+        wrng = np.random.default_rng(7)                                 # identical initial weights on every rank
+        pol = A.create_agent(env, rng=wrng, nna_scale=0.6, nna_scale_critic=7.0, drop_middle_layer=True,
+                             batch_size=args.train_batch, start_steps=2, update_after=2, update_freq=1, update_loops=loops,
+                             act_noise=1.2, trajectory_length=B * env.n_cols * 8, seed=rank,
+                             comm=comm if world > 1 else None)
+        traj = pol.trajectory
+        env.reset()
+        traj.pre_episode()
+
+        def step():
+            pol(env, learning=True)
+            traj.pre_act()
+            pol.maybe_update()
+            env.step_device()
+            traj.post_act()
+            env.reset_diverged(sync=False)
+
+        for _ in range(8):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        l0, u0 = env.launch_count, pol.n_updates
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.train_steps):
+            step()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms_local = e0.elapsed_time(e1)
+        per_rank = [ms_local]
+        w = np.concatenate([n.sync_from_device().flat() for n in
+                            (pol.behavior_critic, pol.behavior_actor, pol.target_critic, pol.target_actor)])
+        identical = True
+        if world > 1:
+            t = torch.tensor([ms_local], dtype=torch.float64, device="cuda")
+            allms = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allms, t)
+            per_rank = [float(x.item()) for x in allms]
+            wt = torch.from_numpy(w).cuda()
+            allw = [torch.zeros_like(wt) for _ in range(world)]
+            dist.all_gather(allw, wt)
+            identical = all(bool(torch.equal(x, allw[0])) for x in allw[1:])
+        ms = max(per_rank)
+        rec = {"value": B * world * args.train_steps / (ms * 1e-3), "ms_per_loop_step": ms / args.train_steps,
+               "per_rank_ms_per_loop_step": [x / args.train_steps for x in per_rank],
+               "updates_per_step": (pol.n_updates - u0) / args.train_steps,
+               "gpu_launches_per_step": (env.launch_count - l0) / args.train_steps,
+               "weights_finite": bool(np.all(np.isfinite(w))), "weights_identical_across_ranks": identical,
+               "losses": pol.losses}
+        out["update_loops_%d" % loops] = rec
+        out["transport"] = {L.COMM_NONE: "none (single GPU)", L.COMM_NCCL: "nccl allreduce between phases",
+                            L.COMM_PEER: "NVLink peer-memory exchange inside the gradient kernels"}[pol.transport]
+        env.close()
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -309,7 +393,7 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput: one fused launch per step --------------------------------
+    # ---- device-resident throughput: one rollout(1) call = three launches per step ------------------
     for _ in range(max(args.warmup, 3)):
         env.rollout(1)
     torch.cuda.synchronize()
@@ -346,7 +430,11 @@ def run_ours(args):
     L.check(env._lib.pdeb200_enable_step_timing(env._ctx, 0), env._ctx)
     core_ms = float(np.mean(core_ms))
     t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    per_rank_ms = [total_ms / args.steps]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank_ms = [float(x.item()) / args.steps for x in allt]          # names the straggler when efficiency < 1
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
     value = B * world * args.steps / (total_ms_max * 1e-3)
@@ -456,7 +544,8 @@ def run_ours(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "ks_step_kernel<%s,16,16>" % args.dtype,
+                "traffic": traffic, "traffic_source": "profiles/traffic.json (one ncu --set full capture of this kernel and config; "
+                "not re-measured in this run)" if traffic is not None else None, "peak_source": peak_src, "kernel": "ks_step_kernel<%s,16,16>" % args.dtype,
                 "algorithmic_bytes_per_launch": core_bytes_env * B, "kernel_ms": core_ms,
                 "kernel_share_of_step": core_ms / avg_ms,
                 "phase_ms": {"actuate": phases[0], "core": phases[1], "observe": phases[2]},
@@ -474,7 +563,7 @@ def run_ours(args):
                             "nominal_peak_tflops": 37.0 if args.dtype == "f64" else 75.0}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms_max / args.steps, "per_rank_ms_per_step": per_rank_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic", "config": config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "shards": n_sh, "launches": int(e2e_launches), "host_threads": args.e2e_driver, "cpu_binding": numa,
@@ -495,6 +584,8 @@ def run_ours(args):
         line["cpu_baseline"] = None
     for sh in shards:
         sh.env.close()
+    if not args.no_train:
+        line["train"] = train_record(args, pkg, torch, dist, rank, world, local)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

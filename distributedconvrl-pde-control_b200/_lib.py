@@ -11,6 +11,9 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = PKG / "libpdeb200.so"
 
 OK = 0
+ABI_VERSION = 2
+COMM_NONE, COMM_NCCL, COMM_PEER = 0, 1, 2
+UNIQUE_ID_BYTES = 128
 F32, F64 = 0, 1
 KS, KSEG1D, NS2D, KSEG2D = 0, 1, 2, 3
 CHECK_NONE, CHECK_Y, CHECK_REWARD = 0, 1, 2
@@ -52,6 +55,8 @@ _PROTOS = {
     "pdeb200_step_device": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "pdeb200_step_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "pdeb200_get": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]),
+    "pdeb200_get_env": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t]),
+    "pdeb200_reset_diverged": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "pdeb200_set": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]),
     "pdeb200_device_ptr": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "pdeb200_obs_rows": (C.c_int32, [C.c_void_p]),
@@ -79,6 +84,22 @@ _PROTOS = {
     "pdeb200_ddpg_actor_grads": (C.c_int32, [C.c_void_p, C.c_int64]),
     "pdeb200_ddpg_actor_apply": (C.c_int32, [C.c_void_p, C.c_double, C.c_double]),
     "pdeb200_ddpg_update": (C.c_int32, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int32]),
+    "pdeb200_train_updates": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double,
+                                          C.c_int32, C.c_uint64]),
+    "pdeb200_net_set_params": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]),
+    "pdeb200_opt_get": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pdeb200_opt_set": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "pdeb200_traj_info": (C.c_int32, [C.c_void_p] + [C.POINTER(C.c_int64)] * 5),
+    "pdeb200_traj_get": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdeb200_traj_set": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdeb200_rng_get": (C.c_int32, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    "pdeb200_rng_set": (C.c_int32, [C.c_void_p, C.c_uint64]),
+    "pdeb200_get_batch": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "pdeb200_comm_unique_id": (C.c_int32, [C.c_void_p]),
+    "pdeb200_comm_init": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]),
+    "pdeb200_comm_destroy": (C.c_int32, [C.c_void_p]),
+    "pdeb200_comm_info": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "pdeb200_comm_allreduce_f64": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32]),
     "pdeb200_launch_count": (C.c_int64, [C.c_void_p]),
     "pdeb200_last_step_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
     "pdeb200_last_phase_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
@@ -108,7 +129,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.pdeb200_abi_version() != 1:
+    if lib.pdeb200_abi_version() != ABI_VERSION:
         raise PdeB200Error("libpdeb200.so ABI version mismatch")
     _lib = lib
     return lib

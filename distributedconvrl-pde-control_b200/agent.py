@@ -98,9 +98,27 @@ class CustomNeuralNetworkApproximator:
         return (y.T, used.value) if return_info else y.T
 
     def copyto(self, src):
-        """Base.copyto!(dest, src), custom_nna.jl:26-27"""
-        self.model.load_flat(src.sync_from_device().flat())
-        self.upload()
+        """Base.copyto!(dest, src) = Flux.loadparams!(dest.model, params(src)), custom_nna.jl:26-27: the weights are
+        overwritten, the optimiser state of `dest` is kept (pdeb200_net_set_params)."""
+        flat = src.sync_from_device().flat()
+        self.model.load_flat(flat)
+        L.check(self.env._lib.pdeb200_net_set_params(self.env._ctx, self.net_id, flat.ctypes.data, flat.size), self.env._ctx)
+
+    # -- optimiser state (Flux ADAM: per-parameter (m, v, beta powers)); save()/load() of KSSetup.jl:378-402 ------
+    def opt_state(self):
+        n = self.env._lib.pdeb200_net_num_params(self.env._ctx, self.net_id)
+        m, v, bp = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(2, np.float64)
+        L.check(self.env._lib.pdeb200_opt_get(self.env._ctx, self.net_id, m.ctypes.data, v.ctypes.data, bp.ctypes.data, n), self.env._ctx)
+        return m, v, bp
+
+    def set_opt_state(self, m, v, beta_p):
+        m = np.ascontiguousarray(m, dtype=np.float32).reshape(-1)
+        v = np.ascontiguousarray(v, dtype=np.float32).reshape(-1)
+        bp = np.ascontiguousarray(beta_p, dtype=np.float64).reshape(-1)
+        n = self.env._lib.pdeb200_net_num_params(self.env._ctx, self.net_id)
+        if m.size != n or v.size != n or bp.size != 2:
+            raise ValueError("optimizer state does not match the network (%d parameters)" % n)
+        L.check(self.env._lib.pdeb200_opt_set(self.env._ctx, self.net_id, m.ctypes.data, v.ctypes.data, bp.ctypes.data, n), self.env._ctx)
 
 
 class ZeroPolicy:
@@ -136,13 +154,45 @@ class DeviceTrajectory:
     def post_episode(self):          # PostEpisodeStage: push final state + zero action
         L.check(self.env._lib.pdeb200_traj_episode_end(self.env._ctx), self.env._ctx)
 
+    # -- whole-buffer access in logical order (oldest column first): checkpoints, parity tests -------------------
+    def info(self):
+        """(capacity, n_sa, n_rt): columns held by the state/action and the reward/terminal rings."""
+        return self.positions()[:3]
+
+    def positions(self):
+        """(capacity, n_sa, n_rt, first_sa, first_rt): counts and the 0-based raw ring position of the oldest column --
+        CircularArrayBuffer's `nframes` and `first - 1` (what agent.jld2 stores)."""
+        v = [C.c_int64() for _ in range(5)]
+        L.check(self.env._lib.pdeb200_traj_info(self.env._ctx, *[C.byref(x) for x in v]), self.env._ctx)
+        return tuple(x.value for x in v)
+
+    def get(self):
+        """(state (ns, n_sa), action (na, n_sa), reward (n_rt,), terminal (n_rt,)) in the reference's shapes."""
+        _, n_sa, n_rt = self.info()
+        ns, na = self.env.ns, (self.env.n_actuators * self.env.a_rows if self.env.cfg.mono else self.env.a_rows)
+        s, a = np.empty((n_sa, ns), np.float32), np.empty((n_sa, na), np.float32)
+        r, t = np.empty(n_rt, np.float32), np.empty(n_rt, np.uint8)
+        L.check(self.env._lib.pdeb200_traj_get(self.env._ctx, s.ctypes.data, a.ctypes.data, r.ctypes.data, t.ctypes.data), self.env._ctx)
+        return s.T, a.T, r, t.astype(bool)
+
+    def set(self, state, action, reward, terminal, first_sa=0, first_rt=0):
+        s = np.ascontiguousarray(np.asarray(state, dtype=np.float32).T)
+        a = np.ascontiguousarray(np.asarray(action, dtype=np.float32).T)
+        r = np.ascontiguousarray(reward, dtype=np.float32).reshape(-1)
+        t = np.ascontiguousarray(terminal, dtype=np.uint8).reshape(-1)
+        if s.shape[0] != a.shape[0] or r.size != t.size:
+            raise ValueError("state/action and reward/terminal must have matching column counts")
+        L.check(self.env._lib.pdeb200_traj_set(self.env._ctx, s.shape[0], r.size, int(first_sa), int(first_rt), s.ctypes.data,
+                                               a.ctypes.data, r.ctypes.data, t.ctypes.data), self.env._ctx)
+
 
 class CustomDDPGPolicy:
     """src/PDEagent.jl:121-209 + the update trigger :342-361 + update! :363-418, over the C ABI.
 
     Field names follow the Julia struct (y = discount, p = Polyak factor).  `comm` is an optional
-    object with `allreduce_sum_(torch_tensor)` used for the data-parallel gradient exchange
-    (see parallel.py); None = single GPU.
+    `parallel.Comm`: with more than one rank the context joins the process group (`pdeb200_comm_init`) and
+    every sample / update call becomes a collective whose gradient exchange runs inside the library's kernels
+    over NVLink peer memory; None = single GPU.
     """
 
     def __init__(self, env, *, behavior_actor, behavior_critic, target_actor=None, target_critic=None, y=0.99, p=0.995,
@@ -165,6 +215,7 @@ class CustomDDPGPolicy:
         self.update_step = 0
         self.seed, self._rng_offset = int(seed), 0
         self.comm = comm
+        self.transport = comm.attach(env) if comm is not None and comm.world_size > 1 else L.COMM_NONE
         self.trajectory = DeviceTrajectory(env, trajectory_length)
         self.number_actuators = env.n_envs * env.n_cols       # columns per env step (PDEagent.jl:348-353)
         self.n_updates = 0
@@ -198,9 +249,12 @@ class CustomDDPGPolicy:
             return 0
         if self.update_step % self.update_freq != 0:
             return 0
-        for _ in range(self.update_loops):
-            self.sample()
-            self.update()
+        # update_loops x {pde_sample; update!}: one C call, one CUDA graph on the device
+        lib, ctx = self.env._lib, self.env._ctx
+        L.check(lib.pdeb200_train_updates(ctx, int(self.update_loops), int(self.batch_size), float(self.y), float(self.p),
+                                          float(self.behavior_actor.learning_rate), float(self.behavior_critic.learning_rate),
+                                          int(self.literal_q1), self.seed ^ 0x5DEECE66D), ctx)
+        self.n_updates += self.update_loops
         return self.update_loops
 
     def sample(self, inds=None):
@@ -208,7 +262,9 @@ class CustomDDPGPolicy:
         if inds is not None:
             inds = np.ascontiguousarray(inds, dtype=np.int64)
             L.check(lib.pdeb200_sample(ctx, len(inds), inds.ctypes.data, 0, 0), ctx)
+            self._staged_batch = len(inds)
         else:
+            self._staged_batch = int(self.batch_size)
             L.check(lib.pdeb200_sample(ctx, int(self.batch_size), None, self.seed ^ 0x5DEECE66D, self._rng_offset), ctx)
             self._rng_offset += int(self.batch_size)
 
@@ -218,32 +274,38 @@ class CustomDDPGPolicy:
         s_, a_, s2 = f(s), f(a), f(snext)
         r_ = np.ascontiguousarray(r, dtype=np.float32).reshape(-1)
         t_ = np.ascontiguousarray(t, dtype=np.uint8).reshape(-1)
-        self._explicit_batch = len(r_)
+        self._staged_batch = len(r_)
         L.check(self.env._lib.pdeb200_set_batch(self.env._ctx, len(r_), s_.ctypes.data, a_.ctypes.data, r_.ctypes.data,
                                                 t_.ctypes.data, s2.ctypes.data), self.env._ctx)
 
+    def get_batch(self):
+        """The staged batch as pde_fetch! returns it (PDEagent.jl:322-340): s (ns,B), a (na,B), r (B,), t (B,), s' (ns,B), inds."""
+        lib, ctx, env = self.env._lib, self.env._ctx, self.env
+        ns, na = env.ns, (env.n_actuators * env.a_rows if env.cfg.mono else env.a_rows)
+        B = int(self._staged_batch)
+        s, a, s2 = np.empty((B, ns), np.float32), np.empty((B, na), np.float32), np.empty((B, ns), np.float32)
+        r, t, inds = np.empty(B, np.float32), np.empty(B, np.uint8), np.empty(B, np.int64)
+        L.check(lib.pdeb200_get_batch(ctx, s.ctypes.data, a.ctypes.data, r.ctypes.data, t.ctypes.data, s2.ctypes.data,
+                                      inds.ctypes.data), ctx)
+        return s.T, a.T, r, t.astype(bool), s2.T, inds
+
     # -- DDPG update (PDEagent.jl:363-418) ------------------------------------------------------------
-    def update(self, local_batch=None):
+    def update(self):
+        """update!(policy, batch) on the staged batch.  With a multi-rank `comm` this is a collective: gradients and
+        the quirk-Q1 r-bar are global-batch means, exchanged inside the gradient kernels (no host-side allreduce)."""
         lib, ctx = self.env._lib, self.env._ctx
-        B = int(local_batch or getattr(self, "_explicit_batch", None) or self.batch_size)
-        if self.comm is None or self.comm.world_size == 1:
-            L.check(lib.pdeb200_ddpg_update(ctx, float(self.y), float(self.p), float(self.behavior_actor.learning_rate),
-                                            float(self.behavior_critic.learning_rate), int(self.literal_q1)), ctx)
-        else:
-            comm = self.comm
-            Bg = comm.global_batch(B)
-            n_c = lib.pdeb200_net_num_params(ctx, L.NET_BEHAVIOR_CRITIC)
-            n_a = lib.pdeb200_net_num_params(ctx, L.NET_BEHAVIOR_ACTOR)
-            if self.literal_q1:
-                comm.allreduce_sum_(comm.alias(self.env, L.ARR_STATS, "float64")[:2])     # global sum r (quirk Q1)
-            L.check(lib.pdeb200_ddpg_critic_grads(ctx, float(self.y), int(self.literal_q1), Bg), ctx)
-            g = comm.alias(self.env, L.ARR_GRADS, "float32")
-            comm.allreduce_sum_(g[:n_c])
-            L.check(lib.pdeb200_ddpg_critic_apply(ctx, float(self.behavior_critic.learning_rate)), ctx)
-            L.check(lib.pdeb200_ddpg_actor_grads(ctx, Bg), ctx)
-            comm.allreduce_sum_(g[n_c:n_c + n_a])
-            L.check(lib.pdeb200_ddpg_actor_apply(ctx, float(self.behavior_actor.learning_rate), float(self.p)), ctx)
+        L.check(lib.pdeb200_ddpg_update(ctx, float(self.y), float(self.p), float(self.behavior_actor.learning_rate),
+                                        float(self.behavior_critic.learning_rate), int(self.literal_q1)), ctx)
         self.n_updates += 1
+
+    def set_sampler_offset(self, offset):
+        """Philox counter of the device sampler used by `maybe_update` (part of a resumable checkpoint)."""
+        L.check(self.env._lib.pdeb200_rng_set(self.env._ctx, int(offset)), self.env._ctx)
+
+    def sampler_offset(self):
+        v = C.c_uint64()
+        L.check(self.env._lib.pdeb200_rng_get(self.env._ctx, C.byref(v)), self.env._ctx)
+        return v.value
 
     def set_update_path(self, path):
         """0 auto, 1 layer-wise CUDA cores, 2 layer-wise tensor cores, 3 layer-wise auto (pdeb200_ddpg_set_path)."""
@@ -274,10 +336,16 @@ def create_agent(env, *, rng, nna_scale=1.0, nna_scale_critic=None, drop_middle_
     return CustomDDPGPolicy(env, behavior_actor=actor, behavior_critic=critic, **kw)
 
 
-def run_episode(policy, env, hook=None, learning=True, max_steps=None):
+def run_episode(policy, env, hook=None, learning=True, max_steps=None, check_done=True):
     """One episode in the stage order of RLCore's `run` (spelled out in the reference at
     scripts/Fluid/setup/FluidSetup.jl:455-519):  reset! -> PreEpisode -> loop { policy -> PreAct
-    (push s,a; update) -> env(action) -> PostAct (push r,t) } -> PostEpisode (dummy push)."""
+    (push s,a; update) -> env(action) -> PostAct (push r,t) } -> PostEpisode (dummy push).
+
+    Batched termination: the B environments share the clock, so the time limit ends the episode for all of them
+    at once; an environment that DIVERGES earlier (PDEenv.jl:226-237) ends only its own episode -- its terminal
+    flag is pushed, then it is reset in place (`pdeb200_reset_diverged`) while the others keep stepping, so no
+    Inf/NaN column is ever integrated further or pushed as a state.  check_done=False skips the per-step
+    read-back of the three counters (fixed-length roll-outs)."""
     traj = policy.trajectory
     env.reset()
     if learning:
@@ -285,6 +353,7 @@ def run_episode(policy, env, hook=None, learning=True, max_steps=None):
     if hook is not None:
         hook.pre_episode(env, policy)
     steps = 0
+    n_diverged = 0
     while True:
         policy(env, learning=learning)
         if learning:
@@ -296,11 +365,17 @@ def run_episode(policy, env, hook=None, learning=True, max_steps=None):
         if hook is not None:
             hook.post_act(env)
         steps += 1
-        if (max_steps is not None and steps >= max_steps) or bool(env.done[0]):
+        counts = env.reset_diverged(sync=check_done)
+        if counts is not None:
+            n_diverged += counts[2]
+            if counts[1] > 0:                       # the time limit: every environment that was not reset reaches it together
+                break
+        if max_steps is not None and steps >= max_steps:
             break
     if learning:
         traj.post_episode()
         policy.post_episode()
     if hook is not None:
         hook.post_episode(env, policy)
+    run_episode.last_diverged = n_diverged
     return steps

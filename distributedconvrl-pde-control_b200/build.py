@@ -33,24 +33,13 @@ def _deps_mtime():
 
 
 def _defines():
-    names = {p.stem for p in sources()}
-    d = [x for x in os.environ.get("PDEB_EXTRA_DEFINES", "").split() if x]
-    if "kseg" in names:
-        d.append("-DPDEB_HAVE_KSEG")
-    if "kseg2d" in names:
-        d.append("-DPDEB_HAVE_KSEG2D")
-    if "ns" in names:
-        d.append("-DPDEB_HAVE_NS")
-    if "agent" in names:
-        d.append("-DPDEB_HAVE_AGENT")
-    return d
+    return [x for x in os.environ.get("PDEB_EXTRA_DEFINES", "").split() if x]
 
 
 def _compile(src, verbose):
     obj = OBJ / (src.stem + ".o")
     newest = max(src.stat().st_mtime, _deps_mtime(), Path(__file__).stat().st_mtime)
-    # stubs.cu depends on WHICH back-ends exist (the -D set), not only on file times: always rebuild it
-    if obj.exists() and obj.stat().st_mtime >= newest and src.stem != "stubs":
+    if obj.exists() and obj.stat().st_mtime >= newest:
         return obj, False
     cmd = ["nvcc", *NVCC_FLAGS, *_defines(), "-c", str(src), "-o", str(obj)]
     if verbose:
@@ -75,7 +64,7 @@ def build(verbose=False, force=False):
     rebuilt = any(r for _, r in results)
     if rebuilt or not LIB.exists():
         cmd = ["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs,
-               "-Xcompiler", "-fPIC"]   # static cudart: self-contained next to torch's own runtime
+               "-Xcompiler", "-fPIC", "-ldl"]   # static cudart: self-contained next to torch's own runtime; NCCL is dlopen'ed
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

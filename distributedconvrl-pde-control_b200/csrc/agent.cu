@@ -16,6 +16,7 @@
 #include <cmath>
 #include <vector>
 
+#include "comm.cuh"
 #include "ctx.hpp"
 
 namespace pdeb200 {
@@ -25,6 +26,16 @@ namespace {
 constexpr int TS = 32;                 // samples per tile
 
 struct Ring { int64_t cap = 0, start = 0, len = 0; };
+
+// Device-resident mirror of the state a captured update graph must not receive by value: the ring positions (written by
+// the push kernels), and the sampler's Philox counter (advanced by the sampler itself).
+struct AgentDev {
+    Ring sa, rt;
+    unsigned long long rng_offset;
+};
+
+// stats[] layout (float64[8], PDEB200_ARR_STATS): sums over the GLOBAL batch (all ranks)
+enum { ST_R = 0, ST_R2 = 1, ST_N = 2, ST_C = 3, ST_C2 = 4, ST_Q = 5 };
 
 struct Agent {
     int ns = 0, na = 0;                // rows per state / action column
@@ -45,6 +56,12 @@ struct Agent {
     float* arena = nullptr; size_t arena_cap = 0, arena_used = 0;   // activations of the layer-wise (wide network) path
     int force_wide = 0;                // 1: always use the layer-wise path (tests / measurements)
     int wide_path = 0;                 // layer dispatch there: 0 auto, 1 CUDA cores only, 2 tensor cores wherever possible
+    AgentDev* dev = nullptr;           // device mirror (see AgentDev)
+    bool ring_dirty = true;            // host rings changed without a push kernel (create / pop_tail / set)
+    float* xbuf = nullptr; int xbuf_cap = 0;      // reduced gradient (+ 2 loss sums) of one phase: the exchange's send / receive vector
+    // captured graph of pdeb200_train_updates
+    cudaGraphExec_t graph = nullptr;
+    struct GraphKey { int n = 0, batch = 0, literal = 0; double gamma = 0, polyak = 0, lr_a = 0, lr_c = 0; uint64_t seed = 0; } gkey;
 };
 
 Agent* ag(pdeb200_ctx* c) { return static_cast<Agent*>(c->agent); }
@@ -52,10 +69,13 @@ Agent* ag(pdeb200_ctx* c) { return static_cast<Agent*>(c->agent); }
 // ---------------------------------------------------------------------------------------------
 // replay kernels
 // ---------------------------------------------------------------------------------------------
+// `after`: the ring as it stands once this push has landed -- mirrored into device memory for the captured sampler
 template <typename T>
 __global__ void push_sa_kernel(int64_t n, int ns, int na, int64_t cap, int64_t pos0, const T* __restrict__ state,
-                               const T* __restrict__ action, int zero_action, float* rstate, float* raction) {
+                               const T* __restrict__ action, int zero_action, float* rstate, float* raction, AgentDev* dev,
+                               Ring after) {
     const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (col == 0) dev->sa = after;
     if (col >= n) return;
     const int64_t dst = (pos0 + col) % cap;
     for (int r = 0; r < ns; ++r) rstate[dst * ns + r] = (float)state[col * ns + r];
@@ -64,8 +84,9 @@ __global__ void push_sa_kernel(int64_t n, int ns, int na, int64_t cap, int64_t p
 
 template <typename T>
 __global__ void push_rt_kernel(int64_t n, int cols_per_env, int64_t cap, int64_t pos0, const T* __restrict__ reward,
-                               const uint8_t* __restrict__ done, float* rreward, uint8_t* rterminal) {
+                               const uint8_t* __restrict__ done, float* rreward, uint8_t* rterminal, AgentDev* dev, Ring after) {
     const int64_t col = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (col == 0) dev->rt = after;
     if (col >= n) return;
     const int64_t dst = (pos0 + col) % cap;
     rreward[dst] = (float)reward[col];
@@ -89,14 +110,28 @@ __device__ __forceinline__ uint64_t philox_u64(uint64_t seed, uint64_t ctr) {
     return ((uint64_t)c0 << 32) | c1;
 }
 
+__global__ void ring_sync_kernel(AgentDev* dev, Ring sa, Ring rt) { dev->sa = sa; dev->rt = rt; }
+__global__ void rng_set_kernel(AgentDev* dev, unsigned long long off) { dev->rng_offset = off; }
+
+// Completion of the batch statistics by ONE thread: sum over all ranks (peer-memory exchange, comm.cuh), publish
+__device__ __forceinline__ void publish_stats(const CommDev& cm, double sum_r, double sum_r2, int n_local, double* stats) {
+    double v3[3] = {sum_r, sum_r2, (double)n_local};
+    if (cm.nranks > 1) comm_allreduce_stats(cm, v3);
+    stats[ST_R] = v3[0]; stats[ST_R2] = v3[1]; stats[ST_N] = v3[2];
+    stats[ST_C] = stats[ST_C2] = stats[ST_Q] = 0.0;
+}
+
 // sampled batch: inds ~ U{0 .. range-1} (reference: rand(rng, 1:length(t)-number_actuators, batch_size)), gather,
-// reward statistics
+// reward statistics.  dev_state = 1: ring positions and the Philox counter come from the device mirror (captured
+// graph: pdeb200_train_updates), and the counter is advanced by n; 0: from the arguments (pdeb200_sample).
 __global__ void __launch_bounds__(128)
-fetch_kernel(int n, int ns, int na, int64_t ncols, Ring sa, Ring rt, int64_t* inds, int draw, int64_t range, uint64_t seed,
-             uint64_t offset, const float* __restrict__ rstate, const float* __restrict__ raction,
+fetch_kernel(int n, int ns, int na, int64_t ncols, Ring sa, Ring rt, int64_t* inds, int draw, uint64_t seed,
+             uint64_t offset, int dev_state, AgentDev* dev, const float* __restrict__ rstate, const float* __restrict__ raction,
              const float* __restrict__ rreward, const uint8_t* __restrict__ rterminal, float* bs, float* ba, float* br,
-             uint8_t* bt, float* bs2, double* stat_part, unsigned int* ticket, double* stats) {
+             uint8_t* bt, float* bs2, double* stat_part, unsigned int* ticket, double* stats, const __grid_constant__ CommDev cm) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (dev_state) { sa = dev->sa; rt = dev->rt; offset = dev->rng_offset; }
+    const int64_t range = rt.len - ncols;
     double r1 = 0.0, r2 = 0.0;
     if (i < n) {
         int64_t ind;
@@ -113,8 +148,8 @@ fetch_kernel(int n, int ns, int na, int64_t ncols, Ring sa, Ring rt, int64_t* in
         bt[i] = rterminal[pr];
         r1 = rv; r2 = (double)rv * rv;
     }
-    // stats[0] = sum r, stats[1] = sum r^2 over the local batch, in a fixed order: shuffle tree per warp, warps and
-    // CTAs ascending; the last CTA to finish (ticket counter) adds the per-CTA sums -- no separate launch
+    // sum r, sum r^2 over the local batch in a fixed order: shuffle tree per warp, warps and CTAs ascending; the last CTA
+    // to finish (ticket counter) adds the per-CTA sums and runs the cross-rank exchange -- no separate launch
     __shared__ double s_p[2][4];
     __shared__ bool s_last;
 #pragma unroll
@@ -131,14 +166,15 @@ fetch_kernel(int n, int ns, int na, int64_t ncols, Ring sa, Ring rt, int64_t* in
             __threadfence();
             double sa_ = 0.0, sb_ = 0.0;
             for (unsigned int k = 0; k < gridDim.x; ++k) { sa_ += __ldcg(stat_part + 2 * k); sb_ += __ldcg(stat_part + 2 * k + 1); }
-            stats[0] = sa_; stats[1] = sb_; stats[2] = stats[3] = stats[4] = 0.0;
+            publish_stats(cm, sa_, sb_, n, stats);
+            if (dev_state) dev->rng_offset = offset + (unsigned long long)n;
             *ticket = 0;
         }
     }
 }
 
-// stats[0] = sum r, stats[1] = sum r^2 over the local batch (single CTA, fixed order)
-__global__ void reward_stats_kernel(int n, const float* __restrict__ br, double* stats) {
+// sum r, sum r^2 of an explicit batch (single CTA, fixed order), then summed over the ranks like the sampler's
+__global__ void reward_stats_kernel(int n, const float* __restrict__ br, double* stats, const __grid_constant__ CommDev cm) {
     __shared__ double s0[256], s1[256];
     double a = 0, b = 0;
     int i = threadIdx.x;
@@ -157,7 +193,7 @@ __global__ void reward_stats_kernel(int n, const float* __restrict__ br, double*
         if (threadIdx.x < o) { s0[threadIdx.x] += s0[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { stats[0] = s0[0]; stats[1] = s1[0]; stats[2] = stats[3] = stats[4] = 0.0; }
+    if (threadIdx.x == 0) publish_stats(cm, s0[0], s1[0], n, stats);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -270,19 +306,26 @@ struct DdpgArgs {
     int batch, ns, na;
     const float *s, *a, *r, *s2;
     const uint8_t* t;
-    float gamma; int literal_q1; double inv_global_batch;
-    const double* stats;            // stats[0] = GLOBAL sum of rewards (after the caller's allreduce)
+    float gamma; int literal_q1;
+    double inv_global_batch;        // > 0: given by the caller (four-phase API); 0: 1 / stats[ST_N] (sampler's global count)
+    const double* stats;            // stats[ST_R] = GLOBAL sum of rewards
     float* partials;                // [gridDim.x][n_acc + 2]
     int n_acc;                      // parameters accumulated (critic or actor)
     int wmax;                       // widest activation row over all nets (incl. ns+na)
-    // single-GPU fused tail: the last CTA to finish reduces the partials (fixed order) and applies ADAM + Polyak
+    // fused tail: the last CTA to finish reduces the partials (fixed order), exchanges the result with the peer GPUs
+    // (cm.nranks > 1) and applies ADAM + Polyak
     int fuse;
     unsigned int* ticket;
     float* grads; double* stats_out; int stat0;
+    float* xbuf;                    // n_acc + 2 floats: reduced gradient + loss sums, send / receive vector of the exchange
     float *x, *m, *v, *target;
-    double eta, b1, b2, bp1, bp2, eps; float polyak;
-    float* losses; double n_global; int literal_loss;
+    double* betap;                  // device-resident beta powers of this network's ADAM (read, then advanced)
+    double eta, b1, b2, eps; float polyak;
+    float* losses; int literal_loss;
+    CommDev cm;
 };
+
+__device__ __forceinline__ double inv_gb(const DdpgArgs& D) { return D.inv_global_batch > 0.0 ? D.inv_global_batch : 1.0 / D.stats[ST_N]; }
 
 __device__ void fused_tail(const DdpgArgs& D);
 
@@ -306,7 +349,8 @@ __global__ void __launch_bounds__(512) ddpg_critic_kernel(const __grid_constant_
     for (int q = threadIdx.x; q < D.n_acc; q += blockDim.x) acc[q] = 0.f;
     if (threadIdx.x < 2) s_c[threadIdx.x] = 0.0;
     const int nin = D.ns + D.na;
-    const float rbar = (float)(D.stats[0] * D.inv_global_batch);
+    const double igb = inv_gb(D);
+    const float rbar = (float)(D.stats[ST_R] * igb);
     const int n_tiles = (D.batch + TS - 1) / TS;
     __syncthreads();
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -360,7 +404,7 @@ __global__ void __launch_bounds__(512) ddpg_critic_kernel(const __grid_constant_
             if (i0 + i < D.batch) {
                 const float c = tgt[i] - qv[i];
                 const float rr = D.literal_q1 ? rbar : D.r[i0 + i];
-                dq = (float)(-2.0 * D.inv_global_batch) * (rr + c);
+                dq = (float)(-2.0 * igb) * (rr + c);
                 const double cl = D.literal_q1 ? (double)c : (double)(D.r[i0 + i] + c);
                 atomicAdd(&s_c[0], cl); atomicAdd(&s_c[1], cl * cl);
             }
@@ -391,6 +435,7 @@ __global__ void __launch_bounds__(512) ddpg_actor_kernel(const __grid_constant__
     if (threadIdx.x == 0) s_q = 0.0;
     const int nin = D.ns + D.na;
     const int n_tiles = (D.batch + TS - 1) / TS;
+    const double igb = inv_gb(D);
     __syncthreads();
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int i0 = tile * TS;
@@ -409,7 +454,7 @@ __global__ void __launch_bounds__(512) ddpg_actor_kernel(const __grid_constant__
         const float* qv = actsC[D.C.n_layers];
         for (int i = threadIdx.x; i < TS; i += blockDim.x) {
             const bool ok = i0 + i < D.batch;
-            scratch0[i] = ok ? (float)(-D.inv_global_batch) : 0.f;
+            scratch0[i] = ok ? (float)(-igb) : 0.f;
             if (ok) atomicAdd(&s_q, (double)qv[i]);
         }
         __syncthreads();
@@ -465,9 +510,17 @@ __device__ __forceinline__ double ordered_sum_cg(const float* partials, int n_bl
     return s;
 }
 
+// critic_loss / actor_loss (PDEagent.jl:393-396, 403-407) from the global sums
+__device__ __forceinline__ float critic_loss_from(const double* st, int literal) {
+    // literal: mean_{ij} (r_j + c_i)^2 = sum c^2/B + 2 sum c sum r / B^2 + sum r^2 / B ; per-sample: sum c'^2 / B
+    const double B = st[ST_N];
+    return (float)(literal ? st[ST_C2] / B + 2.0 * st[ST_C] * st[ST_R] / (B * B) + st[ST_R2] / B : st[ST_C2] / B);
+}
+
 // Tail of the fused gradient kernels: every CTA has written its partials; the last one to arrive (ticket counter,
-// self-resetting) does reduce_partials_kernel -> adam_kernel -> polyak_kernel -> losses_kernel in one go: same
-// fixed-order sums, same ADAM / Polyak arithmetic.
+// self-resetting) reduces them in a fixed order, sums the result over the ranks through NVLink peer memory
+// (comm_allreduce_cta -- the path's one collective, executed here instead of between launches), then applies ADAM, the
+// target's Polyak step and the losses.  Identical arithmetic on every rank => identical weights on every rank.
 __device__ void fused_tail(const DdpgArgs& D) {
     __shared__ bool s_last;
     __threadfence();
@@ -477,30 +530,34 @@ __device__ void fused_tail(const DdpgArgs& D) {
     if (!s_last) return;
     __threadfence();
     const size_t stride = (size_t)(D.n_acc + 2);
-    for (int q = threadIdx.x; q < D.n_acc + 2; q += blockDim.x) {
-        const double s = ordered_sum_cg(D.partials, (int)gridDim.x, stride, q);
-        if (q >= D.n_acc) {
-            D.stats_out[D.stat0 + (q - D.n_acc)] = s;
-            if (D.losses && q == D.n_acc) {
-                const double B = D.n_global;
-                const double* st = D.stats_out;
-                D.losses[0] = (float)(D.literal_loss ? st[3] / B + 2.0 * st[2] * st[0] / (B * B) + st[1] / B : st[3] / B);
-                D.losses[1] = (float)(-s / D.n_global);
-            }
-            continue;
+    for (int q = threadIdx.x; q < D.n_acc + 2; q += blockDim.x)
+        D.xbuf[q] = (float)ordered_sum_cg(D.partials, (int)gridDim.x, stride, q);
+    __syncthreads();
+    if (D.cm.nranks > 1) comm_allreduce_cta(D.cm, D.xbuf, D.xbuf, D.n_acc + 2);
+    const double bp1 = D.betap[0], bp2 = D.betap[1];
+    if (threadIdx.x == 0) {
+        const double s0 = (double)D.xbuf[D.n_acc], s1 = (double)D.xbuf[D.n_acc + 1];
+        D.stats_out[D.stat0] = s0;
+        if (D.stat0 == ST_C) D.stats_out[ST_C2] = s1;
+        if (D.losses) {                                   // actor phase: both losses are complete now
+            D.losses[0] = critic_loss_from(D.stats_out, D.literal_loss);
+            D.losses[1] = (float)(-s0 / D.stats_out[ST_N]);
         }
-        const float g = (float)s;
+    }
+    for (int q = threadIdx.x; q < D.n_acc; q += blockDim.x) {
+        const float g = D.xbuf[q];
         D.grads[q] = g;
         const double gi = g;
         const float mi = (float)(D.b1 * (double)D.m[q] + (1.0 - D.b1) * gi);
         const float vi = (float)(D.b2 * (double)D.v[q] + (1.0 - D.b2) * gi * gi);
         D.m[q] = mi; D.v[q] = vi;
-        const float delta = (float)((double)mi / (1.0 - D.bp1) / (sqrt((double)vi / (1.0 - D.bp2)) + D.eps) * D.eta);
+        const float delta = (float)((double)mi / (1.0 - bp1) / (sqrt((double)vi / (1.0 - bp2)) + D.eps) * D.eta);
         const float xn = D.x[q] - delta;
         D.x[q] = xn;
         D.target[q] = D.polyak * D.target[q] + (1.f - D.polyak) * xn;
     }
-    if (threadIdx.x == 0) *D.ticket = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) { D.betap[0] = bp1 * D.b1; D.betap[1] = bp2 * D.b2; *D.ticket = 0; }
 }
 
 // grads[q] = sum over CTAs (fixed order); tail sums go to stats
@@ -513,17 +570,22 @@ __global__ void reduce_partials_kernel(int n_blocks, int n_acc, const float* __r
     else stats[stat0 + (q - n_acc)] = s;
 }
 
-// Flux ADAM on Float32 arrays with Float64 hyper-parameters; optional Polyak pair (dest = p*dest + (1-p)*src).
+// Flux ADAM on Float32 arrays with Float64 hyper-parameters.  The running beta powers live on the device; the last
+// block to finish (ticket) advances them -- every block has read them by then.
 __global__ void adam_kernel(int n, float* x, float* m, float* v, const float* __restrict__ g, double eta, double b1,
-                            double b2, double bp1, double bp2, double eps) {
+                            double b2, double* betap, double eps, unsigned int* ticket) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double gi = g[i];
-    const float mi = (float)(b1 * (double)m[i] + (1.0 - b1) * gi);
-    const float vi = (float)(b2 * (double)v[i] + (1.0 - b2) * gi * gi);
-    m[i] = mi; v[i] = vi;
-    const float delta = (float)((double)mi / (1.0 - bp1) / (sqrt((double)vi / (1.0 - bp2)) + eps) * eta);
-    x[i] -= delta;
+    const double bp1 = betap[0], bp2 = betap[1];
+    if (i < n) {
+        const double gi = g[i];
+        const float mi = (float)(b1 * (double)m[i] + (1.0 - b1) * gi);
+        const float vi = (float)(b2 * (double)v[i] + (1.0 - b2) * gi * gi);
+        m[i] = mi; v[i] = vi;
+        const float delta = (float)((double)mi / (1.0 - bp1) / (sqrt((double)vi / (1.0 - bp2)) + eps) * eta);
+        x[i] -= delta;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(ticket, 1u) == gridDim.x - 1) { betap[0] = bp1 * b1; betap[1] = bp2 * b2; *ticket = 0; }
 }
 
 __global__ void polyak_kernel(int n, float* dest, const float* __restrict__ src, float p) {
@@ -532,24 +594,33 @@ __global__ void polyak_kernel(int n, float* dest, const float* __restrict__ src,
     dest[i] = p * dest[i] + (1.f - p) * src[i];
 }
 
-// critic_loss / actor_loss (PDEagent.jl:393-396, 403-407) from the reduced sums
-__global__ void losses_kernel(const double* stats, double n_global, int literal, int which, float* losses) {
-    if (which == 0) {
-        // literal: mean_{ij} (r_j + c_i)^2 = sum c^2/B + 2 sum c sum r / B^2 + sum r^2 / B ; per-sample: sum c'^2 / B
-        const double B = n_global;
-        losses[0] = (float)(literal ? stats[3] / B + 2.0 * stats[2] * stats[0] / (B * B) + stats[1] / B : stats[3] / B);
-    } else {
-        losses[1] = (float)(-stats[4] / n_global);
-    }
+// n_global > 0: the caller's global batch (four-phase API) replaces the sampler's count
+__global__ void losses_kernel(double* stats, double n_global, int literal, int which, float* losses) {
+    if (n_global > 0.0) stats[ST_N] = n_global;
+    if (which == 0) losses[0] = critic_loss_from(stats, literal);
+    else losses[1] = (float)(-stats[ST_Q] / stats[ST_N]);
+}
+
+void drop_graph(Agent* a) {
+    if (a && a->graph) { cudaGraphExecDestroy(a->graph); a->graph = nullptr; }
 }
 
 int32_t ensure_partials(pdeb200_ctx* c, int n_blocks, int n_acc) {
     Agent* a = ag(c);
     const size_t need = (size_t)n_blocks * (n_acc + 2);
     if (need > a->partials_floats) {
+        PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+        drop_graph(a);
         if (a->partials) cudaFree(a->partials);
         PDEB_CUDA(c, cudaMalloc(&a->partials, need * sizeof(float)));
         a->partials_floats = need;
+    }
+    if (n_acc + 2 > a->xbuf_cap) {
+        PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+        drop_graph(a);
+        if (a->xbuf) cudaFree(a->xbuf);
+        PDEB_CUDA(c, cudaMalloc(&a->xbuf, (size_t)(n_acc + 2) * sizeof(float)));
+        a->xbuf_cap = n_acc + 2;
     }
     return PDEB200_OK;
 }
@@ -563,12 +634,19 @@ int32_t ensure_agent(pdeb200_ctx* c) {
     c->agent = a;
     PDEB_CUDA(c, cudaMalloc(&a->stats, 8 * sizeof(double)));
     PDEB_CUDA(c, cudaMemset(a->stats, 0, 8 * sizeof(double)));
+    PDEB_CUDA(c, cudaMalloc(&a->dev, sizeof(AgentDev)));
+    PDEB_CUDA(c, cudaMemset(a->dev, 0, sizeof(AgentDev)));
+    PDEB_CUDA(c, cudaMalloc(&a->tickets, 8 * sizeof(unsigned int)));      // [0] sampler [1] critic [2] actor [3] adam
+    PDEB_CUDA(c, cudaMemset(a->tickets, 0, 8 * sizeof(unsigned int)));
     return PDEB200_OK;
 }
+
 
 int32_t ensure_batch(pdeb200_ctx* c, int batch) {
     Agent* a = ag(c);
     if (batch > a->batch_cap) {
+        PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+        drop_graph(a);
         for (void* p : {(void*)a->bs, (void*)a->ba, (void*)a->br, (void*)a->bs2, (void*)a->bt, (void*)a->inds})
             if (p) cudaFree(p);
         PDEB_CUDA(c, cudaMalloc(&a->bs, (size_t)batch * a->ns * 4));
@@ -581,13 +659,11 @@ int32_t ensure_batch(pdeb200_ctx* c, int batch) {
     }
     const int grid = (batch + 127) / 128;
     if (grid > a->stat_part_cap) {
+        PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+        drop_graph(a);
         if (a->stat_part) cudaFree(a->stat_part);
         PDEB_CUDA(c, cudaMalloc(&a->stat_part, (size_t)2 * grid * sizeof(double)));
         a->stat_part_cap = grid;
-    }
-    if (!a->tickets) {
-        PDEB_CUDA(c, cudaMalloc(&a->tickets, 4 * sizeof(unsigned int)));
-        PDEB_CUDA(c, cudaMemsetAsync(a->tickets, 0, 4 * sizeof(unsigned int), c->stream));
     }
     a->batch = batch;
     return PDEB200_OK;
@@ -604,6 +680,8 @@ int32_t check_nets(pdeb200_ctx* c) {
         return fail(c, PDEB200_EINVAL, "ddpg: target networks must have the behavior networks' shapes");
     const int want = C.n_params + A.n_params;
     if (c->n_grads != want) {
+        PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+        drop_graph(a);
         if (c->d_grads) cudaFree(c->d_grads);
         PDEB_CUDA(c, cudaMalloc(&c->d_grads, (size_t)want * sizeof(float)));
         PDEB_CUDA(c, cudaMemset(c->d_grads, 0, (size_t)want * sizeof(float)));
@@ -615,6 +693,7 @@ int32_t check_nets(pdeb200_ctx* c) {
 int net_wmax(const HostNet& n) { int w = 0; for (int l = 0; l <= n.n_layers; ++l) w = std::max(w, n.sizes[l]); return w; }
 int net_act_floats(const HostNet& n) { int s = 0; for (int l = 0; l <= n.n_layers; ++l) s += TS * n.sizes[l]; return s; }
 
+// global_batch > 0: the caller's count (four-phase API); 0: the sampler's global count on the device (stats[ST_N])
 DdpgArgs make_args(pdeb200_ctx* c, double gamma, int literal, int64_t global_batch) {
     Agent* a = ag(c);
     DdpgArgs D;
@@ -622,11 +701,11 @@ DdpgArgs make_args(pdeb200_ctx* c, double gamma, int literal, int64_t global_bat
     D.At = c->nets[PDEB200_NET_TARGET_ACTOR].dev(); D.Ct = c->nets[PDEB200_NET_TARGET_CRITIC].dev();
     D.batch = a->batch; D.ns = a->ns; D.na = a->na;
     D.s = a->bs; D.a = a->ba; D.r = a->br; D.s2 = a->bs2; D.t = a->bt;
-    D.gamma = (float)gamma; D.literal_q1 = literal; D.inv_global_batch = 1.0 / (double)global_batch;
+    D.gamma = (float)gamma; D.literal_q1 = literal; D.inv_global_batch = global_batch > 0 ? 1.0 / (double)global_batch : 0.0;
     D.stats = a->stats; D.partials = nullptr; D.n_acc = 0;
-    D.fuse = 0; D.ticket = nullptr; D.grads = nullptr; D.stats_out = a->stats; D.stat0 = 0;
-    D.x = D.m = D.v = D.target = nullptr; D.eta = D.b1 = D.b2 = D.bp1 = D.bp2 = D.eps = 0.0; D.polyak = 0.f;
-    D.losses = nullptr; D.n_global = (double)global_batch; D.literal_loss = literal;
+    D.fuse = 0; D.ticket = nullptr; D.grads = nullptr; D.stats_out = a->stats; D.stat0 = 0; D.xbuf = a->xbuf;
+    D.x = D.m = D.v = D.target = nullptr; D.betap = nullptr; D.eta = D.b1 = D.b2 = D.eps = 0.0; D.polyak = 0.f;
+    D.losses = nullptr; D.literal_loss = literal;
     D.wmax = std::max({net_wmax(c->nets[0]), net_wmax(c->nets[1]), a->ns + a->na});
     return D;
 }
@@ -690,7 +769,7 @@ __global__ void __launch_bounds__(1024) critic_dq_kernel(int B, const float* __r
                                                          float gamma, int literal, double inv_gb, double* stats, float* dq,
                                                          long long lddq) {
     __shared__ double s0[1024], s1[1024];
-    const float rbar = (float)(stats[0] * inv_gb);
+    const float rbar = (float)(stats[ST_R] * inv_gb);
     double a = 0, b = 0;
     for (int i = threadIdx.x; i < B; i += blockDim.x) {
         const float cc = gamma * (1.f - (float)t[i]) * qt[(long long)i * ldqt] - q[(long long)i * ldq];
@@ -705,7 +784,7 @@ __global__ void __launch_bounds__(1024) critic_dq_kernel(int B, const float* __r
         if (threadIdx.x < o) { s0[threadIdx.x] += s0[threadIdx.x + o]; s1[threadIdx.x] += s1[threadIdx.x + o]; }
         __syncthreads();
     }
-    if (threadIdx.x == 0) { stats[2] = s0[0]; stats[3] = s1[0]; }
+    if (threadIdx.x == 0) { stats[ST_C] = s0[0]; stats[ST_C2] = s1[0]; }
 }
 
 __global__ void __launch_bounds__(1024) actor_dq_kernel(int B, const float* __restrict__ q, long long ldq, double inv_gb, double* stats,
@@ -719,7 +798,7 @@ __global__ void __launch_bounds__(1024) actor_dq_kernel(int B, const float* __re
         if (threadIdx.x < o) s0[threadIdx.x] += s0[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) { stats[4] = s0[0]; stats[5] = 0.0; }
+    if (threadIdx.x == 0) stats[ST_Q] = s0[0];
 }
 
 // d[m][n] *= act'(out[m][n])
@@ -832,9 +911,7 @@ int32_t wide_critic_grads(pdeb200_ctx* c, double gamma, int literal, int64_t glo
                                                  a->stats, dq, 4);
     c->launches += 4;
     if ((rc = wide_backward(c, C, B, acts_c, dq, 4, c->d_grads, false, nullptr, nullptr))) return rc;
-    losses_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)global_batch, literal, 0, c->d_losses);
     PDEB_CUDA(c, cudaGetLastError());
-    c->launches += 1;
     return PDEB200_OK;
 }
 
@@ -866,22 +943,28 @@ int32_t wide_actor_grads(pdeb200_ctx* c, int64_t global_batch) {
     concat_kernel<<<(unsigned)(((long long)B * lda + 255) / 256), 256, 0, c->stream>>>(B, 0, na, lda, nullptr, dx + ns, (int)lddx, da);
     c->launches += 1;
     if ((rc = wide_backward(c, A, B, acts_a, da, lda, c->d_grads + C.n_params, false, nullptr, nullptr))) return rc;
-    losses_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)global_batch, 0, 1, c->d_losses);
     PDEB_CUDA(c, cudaGetLastError());
-    c->launches += 1;
     return PDEB200_OK;
 }
 
 }  // namespace
 
+
 double* agent_stats(pdeb200_ctx* c) { return c->agent ? ag(c)->stats : nullptr; }
+
+void agent_invalidate_graph(pdeb200_ctx* c) {
+    if (!c->agent) return;
+    if (ag(c)->graph && c->stream) cudaStreamSynchronize(c->stream);
+    drop_graph(ag(c));
+}
 
 void agent_free(pdeb200_ctx* c) {
     Agent* a = ag(c);
     if (!a) return;
+    drop_graph(a);
     for (void* p : {(void*)a->state, (void*)a->action, (void*)a->reward, (void*)a->terminal, (void*)a->bs, (void*)a->ba,
                     (void*)a->br, (void*)a->bs2, (void*)a->bt, (void*)a->inds, (void*)a->stats, (void*)a->partials,
-                    (void*)a->arena})
+                    (void*)a->arena, (void*)a->stat_part, (void*)a->tickets, (void*)a->dev, (void*)a->xbuf})
         if (p) cudaFree(p);
     delete a;
     c->agent = nullptr;
@@ -890,6 +973,41 @@ void agent_free(pdeb200_ctx* c) {
 }  // namespace pdeb200
 
 using namespace pdeb200;
+
+// ---- replay rings ---------------------------------------------------------------------------------------------------
+static void ring_advance(Ring& r, int64_t n) {
+    const int64_t over = std::max<int64_t>(0, r.len + n - r.cap);
+    r.len = std::min(r.cap, r.len + n);
+    r.start = (r.start + over) % r.cap;
+}
+
+// host rings changed without a push kernel: refresh the device mirror
+static int32_t sync_rings(pdeb200_ctx* c) {
+    Agent* a = ag(c);
+    if (!a->ring_dirty) return PDEB200_OK;
+    ring_sync_kernel<<<1, 1, 0, c->stream>>>(a->dev, a->sa, a->rt);
+    PDEB_CUDA(c, cudaGetLastError());
+    a->ring_dirty = false;
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
+static int32_t push_sa(pdeb200_ctx* c, int zero_action) {
+    Agent* a = ag(c);
+    if (!a || !a->state) return fail(c, PDEB200_ESTATE, "trajectory not created");
+    const int64_t n = a->ncols, pos0 = (a->sa.start + a->sa.len) % a->sa.cap, cap = a->sa.cap;
+    const int tpb = 128; const int grid = (int)((n + tpb - 1) / tpb);
+    ring_advance(a->sa, n);
+    if (c->cfg.dtype == PDEB200_F64)
+        push_sa_kernel<double><<<grid, tpb, 0, c->stream>>>(n, a->ns, a->na, cap, pos0, (const double*)c->state,
+                                                            (const double*)c->action_in, zero_action, a->state, a->action, a->dev, a->sa);
+    else
+        push_sa_kernel<float><<<grid, tpb, 0, c->stream>>>(n, a->ns, a->na, cap, pos0, (const float*)c->state,
+                                                           (const float*)c->action_in, zero_action, a->state, a->action, a->dev, a->sa);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return PDEB200_OK;
+}
 
 extern "C" {
 
@@ -900,10 +1018,14 @@ int32_t pdeb200_traj_create(pdeb200_ctx* c, int64_t capacity) {
     if (rc) return rc;
     Agent* a = ag(c);
     if (capacity < 2 * a->ncols) return fail(c, PDEB200_EINVAL, "traj_create: capacity must hold at least two env steps of columns");
+    agent_invalidate_graph(c);
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
     for (void* p : {(void*)a->state, (void*)a->action, (void*)a->reward, (void*)a->terminal})
         if (p) cudaFree(p);
+    a->state = a->action = a->reward = nullptr; a->terminal = nullptr;
     a->sa = Ring{capacity + 1, 0, 0};
     a->rt = Ring{capacity, 0, 0};
+    a->ring_dirty = true;
     PDEB_CUDA(c, cudaMalloc(&a->state, (size_t)(capacity + 1) * a->ns * 4));
     PDEB_CUDA(c, cudaMalloc(&a->action, (size_t)(capacity + 1) * a->na * 4));
     PDEB_CUDA(c, cudaMalloc(&a->reward, (size_t)capacity * 4));
@@ -917,25 +1039,87 @@ int32_t pdeb200_traj_length(const pdeb200_ctx* c, int64_t* length) {
     return PDEB200_OK;
 }
 
-static void ring_advance(Ring& r, int64_t n) {
-    const int64_t over = std::max<int64_t>(0, r.len + n - r.cap);
-    r.len = std::min(r.cap, r.len + n);
-    r.start = (r.start + over) % r.cap;
+int32_t pdeb200_traj_info(const pdeb200_ctx* c, int64_t* capacity, int64_t* n_sa, int64_t* n_rt, int64_t* first_sa, int64_t* first_rt) {
+    if (!c || !c->agent || !static_cast<Agent*>(c->agent)->state) return fail(c, PDEB200_ESTATE, "traj_info: no trajectory");
+    const Agent* a = static_cast<Agent*>(c->agent);
+    if (capacity) *capacity = a->rt.cap;
+    if (n_sa) *n_sa = a->sa.len;
+    if (n_rt) *n_rt = a->rt.len;
+    if (first_sa) *first_sa = a->sa.start;
+    if (first_rt) *first_rt = a->rt.start;
+    return PDEB200_OK;
 }
 
-static int32_t push_sa(pdeb200_ctx* c, int zero_action) {
+// ring -> logical order: two contiguous pieces [start, cap) and [0, start + len - cap)
+static cudaError_t ring_read(const Ring& r, size_t row_bytes, const void* ring, void* dst, cudaStream_t st) {
+    if (!dst || r.len == 0) return cudaSuccess;
+    const int64_t first = std::min(r.len, r.cap - r.start);
+    cudaError_t e = cudaMemcpyAsync(dst, (const char*)ring + r.start * row_bytes, first * row_bytes, cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess || first == r.len) return e;
+    return cudaMemcpyAsync((char*)dst + first * row_bytes, ring, (r.len - first) * row_bytes, cudaMemcpyDeviceToHost, st);
+}
+
+int32_t pdeb200_traj_get(pdeb200_ctx* c, float* state, float* action, float* reward, uint8_t* terminal) {
+    if (!c) return PDEB200_EINVAL;
     Agent* a = ag(c);
-    if (!a || !a->state) return fail(c, PDEB200_ESTATE, "trajectory not created");
-    const int64_t n = a->ncols, pos0 = (a->sa.start + a->sa.len) % a->sa.cap;
-    const int tpb = 128; const int grid = (int)((n + tpb - 1) / tpb);
-    if (c->cfg.dtype == PDEB200_F64)
-        push_sa_kernel<double><<<grid, tpb, 0, c->stream>>>(n, a->ns, a->na, a->sa.cap, pos0, (const double*)c->state,
-                                                            (const double*)c->action_in, zero_action, a->state, a->action);
-    else
-        push_sa_kernel<float><<<grid, tpb, 0, c->stream>>>(n, a->ns, a->na, a->sa.cap, pos0, (const float*)c->state,
-                                                           (const float*)c->action_in, zero_action, a->state, a->action);
+    if (!a || !a->state) return fail(c, PDEB200_ESTATE, "traj_get: no trajectory");
+    cudaSetDevice(c->device);
+    PDEB_CUDA(c, ring_read(a->sa, (size_t)a->ns * 4, a->state, state, c->stream));
+    PDEB_CUDA(c, ring_read(a->sa, (size_t)a->na * 4, a->action, action, c->stream));
+    PDEB_CUDA(c, ring_read(a->rt, 4, a->reward, reward, c->stream));
+    PDEB_CUDA(c, ring_read(a->rt, 1, a->terminal, terminal, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+// logical order -> ring with its oldest column at raw position `start`
+static cudaError_t ring_write(const Ring& r, size_t row_bytes, void* ring, const void* src, cudaStream_t st) {
+    if (r.len == 0) return cudaSuccess;
+    const int64_t first = std::min(r.len, r.cap - r.start);
+    cudaError_t e = cudaMemcpyAsync((char*)ring + r.start * row_bytes, src, first * row_bytes, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess || first == r.len) return e;
+    return cudaMemcpyAsync(ring, (const char*)src + first * row_bytes, (r.len - first) * row_bytes, cudaMemcpyHostToDevice, st);
+}
+
+int32_t pdeb200_traj_set(pdeb200_ctx* c, int64_t n_sa, int64_t n_rt, int64_t first_sa, int64_t first_rt, const float* state,
+                         const float* action, const float* reward, const uint8_t* terminal) {
+    if (!c) return PDEB200_EINVAL;
+    Agent* a = ag(c);
+    if (!a || !a->state) return fail(c, PDEB200_ESTATE, "traj_set: no trajectory (pdeb200_traj_create first)");
+    if (n_sa < 0 || n_rt < 0 || n_sa > a->sa.cap || n_rt > a->rt.cap || (n_sa && (!state || !action)) || (n_rt && (!reward || !terminal)) ||
+        first_sa < 0 || first_sa >= a->sa.cap || first_rt < 0 || first_rt >= a->rt.cap)
+        return fail(c, PDEB200_EINVAL, "traj_set: bad sizes, ring positions or null arrays");
+    cudaSetDevice(c->device);
+    a->sa.start = first_sa; a->sa.len = n_sa;
+    a->rt.start = first_rt; a->rt.len = n_rt;
+    a->ring_dirty = true;
+    PDEB_CUDA(c, ring_write(a->sa, (size_t)a->ns * 4, a->state, state, c->stream));
+    PDEB_CUDA(c, ring_write(a->sa, (size_t)a->na * 4, a->action, action, c->stream));
+    PDEB_CUDA(c, ring_write(a->rt, 4, a->reward, reward, c->stream));
+    PDEB_CUDA(c, ring_write(a->rt, 1, a->terminal, terminal, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_rng_get(pdeb200_ctx* c, uint64_t* offset) {
+    if (!c || !offset) return PDEB200_EINVAL;
+    cudaSetDevice(c->device);
+    int32_t rc = ensure_agent(c);
+    if (rc) return rc;
+    unsigned long long v = 0;
+    PDEB_CUDA(c, cudaMemcpyAsync(&v, &ag(c)->dev->rng_offset, sizeof(v), cudaMemcpyDeviceToHost, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    *offset = v;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_rng_set(pdeb200_ctx* c, uint64_t offset) {
+    if (!c) return PDEB200_EINVAL;
+    cudaSetDevice(c->device);
+    int32_t rc = ensure_agent(c);
+    if (rc) return rc;
+    rng_set_kernel<<<1, 1, 0, c->stream>>>(ag(c)->dev, (unsigned long long)offset);
     PDEB_CUDA(c, cudaGetLastError());
-    ring_advance(a->sa, n);
     c->launches += 1;
     return PDEB200_OK;
 }
@@ -959,16 +1143,16 @@ int32_t pdeb200_traj_push_post(pdeb200_ctx* c) {
     cudaSetDevice(c->device);
     Agent* a = ag(c);
     if (!a || !a->reward) return fail(c, PDEB200_ESTATE, "trajectory not created");
-    const int64_t n = a->ncols, pos0 = (a->rt.start + a->rt.len) % a->rt.cap;
+    const int64_t n = a->ncols, pos0 = (a->rt.start + a->rt.len) % a->rt.cap, cap = a->rt.cap;
     const int tpb = 128; const int grid = (int)((n + tpb - 1) / tpb);
-    if (c->cfg.dtype == PDEB200_F64)
-        push_rt_kernel<double><<<grid, tpb, 0, c->stream>>>(n, c->n_cols, a->rt.cap, pos0, (const double*)c->reward, c->done,
-                                                            a->reward, a->terminal);
-    else
-        push_rt_kernel<float><<<grid, tpb, 0, c->stream>>>(n, c->n_cols, a->rt.cap, pos0, (const float*)c->reward, c->done,
-                                                           a->reward, a->terminal);
-    PDEB_CUDA(c, cudaGetLastError());
     ring_advance(a->rt, n);
+    if (c->cfg.dtype == PDEB200_F64)
+        push_rt_kernel<double><<<grid, tpb, 0, c->stream>>>(n, c->n_cols, cap, pos0, (const double*)c->reward, c->done,
+                                                            a->reward, a->terminal, a->dev, a->rt);
+    else
+        push_rt_kernel<float><<<grid, tpb, 0, c->stream>>>(n, c->n_cols, cap, pos0, (const float*)c->reward, c->done,
+                                                           a->reward, a->terminal, a->dev, a->rt);
+    PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
 }
@@ -977,9 +1161,27 @@ int32_t pdeb200_traj_pop_tail(pdeb200_ctx* c) {
     if (!c) return PDEB200_EINVAL;
     Agent* a = ag(c);
     if (!a || !a->state) return fail(c, PDEB200_ESTATE, "trajectory not created");
-    if (a->rt.len > 0) a->sa.len = std::max<int64_t>(0, a->sa.len - a->ncols);       // PDEagent.jl:243-251
+    if (a->rt.len > 0) { a->sa.len = std::max<int64_t>(0, a->sa.len - a->ncols); a->ring_dirty = true; }      // PDEagent.jl:243-251
     return PDEB200_OK;
 }
+
+}  // extern "C"
+
+// ---- sampler ---------------------------------------------------------------------------------------------------------
+// one launch: index draw (device Philox unless the host supplied indices), gather, reward statistics (+ their exchange)
+static int32_t sample_launch(pdeb200_ctx* c, int batch, int draw, uint64_t seed, uint64_t offset, int dev_state) {
+    Agent* a = ag(c);
+    const int tpb = 128, grid = (batch + tpb - 1) / tpb;
+    fetch_kernel<<<grid, tpb, 0, c->stream>>>(batch, a->ns, a->na, a->ncols, a->sa, a->rt, a->inds, draw, seed, offset, dev_state,
+                                              a->dev, a->state, a->action, a->reward, a->terminal, a->bs, a->ba, a->br, a->bt,
+                                              a->bs2, a->stat_part, a->tickets, a->stats, comm_dev(c));
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    if (comm_nranks(c) > 1 && comm_transport(c) == PDEB200_COMM_NCCL) return comm_allreduce_f64(c, a->stats, 3);
+    return PDEB200_OK;
+}
+
+extern "C" {
 
 int32_t pdeb200_sample(pdeb200_ctx* c, int32_t batch, const int64_t* inds_host, uint64_t seed, uint64_t offset) {
     if (!c || batch < 1) return fail(c, PDEB200_EINVAL, "sample: bad argument");
@@ -990,18 +1192,12 @@ int32_t pdeb200_sample(pdeb200_ctx* c, int32_t batch, const int64_t* inds_host, 
     if (range < 1) return fail(c, PDEB200_ESTATE, "sample: trajectory shorter than one env step of columns");
     int32_t rc = ensure_batch(c, batch);
     if (rc) return rc;
-    const int tpb = 128, grid = (batch + tpb - 1) / tpb;
     if (inds_host) {
         for (int i = 0; i < batch; ++i)
             if (inds_host[i] < 0 || inds_host[i] >= range) return fail(c, PDEB200_EINVAL, "sample: index out of range");
         PDEB_CUDA(c, cudaMemcpyAsync(a->inds, inds_host, (size_t)batch * 8, cudaMemcpyHostToDevice, c->stream));
     }
-    // one launch: index draw (device Philox unless the host supplied indices), gather, reward statistics
-    fetch_kernel<<<grid, tpb, 0, c->stream>>>(batch, a->ns, a->na, a->ncols, a->sa, a->rt, a->inds, inds_host ? 0 : 1, range, seed,
-                                              offset, a->state, a->action, a->reward, a->terminal, a->bs, a->ba, a->br, a->bt,
-                                              a->bs2, a->stat_part, a->tickets, a->stats);
-    PDEB_CUDA(c, cudaGetLastError());
-    c->launches += 1;
+    if ((rc = sample_launch(c, batch, inds_host ? 0 : 1, seed, offset, 0))) return rc;
     if (inds_host) PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
     return PDEB200_OK;
 }
@@ -1019,9 +1215,26 @@ int32_t pdeb200_set_batch(pdeb200_ctx* c, int32_t batch, const float* s, const f
     PDEB_CUDA(c, cudaMemcpyAsync(a->br, r, (size_t)batch * 4, cudaMemcpyHostToDevice, c->stream));
     PDEB_CUDA(c, cudaMemcpyAsync(a->bt, t, (size_t)batch, cudaMemcpyHostToDevice, c->stream));
     PDEB_CUDA(c, cudaMemcpyAsync(a->bs2, s2, (size_t)batch * a->ns * 4, cudaMemcpyHostToDevice, c->stream));
-    reward_stats_kernel<<<1, 256, 0, c->stream>>>(batch, a->br, a->stats);
-    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    reward_stats_kernel<<<1, 256, 0, c->stream>>>(batch, a->br, a->stats, comm_dev(c));
     c->launches += 1;
+    if (comm_nranks(c) > 1 && comm_transport(c) == PDEB200_COMM_NCCL && (rc = comm_allreduce_f64(c, a->stats, 3))) return rc;
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_get_batch(pdeb200_ctx* c, float* s, float* a_, float* r, uint8_t* t, float* s2, int64_t* inds) {
+    if (!c) return PDEB200_EINVAL;
+    Agent* a = ag(c);
+    if (!a || !a->batch) return fail(c, PDEB200_ESTATE, "get_batch: no batch (pdeb200_sample / pdeb200_set_batch first)");
+    cudaSetDevice(c->device);
+    const size_t B = a->batch;
+    if (s) PDEB_CUDA(c, cudaMemcpyAsync(s, a->bs, B * a->ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (a_) PDEB_CUDA(c, cudaMemcpyAsync(a_, a->ba, B * a->na * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (r) PDEB_CUDA(c, cudaMemcpyAsync(r, a->br, B * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (t) PDEB_CUDA(c, cudaMemcpyAsync(t, a->bt, B, cudaMemcpyDeviceToHost, c->stream));
+    if (s2) PDEB_CUDA(c, cudaMemcpyAsync(s2, a->bs2, B * a->ns * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (inds) PDEB_CUDA(c, cudaMemcpyAsync(inds, a->inds, B * 8, cudaMemcpyDeviceToHost, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
     return PDEB200_OK;
 }
 
@@ -1029,72 +1242,177 @@ int32_t pdeb200_ddpg_set_path(pdeb200_ctx* c, int32_t path) {
     if (!c || path < 0 || path > 3) return fail(c, PDEB200_EINVAL, "ddpg_set_path: bad argument");
     int32_t rc = ensure_agent(c);
     if (rc) return rc;
+    agent_invalidate_graph(c);
     ag(c)->force_wide = path != 0;
     ag(c)->wide_path = path == 3 ? 0 : path;
     return PDEB200_OK;
 }
 
-// fused tail of the single-GPU update: learning rate, Polyak factor (lr <= 0: not fused)
-struct FuseTail { double lr = 0.0, polyak = 0.0; int literal = 0; };
-static int32_t critic_grads_impl(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch, bool reduce,
-                                 const FuseTail* ft = nullptr);
-static int32_t actor_grads_impl(pdeb200_ctx* c, int64_t global_batch, bool reduce, const FuseTail* ft = nullptr);
+}  // extern "C"
 
-int32_t pdeb200_ddpg_critic_grads(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch) {
-    return critic_grads_impl(c, gamma, literal_q1, global_batch, true);
-}
+// ---- DDPG update -------------------------------------------------------------------------------------------------------
+namespace {
 
-// reduce = false: leave the per-CTA partials unreduced (the fused tail `ft` consumes them); returns 1 if the
-// layer-wise path ran instead (gradients already reduced in d_grads)
-static int32_t critic_grads_impl(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch, bool reduce,
-                                 const FuseTail* ft) {
-    if (!c) return PDEB200_EINVAL;
-    cudaSetDevice(c->device);
+// How one update runs for the current networks and batch.  Decided ONCE for both phases: the fused shared-memory
+// kernels need the critic AND the actor phase to fit; otherwise both take the layer-wise GEMM path.
+struct Plan {
+    bool fused = false;
+    size_t smem_c = 0, smem_a = 0;
+    int tpb_c = 0, tpb_a = 0, n_blocks = 0, wmax = 0;
+};
+
+int32_t plan_update(pdeb200_ctx* c, Plan* P) {
     Agent* a = ag(c);
     if (!a || !a->batch) return fail(c, PDEB200_ESTATE, "ddpg: no batch (pdeb200_sample / pdeb200_set_batch first)");
     int32_t rc = check_nets(c);
     if (rc) return rc;
-    if (global_batch < a->batch) return fail(c, PDEB200_EINVAL, "ddpg: global_batch < local batch");
-    const HostNet& C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
-    DdpgArgs D = make_args(c, gamma, literal_q1, global_batch);
-    D.n_acc = C.n_params;
+    const HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+    P->wmax = std::max({net_wmax(c->nets[0]), net_wmax(c->nets[1]), a->ns + a->na});
+    P->smem_c = ((size_t)net_act_floats(C) + 2 * (size_t)TS * P->wmax + (size_t)TS * (a->ns + a->na) + TS + C.n_params) * 4;
+    P->smem_a = ((size_t)net_act_floats(C) + net_act_floats(A) + 2 * (size_t)TS * P->wmax + A.n_params) * 4;
+    P->fused = !a->force_wide && P->smem_c <= 220 * 1024 && P->smem_a <= 220 * 1024;
     const int n_tiles = (a->batch + TS - 1) / TS;
-    const int n_blocks = std::min(n_tiles, 2 * 148);
-    if ((rc = ensure_partials(c, n_blocks, D.n_acc))) return rc;
-    D.partials = a->partials;
-    const size_t smem = ((size_t)net_act_floats(C) + 2 * (size_t)TS * D.wmax + (size_t)TS * (a->ns + a->na) + TS + D.n_acc) * 4;
-    if (smem > 220 * 1024 || a->force_wide) {                                                              // layer-wise GEMM path
-        rc = wide_critic_grads(c, gamma, literal_q1, global_batch);
-        return rc ? rc : (reduce ? PDEB200_OK : 1);
+    P->n_blocks = std::min(n_tiles, 2 * 148);
+    P->tpb_c = block_threads(P->wmax, C.n_params);
+    P->tpb_a = block_threads(P->wmax, A.n_params);
+    if ((rc = ensure_partials(c, P->n_blocks, std::max(C.n_params, A.n_params)))) return rc;
+    if (P->fused) {
+        PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_c));
+        PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_a));
     }
-    PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tpb = block_threads(D.wmax, D.n_acc);
-    if (ft) {
-        HostNet& Cw = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
-        D.fuse = 1; D.ticket = a->tickets + 1; D.grads = c->d_grads; D.stat0 = 2;
-        D.x = Cw.d_params; D.m = Cw.d_m; D.v = Cw.d_v; D.target = c->nets[PDEB200_NET_TARGET_CRITIC].d_params;
-        D.eta = ft->lr; D.b1 = 0.9; D.b2 = 0.999; D.bp1 = Cw.beta_p[0]; D.bp2 = Cw.beta_p[1]; D.eps = 1e-8; D.polyak = (float)ft->polyak;
-        Cw.beta_p[0] *= 0.9; Cw.beta_p[1] *= 0.999;
+    return PDEB200_OK;
+}
+
+struct Hyper { double gamma, polyak, lr_a, lr_c; int literal; };
+
+// Gradient kernels of the shared-memory path.  tail != nullptr: the last CTA reduces, exchanges (cm) and applies the
+// optimiser; otherwise the per-CTA partials are reduced into ARR_GRADS by a second launch.  global_batch: see make_args.
+int32_t critic_kernel_launch(pdeb200_ctx* c, const Plan& P, double gamma, int literal, int64_t global_batch, const Hyper* tail) {
+    Agent* a = ag(c);
+    HostNet& Cw = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+    DdpgArgs D = make_args(c, gamma, literal, global_batch);
+    D.n_acc = Cw.n_params; D.wmax = P.wmax; D.partials = a->partials; D.stat0 = ST_C;
+    if (tail) {
+        D.fuse = 1; D.ticket = a->tickets + 1; D.grads = c->d_grads; D.cm = comm_dev(c);
+        D.x = Cw.d_params; D.m = Cw.d_m; D.v = Cw.d_v; D.target = c->nets[PDEB200_NET_TARGET_CRITIC].d_params; D.betap = Cw.d_betap;
+        D.eta = tail->lr_c; D.b1 = 0.9; D.b2 = 0.999; D.eps = 1e-8; D.polyak = (float)tail->polyak;
     }
-    ddpg_critic_kernel<<<n_blocks, tpb, smem, c->stream>>>(D);
-    a->n_blocks = n_blocks;
+    ddpg_critic_kernel<<<P.n_blocks, P.tpb_c, P.smem_c, c->stream>>>(D);
     c->launches += 1;
-    if (reduce) {
-        reduce_partials_kernel<<<(D.n_acc + 2 + 127) / 128, 128, 0, c->stream>>>(n_blocks, D.n_acc, a->partials, c->d_grads, a->stats, 2);
-        losses_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)global_batch, literal_q1, 0, c->d_losses);
-        c->launches += 2;
+    if (!tail) {
+        reduce_partials_kernel<<<(D.n_acc + 2 + 127) / 128, 128, 0, c->stream>>>(P.n_blocks, D.n_acc, a->partials, c->d_grads, a->stats, ST_C);
+        c->launches += 1;
     }
     PDEB_CUDA(c, cudaGetLastError());
     return PDEB200_OK;
 }
 
-static int32_t adam_apply(pdeb200_ctx* c, HostNet& n, const float* g, double lr) {
-    adam_kernel<<<(n.n_params + 127) / 128, 128, 0, c->stream>>>(n.n_params, n.d_params, n.d_m, n.d_v, g, lr, 0.9, 0.999,
-                                                                  n.beta_p[0], n.beta_p[1], 1e-8);
+int32_t actor_kernel_launch(pdeb200_ctx* c, const Plan& P, int64_t global_batch, const Hyper* tail) {
+    Agent* a = ag(c);
+    HostNet& Aw = c->nets[PDEB200_NET_BEHAVIOR_ACTOR];
+    const int n_c = c->nets[PDEB200_NET_BEHAVIOR_CRITIC].n_params;
+    DdpgArgs D = make_args(c, 0.0, tail ? tail->literal : 0, global_batch);
+    D.n_acc = Aw.n_params; D.wmax = P.wmax; D.partials = a->partials; D.stat0 = ST_Q;
+    if (tail) {
+        D.fuse = 1; D.ticket = a->tickets + 2; D.grads = c->d_grads + n_c; D.cm = comm_dev(c);
+        D.x = Aw.d_params; D.m = Aw.d_m; D.v = Aw.d_v; D.target = c->nets[PDEB200_NET_TARGET_ACTOR].d_params; D.betap = Aw.d_betap;
+        D.eta = tail->lr_a; D.b1 = 0.9; D.b2 = 0.999; D.eps = 1e-8; D.polyak = (float)tail->polyak;
+        D.losses = c->d_losses;
+    }
+    ddpg_actor_kernel<<<P.n_blocks, P.tpb_a, P.smem_a, c->stream>>>(D);
+    c->launches += 1;
+    if (!tail) {
+        reduce_partials_kernel<<<(D.n_acc + 2 + 127) / 128, 128, 0, c->stream>>>(P.n_blocks, D.n_acc, a->partials, c->d_grads + n_c, a->stats, ST_Q);
+        c->launches += 1;
+    }
     PDEB_CUDA(c, cudaGetLastError());
-    n.beta_p[0] *= 0.9; n.beta_p[1] *= 0.999;
+    return PDEB200_OK;
+}
+
+int32_t adam_apply(pdeb200_ctx* c, HostNet& n, const float* g, double lr) {
+    adam_kernel<<<(n.n_params + 127) / 128, 128, 0, c->stream>>>(n.n_params, n.d_params, n.d_m, n.d_v, g, lr, 0.9, 0.999, n.d_betap, 1e-8,
+                                                                  ag(c)->tickets + 3);
+    PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
+}
+
+int32_t losses_launch(pdeb200_ctx* c, int64_t global_batch, int literal, int which) {
+    losses_kernel<<<1, 1, 0, c->stream>>>(ag(c)->stats, (double)global_batch, literal, which, c->d_losses);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
+// gradient phases into ARR_GRADS (reduced over this rank's CTAs, not over ranks), by whichever path the plan chose
+int32_t critic_phase(pdeb200_ctx* c, const Plan& P, double gamma, int literal, int64_t global_batch) {
+    return P.fused ? critic_kernel_launch(c, P, gamma, literal, global_batch, nullptr) : wide_critic_grads(c, gamma, literal, global_batch);
+}
+int32_t actor_phase(pdeb200_ctx* c, const Plan& P, int64_t global_batch) {
+    return P.fused ? actor_kernel_launch(c, P, global_batch, nullptr) : wide_actor_grads(c, global_batch);
+}
+
+int32_t polyak_both(pdeb200_ctx* c, double polyak) {
+    HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+    HostNet &At = c->nets[PDEB200_NET_TARGET_ACTOR], &Ct = c->nets[PDEB200_NET_TARGET_CRITIC];
+    polyak_kernel<<<(A.n_params + 127) / 128, 128, 0, c->stream>>>(A.n_params, At.d_params, A.d_params, (float)polyak);
+    polyak_kernel<<<(C.n_params + 127) / 128, 128, 0, c->stream>>>(C.n_params, Ct.d_params, C.d_params, (float)polyak);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    return PDEB200_OK;
+}
+
+// can the optimiser run in the gradient kernels' tails (two launches per update)?
+bool tail_fusable(pdeb200_ctx* c, const Plan& P) {
+    if (!P.fused) return false;
+    const int nr = comm_nranks(c);
+    if (nr == 1) return true;
+    const int n_max = std::max(c->nets[PDEB200_NET_BEHAVIOR_CRITIC].n_params, c->nets[PDEB200_NET_BEHAVIOR_ACTOR].n_params);
+    return comm_transport(c) == PDEB200_COMM_PEER && n_max + 2 <= comm_cap(c);
+}
+
+// One whole update on the staged batch (PDEagent.jl:363-418).
+int32_t enqueue_update(pdeb200_ctx* c, const Plan& P, const Hyper& H) {
+    Agent* a = ag(c);
+    int32_t rc;
+    if (tail_fusable(c, P)) {
+        // two launches: {critic gradients; last CTA: reduce + exchange + ADAM + Polyak} {actor gradients; last CTA: same +
+        // losses}.  The target critic is not read after the critic phase and the behavior critic is not written by the
+        // actor phase, so its Polyak step can run right after its ADAM step (reference order: both at the end,
+        // PDEagent.jl:411-417).  The global batch count comes from the sampler's statistics on the device.
+        if ((rc = critic_kernel_launch(c, P, H.gamma, H.literal, 0, &H))) return rc;
+        return actor_kernel_launch(c, P, 0, &H);
+    }
+    // layer-wise (wide network) path, or NCCL transport: allreduce between the gradient and the optimiser kernels.
+    // Shared-memory kernels read the global batch count from the sampler's statistics (gb = 0); the layer-wise path
+    // takes it by value = batch x nranks (equal local batches required there).
+    const int nr = comm_nranks(c);
+    const int64_t gb = P.fused ? 0 : (int64_t)a->batch * nr;
+    HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+    if ((rc = critic_phase(c, P, H.gamma, H.literal, gb))) return rc;
+    if (nr > 1 && ((rc = comm_allreduce_f32(c, c->d_grads, C.n_params)) || (rc = comm_allreduce_f64(c, a->stats + ST_C, 2)))) return rc;
+    if ((rc = losses_launch(c, gb, H.literal, 0))) return rc;
+    if ((rc = adam_apply(c, C, c->d_grads, H.lr_c))) return rc;
+    if ((rc = actor_phase(c, P, gb))) return rc;
+    if (nr > 1 && ((rc = comm_allreduce_f32(c, c->d_grads + C.n_params, A.n_params)) || (rc = comm_allreduce_f64(c, a->stats + ST_Q, 1)))) return rc;
+    if ((rc = losses_launch(c, gb, H.literal, 1))) return rc;
+    if ((rc = adam_apply(c, A, c->d_grads + C.n_params, H.lr_a))) return rc;
+    return polyak_both(c, H.polyak);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t pdeb200_ddpg_critic_grads(pdeb200_ctx* c, double gamma, int32_t literal_q1, int64_t global_batch) {
+    if (!c) return PDEB200_EINVAL;
+    cudaSetDevice(c->device);
+    Plan P;
+    int32_t rc = plan_update(c, &P);
+    if (rc) return rc;
+    if (global_batch < ag(c)->batch) return fail(c, PDEB200_EINVAL, "ddpg: global_batch < local batch");
+    if ((rc = critic_phase(c, P, gamma, literal_q1, global_batch))) return rc;
+    return losses_launch(c, global_batch, literal_q1, 0);
 }
 
 int32_t pdeb200_ddpg_critic_apply(pdeb200_ctx* c, double lr) {
@@ -1103,85 +1421,84 @@ int32_t pdeb200_ddpg_critic_apply(pdeb200_ctx* c, double lr) {
     return adam_apply(c, c->nets[PDEB200_NET_BEHAVIOR_CRITIC], c->d_grads, lr);
 }
 
-int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* c, int64_t global_batch) { return actor_grads_impl(c, global_batch, true); }
-
-static int32_t actor_grads_impl(pdeb200_ctx* c, int64_t global_batch, bool reduce, const FuseTail* ft) {
+int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* c, int64_t global_batch) {
     if (!c) return PDEB200_EINVAL;
     cudaSetDevice(c->device);
-    Agent* a = ag(c);
-    if (!a || !a->batch) return fail(c, PDEB200_ESTATE, "ddpg: no batch");
-    int32_t rc = check_nets(c);
+    Plan P;
+    int32_t rc = plan_update(c, &P);
     if (rc) return rc;
-    const HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
-    DdpgArgs D = make_args(c, 0.0, 0, global_batch);
-    D.n_acc = A.n_params;
-    const int n_tiles = (a->batch + TS - 1) / TS;
-    const int n_blocks = std::min(n_tiles, 2 * 148);
-    if ((rc = ensure_partials(c, n_blocks, D.n_acc))) return rc;
-    D.partials = a->partials;
-    const size_t smem = ((size_t)net_act_floats(C) + net_act_floats(A) + 2 * (size_t)TS * D.wmax + D.n_acc) * 4;
-    if (smem > 220 * 1024 || a->force_wide) {                                                              // layer-wise GEMM path
-        rc = wide_actor_grads(c, global_batch);
-        return rc ? rc : (reduce ? PDEB200_OK : 1);
-    }
-    PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tpb = block_threads(D.wmax, D.n_acc);
-    if (ft) {
-        HostNet& Aw = c->nets[PDEB200_NET_BEHAVIOR_ACTOR];
-        D.fuse = 1; D.ticket = a->tickets + 2; D.grads = c->d_grads + C.n_params; D.stat0 = 4;
-        D.x = Aw.d_params; D.m = Aw.d_m; D.v = Aw.d_v; D.target = c->nets[PDEB200_NET_TARGET_ACTOR].d_params;
-        D.eta = ft->lr; D.b1 = 0.9; D.b2 = 0.999; D.bp1 = Aw.beta_p[0]; D.bp2 = Aw.beta_p[1]; D.eps = 1e-8; D.polyak = (float)ft->polyak;
-        D.losses = c->d_losses; D.literal_loss = ft->literal;
-        Aw.beta_p[0] *= 0.9; Aw.beta_p[1] *= 0.999;
-    }
-    ddpg_actor_kernel<<<n_blocks, tpb, smem, c->stream>>>(D);
-    a->n_blocks = n_blocks;
-    c->launches += 1;
-    if (reduce) {
-        reduce_partials_kernel<<<(D.n_acc + 2 + 127) / 128, 128, 0, c->stream>>>(n_blocks, D.n_acc, a->partials,
-                                                                                  c->d_grads + C.n_params, a->stats, 4);
-        losses_kernel<<<1, 1, 0, c->stream>>>(a->stats, (double)global_batch, 0, 1, c->d_losses);
-        c->launches += 2;
-    }
-    PDEB_CUDA(c, cudaGetLastError());
-    return PDEB200_OK;
+    if (global_batch < ag(c)->batch) return fail(c, PDEB200_EINVAL, "ddpg: global_batch < local batch");
+    if ((rc = actor_phase(c, P, global_batch))) return rc;
+    return losses_launch(c, global_batch, 0, 1);
 }
 
 int32_t pdeb200_ddpg_actor_apply(pdeb200_ctx* c, double lr, double polyak) {
     if (!c || !c->d_grads) return fail(c, PDEB200_ESTATE, "ddpg: no gradients");
     cudaSetDevice(c->device);
     HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
-    HostNet &At = c->nets[PDEB200_NET_TARGET_ACTOR], &Ct = c->nets[PDEB200_NET_TARGET_CRITIC];
     int32_t rc = adam_apply(c, A, c->d_grads + C.n_params, lr);
     if (rc) return rc;
-    polyak_kernel<<<(A.n_params + 127) / 128, 128, 0, c->stream>>>(A.n_params, At.d_params, A.d_params, (float)polyak);
-    polyak_kernel<<<(C.n_params + 127) / 128, 128, 0, c->stream>>>(C.n_params, Ct.d_params, C.d_params, (float)polyak);
-    PDEB_CUDA(c, cudaGetLastError());
-    c->launches += 2;
-    return PDEB200_OK;
+    return polyak_both(c, polyak);
 }
 
 int32_t pdeb200_ddpg_update(pdeb200_ctx* c, double gamma, double polyak, double lr_actor, double lr_critic, int32_t literal_q1) {
     if (!c || !c->agent) return fail(c, PDEB200_ESTATE, "ddpg_update: no batch");
     cudaSetDevice(c->device);
+    Plan P;
+    int32_t rc = plan_update(c, &P);
+    if (rc) return rc;
+    const Hyper H{gamma, polyak, lr_actor, lr_critic, literal_q1};
+    return enqueue_update(c, P, H);
+}
+
+int32_t pdeb200_train_updates(pdeb200_ctx* c, int32_t n_updates, int32_t batch, double gamma, double polyak, double lr_actor,
+                              double lr_critic, int32_t literal_q1, uint64_t seed) {
+    if (!c || n_updates < 1 || batch < 1) return fail(c, PDEB200_EINVAL, "train_updates: bad argument");
+    cudaSetDevice(c->device);
     Agent* a = ag(c);
-    const int64_t B = a->batch;
-    // Fused single-GPU path: two launches -- {critic gradients; last CTA: reduce + ADAM + Polyak} {actor gradients; last
-    // CTA: reduce + ADAM + Polyak + losses}.  The target critic is not read after the critic phase and the behavior
-    // critic is not written by the actor phase, so its Polyak step can run right after its ADAM step (reference order:
-    // both at the end, PDEagent.jl:411-417).  The layer-wise (wide network) path applies its updates separately.
-    const bool wide = a->force_wide != 0;
-    FuseTail fc; fc.lr = lr_critic; fc.polyak = polyak; fc.literal = literal_q1;
-    FuseTail fa; fa.lr = lr_actor; fa.polyak = polyak; fa.literal = literal_q1;
-    int32_t rc = critic_grads_impl(c, gamma, literal_q1, B, false, wide ? nullptr : &fc);
-    if (rc < 0) return rc;
-    if (rc == 1) {                       // layer-wise path: gradients are already reduced
-        if ((rc = pdeb200_ddpg_critic_apply(c, lr_critic))) return rc;
-        if ((rc = pdeb200_ddpg_actor_grads(c, B))) return rc;
-        return pdeb200_ddpg_actor_apply(c, lr_actor, polyak);
+    if (!a || !a->state) return fail(c, PDEB200_ESTATE, "train_updates: trajectory not created");
+    if (a->rt.len - a->ncols < 1) return fail(c, PDEB200_ESTATE, "train_updates: trajectory shorter than one env step of columns");
+    int32_t rc = ensure_batch(c, batch);
+    if (rc) return rc;
+    Plan P;
+    if ((rc = plan_update(c, &P))) return rc;
+    if ((rc = sync_rings(c))) return rc;
+    const Hyper H{gamma, polyak, lr_actor, lr_critic, literal_q1};
+    static const bool no_graph = [] { const char* e = getenv("PDEB200_NO_GRAPH"); return e && atoi(e) != 0; }();
+    if (no_graph || !tail_fusable(c, P)) {
+        for (int k = 0; k < n_updates; ++k) {
+            if ((rc = sample_launch(c, batch, 1, seed, 0, 1))) return rc;
+            if ((rc = enqueue_update(c, P, H))) return rc;
+        }
+        return PDEB200_OK;
     }
-    if ((rc = actor_grads_impl(c, B, false, &fa)) < 0) return rc;
-    PDEB_CUDA(c, cudaGetLastError());
+    // update_loops x {sample, critic, actor} as one graph: everything that changes between launches (ring positions,
+    // Philox counter, beta powers, exchange epochs) lives in device memory
+    Agent::GraphKey k;
+    k.n = n_updates; k.batch = batch; k.literal = literal_q1; k.gamma = gamma; k.polyak = polyak; k.lr_a = lr_actor; k.lr_c = lr_critic; k.seed = seed;
+    const Agent::GraphKey& o = a->gkey;
+    const bool same = a->graph && o.n == k.n && o.batch == k.batch && o.literal == k.literal && o.gamma == k.gamma && o.polyak == k.polyak &&
+                      o.lr_a == k.lr_a && o.lr_c == k.lr_c && o.seed == k.seed;
+    if (!same) {
+        drop_graph(a);
+        const int64_t l0 = c->launches;
+        PDEB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        for (int i = 0; i < n_updates && !rc; ++i) {
+            rc = sample_launch(c, batch, 1, seed, 0, 1);
+            if (!rc) rc = enqueue_update(c, P, H);
+        }
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        c->launches = l0;
+        if (rc) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) return fail(c, PDEB200_ECUDA, std::string("train_updates: graph capture failed: ") + cudaGetErrorString(e));
+        const cudaError_t e2 = cudaGraphInstantiate(&a->graph, g, 0);
+        cudaGraphDestroy(g);
+        if (e2 != cudaSuccess) { a->graph = nullptr; return fail(c, PDEB200_ECUDA, std::string("train_updates: cudaGraphInstantiate: ") + cudaGetErrorString(e2)); }
+        a->gkey = k;
+    }
+    PDEB_CUDA(c, cudaGraphLaunch(a->graph, c->stream));
+    c->launches += (int64_t)3 * n_updates;
     return PDEB200_OK;
 }
 

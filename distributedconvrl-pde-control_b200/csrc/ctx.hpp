@@ -21,7 +21,8 @@ struct HostNet {
     float* d_params = nullptr;      // weights
     float* d_m = nullptr;           // ADAM first moment
     float* d_v = nullptr;           // ADAM second moment
-    double beta_p[2] = {0.9, 0.999};  // running beta powers (Flux ADAM state `βp`)
+    double* d_betap = nullptr;      // running beta powers (Flux ADAM state `βp`), 2 doubles ON THE DEVICE: advanced by the
+                                    // optimiser kernels themselves so that a captured CUDA graph needs no host-side state
     NetDev dev() const {
         NetDev n;
         n.params = d_params; n.n_layers = n_layers;
@@ -58,7 +59,7 @@ struct pdeb200_ctx {
     void *y = nullptr, *y0 = nullptr, *p = nullptr, *state = nullptr, *action = nullptr, *action_in = nullptr,
          *delta_action = nullptr, *reward = nullptr, *sensors = nullptr;
     uint8_t* done = nullptr; double* time = nullptr; int* steps = nullptr;
-    uint8_t* d_mask = nullptr; double* d_rsum = nullptr; void* d_noise = nullptr; void* vmax = nullptr;
+    uint8_t* d_mask = nullptr; int* d_counts = nullptr; double* d_rsum = nullptr; void* d_noise = nullptr; void* vmax = nullptr;
 
     // bases
     pdeb200::EllHost sens, actT;
@@ -79,6 +80,7 @@ struct pdeb200_ctx {
     pdeb200::HostNet nets[4];
     float* d_grads = nullptr; int n_grads = 0; float* d_losses = nullptr;
     void* agent = nullptr;
+    void* comm = nullptr;           // pdeb200::Comm (comm.cu) after pdeb200_comm_init
 
     // timing
     bool timing = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr; bool timed = false;
@@ -153,5 +155,17 @@ int32_t dense_wgrad(pdeb200_ctx* c, int M, int K, int N, const float* dY, long l
 
 void agent_free(pdeb200_ctx* c);
 double* agent_stats(pdeb200_ctx* c);   // 8 doubles, or nullptr before the first batch
+void agent_invalidate_graph(pdeb200_ctx* c);   // networks / rings / communicator changed: drop the captured update graph
+
+// multi-GPU (comm.cu)
+struct CommDev;
+CommDev comm_dev(const pdeb200_ctx* c);                 // nranks = 1 unless the peer-memory transport is up
+int comm_nranks(const pdeb200_ctx* c);
+int comm_transport(const pdeb200_ctx* c);
+int comm_cap(const pdeb200_ctx* c);
+int32_t comm_allreduce_f32(pdeb200_ctx* c, float* dev, size_t n);      // NCCL on the context's stream
+int32_t comm_allreduce_f64(pdeb200_ctx* c, double* dev, size_t n);
+int32_t comm_check(pdeb200_ctx* c);                    // PDEB200_ECOMM if a peer wait timed out
+void comm_free(pdeb200_ctx* c);
 
 }  // namespace pdeb200

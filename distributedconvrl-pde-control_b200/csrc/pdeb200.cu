@@ -24,6 +24,19 @@ __global__ void reset_copy_kernel(int y_elems, int p_elems, const uint8_t* __res
     for (int i = threadIdx.x; i < p_elems; i += blockDim.x) p[(size_t)env * p_elems + i] = T(0);
 }
 
+// Batched termination: mask[b] = done[b] although the clock of b has not reached te, i.e. b diverged (PDEenv.jl:226-237);
+// counts = {done, time limit, diverged}
+__global__ void diverged_mask_kernel(int n_envs, const uint8_t* __restrict__ done, const double* __restrict__ time, double te,
+                                     uint8_t* mask, int* counts) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_envs) return;
+    const bool dn = done[b] != 0, tl = time[b] >= te;
+    mask[b] = dn && !tl;
+    if (dn) atomicAdd(counts + 0, 1);
+    if (dn && tl) atomicAdd(counts + 1, 1);
+    if (dn && !tl) atomicAdd(counts + 2, 1);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Policy forward: actions = clamp(actor(state) [+ noise * act_noise], +-act_limit)
 // src/PDEagent.jl:189, 201-204.  One thread per column.
@@ -444,6 +457,8 @@ int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** 
     }
     if (cfg->mono) {
         if (cfg->problem != PDEB200_KS) return bail(fail(c, PDEB200_EUNSUPPORTED, "mono (global agent) exists for KS only"));
+        if (cfg->memory_size > 0)      // KSglobalSetup.jl:240-246 appends env.action rows; no shipped script uses it
+            return bail(fail(c, PDEB200_EUNSUPPORTED, "mono (global agent) with memory_size > 0 is not implemented"));
         c->n_cols = 1; c->n_rew = 1; c->obs_rows = cfg->n_sensors * cfg->temporal_steps + cfg->memory_size;
     } else {
         c->n_cols = cfg->n_actuators; c->n_rew = cfg->n_actuators;
@@ -462,7 +477,7 @@ int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** 
               alloc((void**)&c->time, B * 8) && alloc((void**)&c->steps, B * 4) && alloc((void**)&c->d_mask, B) &&
               alloc((void**)&c->d_rsum, B * 8) && alloc(&c->d_noise, nact * e) && alloc(&c->vmax, B * e) &&
               alloc((void**)&c->d_a2s, cfg->n_actuators * 4) && alloc(&c->d_sens_sum, cfg->n_sensors * e) &&
-              alloc((void**)&c->d_losses, 8);
+              alloc((void**)&c->d_losses, 8) && alloc((void**)&c->d_counts, 16);
     if (!ok) return bail(fail(c, PDEB200_ECUDA, std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError())));
     int32_t rc = PDEB200_OK;
     switch (cfg->problem) {
@@ -480,14 +495,14 @@ int32_t pdeb200_destroy(pdeb200_ctx* c) {
     if (!c) return PDEB200_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    ks_free(c); kseg_free(c); ns_free(c); agent_free(c);
+    ks_free(c); kseg_free(c); ns_free(c); agent_free(c); comm_free(c);
     for (void* p : {c->y, c->y0, c->p, c->state, c->action, c->action_in, c->delta_action, c->reward, c->sensors,
                     (void*)c->done, (void*)c->time, (void*)c->steps, (void*)c->d_mask, (void*)c->d_rsum, c->d_noise, c->vmax,
                     (void*)c->d_a2s, c->d_sens_sum, (void*)c->sens.d_idx, c->sens.d_w, (void*)c->actT.d_idx, c->actT.d_w,
-                    (void*)c->d_grads, (void*)c->d_losses})
+                    (void*)c->d_grads, (void*)c->d_losses, (void*)c->d_counts})
         if (p) cudaFree(p);
     for (auto& n : c->nets)
-        for (float* p : {n.d_params, n.d_m, n.d_v})
+        for (void* p : {(void*)n.d_params, (void*)n.d_m, (void*)n.d_v, (void*)n.d_betap})
             if (p) cudaFree(p);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -553,6 +568,24 @@ int32_t pdeb200_reset(pdeb200_ctx* c, const uint8_t* mask) {
     return PDEB200_OK;
 }
 
+int32_t pdeb200_reset_diverged(pdeb200_ctx* c, int32_t* counts) {
+    if (!c) return PDEB200_EINVAL;
+    if (!c->bases_set || !c->y0_set) return fail(c, PDEB200_ESTATE, "reset_diverged: set_bases and set_y0 first");
+    cudaSetDevice(c->device);
+    PDEB_CUDA(c, cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(int), c->stream));
+    diverged_mask_kernel<<<(c->cfg.n_envs + 255) / 256, 256, 0, c->stream>>>(c->cfg.n_envs, c->done, c->time, c->cfg.te, c->d_mask,
+                                                                               c->d_counts);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    int32_t rc = c->cfg.dtype == PDEB200_F64 ? reset_t<double>(c, c->d_mask) : reset_t<float>(c, c->d_mask);
+    if (rc) return rc;
+    if (counts) {
+        PDEB_CUDA(c, cudaMemcpyAsync(counts, c->d_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return PDEB200_OK;
+}
+
 int32_t pdeb200_step_device(pdeb200_ctx* c, const void* actions_dev) {
     if (!c) return PDEB200_EINVAL;
     cudaSetDevice(c->device);
@@ -602,6 +635,21 @@ int32_t pdeb200_get(pdeb200_ctx* c, int32_t which, void* dst, size_t bytes) {
     return PDEB200_OK;
 }
 
+int32_t pdeb200_get_env(pdeb200_ctx* c, int32_t which, int32_t env_index, void* dst, size_t bytes) {
+    if (!c || !dst) return fail(c, PDEB200_EINVAL, "get_env: null argument");
+    if (env_index < 0 || env_index >= c->cfg.n_envs) return fail(c, PDEB200_EINVAL, "get_env: environment index out of range");
+    if (which == PDEB200_ARR_GRADS || which == PDEB200_ARR_LOSSES || which == PDEB200_ARR_STATS)
+        return fail(c, PDEB200_EINVAL, "get_env: not a per-environment array");
+    cudaSetDevice(c->device);
+    ArrInfo a = arr_info(c, which);
+    if (!a.ptr) return fail(c, PDEB200_EINVAL, "get_env: unknown or unallocated array");
+    const size_t per = a.bytes / (size_t)c->cfg.n_envs;
+    if (bytes != per) return fail(c, PDEB200_EINVAL, "get_env: size mismatch (expected " + std::to_string(per) + " bytes)");
+    PDEB_CUDA(c, cudaMemcpyAsync(dst, (const char*)a.ptr + per * (size_t)env_index, per, cudaMemcpyDeviceToHost, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
 int32_t pdeb200_set(pdeb200_ctx* c, int32_t which, const void* src, size_t bytes) {
     if (!c || !src) return fail(c, PDEB200_EINVAL, "set: null argument");
     cudaSetDevice(c->device);
@@ -642,16 +690,54 @@ int32_t pdeb200_net_set(pdeb200_ctx* c, int32_t net, int32_t n_layers, const int
     }
     for (int l = 0; l <= n_layers; ++l) n.sizes[l] = sizes[l];
     if (total != n.n_params || !n.d_params) {
+        PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
         for (float** p : {&n.d_params, &n.d_m, &n.d_v}) { if (*p) cudaFree(*p); *p = nullptr; }
         PDEB_CUDA(c, cudaMalloc(&n.d_params, total * sizeof(float)));
         PDEB_CUDA(c, cudaMalloc(&n.d_m, total * sizeof(float)));
         PDEB_CUDA(c, cudaMalloc(&n.d_v, total * sizeof(float)));
     }
+    if (!n.d_betap) PDEB_CUDA(c, cudaMalloc(&n.d_betap, 2 * sizeof(double)));
     n.n_layers = n_layers; n.n_params = total;
+    agent_invalidate_graph(c);                      // a captured update graph holds the old pointers / shapes
+    const double bp0[2] = {0.9, 0.999};             // a fresh Flux.ADAM: zero moments, beta powers (beta1, beta2)
     PDEB_CUDA(c, cudaMemcpyAsync(n.d_params, params, total * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     PDEB_CUDA(c, cudaMemsetAsync(n.d_m, 0, total * sizeof(float), c->stream));
     PDEB_CUDA(c, cudaMemsetAsync(n.d_v, 0, total * sizeof(float), c->stream));
-    n.beta_p[0] = 0.9; n.beta_p[1] = 0.999;
+    PDEB_CUDA(c, cudaMemcpyAsync(n.d_betap, bp0, sizeof(bp0), cudaMemcpyHostToDevice, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_net_set_params(pdeb200_ctx* c, int32_t net, const float* params, size_t n_params) {
+    if (!c || net < 0 || net > 3 || !params) return fail(c, PDEB200_EINVAL, "net_set_params: bad argument");
+    HostNet& n = c->nets[net];
+    if (!n.d_params || (size_t)n.n_params != n_params) return fail(c, PDEB200_EINVAL, "net_set_params: network unset or size mismatch");
+    cudaSetDevice(c->device);
+    PDEB_CUDA(c, cudaMemcpyAsync(n.d_params, params, n_params * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_opt_get(pdeb200_ctx* c, int32_t net, float* m, float* v, double* beta_p2, size_t n_params) {
+    if (!c || net < 0 || net > 3) return fail(c, PDEB200_EINVAL, "opt_get: bad argument");
+    HostNet& n = c->nets[net];
+    if (!n.d_params || (size_t)n.n_params != n_params) return fail(c, PDEB200_EINVAL, "opt_get: network unset or size mismatch");
+    cudaSetDevice(c->device);
+    if (m) PDEB_CUDA(c, cudaMemcpyAsync(m, n.d_m, n_params * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (v) PDEB_CUDA(c, cudaMemcpyAsync(v, n.d_v, n_params * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (beta_p2) PDEB_CUDA(c, cudaMemcpyAsync(beta_p2, n.d_betap, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_opt_set(pdeb200_ctx* c, int32_t net, const float* m, const float* v, const double* beta_p2, size_t n_params) {
+    if (!c || net < 0 || net > 3) return fail(c, PDEB200_EINVAL, "opt_set: bad argument");
+    HostNet& n = c->nets[net];
+    if (!n.d_params || (size_t)n.n_params != n_params) return fail(c, PDEB200_EINVAL, "opt_set: network unset or size mismatch");
+    cudaSetDevice(c->device);
+    if (m) PDEB_CUDA(c, cudaMemcpyAsync(n.d_m, m, n_params * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (v) PDEB_CUDA(c, cudaMemcpyAsync(n.d_v, v, n_params * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    if (beta_p2) PDEB_CUDA(c, cudaMemcpyAsync(n.d_betap, beta_p2, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
     return PDEB200_OK;
 }

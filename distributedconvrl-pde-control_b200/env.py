@@ -2,8 +2,8 @@
 
 Same field names, argument meaning and call order as the Julia struct
 (PDEenv.jl:26-62); the four closures `prepare_action` / `do_step` /
-`reward_function` / `featurize` (PDEenv.jl:31-35) are replaced by ONE fused
-sm_100a kernel launch per env step (csrc/*_step.cuh).  The environment batch B
+`reward_function` / `featurize` (PDEenv.jl:31-35) are replaced by the library's
+env step (csrc/: actuation -> PDE core -> observation, three sm_100a launches on one stream).  The environment batch B
 is folded into the actuator (column) axis exactly as SURVEY.md 8b prescribes, so
 every array has the reference's Julia shape with `n_act*B` columns:
 
@@ -133,6 +133,32 @@ class PDEenv:
         L.check(self._lib.pdeb200_get(self._ctx, which, out.ctypes.data, out.nbytes), self._ctx)
         return out
 
+    def get_env(self, which, b):
+        """One environment's slice of a per-environment array (no whole-batch copy)."""
+        n, dt = self._elems(which)
+        out = np.empty(n // self.n_envs, dtype=dt)
+        L.check(self._lib.pdeb200_get_env(self._ctx, which, int(b), out.ctypes.data, out.nbytes), self._ctx)
+        return out
+
+    def y_of(self, b):
+        """env.y of environment b in the reference's shape ((nx,), (2,nx), (2,nx,ny), complex (ny,nx))."""
+        flat = self.get_env(L.ARR_Y, b)
+        saved, self.n_envs = self.n_envs, 1
+        try:
+            return self._y_view(flat)[..., 0]
+        finally:
+            self.n_envs = saved
+
+    def p_of(self, b):
+        flat = self.get_env(L.ARR_P, b)
+        if self.problem == L.NS2D:
+            saved, self.n_envs = self.n_envs, 1
+            try:
+                return self._y_view(flat)[..., 0]
+            finally:
+                self.n_envs = saved
+        return flat
+
     def put(self, which, arr):
         n, dt = self._elems(which)
         a = np.ascontiguousarray(arr, dtype=dt).reshape(-1)
@@ -259,6 +285,16 @@ class PDEenv:
                 raise ValueError("mask must have n_envs entries")
         L.check(self._lib.pdeb200_reset(self._ctx, m.ctypes.data if m is not None else None), self._ctx)
 
+    def reset_diverged(self, sync=True):
+        """Batched termination (PDEenv.jl:226-240 per environment): reset the environments that diverged before the time
+        limit; returns (n_done, n_time_limit, n_diverged) -- or None with sync=False (nothing read back)."""
+        if not sync:
+            L.check(self._lib.pdeb200_reset_diverged(self._ctx, None), self._ctx)
+            return None
+        counts = np.zeros(3, dtype=np.int32)
+        L.check(self._lib.pdeb200_reset_diverged(self._ctx, counts.ctypes.data), self._ctx)
+        return int(counts[0]), int(counts[1]), int(counts[2])
+
     def _action_to_memory(self, action):
         a = np.asarray(action, dtype=self.np_dtype)
         n = self.n_envs * self.n_actuators
@@ -269,7 +305,7 @@ class PDEenv:
         raise ValueError("action must have shape (%d, %d)" % (self.a_rows, n))
 
     def __call__(self, action):
-        """env(action), PDEenv.jl:195-241 -- one fused kernel launch for all environments."""
+        """env(action), PDEenv.jl:195-241 for all environments (three launches, no host synchronisation inside)."""
         a = self._action_to_memory(action)
         L.check(self._lib.pdeb200_step(self._ctx, a.ctypes.data), self._ctx)
 
@@ -307,6 +343,10 @@ class PDEenv:
         ptr = None
         if noise is not None:
             noise = np.ascontiguousarray(noise, dtype=np.float64)
+            n_out = self.n_actuators * self.a_rows if self.cfg.mono else self.a_rows
+            want = self.n_envs * self.n_cols * (n_out - (0 if self.cfg.mono else self.cfg.memory_size))
+            if noise.size != want:
+                raise ValueError("noise must have %d entries ([B][n_cols][na - mem]), got %d" % (want, noise.size))
             ptr = noise.ctypes.data
         L.check(self._lib.pdeb200_policy_act(self._ctx, ptr, float(act_noise), float(act_limit)), self._ctx)
 
@@ -315,7 +355,7 @@ class PDEenv:
                 self._ctx)
 
     def rollout(self, n_steps, act_limit=1.0, reward_sum=False):
-        """n_steps x {actor forward -> env step} in one launch (evaluation loop, src/plotting.jl:55-73)."""
+        """n_steps x {actor forward -> env step} enqueued by one call (evaluation loop, src/plotting.jl:55-73)."""
         out = np.zeros(self.n_envs, dtype=np.float64) if reward_sum else None
         L.check(self._lib.pdeb200_rollout(self._ctx, int(n_steps), float(act_limit),
                                           out.ctypes.data if out is not None else None), self._ctx)

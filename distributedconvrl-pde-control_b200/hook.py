@@ -51,19 +51,20 @@ class PDEhook:
         self.reward += float(r.mean())
         self._ret += r.reshape(env.n_envs, -1).mean(axis=1)
         if self.collect_bestDF:
-            b, na = self.track_env, env.n_actuators
-            y = env.y
+            # only the tracked environment's slices cross PCIe (pdeb200_get_env), not the whole batch
+            from . import _lib as L
+            b = self.track_env
             self.currentDF.append({
-                "timestep": int(env.steps[b]),
-                "action": env.action[:, b * na:(b + 1) * na].reshape(-1).copy(),
-                "p": env.p[..., b].copy(),
-                "y": y[..., b].copy(),
+                "timestep": int(env.get_env(L.ARR_STEPS, b)[0]),
+                "action": env.get_env(L.ARR_ACTION, b).reshape(env.n_actuators, env.a_rows).T.reshape(-1).copy(),
+                "p": env.p_of(b).copy(),
+                "y": env.y_of(b).copy(),
                 "reward": r.reshape(env.n_envs, -1)[b].copy(),
             })
 
     # PostEpisodeStage, PDEhook.jl:65-97
     def post_episode(self, env, policy):
-        finished = bool(np.all(env.time >= env.te))
+        finished = bool(np.any(env.time >= env.te))     # the shared clock ran out (diverged envs were reset on the way)
         if finished and self.ep >= self.min_best_episode:
             self.rewards_compare.append(self.reward)
             if self.collect_NNA and self.reward >= max(self.rewards_compare):
@@ -72,8 +73,7 @@ class PDEhook:
                 if self.collect_bestDF:
                     self.bestDF = list(self.currentDF)
         if not finished:
-            y = env.y
-            if any(self.error_detection(y[..., b]) for b in range(env.n_envs)):
+            if self.error_detection(env.y_of(self.track_env)):
                 self.errored_episodes.append(self.ep)
         if self.collect_history:
             self.history.append(self.currentDF)

@@ -24,7 +24,10 @@
  *   policy loop in plot_heat        src/plotting.jl:55-73   pdeb200_rollout (fused actor + env step, K steps / launch)
  *   trajectory update! overloads   src/PDEagent.jl:237-314 pdeb200_traj_push_pre / _post / _episode_end / _pop_tail
  *   pde_sample / pde_fetch!        src/PDEagent.jl:317-340 pdeb200_sample
- *   update!(policy, batch)         src/PDEagent.jl:363-418 pdeb200_ddpg_grads + pdeb200_ddpg_apply (allreduce between)
+ *   update!(policy, batch)         src/PDEagent.jl:363-418 pdeb200_ddpg_update (gradient exchange over NVLink peer memory inside)
+ *   update!(policy, traj, env, ::PreActStage)  src/PDEagent.jl:342-361  pdeb200_train_updates (update_loops x {sample, update}, one CUDA graph)
+ *   Flux.Optimise.ADAM state / save() / load()  scripts/KS/setup/KSSetup.jl:378-402  pdeb200_opt_get/set, pdeb200_traj_get/set
+ *   (no counterpart: the reference is single-process)       pdeb200_comm_unique_id / pdeb200_comm_init
  *
  * Conventions
  *   - every call returns int32 status: 0 = OK, negative = error; the message is
@@ -53,11 +56,11 @@
 extern "C" {
 #endif
 
-#define PDEB200_ABI_VERSION 1
+#define PDEB200_ABI_VERSION 2
 
 typedef struct pdeb200_ctx pdeb200_ctx;
 
-enum { PDEB200_OK = 0, PDEB200_EINVAL = -1, PDEB200_ECUDA = -2, PDEB200_EUNSUPPORTED = -3, PDEB200_ESTATE = -4 };
+enum { PDEB200_OK = 0, PDEB200_EINVAL = -1, PDEB200_ECUDA = -2, PDEB200_EUNSUPPORTED = -3, PDEB200_ESTATE = -4, PDEB200_ECOMM = -5 };
 enum { PDEB200_F32 = 0, PDEB200_F64 = 1 };
 enum { PDEB200_KS = 0, PDEB200_KSEG1D = 1, PDEB200_NS2D = 2, PDEB200_KSEG2D = 3 };
 enum { PDEB200_CHECK_NONE = 0, PDEB200_CHECK_Y = 1, PDEB200_CHECK_REWARD = 2 };   /* src/PDEenv.jl:226-240 */
@@ -80,7 +83,7 @@ enum {
     PDEB200_ARR_LOSSES = 11,      /* {critic_loss, actor_loss}               float32 */
     PDEB200_ARR_SENSORS = 12,     /* raw sensor dots [B][fields][n_sensors]  dtype   */
     PDEB200_ARR_ACTION_IN = 13,   /* staged action of the last policy_act    dtype   */
-    PDEB200_ARR_STATS = 14        /* batch sums {sum r, sum r^2, ...}        float64[8] (data-parallel r-bar, quirk Q1) */
+    PDEB200_ARR_STATS = 14        /* batch sums over ALL ranks {sum r, sum r^2, n, sum c, sum c^2, sum q(actor)}  float64[8] (quirk Q1 r-bar) */
 };
 
 typedef struct pdeb200_config {
@@ -138,6 +141,12 @@ int32_t pdeb200_set_y0(pdeb200_ctx* ctx, const double* y0, int32_t broadcast);
 /* ---- environment ------------------------------------------------------------------------ */
 /* RLBase.reset!(env) for the masked environments (mask == NULL: all). */
 int32_t pdeb200_reset(pdeb200_ctx* ctx, const uint8_t* mask);
+/* Batched termination.  The reference ends the episode of THE environment that diverged (src/PDEenv.jl:226-240); with B
+ * environments per context the ones whose done flag is set although their clock has not reached te are reset in place
+ * (reset! semantics) while the others keep stepping -- their terminal flag has already been pushed to the replay ring, so
+ * the TD target never bootstraps across the reset.  counts: optional HOST int32[3] = {done, time limit reached, diverged
+ * and reset}; NULL: enqueue and return without synchronising. */
+int32_t pdeb200_reset_diverged(pdeb200_ctx* ctx, int32_t* counts);
 /* env(action): actions is a HOST array [B][n_act][1+mem] of the context dtype.
  * Copies it to the device, runs the fused step, leaves results on the device. */
 int32_t pdeb200_step(pdeb200_ctx* ctx, const void* actions_host);
@@ -149,6 +158,8 @@ int32_t pdeb200_step_device(pdeb200_ctx* ctx, const void* actions_dev);
 int32_t pdeb200_step_host(pdeb200_ctx* ctx, const void* actions_host, void* y_out, void* reward_out,
                           void* state_out, uint8_t* done_out);
 int32_t pdeb200_get(pdeb200_ctx* ctx, int32_t which, void* host_dst, size_t bytes);
+/* One environment's slice of a per-environment array (PDEhook's tracked environment: src/PDEhook.jl:54-62). */
+int32_t pdeb200_get_env(pdeb200_ctx* ctx, int32_t which, int32_t env_index, void* host_dst, size_t bytes);
 int32_t pdeb200_set(pdeb200_ctx* ctx, int32_t which, const void* host_src, size_t bytes);
 int32_t pdeb200_device_ptr(pdeb200_ctx* ctx, int32_t which, void** ptr, size_t* bytes);
 int32_t pdeb200_obs_rows(const pdeb200_ctx* ctx);      /* ns = size(state_space)[1] */
@@ -201,23 +212,74 @@ int32_t pdeb200_set_batch(pdeb200_ctx* ctx, int32_t batch, const float* s, const
                           const uint8_t* t, const float* snext);
 
 /* ---- DDPG update (PDEagent.jl:363-418) -------------------------------------------------- */
-/* Phase 1: target values + critic gradient into ARR_GRADS[0 .. n_critic).
- * literal_q1 = 1 reproduces the reference's (1,B) x (B,) broadcast in the critic loss
- * (SURVEY.md quirk Q1); 0 = per-sample TD target.  global_batch = total columns over all ranks. */
-int32_t pdeb200_ddpg_critic_grads(pdeb200_ctx* ctx, double gamma, int32_t literal_q1, int64_t global_batch);
-/* ADAM step on the behavior critic from ARR_GRADS (after the caller's allreduce). */
-int32_t pdeb200_ddpg_critic_apply(pdeb200_ctx* ctx, double lr);
-/* Phase 2: actor gradient through the UPDATED critic into ARR_GRADS[n_critic ..). */
-int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* ctx, int64_t global_batch);
-/* ADAM on the actor, then Polyak on both targets: dest = p*dest + (1-p)*src. */
-int32_t pdeb200_ddpg_actor_apply(pdeb200_ctx* ctx, double lr, double polyak);
+/* The whole update on the batch staged by pdeb200_sample / pdeb200_set_batch: targets, critic gradient, ADAM on the
+ * critic, actor gradient through the UPDATED critic, ADAM on the actor, Polyak on both targets, losses.
+ * literal_q1 = 1 reproduces the reference's (1,B) x (B,) broadcast in the critic loss; 0 = per-sample
+ * TD target.  Shipped network sizes: two launches; the last CTA of each gradient kernel reduces the per-CTA partials in a
+ * fixed order and applies the optimiser.  After pdeb200_comm_init this call is a COLLECTIVE: that same CTA exchanges
+ * the reduced gradient with every peer GPU over NVLink peer memory (fixed rank-order sum, weights stay bit-identical on
+ * all ranks); gradients and r-bar are means over the GLOBAL batch (sum of the ranks' local batches). */
+int32_t pdeb200_ddpg_update(pdeb200_ctx* ctx, double gamma, double polyak, double lr_actor, double lr_critic,
+                            int32_t literal_q1);
+/* update!(policy, traj, env, ::PreActStage) (PDEagent.jl:342-361): n_updates x { pde_sample(batch) ; update!(batch) } with
+ * device-drawn indices (Philox stream `seed`, counter kept on the device), enqueued as ONE CUDA graph on the context's
+ * stream (captured on first use, replayed afterwards).  Collective after pdeb200_comm_init.  Enqueues and returns. */
+int32_t pdeb200_train_updates(pdeb200_ctx* ctx, int32_t n_updates, int32_t batch, double gamma, double polyak, double lr_actor,
+                              double lr_critic, int32_t literal_q1, uint64_t seed);
 /* Which kernels run the update: 0 = auto (fused shared-memory kernels when the four networks fit, otherwise the
  * layer-wise GEMM path: tcgen05 tensor cores for dense layers, CUDA cores for thin ones); 1 = layer-wise, CUDA cores
  * only; 2 = layer-wise, tensor cores wherever the layout allows; 3 = layer-wise, automatic per-layer choice. */
 int32_t pdeb200_ddpg_set_path(pdeb200_ctx* ctx, int32_t path);
-/* Single-GPU convenience: all four phases back to back. */
-int32_t pdeb200_ddpg_update(pdeb200_ctx* ctx, double gamma, double polyak, double lr_actor, double lr_critic,
-                            int32_t literal_q1);
+/* The four phases separately, for hosts that run their OWN gradient exchange between them (never needed with
+ * pdeb200_comm_init): critic gradient into ARR_GRADS[0 .. n_critic) scaled by 1/global_batch, ADAM on the critic from
+ * ARR_GRADS, actor gradient through the updated critic into ARR_GRADS[n_critic ..), ADAM on the actor + Polyak. */
+int32_t pdeb200_ddpg_critic_grads(pdeb200_ctx* ctx, double gamma, int32_t literal_q1, int64_t global_batch);
+int32_t pdeb200_ddpg_critic_apply(pdeb200_ctx* ctx, double lr);
+int32_t pdeb200_ddpg_actor_grads(pdeb200_ctx* ctx, int64_t global_batch);
+int32_t pdeb200_ddpg_actor_apply(pdeb200_ctx* ctx, double lr, double polyak);
+
+/* ---- checkpoint state (save() / load(), scripts/KS/setup/KSSetup.jl:378-402) ----------------------------------- */
+/* Overwrite the weights only, keeping the optimiser state (Flux.loadparams!, src/custom_nna.jl:26-27);
+ * pdeb200_net_set (re)creates the network and resets ADAM like constructing a fresh Flux.ADAM. */
+int32_t pdeb200_net_set_params(pdeb200_ctx* ctx, int32_t net, const float* params, size_t n_params);
+/* Flux ADAM state of one network: first / second moments (float32, parameter layout) and the running beta powers
+ * `(beta1^t, beta2^t)` (the `(2,)` Float64 arrays of agent.jld2).  Any output pointer may be NULL. */
+int32_t pdeb200_opt_get(pdeb200_ctx* ctx, int32_t net, float* m, float* v, double* beta_p2, size_t n_params);
+int32_t pdeb200_opt_set(pdeb200_ctx* ctx, int32_t net, const float* m, const float* v, const double* beta_p2, size_t n_params);
+/* The replay rings in LOGICAL order (index 0 = oldest column): state [n_sa][ns], action [n_sa][na] (n_sa state/action
+ * columns), reward [n_rt], terminal [n_rt].  traj_info returns the counts and the raw (0-based) ring positions of the
+ * oldest column of the state/action and reward/terminal rings -- RLCore's CircularArrayBuffer `nframes` and `first - 1`
+ * as saved in agent.jld2; get/set copy whole rings (set: n_sa <= capacity+1, n_rt <= capacity; first_* place the oldest
+ * column so that a restored ring keeps writing where the saved one would).  Any output pointer may be NULL. */
+int32_t pdeb200_traj_info(const pdeb200_ctx* ctx, int64_t* capacity, int64_t* n_sa, int64_t* n_rt, int64_t* first_sa,
+                          int64_t* first_rt);
+int32_t pdeb200_traj_get(pdeb200_ctx* ctx, float* state, float* action, float* reward, uint8_t* terminal);
+int32_t pdeb200_traj_set(pdeb200_ctx* ctx, int64_t n_sa, int64_t n_rt, int64_t first_sa, int64_t first_rt, const float* state,
+                         const float* action, const float* reward, const uint8_t* terminal);
+/* Sampler counter of pdeb200_train_updates (device resident; part of a resumable checkpoint). */
+int32_t pdeb200_rng_get(pdeb200_ctx* ctx, uint64_t* offset);
+int32_t pdeb200_rng_set(pdeb200_ctx* ctx, uint64_t offset);
+/* The batch staged by the last pdeb200_sample / pdeb200_set_batch (host float32 / uint8 / int64 outputs, any may be NULL):
+ * what pde_fetch! returns (PDEagent.jl:322-340). */
+int32_t pdeb200_get_batch(pdeb200_ctx* ctx, float* s, float* a, float* r, uint8_t* t, float* snext, int64_t* inds);
+
+/* ---- multi-GPU (the reference itself is single-process) ----------------------------------- */
+/* One process (or host thread) per GPU, environments sharded by batch index, ONE exchange per DDPG phase.
+ * Rank 0 calls pdeb200_comm_unique_id and distributes the 128 bytes by any host-side means (MPI, a file, a socket,
+ * torch.distributed); every rank then calls pdeb200_comm_init(ctx, id, rank, nranks) -- a collective that (1) joins an
+ * NCCL communicator (bootstrap + fallback transport) and (2) maps every peer's exchange buffer through CUDA IPC so that
+ * the gradient kernels exchange over NVLink / NVSwitch peer memory themselves (transport PDEB200_COMM_PEER).  If peer
+ * mapping is impossible the update falls back to ncclAllReduce between its phases (PDEB200_COMM_NCCL);
+ * PDEB200_COMM_TRANSPORT=nccl|peer forces one.  From then on pdeb200_sample, pdeb200_set_batch, pdeb200_ddpg_update and
+ * pdeb200_train_updates must be called by all ranks in the same order. */
+#define PDEB200_UNIQUE_ID_BYTES 128
+enum { PDEB200_COMM_NONE = 0, PDEB200_COMM_NCCL = 1, PDEB200_COMM_PEER = 2 };
+int32_t pdeb200_comm_unique_id(uint8_t* id128);
+int32_t pdeb200_comm_init(pdeb200_ctx* ctx, const uint8_t* id128, int32_t rank, int32_t nranks);
+int32_t pdeb200_comm_destroy(pdeb200_ctx* ctx);
+int32_t pdeb200_comm_info(const pdeb200_ctx* ctx, int32_t* rank, int32_t* nranks, int32_t* transport);
+/* In-place sum over all ranks of n <= 64 host doubles (episode returns, done counts for PDEhook; NCCL on the stream). */
+int32_t pdeb200_comm_allreduce_f64(pdeb200_ctx* ctx, double* host_inout, int32_t n);
 
 /* ---- introspection ---------------------------------------------------------------------- */
 /* Kernel launches issued by this context since creation (bench.py's gpu_launches). */

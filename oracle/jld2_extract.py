@@ -95,20 +95,39 @@ def main():
     y0 = [a for _, a in numeric_arrays(REF / "scripts/KS/KS22_global-agent/y0.jld2")]
     np.savez_compressed(OUT / "ks22_global_y0.npz", y0=y0[0])
     print("y0", y0[0].shape)
-    # KS agent.jld2: the four networks + ADAM moments (small) and a slice of the replay buffer
-    for tag in ("KS22", "KS200"):
-        arrs = numeric_arrays(REF / f"scripts/KS/{tag}/saves/agent.jld2")
-        small = {}
-        big = {}
-        for n, (off, a) in enumerate(arrs):
-            if a.size <= 4096:
-                small["a%03d" % n] = a
-            else:
-                big["a%03d" % n] = a
-        shapes = {k: (v.shape, str(v.dtype)) for k, v in {**small, **big}.items()}
-        print(tag, "agent arrays:", shapes)
-        sl = {k + "_head": v.reshape(v.shape[0] if v.ndim > 1 else 1, -1)[..., :4096] for k, v in big.items()}
-        np.savez_compressed(OUT / f"{tag.lower()}_agent.npz", **small, **sl)
+    # KS agent.jld2 (written by save(), KSSetup.jl:378-402): the four networks, the ADAM state of the behavior networks and
+    # WINDOWS of the replay rings in logical order (oldest column first) together with the rings' raw positions
+    # (CircularArrayBuffer.first / nframes as stored in the file).  KS22 never wrapped (52 224 of 150 000 columns); KS200
+    # wrapped 3.48 times (522 240 columns pushed), which is what pins the capacity+1 / capacity ring layout.
+    for tag, n_act in (("KS22", 8), ("KS200", 80)):
+        d = _ckpt.load_agent_jld2(REF / f"scripts/KS/{tag}/saves/agent.jld2")
+        rp = d["replay"]
+        n_sa, n_rt = rp["state"].shape[1], rp["reward"].shape[0]
+        cap = rp["capacity"]
+        wins = [(0, 4096)]
+        if n_rt == cap:                                           # wrapped: the raw wrap point of both rings, and the newest columns
+            k_wrap = cap - rp["first_rt"]
+            wins += [(k_wrap - 1024, k_wrap + 1024), (n_rt - 2048, n_rt)]
+        else:
+            wins += [(n_rt - 2048, n_rt)]
+        fx = {"n_act": np.int64(n_act), "capacity": np.int64(cap), "n_sa": np.int64(n_sa), "n_rt": np.int64(n_rt),
+              "first_sa": np.int64(rp["first_sa"]), "first_rt": np.int64(rp["first_rt"]),
+              "episodes": np.int64(128), "steps_per_episode": np.int64(51),
+              "windows": np.asarray(wins, dtype=np.int64),
+              "terminal_sum": np.int64(rp["terminal"].sum())}
+        for w, (lo, hi) in enumerate(wins):
+            hi_sa = min(n_sa, hi + 3 * n_act)                     # state/action columns a fetch at ind < hi can touch
+            fx["w%d_state" % w] = rp["state"][:, lo:hi_sa]
+            fx["w%d_action" % w] = rp["action"][:, lo:hi_sa]
+            fx["w%d_reward" % w] = rp["reward"][lo:hi]
+            fx["w%d_terminal" % w] = rp["terminal"][lo:hi]
+        for name, chain in d["nets"].items():
+            fx["net_" + name] = chain.flat()
+            fx["sizes_" + name] = np.asarray(chain.sizes, dtype=np.int64)
+        for name, (m, v, bp) in d["opt"].items():
+            fx["opt_m_" + name], fx["opt_v_" + name], fx["opt_betap_" + name] = m, v, bp
+        np.savez_compressed(OUT / f"{tag.lower()}_agent.npz", **fx)
+        print(tag, "agent:", {k: (np.shape(v)) for k, v in fx.items()})
 
 
 if __name__ == "__main__":

@@ -84,7 +84,7 @@ def test_replay_ring_matches_oracle_including_wrap(pkg):
     s, a, r, t, s2 = tr.fetch(inds, ncols)
     # read the sampled batch back through a critic-gradient call is indirect; compare via a probe update instead:
     ref = AO.DDPG(actor.copy(), critic.copy())
-    pol.update(local_batch=64)
+    pol.update()
     gc, ga = ref.update(s, a, r, t.astype(bool), s2, True)
     assert relerr(pol.grads(), np.concatenate([AO.flat_grads(gc), AO.flat_grads(ga)])) < 2e-5
     env.close()
@@ -155,4 +155,147 @@ def test_layerwise_ddpg_update_matches_oracle(pkg, shape, path, literal):
         ls = pol.losses
         assert abs(ls["critic_loss"] - float(ref.critic_loss)) < 1e-4 * max(1.0, abs(float(ref.critic_loss)))
         assert abs(ls["actor_loss"] - float(ref.actor_loss)) < 1e-4 * max(1.0, abs(float(ref.actor_loss)))
+    env.close()
+
+
+def test_train_updates_graph_equals_the_same_updates_one_by_one_and_the_oracle(pkg):
+    """pdeb200_train_updates = update_loops x {pde_sample; update!} (PDEagent.jl:357-360) as one CUDA graph with every
+    changing quantity (ring positions, Philox counter, ADAM beta powers) on the device: must equal, bit for bit, the same
+    updates issued one by one with explicit counters -- and the oracle on the batches the device sampled."""
+    rng = np.random.default_rng(21)
+    setup = pkg.setups.KSSetup.ks22(window_size=3)
+    actor, critic = make_nets(rng, 3, 1, 6, 140, False)
+    env_g, pol_g = make_policy(pkg, setup, actor, critic, B=2, trajectory_length=2000, batch_size=96, seed=9)
+    env_1, pol_1 = make_policy(pkg, setup, actor, critic, B=2, trajectory_length=2000, batch_size=96, seed=9)
+    ref = AO.DDPG(actor.copy(), critic.copy())
+    ncols = 16
+    n_rt = 50 * ncols
+    st = rng.normal(0, 0.4, (3, n_rt + ncols)).astype(np.float32)
+    ac = rng.uniform(-1, 1, (1, n_rt + ncols)).astype(np.float32)
+    rw = (-np.abs(rng.normal(0, 0.3, n_rt))).astype(np.float32)
+    tm = rng.random(n_rt) < 0.05
+    for pol in (pol_g, pol_1):
+        pol.trajectory.set(st, ac, rw, tm, first_sa=1234, first_rt=77)        # rings that wrap physically
+    pol_g.update_loops, pol_g.update_after = 5, 1
+    L = pkg.lib
+    for call in range(3):
+        l0 = env_g.launch_count
+        assert pol_g.maybe_update() == 5
+        assert env_g.launch_count - l0 == 15 + (1 if call == 0 else 0)        # 5 x {fetch, critic, actor} (+ ring sync once)
+        for k in range(5):
+            off = (call * 5 + k) * 96
+            L.check(env_1._lib.pdeb200_sample(env_1._ctx, 96, None, 9 ^ 0x5DEECE66D, off), env_1._ctx)
+            pol_1._staged_batch = 96
+            s, a, r, t, s2, inds = pol_1.get_batch()
+            assert np.array_equal(s, st[:, inds]) and np.array_equal(s2, st[:, inds + ncols]) and np.array_equal(r, rw[inds])
+            pol_1.update()
+            ref.update(s, a, r, t, s2, True)
+        wg = np.concatenate([n.sync_from_device().flat() for n in (pol_g.behavior_critic, pol_g.behavior_actor, pol_g.target_critic, pol_g.target_actor)])
+        w1 = np.concatenate([n.sync_from_device().flat() for n in (pol_1.behavior_critic, pol_1.behavior_actor, pol_1.target_critic, pol_1.target_actor)])
+        assert np.array_equal(wg, w1), call
+        want = np.concatenate([n.flat() for n in (ref.C, ref.A, ref.Ct, ref.At)])
+        assert relerr(wg, want) < 5e-5, (call, relerr(wg, want))
+    assert pol_g.sampler_offset() == 15 * 96
+    for a, b in zip(pol_g.behavior_critic.opt_state(), pol_1.behavior_critic.opt_state()):
+        assert np.array_equal(a, b)
+    env_g.close(); env_1.close()
+
+
+def test_full_training_sequence_matches_oracle_trajectory_and_ddpg(pkg):
+    """rollout -> push -> sample(inds) -> update over 3 episodes with a ring that wraps: every fetched batch bit-exact vs the
+    oracle `Trajectory`, weights vs the oracle `DDPG` after every update (PDEagent.jl:237-418 as one sequence)."""
+    rng = np.random.default_rng(33)
+    setup = pkg.setups.KSSetup.ks22(te=0.8)                            # 9 steps per episode (quirk Q7)
+    actor, critic = make_nets(rng, 1, 1, 6, 140)
+    B = 2
+    ncols = B * 8
+    cap = 14 * ncols + 5                                               # < 3 episodes x 9 steps: wraps
+    env, pol = make_policy(pkg, setup, actor, critic, B=B, trajectory_length=cap, start_steps=-1, batch_size=48)
+    env.set_y0(setup.generate_random_init(rng, B).T)
+    tr = AO.Trajectory(cap, 1, 1)
+    ref = AO.DDPG(actor.copy(), critic.copy())
+    L = pkg.lib
+    n_upd = 0
+    for ep in range(3):
+        env.reset()
+        pol.trajectory.pre_episode(); tr.pre_episode(ncols)
+        for step in range(9):
+            noise = rng.normal(size=(ncols,))
+            env.policy_act(noise, 0.3, 1.0)                            # actor + host-supplied exploration noise
+            a = env.get(L.ARR_ACTION_IN).reshape(1, ncols)
+            st = env.state.astype(np.float32)
+            want_a = np.clip(ref.A.forward(st)[0].astype(np.float64) + noise * 0.3, -1, 1)
+            assert np.allclose(a[0], want_a, rtol=1e-5, atol=1e-6)     # policy forward on the CURRENT (updated) weights
+            pol.trajectory.pre_act(); tr.pre_act(st, a.astype(np.float32))
+            if len(tr) > 2 * ncols:
+                inds = rng.integers(0, len(tr) - ncols, 48)
+                pol.sample(inds)
+                s, aa, r, t, s2, _ = pol.get_batch()
+                fs, fa, fr, ft, fs2 = tr.fetch(inds, ncols)
+                assert np.array_equal(s, fs) and np.array_equal(aa, fa) and np.array_equal(r, fr) and np.array_equal(t, ft) and np.array_equal(s2, fs2)
+                pol.update()
+                ref.update(fs, fa, fr, ft, fs2, True)
+                n_upd += 1
+                for dev, orc in ((pol.behavior_critic, ref.C), (pol.behavior_actor, ref.A)):
+                    assert relerr(dev.sync_from_device().flat(), orc.flat()) < 1e-4, (ep, step)
+            env.step_device(); env.synchronize()
+            done = bool(env.done[0])
+            pol.trajectory.post_act(); tr.post_act(env.reward.astype(np.float32), done)
+            assert done == (step == 8)
+        pol.trajectory.post_episode(); tr.post_episode(env.state.astype(np.float32), 1)
+        assert len(pol.trajectory) == len(tr)
+        _, n_sa, n_rt, first_sa, first_rt = pol.trajectory.positions()
+        assert (first_sa, n_sa, first_rt, n_rt) == (tr.state.start, tr.state.len, tr.reward.start, tr.reward.len)
+    assert n_upd > 20 and tr.reward.len == cap                         # the ring did wrap
+    s_all, a_all, r_all, t_all = pol.trajectory.get()
+    idx = np.arange(tr.reward.len)
+    assert np.array_equal(r_all, tr.reward.get(idx)[0]) and np.array_equal(s_all, tr.state.get(np.arange(tr.state.len)))
+    env.close()
+
+
+def test_update_when_only_the_actor_phase_exceeds_shared_memory(pkg):
+    """ADVICE r1: critic phase fits the fused kernels, actor phase does not -> ONE decision for both phases (layer-wise path);
+    the actor and its target must still be updated."""
+    rng = np.random.default_rng(17)
+    ns = 3
+    setup = pkg.setups.KSSetup.ks22(window_size=3)
+    F = np.float32
+    g = lambda o, i: ((rng.random((o, i), dtype=F) - F(0.5)) * F(np.sqrt(24.0 / (o + i)))).astype(F)
+    actor = AO.Net([(g(64, ns), np.zeros(64, F), "relu"), (g(64, 64), np.zeros(64, F), "relu"), (g(1, 64), np.zeros(1, F), "tanh")])
+    critic = AO.Net([(g(500, ns + 1), np.zeros(500, F), "relu"), (g(1, 500), np.zeros(1, F), None)])
+    env, pol = make_policy(pkg, setup, actor, critic)
+    ref = AO.DDPG(actor.copy(), critic.copy())
+    a0 = pol.behavior_actor.sync_from_device().flat().copy()
+    for it in range(2):
+        s, a, r, t, s2 = batch(rng, ns, 1, 200)
+        pol.set_batch(s, a, r, t, s2)
+        pol.update()
+        ref.update(s, a, r, t, s2, True)
+        for dev, orc in ((pol.behavior_critic, ref.C), (pol.behavior_actor, ref.A), (pol.target_critic, ref.Ct), (pol.target_actor, ref.At)):
+            assert relerr(dev.sync_from_device().flat(), orc.flat()) < 2e-4
+    assert not np.array_equal(a0, pol.behavior_actor.sync_from_device().flat())
+    env.close()
+
+
+def test_diverged_environment_ends_only_its_own_episode(pkg):
+    """PDEenv.jl:226-237 ends the episode of the environment whose |y| exceeds max_value.  Batched: that environment's
+    terminal flag is pushed, it is reset in place, the others keep stepping to the time limit; no non-finite column ever
+    reaches the replay ring."""
+    rng = np.random.default_rng(2)
+    setup = pkg.setups.KSSetup.ks22()
+    B = 4
+    y0 = setup.generate_random_init(rng, B)
+    y0[2] *= 8.0                                                       # max|y| = 46 > max_value after one step: diverges at once, every time
+    env = setup.make_env(n_envs=B, dtype="f64", y0=y0)
+    pol = pkg.agent.create_agent(env, rng=rng, nna_scale=0.6, nna_scale_critic=7.0, drop_middle_layer=True, batch_size=64,
+                                 start_steps=2, update_after=3, update_loops=2, trajectory_length=10_000)
+    n = pkg.agent.run_episode(pol, env)
+    assert n == 51                                                     # the healthy environments reach te = 5 (quirk Q7)
+    assert pkg.agent.run_episode.last_diverged == 50                   # env 2: every step but the last (time limit wins there)
+    s, a, r, t = pol.trajectory.get()
+    assert np.all(np.isfinite(s)) and np.all(np.isfinite(r))
+    t = t.reshape(51, B, 8)
+    assert t[:50, 2].all() and not t[:50, [0, 1, 3]].any() and t[50].all()
+    w = pol.behavior_actor.sync_from_device().flat()
+    assert np.all(np.isfinite(w))
     env.close()

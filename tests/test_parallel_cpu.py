@@ -30,6 +30,10 @@ def _worker(rank, world, port, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     par = importlib.import_module("distributedconvrl-pde-control_b200.parallel")
     comm = par.Comm(dist)
+    # the host channel that carries pdeb200_comm_unique_id's 128 bytes from rank 0 to everyone (parallel.Comm.attach)
+    uid = bytes(range(128)) if rank == 0 else b""
+    got = comm.broadcast_bytes(uid, 128, src=0)
+    assert got == bytes(range(128)), "unique-id broadcast over the host channel"
     rng = np.random.default_rng(0)                      # same nets + global batch on both ranks
     A, Cn = make_nets(rng, 1, 1, 6, 140)
     Bg = 12
