@@ -1277,8 +1277,8 @@ int32_t plan_update(pdeb200_ctx* c, Plan* P) {
     P->tpb_a = block_threads(P->wmax, A.n_params);
     if ((rc = ensure_partials(c, P->n_blocks, std::max(C.n_params, A.n_params)))) return rc;
     if (P->fused) {
-        PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_critic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_c));
-        PDEB_CUDA(c, cudaFuncSetAttribute(ddpg_actor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P->smem_a));
+        PDEB_CUDA(c, ensure_dyn_smem(ddpg_critic_kernel, P->smem_c, c->device));
+        PDEB_CUDA(c, ensure_dyn_smem(ddpg_actor_kernel, P->smem_a, c->device));
     }
     return PDEB200_OK;
 }

@@ -4,7 +4,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <map>
+#include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/pdeb200.h"
@@ -102,6 +105,22 @@ inline int32_t fail(const pdeb200_ctx* c, int32_t code, const std::string& msg) 
         if (e__ != cudaSuccess)                                                                      \
             return pdeb200::fail(ctx, PDEB200_ECUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
     } while (0)
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is ONE value per (kernel, device) for the whole process.  Contexts driven
+// from different host threads (bench.py's e2e shards, one-thread-per-GPU hosts) share it, so it is only ever RAISED, under
+// a lock: a per-thread cache (round 1) let a thread with a smaller batch lower it under another thread's larger launch.
+template <typename K>
+inline cudaError_t ensure_dyn_smem(K kernel, size_t bytes, int device) {
+    static std::mutex mu;
+    static std::map<std::pair<const void*, int>, size_t> have;
+    if (bytes <= 48 * 1024) return cudaSuccess;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = have[{(const void*)kernel, device}];
+    if (bytes <= cur) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) cur = bytes;
+    return e;
+}
 
 template <typename T> struct DT;
 template <> struct DT<float>  { static constexpr int id = PDEB200_F32; };

@@ -168,11 +168,7 @@ int32_t launch(pdeb200_ctx* c) {
     const int grid = (n_pairs + PAIRS - 1) / PAIRS;
     const size_t smem = ks_smem_bytes<T, N1, N2>(PAIRS);
     auto kern = ks_step_kernel<T, N1, N2>;
-    static thread_local size_t configured[64] = {0};
-    if (smem > configured[c->device & 63]) {
-        PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[c->device & 63] = smem;
-    }
+    PDEB_CUDA(c, ensure_dyn_smem(kern, smem, c->device));
     kern<<<grid, warps * 32, smem, c->stream>>>(A);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;

@@ -129,8 +129,7 @@ int32_t launch(pdeb200_ctx* c) {
     const int tpb = ((E * g.nx + 31) / 32) * 32;
     const size_t smem = (size_t)2 * E * g.nx * 2 * sizeof(T);
     auto kern = tpb <= 512 ? kseg_step_kernel<T, 512> : kseg_step_kernel<T, 1024>;
-    if (smem > 48 * 1024)
-        PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDEB_CUDA(c, ensure_dyn_smem(kern, smem, c->device));
     kern<<<(g.n_envs + E - 1) / E, tpb, smem, c->stream>>>(A);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;

@@ -184,7 +184,7 @@ int32_t launch(pdeb200_ctx* c) {
     const size_t smem = (size_t)2 * (A.rows + 2) * g.nx * 2 * sizeof(T);
     const bool full = g.nx == kTX && g.ny == kCS * kStrips * kR;
     auto kern = full ? kseg2d_step_kernel<T, true> : kseg2d_step_kernel<T, false>;
-    PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDEB_CUDA(c, ensure_dyn_smem(kern, smem, c->device));
     PDEB_CUDA(c, cudaMemsetAsync(c->vmax, 0, (size_t)g.n_envs * sizeof(T), c->stream));
     kern<<<g.n_envs * kCS, kTX * kStrips, smem, c->stream>>>(A);
     PDEB_CUDA(c, cudaGetLastError());

@@ -135,11 +135,7 @@ int sm_count(const pdeb200_ctx* c) {
 
 template <bool T, bool B>
 int32_t configure_tc(pdeb200_ctx* c) {
-    static thread_local bool done = false;
-    if (!done) {
-        PDEB_CUDA(c, cudaFuncSetAttribute(tc::dense_tc_kernel<T, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-        done = true;
-    }
+    PDEB_CUDA(c, ensure_dyn_smem(tc::dense_tc_kernel<T, B>, (size_t)tc::SMEM_BYTES, c->device));
     return PDEB200_OK;
 }
 

@@ -534,7 +534,7 @@ size_t smem_c(int N) {
 template <typename K>
 int32_t set_smem(pdeb200_ctx* c, K kern, size_t bytes) {
     if (bytes > 227 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "NS: shared-memory budget exceeded");
-    PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    PDEB_CUDA(c, ensure_dyn_smem(kern, bytes, c->device));
     return PDEB200_OK;
 }
 

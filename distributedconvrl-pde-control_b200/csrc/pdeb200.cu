@@ -254,8 +254,7 @@ int32_t actuate_t(pdeb200_ctx* c, const void* actions_dev, int use_actor, double
                (mode == -1 ? (size_t)2 * A.actor_wmax * tpb * sizeof(float) : 0);
     }
     if (smem > 200 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "actuate: actor too large for shared memory");
-    if (smem > 48 * 1024)
-        PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PDEB_CUDA(c, ensure_dyn_smem(kern, smem, c->device));
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
     const int groups = (c->cfg.n_envs + E - 1) / E;
@@ -780,12 +779,12 @@ static int32_t policy_launch(pdeb200_ctx* c, const void* d_noise, int use_rng, u
     const int mode = (two && a.sizes[0] == 1) ? 1 : (two && a.sizes[0] == 3) ? 3 : -1;
     if (c->cfg.dtype == PDEB200_F64) {
         auto kern = mode == 1 ? policy_kernel<double, 1, 6> : mode == 3 ? policy_kernel<double, 3, 6> : policy_kernel<double, -1, 0>;
-        if (smem > 48 * 1024) PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PDEB_CUDA(c, ensure_dyn_smem(kern, smem, c->device));
         kern<<<grid, tpb, smem, c->stream>>>(a.dev(), a.n_params, wmax, ncol, c->obs_rows, c->a_rows, mem, (const double*)c->state,
                                             (double*)c->action_in, (const double*)d_noise, use_rng, seed, offset, act_noise, act_limit);
     } else {
         auto kern = mode == 1 ? policy_kernel<float, 1, 6> : mode == 3 ? policy_kernel<float, 3, 6> : policy_kernel<float, -1, 0>;
-        if (smem > 48 * 1024) PDEB_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PDEB_CUDA(c, ensure_dyn_smem(kern, smem, c->device));
         kern<<<grid, tpb, smem, c->stream>>>(a.dev(), a.n_params, wmax, ncol, c->obs_rows, c->a_rows, mem, (const float*)c->state,
                                             (float*)c->action_in, (const float*)d_noise, use_rng, seed, offset, (float)act_noise,
                                             (float)act_limit);

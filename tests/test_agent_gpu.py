@@ -291,7 +291,7 @@ def test_diverged_environment_ends_only_its_own_episode(pkg):
                                  start_steps=2, update_after=3, update_loops=2, trajectory_length=10_000)
     n = pkg.agent.run_episode(pol, env)
     assert n == 51                                                     # the healthy environments reach te = 5 (quirk Q7)
-    assert pkg.agent.run_episode.last_diverged == 50                   # env 2: every step but the last (time limit wins there)
+    assert pkg.agent.run_episode.last_diverged == 51                   # env 2 every step: its clock restarts with each reset
     s, a, r, t = pol.trajectory.get()
     assert np.all(np.isfinite(s)) and np.all(np.isfinite(r))
     t = t.reshape(51, B, 8)
