@@ -506,6 +506,13 @@ __device__ __forceinline__ double ordered_sum_cg(const float* partials, int n_bl
 #pragma unroll
         for (int u = 0; u < 32; ++u) s += (double)v[u];
     }
+    for (; b + 8 <= n_blocks; b += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(partials + (size_t)(b + u) * stride + q);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += (double)v[u];
+    }
     for (; b < n_blocks; ++b) s += (double)__ldcg(partials + (size_t)b * stride + q);
     return s;
 }
@@ -559,6 +566,8 @@ __device__ void fused_tail(const DdpgArgs& D) {
     __syncthreads();
     if (threadIdx.x == 0) { D.betap[0] = bp1 * D.b1; D.betap[1] = bp2 * D.b2; *D.ticket = 0; }
 }
+
+#include "ddpg_fast.cuh"
 
 // grads[q] = sum over CTAs (fixed order); tail sums go to stats
 __global__ void reduce_partials_kernel(int n_blocks, int n_acc, const float* __restrict__ partials, float* grads,
@@ -1259,7 +1268,80 @@ struct Plan {
     bool fused = false;
     size_t smem_c = 0, smem_a = 0;
     int tpb_c = 0, tpb_a = 0, n_blocks = 0, wmax = 0;
+    // register-resident kernels for the shipped two-layer shapes (ddpg_fast.cuh)
+    bool fast = false;
+    int f_ns = 0, f_cfg = 0, f_warps = 0, f_grid = 0, f_nx_c = 0, f_nx_a = 0;
+    size_t f_smem_c = 0, f_smem_a = 0;
 };
+
+template <int NS, int UPLC, int WC>
+int32_t fast_configure(pdeb200_ctx* c, Plan* P) {
+    using Geo = FastGeom<NS, UPLC, WC>;
+    P->f_smem_c = Geo::smem_bytes(P->f_warps, P->f_nx_c);
+    P->f_smem_a = Geo::smem_bytes(P->f_warps, P->f_nx_a);
+    if (P->f_smem_c > 220 * 1024) { P->fast = false; return PDEB200_OK; }
+    PDEB_CUDA(c, ensure_dyn_smem(ddpg_fast_critic_kernel<NS, UPLC, WC>, P->f_smem_c, c->device));
+    PDEB_CUDA(c, ensure_dyn_smem(ddpg_fast_actor_kernel<NS, UPLC, WC>, P->f_smem_a, c->device));
+    return PDEB200_OK;
+}
+
+template <int NS, int UPLC, int WC>
+void fast_launch_t(pdeb200_ctx* c, const Plan& P, const FastArgs& Fc, const FastArgs& Fa) {
+    ddpg_fast_critic_kernel<NS, UPLC, WC><<<P.f_grid, P.f_warps * 32, P.f_smem_c, c->stream>>>(Fc);
+    ddpg_fast_actor_kernel<NS, UPLC, WC><<<P.f_grid, P.f_warps * 32, P.f_smem_a, c->stream>>>(Fa);
+}
+
+#define PDEB_FAST_DISPATCH(P, CALL)                                                     \
+    do {                                                                               \
+        if ((P).f_cfg == 0) {                                                          \
+            switch ((P).f_ns) {                                                        \
+                case 1: CALL(1, 5, 1); break;                                          \
+                case 3: CALL(3, 5, 1); break;                                          \
+            }                                                                          \
+        } else {                                                                       \
+            switch ((P).f_ns) {                                                        \
+                case 1: CALL(1, 3, 4); break;                                          \
+                case 3: CALL(3, 3, 4); break;                                          \
+                case 9: CALL(9, 3, 4); break;                                          \
+                case 12: CALL(12, 3, 4); break;                                        \
+            }                                                                          \
+        }                                                                              \
+    } while (0)
+
+// two-layer relu networks with one action row in one of the compiled shapes?
+int32_t plan_fast(pdeb200_ctx* c, Plan* P) {
+    Agent* a = ag(c);
+    static const bool off = [] { const char* e = getenv("PDEB200_DDPG_FAST"); return e && atoi(e) == 0; }();
+    static const int env_warps = [] { const char* e = getenv("PDEB200_DDPG_WARPS"); return e ? atoi(e) : 0; }();
+    const HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+    const HostNet &At = c->nets[PDEB200_NET_TARGET_ACTOR], &Ct = c->nets[PDEB200_NET_TARGET_CRITIC];
+    P->fast = false;
+    if (off || a->force_wide || a->na != 1 || A.n_layers != 2 || C.n_layers != 2 || At.n_layers != 2 || Ct.n_layers != 2) return PDEB200_OK;
+    const int ns = A.sizes[0], ha = A.sizes[1], hc = C.sizes[1];
+    if (!(ns == 1 || ns == 3 || ns == 9 || ns == 12) || ha > 32 || hc > 384) return PDEB200_OK;
+    if (A.acts[0] != PDEB200_ACT_RELU || C.acts[0] != PDEB200_ACT_RELU || C.acts[1] != PDEB200_ACT_IDENTITY) return PDEB200_OK;
+    for (int l = 0; l <= 2; ++l)
+        if (At.sizes[l] != A.sizes[l] || Ct.sizes[l] != C.sizes[l]) return PDEB200_OK;
+    if (At.acts[0] != A.acts[0] || At.acts[1] != A.acts[1] || Ct.acts[0] != C.acts[0] || Ct.acts[1] != C.acts[1]) return PDEB200_OK;
+    P->fast = true;
+    P->f_ns = ns;
+    P->f_cfg = (hc <= 160 && ns <= 3) ? 0 : 1;      // (UPL 5, 1 warp per tile) or (UPL 3, 4 warps per tile: hc <= 384, wide inputs)
+    const int wc = P->f_cfg == 0 ? 1 : 4;
+    P->f_warps = env_warps > 0 ? std::max(wc, env_warps / wc * wc) : 8;
+    P->f_warps = std::min(P->f_warps, 8);
+    const int teams = P->f_warps / wc;
+    const int n_tiles = (a->batch + 31) / 32;
+    P->f_grid = std::max(1, std::min((n_tiles + teams - 1) / teams, 148));
+    P->f_nx_c = 2 * C.n_params + kXTail;
+    P->f_nx_a = A.n_params + kXTail;
+    if (comm_nranks(c) > 1 && P->f_nx_c > comm_cap(c)) { P->fast = false; return PDEB200_OK; }
+    int32_t rc = ensure_partials(c, P->f_grid, P->f_nx_c - 2);
+    if (rc) return rc;
+#define PDEB_CFG(NS_, U_, W_) rc = fast_configure<NS_, U_, W_>(c, P)
+    PDEB_FAST_DISPATCH(*P, PDEB_CFG);
+#undef PDEB_CFG
+    return rc;
+}
 
 int32_t plan_update(pdeb200_ctx* c, Plan* P) {
     Agent* a = ag(c);
@@ -1280,10 +1362,40 @@ int32_t plan_update(pdeb200_ctx* c, Plan* P) {
         PDEB_CUDA(c, ensure_dyn_smem(ddpg_critic_kernel, P->smem_c, c->device));
         PDEB_CUDA(c, ensure_dyn_smem(ddpg_actor_kernel, P->smem_a, c->device));
     }
-    return PDEB200_OK;
+    return plan_fast(c, P);
 }
 
 struct Hyper { double gamma, polyak, lr_a, lr_c; int literal; };
+
+// One update with the register-resident kernels: two launches.  fetch = 1: the critic kernel draws and gathers the batch
+// itself from the rings (device-resident ring positions and Philox counter).
+int32_t fast_update_launch(pdeb200_ctx* c, const Plan& P, const Hyper& H, int fetch, uint64_t seed) {
+    Agent* a = ag(c);
+    HostNet &A = c->nets[PDEB200_NET_BEHAVIOR_ACTOR], &C = c->nets[PDEB200_NET_BEHAVIOR_CRITIC];
+    HostNet &At = c->nets[PDEB200_NET_TARGET_ACTOR], &Ct = c->nets[PDEB200_NET_TARGET_CRITIC];
+    FastArgs F;
+    F.pA = A.d_params; F.pC = C.d_params; F.pAt = At.d_params; F.pCt = Ct.d_params;
+    F.ns = A.sizes[0]; F.ha = A.sizes[1]; F.hc = C.sizes[1]; F.actA2 = A.acts[1];
+    F.nA = A.n_params; F.nC = C.n_params; F.batch = a->batch;
+    F.bs = a->bs; F.ba = a->ba; F.br = a->br; F.bs2 = a->bs2; F.bt = a->bt; F.inds = a->inds;
+    F.fetch = fetch; F.seed = seed; F.dev = a->dev; F.ncols = a->ncols;
+    F.rstate = a->state; F.raction = a->action; F.rreward = a->reward; F.rterminal = a->terminal;
+    F.gamma = (float)H.gamma; F.literal = H.literal;
+    F.partials = a->partials; F.xbuf = a->xbuf; F.stats = a->stats; F.losses = c->d_losses;
+    F.b1 = 0.9; F.b2 = 0.999; F.eps = 1e-8; F.polyak = (float)H.polyak;
+    F.cm = comm_dev(c);
+    FastArgs Fc = F, Fa = F;
+    Fc.n_x = P.f_nx_c; Fc.ticket = a->tickets + 1; Fc.grads = c->d_grads;
+    Fc.x = C.d_params; Fc.m = C.d_m; Fc.v = C.d_v; Fc.target = Ct.d_params; Fc.betap = C.d_betap; Fc.eta = H.lr_c;
+    Fa.n_x = P.f_nx_a; Fa.ticket = a->tickets + 2; Fa.grads = c->d_grads + C.n_params; Fa.fetch = 0;
+    Fa.x = A.d_params; Fa.m = A.d_m; Fa.v = A.d_v; Fa.target = At.d_params; Fa.betap = A.d_betap; Fa.eta = H.lr_a;
+#define PDEB_LAUNCH(NS_, U_, W_) fast_launch_t<NS_, U_, W_>(c, P, Fc, Fa)
+    PDEB_FAST_DISPATCH(P, PDEB_LAUNCH);
+#undef PDEB_LAUNCH
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    return PDEB200_OK;
+}
 
 // Gradient kernels of the shared-memory path.  tail != nullptr: the last CTA reduces, exchanges (cm) and applies the
 // optimiser; otherwise the per-CTA partials are reduced into ARR_GRADS by a second launch.  global_batch: see make_args.
@@ -1375,6 +1487,7 @@ bool tail_fusable(pdeb200_ctx* c, const Plan& P) {
 int32_t enqueue_update(pdeb200_ctx* c, const Plan& P, const Hyper& H) {
     Agent* a = ag(c);
     int32_t rc;
+    if (P.fast && tail_fusable(c, P)) return fast_update_launch(c, P, H, 0, 0);
     if (tail_fusable(c, P)) {
         // two launches: {critic gradients; last CTA: reduce + exchange + ADAM + Polyak} {actor gradients; last CTA: same +
         // losses}.  The target critic is not read after the critic phase and the behavior critic is not written by the
@@ -1465,11 +1578,15 @@ int32_t pdeb200_train_updates(pdeb200_ctx* c, int32_t n_updates, int32_t batch, 
     if ((rc = sync_rings(c))) return rc;
     const Hyper H{gamma, polyak, lr_actor, lr_critic, literal_q1};
     static const bool no_graph = [] { const char* e = getenv("PDEB200_NO_GRAPH"); return e && atoi(e) != 0; }();
+    const bool fast = P.fast && tail_fusable(c, P);            // sampler fused into the critic kernel: two launches per update
+    auto one_update = [&]() -> int32_t {
+        if (fast) return fast_update_launch(c, P, H, 1, seed);
+        int32_t r = sample_launch(c, batch, 1, seed, 0, 1);
+        return r ? r : enqueue_update(c, P, H);
+    };
     if (no_graph || !tail_fusable(c, P)) {
-        for (int k = 0; k < n_updates; ++k) {
-            if ((rc = sample_launch(c, batch, 1, seed, 0, 1))) return rc;
-            if ((rc = enqueue_update(c, P, H))) return rc;
-        }
+        for (int k = 0; k < n_updates; ++k)
+            if ((rc = one_update())) return rc;
         return PDEB200_OK;
     }
     // update_loops x {sample, critic, actor} as one graph: everything that changes between launches (ring positions,
@@ -1483,10 +1600,7 @@ int32_t pdeb200_train_updates(pdeb200_ctx* c, int32_t n_updates, int32_t batch, 
         drop_graph(a);
         const int64_t l0 = c->launches;
         PDEB_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-        for (int i = 0; i < n_updates && !rc; ++i) {
-            rc = sample_launch(c, batch, 1, seed, 0, 1);
-            if (!rc) rc = enqueue_update(c, P, H);
-        }
+        for (int i = 0; i < n_updates && !rc; ++i) rc = one_update();
         cudaGraph_t g = nullptr;
         const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
         c->launches = l0;
@@ -1498,7 +1612,7 @@ int32_t pdeb200_train_updates(pdeb200_ctx* c, int32_t n_updates, int32_t batch, 
         a->gkey = k;
     }
     PDEB_CUDA(c, cudaGraphLaunch(a->graph, c->stream));
-    c->launches += (int64_t)3 * n_updates;
+    c->launches += (int64_t)(fast ? 2 : 3) * n_updates;
     return PDEB200_OK;
 }
 

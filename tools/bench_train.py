@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=12)
     ap.add_argument("--middle", action="store_true", help="drop_middle_layer = false (wide critic 2-140-140-1 on tensor cores)")
+    ap.add_argument("--updates-only", action="store_true", help="after the warm-up time only pdeb200_train_updates (us per DDPG update)")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -66,6 +67,25 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    if args.updates_only:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):
+            pol.maybe_update()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0.record(stream)
+        for _ in range(args.steps):
+            pol.maybe_update()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if rank == 0:
+            print(json.dumps({"n_gpus": world, "batch": args.batch, "update_loops": args.update_loops,
+                              "us_per_update": 1e3 * e0.elapsed_time(e1) / (args.steps * args.update_loops), "losses": pol.losses}))
+        env.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     l0, u0 = env.launch_count, pol.n_updates
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
