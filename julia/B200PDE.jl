@@ -6,14 +6,18 @@
 #
 # NOTE: Julia is not installed in the build image, so this file has been syntax-reviewed only; the same
 # entry points are exercised through Python ctypes in tests/ (the C ABI is language neutral).
+# julia/B200PDEAgent.jl (included after src/PDEagent.jl) adds the device trajectory with the reference's `update!`
+# overload set and the device-backed policy functor.
 module B200PDE
 
 const LIB = get(ENV, "PDEB200_LIB", joinpath(@__DIR__, "..", "distributedconvrl-pde-control_b200", "libpdeb200.so"))
 
 const KS, KSEG1D, NS2D, KSEG2D = Int32(0), Int32(1), Int32(2), Int32(3)
 const F32, F64 = Int32(0), Int32(1)
-const ARR_Y, ARR_P, ARR_STATE, ARR_ACTION, ARR_DELTA_ACTION, ARR_REWARD, ARR_DONE, ARR_TIME, ARR_STEPS =
-    Int32.(0:8)
+const ARR_Y, ARR_P, ARR_STATE, ARR_ACTION, ARR_DELTA_ACTION, ARR_REWARD, ARR_DONE, ARR_TIME, ARR_STEPS, ARR_Y0, ARR_GRADS,
+      ARR_LOSSES, ARR_SENSORS, ARR_ACTION_IN, ARR_STATS = Int32.(0:14)
+const NET_BEHAVIOR_ACTOR, NET_BEHAVIOR_CRITIC, NET_TARGET_ACTOR, NET_TARGET_CRITIC = Int32.(0:3)
+const ACT_IDENTITY, ACT_RELU, ACT_TANH = Int32.(0:2)
 
 # struct pdeb200_config (field order and types must match include/pdeb200.h)
 Base.@kwdef mutable struct Config
@@ -181,6 +185,95 @@ end
 sample!(c::Ctx, batch::Integer; seed = 0, offset = 0) =
     check(ccall((:pdeb200_sample, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int64}, UInt64, UInt64),
                 c.ptr, Int32(batch), C_NULL, UInt64(seed), UInt64(offset)), c.ptr)
+
+# update!(policy, traj, env, ::PreActStage) (src/PDEagent.jl:342-361): update_loops x { pde_sample ; update! } as ONE call
+# (one CUDA graph on the device; a collective after comm_init!)
+train_updates!(c::Ctx, n_updates::Integer, batch::Integer; γ = 0.99, p = 0.995, lr_actor = 5e-4, lr_critic = 1e-3,
+               literal_q1 = true, seed = 0) =
+    check(ccall((:pdeb200_train_updates, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Float64, Float64, Float64, Float64, Int32, UInt64),
+                c.ptr, Int32(n_updates), Int32(batch), γ, p, lr_actor, lr_critic, Int32(literal_q1), UInt64(seed)), c.ptr)
+
+# pde_fetch!'s result for the staged batch (src/PDEagent.jl:322-340): (s, a, r, t, s′, inds) in the reference's shapes
+function get_batch(c::Ctx, batch::Integer, ns::Integer, na::Integer)
+    s = Matrix{Float32}(undef, ns, batch); a = Matrix{Float32}(undef, na, batch); s2 = Matrix{Float32}(undef, ns, batch)
+    r = Vector{Float32}(undef, batch); t = Vector{UInt8}(undef, batch); inds = Vector{Int64}(undef, batch)
+    check(ccall((:pdeb200_get_batch, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}, Ptr{Float32}, Ptr{Int64}),
+                c.ptr, s, a, r, t, s2, inds), c.ptr)
+    (state = s, action = a, reward = r, terminal = t .!= 0, next_state = s2), inds .+ 1
+end
+
+# ---- batched termination (src/PDEenv.jl:226-240 per environment) ---------------------------------------------
+# returns (n_done, n_time_limit, n_diverged_and_reset); sync = false enqueues without reading the counters back
+function reset_diverged!(c::Ctx; sync = true)
+    counts = zeros(Int32, 3)
+    check(ccall((:pdeb200_reset_diverged, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}), c.ptr, sync ? pointer(counts) : C_NULL), c.ptr)
+    Tuple(counts)
+end
+
+# one environment's slice (PDEhook's tracked environment, src/PDEhook.jl:54-62)
+get_env!(c::Ctx, which::Int32, env_index::Integer, dst::Array) =
+    check(ccall((:pdeb200_get_env, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}, Csize_t),
+                c.ptr, which, Int32(env_index - 1), dst, sizeof(dst)), c.ptr)
+
+# ---- checkpoint state: save() / load() (scripts/KS/setup/KSSetup.jl:378-402) -------------------------------------
+# Flux.loadparams! semantics: weights only, optimiser state kept (src/custom_nna.jl:26-27)
+net_set_params!(c::Ctx, net::Int32, flat::Vector{Float32}) =
+    check(ccall((:pdeb200_net_set_params, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float32}, Csize_t), c.ptr, net, flat, length(flat)), c.ptr)
+# Flux ADAM state (m, v, βp) of one network in the flat parameter layout: sync into / from `optimizer.state` around save()/load()
+function opt_get(c::Ctx, net::Int32, n_params::Integer)
+    m = Vector{Float32}(undef, n_params); v = Vector{Float32}(undef, n_params); βp = Vector{Float64}(undef, 2)
+    check(ccall((:pdeb200_opt_get, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float32}, Ptr{Float32}, Ptr{Float64}, Csize_t),
+                c.ptr, net, m, v, βp, n_params), c.ptr)
+    m, v, βp
+end
+opt_set!(c::Ctx, net::Int32, m::Vector{Float32}, v::Vector{Float32}, βp::Vector{Float64}) =
+    check(ccall((:pdeb200_opt_set, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float32}, Ptr{Float32}, Ptr{Float64}, Csize_t),
+                c.ptr, net, m, v, βp, length(m)), c.ptr)
+# replay rings <-> RLCore's CircularArrayBuffers: logical order + (first - 1) raw positions, as agent.jld2 stores them
+function traj_info(c::Ctx)
+    v = [Ref{Int64}(0) for _ in 1:5]
+    check(ccall((:pdeb200_traj_info, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Int64}, Ref{Int64}),
+                c.ptr, v[1], v[2], v[3], v[4], v[5]), c.ptr)
+    (capacity = v[1][], n_sa = v[2][], n_rt = v[3][], first_sa = v[4][], first_rt = v[5][])
+end
+function traj_get(c::Ctx, ns::Integer, na::Integer)
+    i = traj_info(c)
+    s = Matrix{Float32}(undef, ns, i.n_sa); a = Matrix{Float32}(undef, na, i.n_sa)
+    r = Vector{Float32}(undef, i.n_rt); t = Vector{UInt8}(undef, i.n_rt)
+    check(ccall((:pdeb200_traj_get, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}), c.ptr, s, a, r, t), c.ptr)
+    s, a, r, t .!= 0
+end
+traj_set!(c::Ctx, s::Matrix{Float32}, a::Matrix{Float32}, r::Vector{Float32}, t::Vector{UInt8}; first_sa = 0, first_rt = 0) =
+    check(ccall((:pdeb200_traj_set, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{UInt8}),
+                c.ptr, size(s, 2), length(r), Int64(first_sa), Int64(first_rt), s, a, r, t), c.ptr)
+function rng_get(c::Ctx)
+    v = Ref{UInt64}(0)
+    check(ccall((:pdeb200_rng_get, LIB), Int32, (Ptr{Cvoid}, Ref{UInt64}), c.ptr, v), c.ptr)
+    v[]
+end
+rng_set!(c::Ctx, offset::Integer) = check(ccall((:pdeb200_rng_set, LIB), Int32, (Ptr{Cvoid}, UInt64), c.ptr, UInt64(offset)), c.ptr)
+
+# ---- multi-GPU: one Julia process (or task with its own device) per GPU (SURVEY.md 8b / 8e) -----------------------
+# rank 0:  id = comm_unique_id()  -> ship the 128 bytes to the other ranks (MPI.Bcast!, a file, Distributed.remotecall ...)
+# every rank: comm_init!(ctx, id, rank, nranks)   (0-based rank).  Afterwards sample! / ddpg_update! / train_updates! are
+# collectives and the gradient exchange runs inside the library's kernels over NVLink peer memory.
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:pdeb200_comm_unique_id, LIB), Int32, (Ptr{UInt8},), id))
+    id
+end
+comm_init!(c::Ctx, id::Vector{UInt8}, rank::Integer, nranks::Integer) =
+    check(ccall((:pdeb200_comm_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}, Int32, Int32), c.ptr, id, Int32(rank), Int32(nranks)), c.ptr)
+comm_destroy!(c::Ctx) = check(ccall((:pdeb200_comm_destroy, LIB), Int32, (Ptr{Cvoid},), c.ptr), c.ptr)
+function comm_info(c::Ctx)
+    r = Ref{Int32}(0); n = Ref{Int32}(1); t = Ref{Int32}(0)
+    check(ccall((:pdeb200_comm_info, LIB), Int32, (Ptr{Cvoid}, Ref{Int32}, Ref{Int32}, Ref{Int32}), c.ptr, r, n, t), c.ptr)
+    (rank = r[], nranks = n[], transport = (:none, :nccl, :peer)[t[] + 1])
+end
+# in-place sum over the ranks of up to 64 host Float64 (episode returns / done counts for PDEhook)
+comm_allreduce!(c::Ctx, v::Vector{Float64}) =
+    check(ccall((:pdeb200_comm_allreduce_f64, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), c.ptr, v, Int32(length(v))), c.ptr)
 
 # 0 = auto (fused shared-memory kernels / layer-wise GEMM path for wide networks), 1-3 force the layer-wise path
 ddpg_set_path!(c::Ctx, path::Integer) =
