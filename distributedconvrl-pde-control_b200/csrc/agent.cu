@@ -12,6 +12,8 @@
 // The networks are tiny (KS: 19 + 561 parameters), so the contraction is far too thin for tensor
 // cores: one CTA processes tiles of 32 samples, thread-per-unit forward, thread-per-(unit,input)
 // gradient accumulation in shared memory, per-CTA partials reduced in fixed order (deterministic).
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cmath>
 #include <vector>
@@ -56,6 +58,7 @@ struct Agent {
     float* arena = nullptr; size_t arena_cap = 0, arena_used = 0;   // activations of the layer-wise (wide network) path
     int force_wide = 0;                // 1: always use the layer-wise path (tests / measurements)
     int wide_path = 0;                 // layer dispatch there: 0 auto, 1 CUDA cores only, 2 tensor cores wherever possible
+    unsigned long long* timeline = nullptr;       // PDEB200_DDPG_TIMELINE=1: device timestamps of the update kernels' phases
     AgentDev* dev = nullptr;           // device mirror (see AgentDev)
     bool ring_dirty = true;            // host rings changed without a push kernel (create / pop_tail / set)
     float* xbuf = nullptr; int xbuf_cap = 0;      // reduced gradient (+ 2 loss sums) of one phase: the exchange's send / receive vector
@@ -973,7 +976,7 @@ void agent_free(pdeb200_ctx* c) {
     drop_graph(a);
     for (void* p : {(void*)a->state, (void*)a->action, (void*)a->reward, (void*)a->terminal, (void*)a->bs, (void*)a->ba,
                     (void*)a->br, (void*)a->bs2, (void*)a->bt, (void*)a->inds, (void*)a->stats, (void*)a->partials,
-                    (void*)a->arena, (void*)a->stat_part, (void*)a->tickets, (void*)a->dev, (void*)a->xbuf})
+                    (void*)a->arena, (void*)a->stat_part, (void*)a->tickets, (void*)a->dev, (void*)a->xbuf, (void*)a->timeline})
         if (p) cudaFree(p);
     delete a;
     c->agent = nullptr;
@@ -1247,6 +1250,24 @@ int32_t pdeb200_get_batch(pdeb200_ctx* c, float* s, float* a_, float* r, uint8_t
     return PDEB200_OK;
 }
 
+// PDEB200_DDPG_TIMELINE=1: copy out (and reset) the device timestamps of the update kernels; out: 8 words per kernel record
+// {phase, t_entry, t_loop_done, t_tail_start, t_reduced, t_exchanged, t_end, -}, returns the record count in *n
+int32_t pdeb200_debug_timeline(pdeb200_ctx* c, uint64_t* out, int32_t max_records, int32_t* n) {
+    if (!c || !out || !n) return PDEB200_EINVAL;
+    Agent* a = ag(c);
+    *n = 0;
+    if (!a || !a->timeline) return PDEB200_OK;
+    cudaSetDevice(c->device);
+    std::vector<unsigned long long> h(8192);
+    PDEB_CUDA(c, cudaMemcpyAsync(h.data(), a->timeline, h.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    const int k = (int)std::min<unsigned long long>(h[0], (unsigned long long)std::min(max_records, 500));
+    for (int i = 0; i < k * 8; ++i) out[i] = h[8 + i];
+    *n = k;
+    PDEB_CUDA(c, cudaMemsetAsync(a->timeline, 0, 8 * sizeof(unsigned long long), c->stream));
+    return PDEB200_OK;
+}
+
 int32_t pdeb200_ddpg_set_path(pdeb200_ctx* c, int32_t path) {
     if (!c || path < 0 || path > 3) return fail(c, PDEB200_EINVAL, "ddpg_set_path: bad argument");
     int32_t rc = ensure_agent(c);
@@ -1272,7 +1293,11 @@ struct Plan {
     bool fast = false;
     int f_ns = 0, f_cfg = 0, f_warps = 0, f_grid = 0, f_nx_c = 0, f_nx_a = 0;
     size_t f_smem_c = 0, f_smem_a = 0;
+    int f_cluster = 0;                 // > 0: the whole update as ONE launch of a single thread-block cluster of this many CTAs
+    size_t f_smem_cl = 0;
 };
+
+inline int C_params(const pdeb200_ctx* c) { return c->nets[PDEB200_NET_BEHAVIOR_CRITIC].n_params; }
 
 template <int NS, int UPLC, int WC>
 int32_t fast_configure(pdeb200_ctx* c, Plan* P) {
@@ -1282,7 +1307,48 @@ int32_t fast_configure(pdeb200_ctx* c, Plan* P) {
     if (P->f_smem_c > 220 * 1024) { P->fast = false; return PDEB200_OK; }
     PDEB_CUDA(c, ensure_dyn_smem(ddpg_fast_critic_kernel<NS, UPLC, WC>, P->f_smem_c, c->device));
     PDEB_CUDA(c, ensure_dyn_smem(ddpg_fast_actor_kernel<NS, UPLC, WC>, P->f_smem_a, c->device));
+    // one-cluster form: possible when the batch's tiles fit 16 CTAs' warps in a few rounds and the cluster can be co-scheduled
+    P->f_cluster = 0;
+    static const int want_cluster = [] { const char* e = getenv("PDEB200_DDPG_CLUSTER"); return e ? atoi(e) : 16; }();
+    const int teams = P->f_warps / WC;
+    const int n_tiles = (ag(c)->batch + 31) / 32;
+    const int need = (n_tiles + teams - 1) / teams;                       // CTAs for one tile per team
+    const int per_slice = 2 * ((C_params(c) + 15) / 16) + kXTail;
+    const int max_cs = std::min(want_cluster, 16);
+    const int per_cta = kSlicePF * P->f_warps * 32;                       // parameters one CTA's slice can hold
+    const int min_cs = (C_params(c) + per_cta - 1) / per_cta;
+    if (want_cluster > 0 && need <= 4 * max_cs && min_cs <= max_cs && (comm_nranks(c) == 1 || per_slice <= comm_cap(c) / kMaxSlices)) {
+        int cs = 1;
+        while ((cs < need || cs < min_cs) && cs < max_cs) cs *= 2;
+        const size_t smem = (Geo::base_floats(P->f_warps, P->f_nx_c) + 2 * (size_t)P->f_nx_c) * sizeof(float);
+        auto kern = ddpg_fast_cluster_kernel<NS, UPLC, WC>;
+        if (smem <= 220 * 1024 && ensure_dyn_smem(kern, smem, c->device) == cudaSuccess &&
+            (cs <= 8 || cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cs); cfg.blockDim = dim3(P->f_warps * 32); cfg.dynamicSmemBytes = smem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int n_clusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) == cudaSuccess && n_clusters >= 1) {
+                P->f_cluster = cs; P->f_smem_cl = smem;
+            }
+        }
+        cudaGetLastError();
+    }
     return PDEB200_OK;
+}
+
+template <int NS, int UPLC, int WC>
+void fast_launch_cluster_t(pdeb200_ctx* c, const Plan& P, const FastArgs& Fc, const FastArgs& Fa) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(P.f_cluster); cfg.blockDim = dim3(P.f_warps * 32); cfg.dynamicSmemBytes = P.f_smem_cl; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = P.f_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, ddpg_fast_cluster_kernel<NS, UPLC, WC>, Fc, Fa);
 }
 
 template <int NS, int UPLC, int WC>
@@ -1337,6 +1403,11 @@ int32_t plan_fast(pdeb200_ctx* c, Plan* P) {
     if (comm_nranks(c) > 1 && P->f_nx_c > comm_cap(c)) { P->fast = false; return PDEB200_OK; }
     int32_t rc = ensure_partials(c, P->f_grid, P->f_nx_c - 2);
     if (rc) return rc;
+    static const bool want_tl = [] { const char* e = getenv("PDEB200_DDPG_TIMELINE"); return e && atoi(e) != 0; }();
+    if (want_tl && !a->timeline) {                       // allocated here, never inside a stream capture
+        PDEB_CUDA(c, cudaMalloc(&a->timeline, 8192 * sizeof(unsigned long long)));
+        PDEB_CUDA(c, cudaMemset(a->timeline, 0, 8192 * sizeof(unsigned long long)));
+    }
 #define PDEB_CFG(NS_, U_, W_) rc = fast_configure<NS_, U_, W_>(c, P)
     PDEB_FAST_DISPATCH(*P, PDEB_CFG);
 #undef PDEB_CFG
@@ -1384,11 +1455,20 @@ int32_t fast_update_launch(pdeb200_ctx* c, const Plan& P, const Hyper& H, int fe
     F.partials = a->partials; F.xbuf = a->xbuf; F.stats = a->stats; F.losses = c->d_losses;
     F.b1 = 0.9; F.b2 = 0.999; F.eps = 1e-8; F.polyak = (float)H.polyak;
     F.cm = comm_dev(c);
+    F.tl = a->timeline;
     FastArgs Fc = F, Fa = F;
     Fc.n_x = P.f_nx_c; Fc.ticket = a->tickets + 1; Fc.grads = c->d_grads;
     Fc.x = C.d_params; Fc.m = C.d_m; Fc.v = C.d_v; Fc.target = Ct.d_params; Fc.betap = C.d_betap; Fc.eta = H.lr_c;
     Fa.n_x = P.f_nx_a; Fa.ticket = a->tickets + 2; Fa.grads = c->d_grads + C.n_params; Fa.fetch = 0;
     Fa.x = A.d_params; Fa.m = A.d_m; Fa.v = A.d_v; Fa.target = At.d_params; Fa.betap = A.d_betap; Fa.eta = H.lr_a;
+    if (P.f_cluster > 0) {
+#define PDEB_LAUNCH(NS_, U_, W_) fast_launch_cluster_t<NS_, U_, W_>(c, P, Fc, Fa)
+        PDEB_FAST_DISPATCH(P, PDEB_LAUNCH);
+#undef PDEB_LAUNCH
+        PDEB_CUDA(c, cudaGetLastError());
+        c->launches += 1;
+        return PDEB200_OK;
+    }
 #define PDEB_LAUNCH(NS_, U_, W_) fast_launch_t<NS_, U_, W_>(c, P, Fc, Fa)
     PDEB_FAST_DISPATCH(P, PDEB_LAUNCH);
 #undef PDEB_LAUNCH
@@ -1612,7 +1692,7 @@ int32_t pdeb200_train_updates(pdeb200_ctx* c, int32_t n_updates, int32_t batch, 
         a->gkey = k;
     }
     PDEB_CUDA(c, cudaGraphLaunch(a->graph, c->stream));
-    c->launches += (int64_t)(fast ? 2 : 3) * n_updates;
+    c->launches += (int64_t)(fast ? (P.f_cluster > 0 ? 1 : 2) : 3) * n_updates;
     return PDEB200_OK;
 }
 

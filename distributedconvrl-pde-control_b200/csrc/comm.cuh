@@ -13,7 +13,10 @@
 //   [0, 64)        uint32 gflag[2][8]    epoch stamps of the gradient exchange, [parity][source rank]
 //   [64, 128)      uint32 sflag[2][8]    same for the batch-statistics exchange
 //   [128, 1152)    double sdata[2][8][8] batch statistics {sum r, sum r^2, n}
-//   [2048, ...)    float  gdata[2][8][cap]
+//   [1152, 2176)   uint32 xflag[2][8][16] epoch stamps of the SLICED gradient exchange, [parity][source rank][slice]
+//   [4096, ...)    float  gdata[2][8][cap]
+// Sliced exchange (the one-cluster update kernel, ddpg_fast.cuh): the 16 CTAs of the cluster each own 1/16 of the parameter
+// vector; CTA s exchanges its slice (offset s * cap/16 inside the same per-source slot) under its own flag, all 16 in parallel.
 // Two parities suffice: a rank that writes exchange e+2 has passed the wait of e+1, i.e. has seen every peer's
 // e+1 flag, which each peer stores only after it has finished reading exchange e.
 #pragma once
@@ -23,7 +26,8 @@
 namespace pdeb200 {
 
 constexpr int kMaxRanks = 8;
-constexpr size_t kCommHeaderBytes = 2048;
+constexpr size_t kCommHeaderBytes = 4096;
+constexpr int kMaxSlices = 16;
 
 struct CommDev {
     int rank = 0, nranks = 1;           // nranks <= 1: no exchange
@@ -37,6 +41,9 @@ struct CommDev {
 __device__ __forceinline__ unsigned int* comm_gflag(char* base, int par, int src) { return (unsigned int*)base + par * kMaxRanks + src; }
 __device__ __forceinline__ unsigned int* comm_sflag(char* base, int par, int src) { return (unsigned int*)(base + 64) + par * kMaxRanks + src; }
 __device__ __forceinline__ double* comm_sdata(char* base, int par, int src) { return (double*)(base + 128) + (par * kMaxRanks + src) * 8; }
+__device__ __forceinline__ unsigned int* comm_xflag(char* base, int par, int src, int slice) {
+    return (unsigned int*)(base + 1152) + (par * kMaxRanks + src) * kMaxSlices + slice;
+}
 __device__ __forceinline__ float* comm_gdata(char* base, int cap, int par, int src) {
     return (float*)(base + kCommHeaderBytes) + (size_t)(par * kMaxRanks + src) * cap;
 }
@@ -91,6 +98,33 @@ __device__ __forceinline__ void comm_allreduce_cta(const CommDev& cm, const floa
         out[q] = (float)s;
     }
     if (threadIdx.x == 0) cm.epoch[0] = e;
+    __syncthreads();
+}
+
+// Sum of one SLICE over all ranks, executed by every thread of the CTA that owns the slice (same slice index on every
+// rank).  e: the exchange's epoch stamp (read from cm.epoch[0] at kernel start + phase; the kernel's rank-0 CTA stores the
+// final value back).  n <= cm.cap / kMaxSlices.
+__device__ __forceinline__ void comm_allreduce_slice(const CommDev& cm, unsigned int e, int slice, const float* vec, float* out, int n) {
+    const int par = (int)(e & 1u);
+    const int off = slice * (cm.cap / kMaxSlices);
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        const float v = vec[q];
+#pragma unroll 1
+        for (int p = 0; p < cm.nranks; ++p) comm_gdata(cm.peer[p], cm.cap, par, cm.rank)[off + q] = v;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < cm.nranks) {
+        st_release_sys(comm_xflag(cm.peer[threadIdx.x], par, cm.rank, slice), e);
+        comm_wait_flag(cm, comm_xflag(cm.peer[cm.rank], par, threadIdx.x, slice), e);
+    }
+    __syncthreads();
+    char* own = cm.peer[cm.rank];
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < cm.nranks; ++r) s += (double)__ldcg(comm_gdata(own, cm.cap, par, r) + off + q);
+        out[q] = (float)s;
+    }
     __syncthreads();
 }
 

@@ -296,6 +296,10 @@ int32_t pdeb200_last_phase_ms(pdeb200_ctx* ctx, float* ms3);
 /* Measured CUDA-core FMA peak of this GPU (TFLOP/s, 2 flops per FMA) for dtype PDEB200_F32 / F64: the roofline
  * denominator of the FP-pipe bound kernels (MEASURED_PEAKS.json only carries HBM and bf16 tensor numbers). */
 int32_t pdeb200_measure_fma_peak(pdeb200_ctx* ctx, int32_t dtype, double* tflops);
+/* With PDEB200_DDPG_TIMELINE=1 in the environment the register-resident DDPG kernels stamp %globaltimer at their phase
+ * boundaries; this copies out and resets the records (8 uint64 each: phase 0 critic / 1 actor, t_entry, t_loop_done,
+ * t_tail_start, t_reduced, t_exchanged, t_end, unused; ns).  Measurement support for tools/bench_train.py. */
+int32_t pdeb200_debug_timeline(pdeb200_ctx* ctx, uint64_t* out, int32_t max_records, int32_t* n);
 /* Algorithmic HBM bytes and flops of one env step for this configuration. */
 int32_t pdeb200_step_cost(const pdeb200_ctx* ctx, double* hbm_bytes_per_env, double* flops_per_env);
 

@@ -181,8 +181,9 @@ def test_train_updates_graph_equals_the_same_updates_one_by_one_and_the_oracle(p
     for call in range(3):
         l0 = env_g.launch_count
         assert pol_g.maybe_update() == 5
-        # 5 x {critic (sampler fused), actor} with the register-resident kernels (+ the ring-position sync once)
-        assert env_g.launch_count - l0 == 10 + (1 if call == 0 else 0)
+        # 5 updates, each ONE launch of the one-cluster kernel (sampler + critic + actor + optimiser; two launches where a
+        # 16-CTA cluster cannot be scheduled), + the ring-position sync once
+        assert env_g.launch_count - l0 in (5 + (1 if call == 0 else 0), 10 + (1 if call == 0 else 0))
         for k in range(5):
             off = (call * 5 + k) * 96
             L.check(env_1._lib.pdeb200_sample(env_1._ctx, 96, None, 9 ^ 0x5DEECE66D, off), env_1._ctx)

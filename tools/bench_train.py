@@ -79,6 +79,29 @@ def main():
             pol.maybe_update()
         e1.record(stream)
         torch.cuda.synchronize()
+        if os.environ.get("PDEB200_DDPG_TIMELINE"):
+            buf = np.zeros(500 * 8, dtype=np.uint64)
+            n = C.c_int32()
+            L.check(env._lib.pdeb200_debug_timeline(env._ctx, buf.ctypes.data, 500, C.byref(n)), env._ctx)
+            r = buf[:n.value * 8].reshape(-1, 8).astype(np.int64)
+            if rank == 0 and len(r) > 8:
+                r = r[-40:]
+                t0 = r[0, 1]
+                if r[0, 0] == 2:                 # one-cluster kernel: one record per update
+                    for row in r[:8]:
+                        print("update  entry %7.2f | critic loop %5.2f  sync %5.2f  reduce+exchange+adam %5.2f | actor loop (+sync) %5.2f  sync %5.2f  "
+                              "reduce+exchange+adam+sync %5.2f | kernel %5.2f us" % ((row[1] - t0) / 1e3, (row[2] - row[1]) / 1e3, (row[3] - row[2]) / 1e3,
+                              (row[4] - row[3]) / 1e3, (row[5] - row[4]) / 1e3, (row[6] - row[5]) / 1e3, (row[7] - row[6]) / 1e3, (row[7] - row[1]) / 1e3))
+                    print("mean gap between kernels %.2f us; mean kernel %.2f us" % (((r[1:, 1] - r[:-1, 7]) / 1e3).mean(), ((r[:, 7] - r[:, 1]) / 1e3).mean()))
+                    r = r[:0]
+                for row in r[:12]:
+                    print("phase %d  entry %7.2f  loop %5.2f  wait-for-last-CTA %5.2f  reduce %5.2f  exchange %5.2f  adam %5.2f | kernel %5.2f us"
+                          % (row[0], (row[1] - t0) / 1e3, (row[2] - row[1]) / 1e3, (row[3] - row[2]) / 1e3, (row[4] - row[3]) / 1e3,
+                             (row[5] - row[4]) / 1e3, (row[6] - row[5]) / 1e3, (row[6] - row[1]) / 1e3))
+                gaps = (r[1:, 1] - r[:-1, 6]) / 1e3 if len(r) else np.zeros(1)
+                if len(r):
+                  print("mean gap between kernels %.2f us; mean critic %.2f us, actor %.2f us" % (
+                    gaps.mean(), ((r[:, 6] - r[:, 1])[r[:, 0] == 0]).mean() / 1e3, ((r[:, 6] - r[:, 1])[r[:, 0] == 1]).mean() / 1e3))
         if rank == 0:
             print(json.dumps({"n_gpus": world, "batch": args.batch, "update_loops": args.update_loops,
                               "us_per_update": 1e3 * e0.elapsed_time(e1) / (args.steps * args.update_loops), "losses": pol.losses}))
