@@ -1317,7 +1317,7 @@ int32_t fast_configure(pdeb200_ctx* c, Plan* P) {
     const int max_cs = std::min(want_cluster, 16);
     const int per_cta = kSlicePF * P->f_warps * 32;                       // parameters one CTA's slice can hold
     const int min_cs = (C_params(c) + per_cta - 1) / per_cta;
-    if (want_cluster > 0 && need <= 4 * max_cs && min_cs <= max_cs && (comm_nranks(c) == 1 || per_slice <= comm_cap(c) / kMaxSlices)) {
+    if (want_cluster > 0 && need <= 4 * max_cs && min_cs <= max_cs && (comm_nranks(c) == 1 || per_slice <= comm_cap(c) / 2 / kMaxSlices)) {
         int cs = 1;
         while ((cs < need || cs < min_cs) && cs < max_cs) cs *= 2;
         const size_t smem = (Geo::base_floats(P->f_warps, P->f_nx_c) + 2 * (size_t)P->f_nx_c) * sizeof(float);
@@ -1400,7 +1400,7 @@ int32_t plan_fast(pdeb200_ctx* c, Plan* P) {
     P->f_grid = std::max(1, std::min((n_tiles + teams - 1) / teams, 148));
     P->f_nx_c = 2 * C.n_params + kXTail;
     P->f_nx_a = A.n_params + kXTail;
-    if (comm_nranks(c) > 1 && P->f_nx_c > comm_cap(c)) { P->fast = false; return PDEB200_OK; }
+    if (comm_nranks(c) > 1 && P->f_nx_c > comm_cap(c) / 2) { P->fast = false; return PDEB200_OK; }
     int32_t rc = ensure_partials(c, P->f_grid, P->f_nx_c - 2);
     if (rc) return rc;
     static const bool want_tl = [] { const char* e = getenv("PDEB200_DDPG_TIMELINE"); return e && atoi(e) != 0; }();
@@ -1560,7 +1560,7 @@ bool tail_fusable(pdeb200_ctx* c, const Plan& P) {
     const int nr = comm_nranks(c);
     if (nr == 1) return true;
     const int n_max = std::max(c->nets[PDEB200_NET_BEHAVIOR_CRITIC].n_params, c->nets[PDEB200_NET_BEHAVIOR_ACTOR].n_params);
-    return comm_transport(c) == PDEB200_COMM_PEER && n_max + 2 <= comm_cap(c);
+    return comm_transport(c) == PDEB200_COMM_PEER && n_max + 2 <= comm_cap(c) / 2;
 }
 
 // One whole update on the staged batch (PDEagent.jl:363-418).

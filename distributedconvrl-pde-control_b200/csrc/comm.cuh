@@ -13,10 +13,9 @@
 //   [0, 64)        uint32 gflag[2][8]    epoch stamps of the gradient exchange, [parity][source rank]
 //   [64, 128)      uint32 sflag[2][8]    same for the batch-statistics exchange
 //   [128, 1152)    double sdata[2][8][8] batch statistics {sum r, sum r^2, n}
-//   [1152, 2176)   uint32 xflag[2][8][16] epoch stamps of the SLICED gradient exchange, [parity][source rank][slice]
-//   [4096, ...)    float  gdata[2][8][cap]
+//   [4096, ...)    uint64 ldata[2][8][cap/2]   gradient exchange, one {epoch : float} word per element (flag-in-data, below)
 // Sliced exchange (the one-cluster update kernel, ddpg_fast.cuh): the 16 CTAs of the cluster each own 1/16 of the parameter
-// vector; CTA s exchanges its slice (offset s * cap/16 inside the same per-source slot) under its own flag, all 16 in parallel.
+// vector; CTA s exchanges its slice at offset s * cap/32 inside the same per-source slot, all 16 slices in flight at once.
 // Two parities suffice: a rank that writes exchange e+2 has passed the wait of e+1, i.e. has seen every peer's
 // e+1 flag, which each peer stores only after it has finished reading exchange e.
 #pragma once
@@ -41,9 +40,6 @@ struct CommDev {
 __device__ __forceinline__ unsigned int* comm_gflag(char* base, int par, int src) { return (unsigned int*)base + par * kMaxRanks + src; }
 __device__ __forceinline__ unsigned int* comm_sflag(char* base, int par, int src) { return (unsigned int*)(base + 64) + par * kMaxRanks + src; }
 __device__ __forceinline__ double* comm_sdata(char* base, int par, int src) { return (double*)(base + 128) + (par * kMaxRanks + src) * 8; }
-__device__ __forceinline__ unsigned int* comm_xflag(char* base, int par, int src, int slice) {
-    return (unsigned int*)(base + 1152) + (par * kMaxRanks + src) * kMaxSlices + slice;
-}
 __device__ __forceinline__ float* comm_gdata(char* base, int cap, int par, int src) {
     return (float*)(base + kCommHeaderBytes) + (size_t)(par * kMaxRanks + src) * cap;
 }
@@ -70,62 +66,63 @@ __device__ __forceinline__ void comm_wait_flag(const CommDev& cm, const unsigned
     }
 }
 
-// Sum of `vec[0..n)` over all ranks, executed by every thread of ONE CTA per rank (the last CTA of the producing
-// kernel).  vec: this rank's contribution (global or shared memory); out[q] receives the fixed-order sum (may alias
-// vec).  n <= cm.cap.  All ranks must call it the same number of times (it is a collective).
+// ---- flag-in-data ("LL") transport of the gradient exchanges ------------------------------------------------------------------
+// A separate flag needs  data stores -> system-scope release (a round trip to the peer: every store acknowledged) -> flag
+// store -> peer polls: measured 5 us per exchange on 2 B200s.  Here every element travels as ONE 64-bit store
+// {epoch : float bits} (single-copy atomic), so the receiver polls the data words themselves: one one-way NVLink latency.
+// The gdata region is reinterpreted as uint64 [2][8][cap/2].
+__device__ __forceinline__ unsigned long long* comm_ldata(char* base, int cap, int par, int src) {
+    return (unsigned long long*)(base + kCommHeaderBytes) + (size_t)(par * kMaxRanks + src) * (cap / 2);
+}
+__device__ __forceinline__ void ll_store(unsigned long long* p, float v, unsigned int e) {
+    const unsigned long long w = ((unsigned long long)e << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
+}
+__device__ __forceinline__ float ll_wait(const CommDev& cm, const unsigned long long* p, unsigned int e) {
+    unsigned long long w;
+    const unsigned long long t0 = global_timer_ns();
+    for (;;) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+        if ((unsigned int)(w >> 32) == e) break;
+        if (global_timer_ns() - t0 > cm.timeout_ns) { *cm.err = 1; break; }
+    }
+    return __uint_as_float((unsigned int)w);
+}
+
+// Sum of vec[0..n) over all ranks by the threads of ONE CTA per rank; out may alias vec.  n <= cap/2 (whole-vector form,
+// offset 0) or cap/2/kMaxSlices (sliced form: 16 CTAs of the one-cluster kernel, each with its own offset).  Fixed rank-order
+// sum in double => identical results on every rank.
+__device__ __forceinline__ void comm_allreduce_ll(const CommDev& cm, unsigned int e, int off, const float* vec, float* out, int n) {
+    const int par = (int)(e & 1u);
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        const float v = vec[q];
+#pragma unroll 1
+        for (int p = 0; p < cm.nranks; ++p) ll_store(comm_ldata(cm.peer[p], cm.cap, par, cm.rank) + off + q, v, e);
+    }
+    char* own = cm.peer[cm.rank];
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < cm.nranks; ++r) s += (double)ll_wait(cm, comm_ldata(own, cm.cap, par, r) + off + q, e);
+        out[q] = (float)s;
+    }
+    __syncthreads();
+}
+
+// whole-vector form for the last-CTA tails (two-launch update kernels): epoch from the device counter
 __device__ __forceinline__ void comm_allreduce_cta(const CommDev& cm, const float* vec, float* out, int n) {
     __shared__ unsigned int s_epoch;
     if (threadIdx.x == 0) s_epoch = cm.epoch[0] + 1;
     __syncthreads();
     const unsigned int e = s_epoch;
-    const int par = (int)(e & 1u);
-    for (int q = threadIdx.x; q < n; q += blockDim.x) {
-        const float v = vec[q];
-#pragma unroll 1
-        for (int p = 0; p < cm.nranks; ++p) comm_gdata(cm.peer[p], cm.cap, par, cm.rank)[q] = v;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < cm.nranks) {
-        st_release_sys(comm_gflag(cm.peer[threadIdx.x], par, cm.rank), e);
-        comm_wait_flag(cm, comm_gflag(cm.peer[cm.rank], par, threadIdx.x), e);
-    }
-    __syncthreads();
-    char* own = cm.peer[cm.rank];
-    for (int q = threadIdx.x; q < n; q += blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < cm.nranks; ++r) s += (double)__ldcg(comm_gdata(own, cm.cap, par, r) + q);
-        out[q] = (float)s;
-    }
+    comm_allreduce_ll(cm, e, 0, vec, out, n);
     if (threadIdx.x == 0) cm.epoch[0] = e;
     __syncthreads();
 }
 
-// Sum of one SLICE over all ranks, executed by every thread of the CTA that owns the slice (same slice index on every
-// rank).  e: the exchange's epoch stamp (read from cm.epoch[0] at kernel start + phase; the kernel's rank-0 CTA stores the
-// final value back).  n <= cm.cap / kMaxSlices.
+// sliced form: e = epoch stamp (read from cm.epoch[0] at kernel start + phase; the kernel's rank-0 CTA stores the final value
+// back); slice s uses offset s * cap / 2 / kMaxSlices
 __device__ __forceinline__ void comm_allreduce_slice(const CommDev& cm, unsigned int e, int slice, const float* vec, float* out, int n) {
-    const int par = (int)(e & 1u);
-    const int off = slice * (cm.cap / kMaxSlices);
-    for (int q = threadIdx.x; q < n; q += blockDim.x) {
-        const float v = vec[q];
-#pragma unroll 1
-        for (int p = 0; p < cm.nranks; ++p) comm_gdata(cm.peer[p], cm.cap, par, cm.rank)[off + q] = v;
-    }
-    __threadfence_system();
-    __syncthreads();
-    if ((int)threadIdx.x < cm.nranks) {
-        st_release_sys(comm_xflag(cm.peer[threadIdx.x], par, cm.rank, slice), e);
-        comm_wait_flag(cm, comm_xflag(cm.peer[cm.rank], par, threadIdx.x, slice), e);
-    }
-    __syncthreads();
-    char* own = cm.peer[cm.rank];
-    for (int q = threadIdx.x; q < n; q += blockDim.x) {
-        double s = 0.0;
-        for (int r = 0; r < cm.nranks; ++r) s += (double)__ldcg(comm_gdata(own, cm.cap, par, r) + off + q);
-        out[q] = (float)s;
-    }
-    __syncthreads();
+    comm_allreduce_ll(cm, e, slice * (cm.cap / 2 / kMaxSlices), vec, out, n);
 }
 
 // The batch statistics {sum r, sum r^2, n} summed over all ranks, executed by ONE thread per rank.
