@@ -20,7 +20,7 @@ CHECK_NONE, CHECK_Y, CHECK_REWARD = 0, 1, 2
 ACT_IDENTITY, ACT_RELU, ACT_TANH = 0, 1, 2
 NET_BEHAVIOR_ACTOR, NET_BEHAVIOR_CRITIC, NET_TARGET_ACTOR, NET_TARGET_CRITIC = 0, 1, 2, 3
 (ARR_Y, ARR_P, ARR_STATE, ARR_ACTION, ARR_DELTA_ACTION, ARR_REWARD, ARR_DONE, ARR_TIME, ARR_STEPS, ARR_Y0,
- ARR_GRADS, ARR_LOSSES, ARR_SENSORS, ARR_ACTION_IN, ARR_STATS) = range(15)
+ ARR_GRADS, ARR_LOSSES, ARR_SENSORS, ARR_ACTION_IN, ARR_STATS, ARR_NSUB) = range(16)
 
 
 class Config(C.Structure):
@@ -30,7 +30,8 @@ class Config(C.Structure):
         "temporal_steps", "memory_size", "oversampling", "check_max_value", "mono", "sensors_per_axis", "ifpad")] + \
         [(n, C.c_double) for n in (
             "Lx", "Ly", "dt", "te", "t0", "mu", "nu", "agent_power", "max_value", "obs_scale", "reward_gain",
-            "reward_pow", "reward_div", "reward_offset", "action_punish", "delta_action_punish")]
+            "reward_pow", "reward_div", "reward_offset", "action_punish", "delta_action_punish", "rtol", "atol")] + \
+        [("adaptive", C.c_int32), ("reserved0", C.c_int32)]
 
 
 class PdeB200Error(RuntimeError):

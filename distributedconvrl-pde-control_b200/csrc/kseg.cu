@@ -104,9 +104,146 @@ __global__ void __launch_bounds__(MAXT) kseg_step_kernel(const __grid_constant__
     }
 }
 
+// ---- adaptive-step parity mode ---------------------------------------------------------------------
+// The reference's active stepper: solve(ODEProblem(f, y, (t, t + dt), p), RK4(), reltol = 1e-8, abstol = 1e-8)
+// (KellerSegelSetup.jl:234-239).  OrdinaryDiffEq's step controller is third-party and its step sequence is not pinned by
+// anything the reference ships, so this is an error-controlled integrator of the SAME tableau, not a transliteration:
+// classical RK4 with step doubling (one step of h against two of h/2, e = (y2 - y1)/15, the fifth-order Richardson-
+// extrapolated value y2 + e is kept while the 16x larger error of the single full step is what is held below the tolerance:
+// conservative, the result then sits inside the reference solver's own 1e-8 of the golden rows), error norm = RMS over all
+// 2 nx components of 16 e / (atol + rtol max(|y|, |y_new|)) like OrdinaryDiffEq's default norm, step factor 0.9 err^(-1/5)
+// clamped to [0.2, 5].  One environment per CTA: the step
+// decisions of an environment are its own (per-env step control), uniform across the CTA.
+template <typename T>
+struct KsegAdaptArgs {
+    KsegArgs<T> K;
+    T dt, rtol, atol;
+    int max_steps;
+    T* hlast;                    // [B] last accepted step (0 = not yet known)
+    int* nsub;                   // [B][2] accepted, rejected
+};
+
+// one classical RK4 step of size h from y (registers); CTA barriers inside: every thread of the CTA calls it
+template <typename T>
+__device__ __forceinline__ typename V2<T>::type rk4_once(typename V2<T>::type y, T h, T p, const KsegArgs<T>& A, typename V2<T>::type* l0,
+                                                         typename V2<T>::type* l1, int i, bool on) {
+    const int nx = A.nx;
+    const T h2 = T(0.5) * h, h6 = h / T(6);
+    T k1u = 0, k1v = 0, k2u = 0, k2v = 0, k3u = 0, k3v = 0, k4u = 0, k4v = 0;
+    if (on) l0[i] = y;
+    __syncthreads();
+    if (on) { rhs<T>(l0, i, nx, p, A.c1, A.c2, k1u, k1v); l1[i] = V2<T>::make(y.x + h2 * k1u, y.y + h2 * k1v); }
+    __syncthreads();
+    if (on) { rhs<T>(l1, i, nx, p, A.c1, A.c2, k2u, k2v); l0[i] = V2<T>::make(y.x + h2 * k2u, y.y + h2 * k2v); }
+    __syncthreads();
+    if (on) { rhs<T>(l0, i, nx, p, A.c1, A.c2, k3u, k3v); l1[i] = V2<T>::make(y.x + h * k3u, y.y + h * k3v); }
+    __syncthreads();
+    if (on) {
+        rhs<T>(l1, i, nx, p, A.c1, A.c2, k4u, k4v);
+        y.x = y.x + h6 * (k1u + T(2) * (k2u + k3u) + k4u);
+        y.y = y.y + h6 * (k1v + T(2) * (k2v + k3v) + k4v);
+    }
+    return y;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024) kseg_adaptive_kernel(const __grid_constant__ KsegAdaptArgs<T> A) {
+    using C = typename V2<T>::type;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const KsegArgs<T>& K = A.K;
+    const int nx = K.nx, i = threadIdx.x, env = blockIdx.x;
+    C* l0 = reinterpret_cast<C*>(smem_raw);
+    C* l1 = l0 + nx;
+    __shared__ double s_red[32];
+    __shared__ long long s_max;
+    const bool on = i < nx;
+    if (i == 0) s_max = 0;
+    C* yg = reinterpret_cast<C*>(K.y) + (size_t)env * nx;
+    C y = on ? yg[i] : V2<T>::make(T(0), T(0));
+    const T p = on ? K.p[(size_t)env * nx + i] : T(0);
+    T t = T(0);
+    T h = A.hlast[env] > T(0) ? A.hlast[env] : A.dt / T(K.S);        // warm start: the previous env step's last accepted size
+    int acc = 0, rej = 0;
+    const int n_warps = (blockDim.x + 31) >> 5;
+    while (t < A.dt && acc + rej < A.max_steps) {
+        const bool last = t + h >= A.dt;
+        const T hs = last ? A.dt - t : h;
+        const C y1 = rk4_once<T>(y, hs, p, K, l0, l1, i, on);
+        const C ym = rk4_once<T>(y, T(0.5) * hs, p, K, l0, l1, i, on);
+        const C y2 = rk4_once<T>(ym, T(0.5) * hs, p, K, l0, l1, i, on);
+        // local error of the two-half-step solution and the extrapolated value
+        const T eu = (y2.x - y1.x) / T(15), ev = (y2.y - y1.y) / T(15);
+        const C yn = V2<T>::make(y2.x + eu, y2.y + ev);
+        double e2 = 0.0;
+        if (on) {
+            const double su = (double)A.atol + (double)A.rtol * fmax(fabs((double)y.x), fabs((double)yn.x));
+            const double sv = (double)A.atol + (double)A.rtol * fmax(fabs((double)y.y), fabs((double)yn.y));
+            // controlled quantity: the error of the SINGLE full step (16 e), while the extrapolated two-half-step value is kept
+            const double ru = 16.0 * (double)eu / su, rv = 16.0 * (double)ev / sv;
+            e2 = ru * ru + rv * rv;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+        __syncthreads();                                            // s_red of the previous attempt has been read by everyone
+        if ((i & 31) == 0) s_red[i >> 5] = e2;
+        __syncthreads();
+        double tot = 0.0;
+        for (int w = 0; w < n_warps; ++w) tot += s_red[w];
+        const double err = sqrt(tot / (2.0 * nx));
+        const bool ok = err <= 1.0;                                 // NaN compares false: rejected, step shrinks
+        if (ok) { y = yn; t = last ? A.dt : t + hs; ++acc; }
+        else ++rej;
+        double fac = err == err ? (err > 0.0 ? 0.9 * pow(err, -0.2) : 5.0) : 0.2;
+        fac = fmin(5.0, fmax(0.2, fac));
+        // an accepted step that was truncated to land on t + dt says nothing about the natural step size: keep h
+        if (!(ok && hs < h)) h = (T)((double)hs * fac);
+    }
+    if (i == 0) { A.hlast[env] = h; A.nsub[2 * env] = acc; A.nsub[2 * env + 1] = rej; }
+    if (on) {
+        yg[i] = y; l0[i] = y;
+        const double m = (double)fmax(fabs(y.x), fabs(y.y));
+        atomicMax(&s_max, __double_as_longlong(m));
+    }
+    __syncthreads();
+    if (i == 0) K.vmax_out[env] = (T)__longlong_as_double(s_max);
+    const int ns = K.n_sensors;
+    if (on) {
+        for (int q = i; q < 2 * ns; q += nx) {
+            const int f = q / ns, k = q % ns;
+            T a = T(0);
+            for (int j = 0; j < K.sens.nnz_max; ++j) {
+                const C v = l0[K.sens.idx[j * ns + k]];
+                a += (f ? v.y : v.x) * K.sens.w[j * ns + k];
+            }
+            K.sensors_out[(size_t)env * 2 * ns + q] = a;
+        }
+    }
+}
+
+template <typename T>
+int32_t launch_adaptive(pdeb200_ctx* c) {
+    const pdeb200_config& g = c->cfg;
+    KsegAdaptArgs<T> A;
+    const double dx = g.Lx / g.nx;
+    A.K.nx = g.nx; A.K.S = g.oversampling; A.K.n_sensors = g.n_sensors; A.K.n_envs = g.n_envs; A.K.E = 1;
+    A.K.h = (T)(g.dt / g.oversampling); A.K.c1 = (T)(0.5 / dx); A.K.c2 = (T)(1.0 / (dx * dx));
+    A.K.sens = EllTable<T>{c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows};
+    A.K.y = (T*)c->y; A.K.p = (const T*)c->p; A.K.sensors_out = (T*)c->sensors; A.K.vmax_out = (T*)c->vmax;
+    A.dt = (T)g.dt; A.rtol = (T)g.rtol; A.atol = (T)g.atol; A.max_steps = 100000;
+    A.hlast = (T*)c->d_hlast; A.nsub = c->d_nsub;
+    const int tpb = ((g.nx + 31) / 32) * 32;
+    const size_t smem = (size_t)2 * g.nx * 2 * sizeof(T);
+    PDEB_CUDA(c, ensure_dyn_smem(kseg_adaptive_kernel<T>, smem, c->device));
+    kseg_adaptive_kernel<T><<<g.n_envs, tpb, smem, c->stream>>>(A);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return PDEB200_OK;
+}
+
 template <typename T>
 int32_t launch(pdeb200_ctx* c) {
     const pdeb200_config& g = c->cfg;
+    if (g.adaptive) return launch_adaptive<T>(c);
     KsegArgs<T> A;
     const double dx = g.Lx / g.nx;
     A.nx = g.nx; A.S = g.oversampling; A.n_sensors = g.n_sensors;

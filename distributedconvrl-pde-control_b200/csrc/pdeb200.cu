@@ -369,6 +369,7 @@ ArrInfo arr_info(pdeb200_ctx* c, int which) {
         case PDEB200_ARR_LOSSES: return {c->d_losses, 2 * sizeof(float)};
         case PDEB200_ARR_STATS: return {agent_stats(c), 8 * sizeof(double)};
         case PDEB200_ARR_SENSORS: return {c->sensors, B * c->fields * c->cfg.n_sensors * e};
+        case PDEB200_ARR_NSUB: return {c->d_nsub, B * 2 * sizeof(int)};
     }
     return {nullptr, 0};
 }
@@ -388,6 +389,7 @@ int32_t pdeb200_default_config(int32_t problem, pdeb200_config* cfg) {
     cfg->struct_size = (int32_t)sizeof(pdeb200_config);
     cfg->problem = problem; cfg->dtype = PDEB200_F64; cfg->ny = 1; cfg->n_envs = 1;
     cfg->temporal_steps = 1; cfg->memory_size = 0; cfg->mono = 0; cfg->ifpad = 1;
+    cfg->adaptive = 0; cfg->rtol = 1e-8; cfg->atol = 1e-8;
     cfg->Ly = 1.0; cfg->t0 = 0.0;
     switch (problem) {
         case PDEB200_KS:          // scripts/KS/setup/KSSetup.jl:20-51, 162-184, 201
@@ -429,6 +431,9 @@ int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** 
         cfg->window_size % 2 == 0 || cfg->temporal_steps < 1 || cfg->memory_size < 0)
         return fail(nullptr, PDEB200_EINVAL, "create: bad sizes (n_envs/nx/n_sensors/n_actuators/window/temporal/memory)");
     if (cfg->dtype != PDEB200_F32 && cfg->dtype != PDEB200_F64) return fail(nullptr, PDEB200_EINVAL, "create: bad dtype");
+    if (cfg->adaptive && cfg->problem != PDEB200_KSEG1D)
+        return fail(nullptr, PDEB200_EUNSUPPORTED, "create: adaptive = 1 exists for PDEB200_KSEG1D only");
+    if (cfg->adaptive && !(cfg->rtol > 0.0 && cfg->atol > 0.0)) return fail(nullptr, PDEB200_EINVAL, "create: adaptive needs rtol, atol > 0");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail(nullptr, PDEB200_ECUDA, "create: no CUDA device (this library has no CPU fallback)");
@@ -476,7 +481,8 @@ int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** 
               alloc((void**)&c->time, B * 8) && alloc((void**)&c->steps, B * 4) && alloc((void**)&c->d_mask, B) &&
               alloc((void**)&c->d_rsum, B * 8) && alloc(&c->d_noise, nact * e) && alloc(&c->vmax, B * e) &&
               alloc((void**)&c->d_a2s, cfg->n_actuators * 4) && alloc(&c->d_sens_sum, cfg->n_sensors * e) &&
-              alloc((void**)&c->d_losses, 8) && alloc((void**)&c->d_counts, 16);
+              alloc((void**)&c->d_losses, 8) && alloc((void**)&c->d_counts, 16) && alloc((void**)&c->d_nsub, B * 8) &&
+              alloc(&c->d_hlast, B * 8);
     if (!ok) return bail(fail(c, PDEB200_ECUDA, std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError())));
     int32_t rc = PDEB200_OK;
     switch (cfg->problem) {
@@ -498,7 +504,7 @@ int32_t pdeb200_destroy(pdeb200_ctx* c) {
     for (void* p : {c->y, c->y0, c->p, c->state, c->action, c->action_in, c->delta_action, c->reward, c->sensors,
                     (void*)c->done, (void*)c->time, (void*)c->steps, (void*)c->d_mask, (void*)c->d_rsum, c->d_noise, c->vmax,
                     (void*)c->d_a2s, c->d_sens_sum, (void*)c->sens.d_idx, c->sens.d_w, (void*)c->actT.d_idx, c->actT.d_w,
-                    (void*)c->d_grads, (void*)c->d_losses, (void*)c->d_counts})
+                    (void*)c->d_grads, (void*)c->d_losses, (void*)c->d_counts, (void*)c->d_nsub, c->d_hlast})
         if (p) cudaFree(p);
     for (auto& n : c->nets)
         for (void* p : {(void*)n.d_params, (void*)n.d_m, (void*)n.d_v, (void*)n.d_betap})

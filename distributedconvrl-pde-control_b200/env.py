@@ -123,7 +123,7 @@ class PDEenv:
             L.ARR_DELTA_ACTION: (B * self.n_actuators * self.a_rows, self.np_dtype),
             L.ARR_ACTION_IN: (B * self.n_actuators * self.a_rows, self.np_dtype),
             L.ARR_REWARD: (B * self.n_rew, self.np_dtype), L.ARR_DONE: (B, np.uint8),
-            L.ARR_TIME: (B, np.float64), L.ARR_STEPS: (B, np.int32),
+            L.ARR_TIME: (B, np.float64), L.ARR_STEPS: (B, np.int32), L.ARR_NSUB: (2 * B, np.int32),
             L.ARR_SENSORS: (B * (2 if self.problem in (L.KSEG1D, L.KSEG2D) else 1) * self.n_sensors, self.np_dtype),
         }[which]
 
@@ -227,6 +227,11 @@ class PDEenv:
     @property
     def steps(self):
         return self.get(L.ARR_STEPS)
+
+    @property
+    def substeps(self):
+        """Adaptive-step mode: (accepted, rejected) integrator steps of the last env step, per environment -> (B, 2)."""
+        return self.get(L.ARR_NSUB).reshape(self.n_envs, 2)
 
     @property
     def sensors(self):

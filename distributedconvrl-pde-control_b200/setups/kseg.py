@@ -45,11 +45,13 @@ class KellerSegelSetup:
         y0[:, 1] += a[:, ns:] @ basis
         return y0
 
-    def make_env(self, n_envs=1, dtype="f64", device=0, y0=None):
+    def make_env(self, n_envs=1, dtype="f64", device=0, y0=None, adaptive=False, rtol=1e-8, atol=1e-8):
+        """adaptive=True: the reference's ACTIVE integrator mode -- error-controlled RK4 at (rtol, atol) with per-environment
+        step control (KellerSegelSetup.jl:234-239) instead of `rk4_substeps` fixed substeps."""
         y0 = self.y0_standard() if y0 is None else np.asarray(y0, dtype=np.float64)
         if y0.ndim == 3:                      # (B, 2, nx) -> reference shape (2, nx, B)
             y0 = y0.transpose(1, 2, 0)
-        return PDEenv(problem=L.KSEG1D, n_envs=n_envs, dtype=dtype, device=device, sensor_basis=self.gaussians,
+        return PDEenv(problem=L.KSEG1D, adaptive=int(bool(adaptive)), rtol=float(rtol), atol=float(atol), n_envs=n_envs, dtype=dtype, device=device, sensor_basis=self.gaussians,
                       actuator_basis=self.gaussians_actuators, actuators_to_sensors=self.actuators_to_sensors, y0=y0,
                       nx=self.nx, ny=1, Lx=self.Lx, dt=self.dt, te=self.te, oversampling=self.rk4_substeps,
                       max_value=self.max_value, window_size=self.window_size, temporal_steps=self.temporal_steps,

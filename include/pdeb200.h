@@ -83,6 +83,7 @@ enum {
     PDEB200_ARR_LOSSES = 11,      /* {critic_loss, actor_loss}               float32 */
     PDEB200_ARR_SENSORS = 12,     /* raw sensor dots [B][fields][n_sensors]  dtype   */
     PDEB200_ARR_ACTION_IN = 13,   /* staged action of the last policy_act    dtype   */
+    PDEB200_ARR_NSUB = 15,        /* adaptive mode: {accepted, rejected} substeps of the last env step  int32 [B][2] */
     PDEB200_ARR_STATS = 14        /* batch sums over ALL ranks {sum r, sum r^2, n, sum c, sum c^2, sum q(actor)}  float64[8] (quirk Q1 r-bar) */
 };
 
@@ -115,6 +116,13 @@ typedef struct pdeb200_config {
     double reward_offset;
     double action_punish;
     double delta_action_punish;
+    /* Adaptive-step parity mode.  The reference's ACTIVE Keller-Segel stepper is OrdinaryDiffEq's
+     * adaptive RK4() at reltol = abstol = 1e-8 (KellerSegelSetup.jl:234-239): adaptive = 1 integrates each environment
+     * with its own error-controlled step sequence (classical RK4 + step doubling, RMS error norm like OrdinaryDiffEq's
+     * default) instead of `oversampling` fixed substeps.  KSEG1D only. */
+    double rtol, atol;
+    int32_t adaptive;
+    int32_t reserved0;
 } pdeb200_config;
 
 /* ---- lifecycle -------------------------------------------------------------------------- */

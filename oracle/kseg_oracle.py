@@ -95,6 +95,44 @@ def do_step(cfg, y, p):
     return y
 
 
+def do_step_adaptive(cfg, y, p, rtol=1e-8, atol=1e-8, h0=None, return_stats=False):
+    """Error-controlled RK4 over [t, t+dt] in the role of the reference's `solve(prob, RK4(), reltol=1e-8, abstol=1e-8)`
+    (KellerSegelSetup.jl:234-239).  OrdinaryDiffEq's own controller is third-party and unpinned; this is the
+    controller the CUDA adaptive mode implements: step doubling with the classical tableau, e = (y2 - y1)/15, the
+    extrapolated value y2 + e kept while the (16x larger) error of the single full step is what is held below the
+    tolerance -- conservative, so that the result sits inside the reference solver's own 1e-8 of the golden rows --, RMS error norm over all components against atol + rtol max(|y|, |y_new|), step factor
+    0.9 err^(-1/5) clamped to [0.2, 5], first trial step dt / n_sub (or h0)."""
+    def rk4(y, h):
+        k1 = f(cfg, y, p)
+        k2 = f(cfg, y + 0.5 * h * k1, p)
+        k3 = f(cfg, y + 0.5 * h * k2, p)
+        k4 = f(cfg, y + h * k3, p)
+        return y + (h / 6) * (k1 + 2 * (k2 + k3) + k4)
+    y = np.array(y, dtype=np.float64)
+    t, h = 0.0, (cfg.dt / cfg.n_sub if h0 is None else h0)
+    acc = rej = 0
+    while t < cfg.dt:
+        last = t + h >= cfg.dt
+        hs = cfg.dt - t if last else h
+        y1 = rk4(y, hs)
+        y2 = rk4(rk4(y, 0.5 * hs), 0.5 * hs)
+        e = (y2 - y1) / 15
+        yn = y2 + e
+        sc = atol + rtol * np.maximum(np.abs(y), np.abs(yn))
+        err = float(np.sqrt(np.sum((16 * e / sc) ** 2) / e.size))      # controlled: the error of the single full step, 16 e
+        ok = err <= 1.0
+        if ok:
+            y, t = yn, (cfg.dt if last else t + hs)
+            acc += 1
+        else:
+            rej += 1
+        fac = (0.9 * err ** -0.2 if err > 0 else 5.0) if err == err else 0.2
+        fac = min(5.0, max(0.2, fac))
+        if not (ok and hs < h):
+            h = hs * fac
+    return (y, h, acc, rej) if return_stats else y
+
+
 def do_step_ref(cfg, y, p, tol=1e-12):
     """High-accuracy integration of the same ODE (stand-in for the reference's adaptive solver)."""
     from scipy.integrate import solve_ivp
