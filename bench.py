@@ -52,6 +52,9 @@ def parse():
     ap.add_argument("--train-steps", type=int, default=30, help="timed loop steps per update_loops setting")
     ap.add_argument("--e2e-driver", default="native", choices=["native", "python"],
                     help="host threads of the e2e leg: native std::threads calling the C ABI (libpdeb200_host.so) or Python threads")
+    ap.add_argument("--e2e-calls", default="fused", choices=["fused", "split"],
+                    help="fused: policy(env) + env(action) as ONE C call with one sync and one packed result copy "
+                         "(pdeb200_act_step_host); split: policy_act -> get(ACTION_IN) -> step_host (three syncs, four copies)")
     ap.add_argument("--e2e-shards", type=int, default=4,
                     help="the e2e leg drives the batch as this many env shards (own context + stream + host thread each) "
                          "so that one shard's PCIe copies overlap another shard's kernels")
@@ -460,9 +463,17 @@ def run_ours(args):
             self.h_rew = torch.empty(self.n_act, dtype=tdt).pin_memory()
             self.h_state = torch.empty(self.n_act * self.env.ns, dtype=tdt).pin_memory()
             self.h_done = torch.empty(Bs, dtype=torch.uint8).pin_memory()
+            tot = C.c_size_t()
+            L.check(self.env._lib.pdeb200_result_layout(self.env._ctx, None, None, None, C.byref(tot)), self.env._ctx)
+            self.packed_bytes = tot.value
+            self.h_packed = torch.empty(tot.value, dtype=torch.uint8).pin_memory()      # [reward | state | done], one D2H
 
         def step(self):
             lib, ctx = self.env._lib, self.env._ctx
+            if args.e2e_calls == "fused":
+                L.check(lib.pdeb200_act_step_host(ctx, None, 0.0, 1.0, C.c_void_p(self.h_act.data_ptr()), None,
+                                                  C.c_void_p(self.h_packed.data_ptr()), None, None, None), ctx)
+                return
             L.check(lib.pdeb200_policy_act(ctx, None, 0.0, 1.0), ctx)
             L.check(lib.pdeb200_get(ctx, L.ARR_ACTION_IN, C.c_void_p(self.h_act.data_ptr()), self.n_act * esz), ctx)
             L.check(lib.pdeb200_step_host(ctx, C.c_void_p(self.h_act.data_ptr()), None, C.c_void_p(self.h_rew.data_ptr()),
@@ -478,7 +489,9 @@ def run_ours(args):
             raise SystemExit("bench.py: %s missing (python __graft_entry__.py build)" % hp)
         host_lib = C.CDLL(str(hp))
         host_lib.pdeb200_host_drive.restype = C.c_int32
+        host_lib.pdeb200_host_drive2.restype = C.c_int32
         VP = C.c_void_p * n_sh
+        packs = VP(*[sh.h_packed.data_ptr() for sh in shards])
         ctxs = VP(*[sh.env._ctx.value for sh in shards])
         acts = VP(*[sh.h_act.data_ptr() for sh in shards])
         rews = VP(*[sh.h_rew.data_ptr() for sh in shards])
@@ -490,8 +503,11 @@ def run_ours(args):
         if host_lib is not None:
             # one std::thread per shard, each running policy_act -> get(ACTION_IN) -> step_host through the C ABI
             secs = C.c_double()
-            rc = host_lib.pdeb200_host_drive(C.c_int32(n_sh), ctxs, C.c_int32(n), acts, nbytes, rews, sts, dns, C.c_double(1.0),
-                                             C.byref(secs))
+            if args.e2e_calls == "fused":
+                rc = host_lib.pdeb200_host_drive2(C.c_int32(n_sh), ctxs, C.c_int32(n), acts, packs, C.c_double(1.0), C.byref(secs))
+            else:
+                rc = host_lib.pdeb200_host_drive(C.c_int32(n_sh), ctxs, C.c_int32(n), acts, nbytes, rews, sts, dns, C.c_double(1.0),
+                                                 C.byref(secs))
             if rc:
                 raise SystemExit("bench.py: e2e driver failed with %d" % rc)
             return secs.value
@@ -567,8 +583,11 @@ def run_ours(args):
             "dtype": args.dtype, "data": "synthetic", "config": config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "shards": n_sh, "launches": int(e2e_launches), "host_threads": args.e2e_driver, "cpu_binding": numa,
-                    "call_sequence": "per shard and step: pdeb200_policy_act -> pdeb200_get(ACTION_IN) [D2H] -> "
-                                     "pdeb200_step_host [H2D action; D2H reward, state, done], pinned host buffers"},
+                    "call_sequence": ("per shard and step: pdeb200_act_step_host = policy(env) -> action to the host [D2H] -> env(action) "
+                                      "from the host [H2D] -> [reward | state | done] to the host in one packed copy [D2H]; one "
+                                      "synchronisation; pinned host buffers") if args.e2e_calls == "fused" else
+                                     ("per shard and step: pdeb200_policy_act -> pdeb200_get(ACTION_IN) [D2H] -> "
+                                      "pdeb200_step_host [H2D action; D2H reward, state, done], pinned host buffers")},
             "gpu_launches": int(launches), "clocks": clk, "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -12,6 +12,31 @@
 
 #include "../../../include/pdeb200.h"
 
+// fused = 1: the same two reference-side calls as ONE C call with one synchronisation and one packed result copy
+// (pdeb200_act_step_host); h_packed[k] then receives [reward | state | done] (pdeb200_result_layout).
+extern "C" int32_t pdeb200_host_drive2(int32_t n_shards, pdeb200_ctx** ctxs, int32_t steps, void** h_act, void** h_packed, double act_limit,
+                                       double* seconds_out) {
+    if (n_shards < 1 || !ctxs || steps < 0 || !h_act || !h_packed || !seconds_out) return PDEB200_EINVAL;
+    std::atomic<int> ready{0}, failed{0};
+    std::atomic<bool> go{false};
+    std::vector<std::thread> th;
+    auto work = [&](int k) {
+        ready.fetch_add(1);
+        while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+        for (int i = 0; i < steps; ++i) {
+            const int32_t rc = pdeb200_act_step_host(ctxs[k], nullptr, 0.0, act_limit, h_act[k], nullptr, h_packed[k], nullptr, nullptr, nullptr);
+            if (rc) { failed.store(rc); return; }
+        }
+    };
+    for (int k = 0; k < n_shards; ++k) th.emplace_back(work, k);
+    while (ready.load() < n_shards) std::this_thread::yield();
+    const auto t0 = std::chrono::steady_clock::now();
+    go.store(true, std::memory_order_release);
+    for (auto& t : th) t.join();
+    *seconds_out = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return failed.load();
+}
+
 extern "C" int32_t pdeb200_host_drive(int32_t n_shards, pdeb200_ctx** ctxs, int32_t steps, void** h_act, const size_t* act_bytes,
                                       void** h_reward, void** h_state, uint8_t** h_done, double act_limit, double* seconds_out) {
     if (n_shards < 1 || !ctxs || steps < 0 || !h_act || !act_bytes || !seconds_out) return PDEB200_EINVAL;

@@ -474,16 +474,25 @@ int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** 
         return cudaMemset(*p, 0, bytes ? bytes : 16) == cudaSuccess;
     };
     const size_t nact = B * cfg->n_actuators * c->a_rows;
+    // what a host reads back after every env step lives in ONE block [reward | state | done]: a single D2H copy
+    auto up256 = [](size_t b) { return (b + 255) / 256 * 256; };
+    c->res_reward_off = 0;
+    c->res_state_off = up256(B * c->n_rew * e);
+    c->res_done_off = c->res_state_off + up256(B * c->n_cols * c->obs_rows * e);
+    c->res_bytes = c->res_done_off + up256(B);
     bool ok = alloc(&c->y, B * c->y_elems * e) && alloc(&c->y0, B * c->y_elems * e) && alloc(&c->p, B * c->p_elems * e) &&
-              alloc(&c->state, B * c->n_cols * c->obs_rows * e) && alloc(&c->action, nact * e) &&
-              alloc(&c->action_in, nact * e) && alloc(&c->delta_action, nact * e) && alloc(&c->reward, B * c->n_rew * e) &&
-              alloc(&c->sensors, B * c->fields * cfg->n_sensors * e) && alloc((void**)&c->done, B) &&
+              alloc(&c->result_block, c->res_bytes) && alloc(&c->action, nact * e) &&
+              alloc(&c->action_in, nact * e) && alloc(&c->delta_action, nact * e) &&
+              alloc(&c->sensors, B * c->fields * cfg->n_sensors * e) &&
               alloc((void**)&c->time, B * 8) && alloc((void**)&c->steps, B * 4) && alloc((void**)&c->d_mask, B) &&
               alloc((void**)&c->d_rsum, B * 8) && alloc(&c->d_noise, nact * e) && alloc(&c->vmax, B * e) &&
               alloc((void**)&c->d_a2s, cfg->n_actuators * 4) && alloc(&c->d_sens_sum, cfg->n_sensors * e) &&
               alloc((void**)&c->d_losses, 8) && alloc((void**)&c->d_counts, 16) && alloc((void**)&c->d_nsub, B * 8) &&
               alloc(&c->d_hlast, B * 8);
     if (!ok) return bail(fail(c, PDEB200_ECUDA, std::string("cudaMalloc failed: ") + cudaGetErrorString(cudaGetLastError())));
+    c->reward = (char*)c->result_block + c->res_reward_off;
+    c->state = (char*)c->result_block + c->res_state_off;
+    c->done = (uint8_t*)((char*)c->result_block + c->res_done_off);
     int32_t rc = PDEB200_OK;
     switch (cfg->problem) {
         case PDEB200_KS: rc = ks_setup(c); break;
@@ -501,8 +510,8 @@ int32_t pdeb200_destroy(pdeb200_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     ks_free(c); kseg_free(c); ns_free(c); agent_free(c); comm_free(c);
-    for (void* p : {c->y, c->y0, c->p, c->state, c->action, c->action_in, c->delta_action, c->reward, c->sensors,
-                    (void*)c->done, (void*)c->time, (void*)c->steps, (void*)c->d_mask, (void*)c->d_rsum, c->d_noise, c->vmax,
+    for (void* p : {c->y, c->y0, c->p, c->result_block, c->action, c->action_in, c->delta_action, c->sensors,
+                    (void*)c->time, (void*)c->steps, (void*)c->d_mask, (void*)c->d_rsum, c->d_noise, c->vmax,
                     (void*)c->d_a2s, c->d_sens_sum, (void*)c->sens.d_idx, c->sens.d_w, (void*)c->actT.d_idx, c->actT.d_w,
                     (void*)c->d_grads, (void*)c->d_losses, (void*)c->d_counts, (void*)c->d_nsub, c->d_hlast})
         if (p) cudaFree(p);
@@ -622,6 +631,56 @@ int32_t pdeb200_step_host(pdeb200_ctx* c, const void* actions_host, void* y_out,
         return cudaMemcpyAsync(dst, a.ptr, a.bytes, cudaMemcpyDeviceToHost, c->stream);
     };
     PDEB_CUDA(c, back(PDEB200_ARR_Y, y_out));
+    PDEB_CUDA(c, back(PDEB200_ARR_REWARD, reward_out));
+    PDEB_CUDA(c, back(PDEB200_ARR_STATE, state_out));
+    PDEB_CUDA(c, back(PDEB200_ARR_DONE, done_out));
+    PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    return PDEB200_OK;
+}
+
+static int32_t policy_launch(pdeb200_ctx* c, const void* d_noise, int use_rng, uint64_t seed, uint64_t offset, double act_noise,
+                             double act_limit);
+
+int32_t pdeb200_result_layout(const pdeb200_ctx* c, size_t* reward_off, size_t* state_off, size_t* done_off, size_t* total_bytes) {
+    if (!c) return PDEB200_EINVAL;
+    if (reward_off) *reward_off = c->res_reward_off;
+    if (state_off) *state_off = c->res_state_off;
+    if (done_off) *done_off = c->res_done_off;
+    if (total_bytes) *total_bytes = c->res_bytes;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_act_step_host(pdeb200_ctx* c, const double* noise_host, double act_noise, double act_limit, void* action_out,
+                              void* y_out, void* result_packed, void* reward_out, void* state_out, uint8_t* done_out) {
+    if (!c || !action_out) return fail(c, PDEB200_EINVAL, "act_step_host: null argument");
+    cudaSetDevice(c->device);
+    const void* dn = nullptr;
+    std::vector<float> tmp;
+    if (noise_host) {
+        const int n_out = c->cfg.mono ? c->cfg.n_actuators * c->a_rows : c->a_rows;
+        const size_t n = (size_t)c->cfg.n_envs * c->n_cols * (n_out - (c->cfg.mono ? 0 : c->cfg.memory_size));
+        if (c->esz == 8) PDEB_CUDA(c, cudaMemcpyAsync(c->d_noise, noise_host, n * 8, cudaMemcpyHostToDevice, c->stream));
+        else {
+            tmp.resize(n);
+            for (size_t i = 0; i < n; ++i) tmp[i] = (float)noise_host[i];
+            PDEB_CUDA(c, cudaMemcpyAsync(c->d_noise, tmp.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
+        }
+        dn = c->d_noise;
+    }
+    int32_t rc = policy_launch(c, dn, 0, 0, 0, act_noise, act_limit);
+    if (rc) return rc;
+    // policy(env) hands the action to the host; env(action) takes it from there (stream order: D2H, then H2D of the same buffer)
+    const size_t abytes = (size_t)c->cfg.n_envs * c->cfg.n_actuators * c->a_rows * c->esz;
+    PDEB_CUDA(c, cudaMemcpyAsync(action_out, c->action_in, abytes, cudaMemcpyDeviceToHost, c->stream));
+    PDEB_CUDA(c, cudaMemcpyAsync(c->action_in, action_out, abytes, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = do_step(c, c->action_in, 1, 0, 0.0, nullptr))) return rc;
+    if (y_out) PDEB_CUDA(c, cudaMemcpyAsync(y_out, c->y, (size_t)c->cfg.n_envs * c->y_elems * c->esz, cudaMemcpyDeviceToHost, c->stream));
+    if (result_packed) PDEB_CUDA(c, cudaMemcpyAsync(result_packed, c->result_block, c->res_bytes, cudaMemcpyDeviceToHost, c->stream));
+    auto back = [&](int which, void* dst) -> cudaError_t {
+        if (!dst) return cudaSuccess;
+        ArrInfo a = arr_info(c, which);
+        return cudaMemcpyAsync(dst, a.ptr, a.bytes, cudaMemcpyDeviceToHost, c->stream);
+    };
     PDEB_CUDA(c, back(PDEB200_ARR_REWARD, reward_out));
     PDEB_CUDA(c, back(PDEB200_ARR_STATE, state_out));
     PDEB_CUDA(c, back(PDEB200_ARR_DONE, done_out));

@@ -165,6 +165,14 @@ int32_t pdeb200_step_device(pdeb200_ctx* ctx, const void* actions_dev);
  * Any output pointer may be NULL. */
 int32_t pdeb200_step_host(pdeb200_ctx* ctx, const void* actions_host, void* y_out, void* reward_out,
                           void* state_out, uint8_t* done_out);
+/* `action = policy(env); env(action)` with HOST buffers as ONE call with ONE synchronisation (the drop-in closures' two calls
+ * back to back): actor forward (+ optional host noise, as pdeb200_policy_act) -> the action is copied to action_out (HOST) and
+ * taken back from that buffer as the step's input (stream-ordered D2H then H2D) -> env step -> results to the host.
+ * result_packed: optional HOST buffer of pdeb200_result_layout's total_bytes receiving [reward | state | done] in ONE copy
+ * (they share one device allocation); reward_out / state_out / done_out: optional separate destinations instead. */
+int32_t pdeb200_act_step_host(pdeb200_ctx* ctx, const double* noise_host, double act_noise, double act_limit, void* action_out,
+                              void* y_out, void* result_packed, void* reward_out, void* state_out, uint8_t* done_out);
+int32_t pdeb200_result_layout(const pdeb200_ctx* ctx, size_t* reward_off, size_t* state_off, size_t* done_off, size_t* total_bytes);
 int32_t pdeb200_get(pdeb200_ctx* ctx, int32_t which, void* host_dst, size_t bytes);
 /* One environment's slice of a per-environment array (PDEhook's tracked environment: src/PDEhook.jl:54-62). */
 int32_t pdeb200_get_env(pdeb200_ctx* ctx, int32_t which, int32_t env_index, void* host_dst, size_t bytes);

@@ -96,3 +96,38 @@ def test_policy_noise_and_clamp(pkg):
     assert relerr(env.action, expect) < 1e-6
     assert np.max(np.abs(env.action)) <= 1.0
     env.close()
+
+
+def test_act_step_host_equals_policy_act_then_step_host(pkg, golden):
+    """`action = policy(env); env(action)` as ONE C call (pdeb200_act_step_host, one packed result copy) must give exactly
+    what the two calls give (PDEagent.jl:175-209 then PDEenv.jl:195-241)."""
+    import ctypes as C
+    A = _agent_mod(pkg)
+    L = pkg.lib
+    g = golden("ks200_hook")
+    chain = A.Chain(A.Dense(g["best_W1"], g["best_b1"], "relu"), A.Dense(g["best_W2"], g["best_b2"], "tanh"))
+    setup = pkg.setups.KSSetup.ks200()
+    B = 5
+    y0 = setup.generate_random_init(np.random.default_rng(2), B)
+    envs = [setup.make_env(n_envs=B, dtype="f64", y0=y0) for _ in range(2)]
+    for e in envs:
+        A.CustomNeuralNetworkApproximator(e, L.NET_BEHAVIOR_ACTOR, chain.copy())
+    noise = np.random.default_rng(3).standard_normal(B * 80)
+    a, b = envs
+    offs = [C.c_size_t() for _ in range(4)]
+    L.check(a._lib.pdeb200_result_layout(a._ctx, *[C.byref(o) for o in offs]), a._ctx)
+    r_off, s_off, d_off, total = (o.value for o in offs)
+    act = np.zeros(B * 80)
+    packed = np.zeros(total, dtype=np.uint8)
+    for _ in range(3):
+        L.check(a._lib.pdeb200_act_step_host(a._ctx, noise.ctypes.data, 0.3, 1.0, act.ctypes.data, None, packed.ctypes.data, None, None, None), a._ctx)
+        b.policy_act(noise, 0.3, 1.0)
+        act_b = b.get(L.ARR_ACTION_IN)
+        b(act_b.reshape(1, -1))
+        assert np.array_equal(act, act_b)
+        assert np.array_equal(packed[r_off:r_off + B * 80 * 8].view(np.float64), b.reward)
+        assert np.array_equal(packed[s_off:s_off + B * 80 * 8].view(np.float64), b.get(L.ARR_STATE))
+        assert np.array_equal(packed[d_off:d_off + B], b.get(L.ARR_DONE))
+        assert np.array_equal(a.get(L.ARR_Y), b.get(L.ARR_Y))
+    for e in envs:
+        e.close()
