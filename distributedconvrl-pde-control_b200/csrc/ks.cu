@@ -83,16 +83,16 @@ int32_t setup_t(pdeb200_ctx* c) {
 // equal work per pair the step time is (rounds) x (time of one resident set), so a 1.73-wave grid
 // costs as much as a 2.0-wave one.  cost ~ rounds * resident_pairs; ties go to more resident warps.
 template <typename T, int N1, int N2>
-void plan(const pdeb200_ctx* c, int n_sm, int* warps_out, int* ctas_per_sm_out) {
+void plan(const pdeb200_ctx* c, int n_sm, int* warps_out, int* ctas_per_sm_out, bool lowreg) {
     using G = KsGeom<N1, N2>;
     constexpr int ppw = 32 / G::TP;
-    const int max_warps = KsMaxWarps<T>::value;
+    const int max_warps = lowreg ? KsMaxWarps<T, true>::value : KsMaxWarps<T, false>::value;
     const int n_pairs = (c->cfg.n_envs + 1) / 2;
     static const int forced = [] { const char* e = getenv("PDEB200_KS_WARPS"); return e ? atoi(e) : 0; }();
     double best = 1e300; int bw = 1, bc = 1;
     for (int w = 1; w <= max_warps; ++w) {
         if (forced && w != forced) continue;
-        const size_t smem = ks_smem_bytes<T, N1, N2>(w * ppw) + 1024;
+        const size_t smem = ks_smem_bytes<T, N1, N2>(w * ppw, c->cfg.oversampling > 1) + 1024;
         int cps = std::min((int)((227 * 1024) / smem), max_warps / w);
         if (cps < 1) continue;
         const int ppc = w * ppw;
@@ -149,7 +149,10 @@ int32_t launch(pdeb200_ctx* c) {
     int n_sm = 148;
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, c->device);
     int warps, cps;
-    plan<T, N1, N2>(c, n_sm, &warps, &cps);
+    // few substeps: the low-register variant (12 warps/SM in fp64); PDEB200_KS_LOWREG=0/1 overrides for experiments
+    static const int force_low = [] { const char* e = getenv("PDEB200_KS_LOWREG"); return e ? atoi(e) : -1; }();
+    const bool lowreg = sizeof(T) == 8 && G::RMAX <= 16 && (force_low >= 0 ? force_low != 0 : g.oversampling <= 4);
+    plan<T, N1, N2>(c, n_sm, &warps, &cps, lowreg);
     const int PAIRS = warps * 32 / G::TP;
     KsArgs<T> A;
     A.n_envs = g.n_envs; A.S = g.oversampling; A.n_sensors = g.n_sensors;
@@ -166,8 +169,8 @@ int32_t launch(pdeb200_ctx* c) {
     A.y = (T*)c->y; A.p = (const T*)c->p; A.sensors_out = (T*)c->sensors; A.vmax_out = (T*)c->vmax;
     const int n_pairs = (g.n_envs + 1) / 2;
     const int grid = (n_pairs + PAIRS - 1) / PAIRS;
-    const size_t smem = ks_smem_bytes<T, N1, N2>(PAIRS);
-    auto kern = ks_step_kernel<T, N1, N2>;
+    const size_t smem = ks_smem_bytes<T, N1, N2>(PAIRS, g.oversampling > 1);
+    auto kern = lowreg ? ks_step_kernel<T, N1, N2, true> : ks_step_kernel<T, N1, N2, false>;
     PDEB_CUDA(c, ensure_dyn_smem(kern, smem, c->device));
     kern<<<grid, warps * 32, smem, c->stream>>>(A);
     PDEB_CUDA(c, cudaGetLastError());

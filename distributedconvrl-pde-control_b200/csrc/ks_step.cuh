@@ -64,22 +64,26 @@ template <int N1, int N2> struct KsGeom {
 //   [tw12 | tw21 | c1 | cN] shared by all pairs, then CTA-level arrays
 //   XB[PAIRS][xb] (exchange), PREV[PAIRS][N], F[PAIRS][N].
 // PREV and F are dead after the job loop; the sensor gather table is staged there.
+// with_prev = false (one substep: N^{n-1} is never read, quirk Q2 seeds it from N^n): the PREV array is not allocated
 template <typename T, int N1, int N2>
-__host__ __device__ inline size_t ks_smem_bytes(int pairs_per_cta) {
+__host__ __device__ inline size_t ks_smem_bytes(int pairs_per_cta, bool with_prev = true) {
     using G = KsGeom<N1, N2>;
     using C = typename V2<T>::type;
     size_t shared = (size_t)(N1 == N2 ? 1 : 2) * G::N * sizeof(C) + 2 * (size_t)G::N * sizeof(T);
-    size_t per_pair = ((size_t)G::XB + 2 * G::N) * sizeof(C);
+    size_t per_pair = ((size_t)G::XB + (with_prev ? 2 : 1) * G::N) * sizeof(C);
     return shared + per_pair * pairs_per_cta;
 }
 
 // Register budget: fp64 keeps z and u_hat (4*RMAX doubles) in registers, so it is compiled for 8 resident
 // warps/SM (255 registers); fp32 for 16 warps/SM (128 registers).  The CTA size is a RUNTIME choice
 // (blockDim.x = 32*w, w <= kMaxWarps): the host picks w and the CTAs/SM so that the grid fills whole waves.
-template <typename T> struct KsMaxWarps { static constexpr int value = sizeof(T) == 8 ? 8 : 16; };
+// LOWREG (fp64 only): F stays in shared memory like in fp32, the kernel is compiled for 12 resident warps/SM (168 registers):
+// the variant for few substeps (oversampling <= 4), where the loads / stores / sensor gather around the transforms weigh as
+// much as the transforms and latency hiding matters more than the 64 shared-memory wavefronts F costs per substep.
+template <typename T, bool LOWREG = false> struct KsMaxWarps { static constexpr int value = sizeof(T) == 8 ? (LOWREG ? 12 : 8) : 16; };
 
-template <typename T, int N1, int N2>
-__global__ void __launch_bounds__(KsMaxWarps<T>::value * 32, 1)
+template <typename T, int N1, int N2, bool LOWREG = false>
+__global__ void __launch_bounds__(KsMaxWarps<T, LOWREG>::value * 32, 1)
 ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
     using G = KsGeom<N1, N2>;
     using C = typename V2<T>::type;
@@ -100,11 +104,12 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
     const int pic = threadIdx.x / TP;
     const int pair = blockIdx.x * PAIRS + pic;
     C* xb = s_xb0 + (size_t)pic * G::XB;             // exchange buffer; natural-order y at the end
+    const bool has_prev = A.S > 1;                   // one substep: no N^{n-1} array (host sizes the shared memory accordingly)
     C* s_prev0 = s_xb0 + (size_t)PAIRS * G::XB;
     C* s_prev = s_prev0 + (size_t)pic * N;           // N^{n-1} (raw fft of (N u)^2)
-    C* s_F = s_prev0 + (size_t)PAIRS * N + (size_t)pic * N;   // A_inv*h*p_hat + h*m_hat
+    C* s_F = s_prev0 + (has_prev ? (size_t)PAIRS * N : 0) + (size_t)pic * N;   // A_inv*h*p_hat + h*m_hat
     unsigned char* dead = reinterpret_cast<unsigned char*>(s_prev0);
-    const size_t dead_bytes = (size_t)2 * PAIRS * N * sizeof(C);
+    const size_t dead_bytes = (size_t)(has_prev ? 2 : 1) * PAIRS * N * sizeof(C);
 
 
     const int ea = 2 * pair, eb = 2 * pair + 1;
@@ -114,7 +119,7 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
     T zr[RMAX], zi[RMAX], ur[RMAX], ui[RMAX];
     // F = A_inv*h*p_hat + h*m_hat of this thread's modes: in registers where the register file allows it (fp64 is
     // compiled for 255 registers anyway; fp32 keeps it in shared memory to stay at 128, N > 256 would only spill)
-    constexpr bool F_REGS = sizeof(T) == 8 && RMAX <= 16;
+    constexpr bool F_REGS = sizeof(T) == 8 && RMAX <= 16 && !LOWREG;
     T fr[F_REGS ? RMAX : 1], fi[F_REGS ? RMAX : 1];
 
     // ---- load p into z and y into u (physical layout: thread t < N2 holds n = t + N2*r) -----
@@ -179,7 +184,7 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
                     T f_r, f_i;
                     if (F_REGS) { f_r = fr[r]; f_i = fi[r]; }
                     else { const C f = s_F[k]; f_r = f.x; f_i = f.y; }
-                    s_prev[k] = V2<T>::make(zr[r], zi[r]);
+                    if (has_prev) s_prev[k] = V2<T>::make(zr[r], zi[r]);
                     // u = c1*u + i*cn*(3h/2 N^n - h/2 N^{n-1}) + F  with cn32 = cn*3h/2:  u = c1*u + F + i*cn32*(N^n - N^{n-1}/3)
                     const T tr = fma(-A.third, z1.x, zr[r]);
                     const T ti = fma(-A.third, z1.y, zi[r]);
