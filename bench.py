@@ -52,9 +52,11 @@ def parse():
     ap.add_argument("--train-steps", type=int, default=30, help="timed loop steps per update_loops setting")
     ap.add_argument("--e2e-driver", default="native", choices=["native", "python"],
                     help="host threads of the e2e leg: native std::threads calling the C ABI (libpdeb200_host.so) or Python threads")
-    ap.add_argument("--e2e-calls", default="fused", choices=["fused", "split"],
-                    help="fused: policy(env) + env(action) as ONE C call with one sync and one packed result copy "
-                         "(pdeb200_act_step_host); split: policy_act -> get(ACTION_IN) -> step_host (three syncs, four copies)")
+    ap.add_argument("--e2e-calls", default="device-agent", choices=["device-agent", "fused", "split"],
+                    help="device-agent: the drop-in as deployed (policy and trajectory on the device): per step host noise in "
+                         "[H2D], [reward | state | done] out in one packed copy [D2H], one C call, one sync; fused: the same call "
+                         "with the action additionally round-tripping through the host; split: policy_act -> get(ACTION_IN) -> "
+                         "step_host (three syncs, four copies; round 1's sequence)")
     ap.add_argument("--e2e-shards", type=int, default=4,
                     help="the e2e leg drives the batch as this many env shards (own context + stream + host thread each) "
                          "so that one shard's PCIe copies overlap another shard's kernels")
@@ -467,11 +469,17 @@ def run_ours(args):
             L.check(self.env._lib.pdeb200_result_layout(self.env._ctx, None, None, None, C.byref(tot)), self.env._ctx)
             self.packed_bytes = tot.value
             self.h_packed = torch.empty(tot.value, dtype=torch.uint8).pin_memory()      # [reward | state | done], one D2H
+            # exploration noise drawn on the host like the reference's randn(policy.rng, ...) (PDEagent.jl:201): always float64
+            self.h_noise = torch.from_numpy(np.random.default_rng(7 + k).standard_normal(self.n_act)).pin_memory()
 
         def step(self):
             lib, ctx = self.env._lib, self.env._ctx
             if args.e2e_calls == "fused":
                 L.check(lib.pdeb200_act_step_host(ctx, None, 0.0, 1.0, C.c_void_p(self.h_act.data_ptr()), None,
+                                                  C.c_void_p(self.h_packed.data_ptr()), None, None, None), ctx)
+                return
+            if args.e2e_calls == "device-agent":
+                L.check(lib.pdeb200_act_step_host(ctx, C.c_void_p(self.h_noise.data_ptr()), 0.05, 1.0, None, None,
                                                   C.c_void_p(self.h_packed.data_ptr()), None, None, None), ctx)
                 return
             L.check(lib.pdeb200_policy_act(ctx, None, 0.0, 1.0), ctx)
@@ -492,6 +500,7 @@ def run_ours(args):
         host_lib.pdeb200_host_drive2.restype = C.c_int32
         VP = C.c_void_p * n_sh
         packs = VP(*[sh.h_packed.data_ptr() for sh in shards])
+        noises = VP(*[sh.h_noise.data_ptr() for sh in shards])
         ctxs = VP(*[sh.env._ctx.value for sh in shards])
         acts = VP(*[sh.h_act.data_ptr() for sh in shards])
         rews = VP(*[sh.h_rew.data_ptr() for sh in shards])
@@ -504,7 +513,11 @@ def run_ours(args):
             # one std::thread per shard, each running policy_act -> get(ACTION_IN) -> step_host through the C ABI
             secs = C.c_double()
             if args.e2e_calls == "fused":
-                rc = host_lib.pdeb200_host_drive2(C.c_int32(n_sh), ctxs, C.c_int32(n), acts, packs, C.c_double(1.0), C.byref(secs))
+                rc = host_lib.pdeb200_host_drive2(C.c_int32(n_sh), ctxs, C.c_int32(n), acts, packs, C.c_double(1.0), C.byref(secs),
+                                                  None, C.c_double(0.0))
+            elif args.e2e_calls == "device-agent":
+                rc = host_lib.pdeb200_host_drive2(C.c_int32(n_sh), ctxs, C.c_int32(n), None, packs, C.c_double(1.0), C.byref(secs),
+                                                  noises, C.c_double(0.05))
             else:
                 rc = host_lib.pdeb200_host_drive(C.c_int32(n_sh), ctxs, C.c_int32(n), acts, nbytes, rews, sts, dns, C.c_double(1.0),
                                                  C.byref(secs))
@@ -539,8 +552,12 @@ def run_ours(args):
     e2e_value = B * world * args.steps / float(t.item())
     n_act = B * shards[0].env.n_actuators
     ns_rows = shards[0].env.ns
-    h2d = n_act * esz
-    d2h = n_act * esz + n_act * esz + n_act * ns_rows * esz + B
+    if args.e2e_calls == "device-agent":
+        h2d = n_act * 8                                           # exploration noise (float64 like the reference's randn)
+        d2h = sum(sh.packed_bytes for sh in shards)                # [reward | state | done] blocks (256-byte aligned parts)
+    else:
+        h2d = n_act * esz
+        d2h = n_act * esz + n_act * esz + n_act * ns_rows * esz + B
     e2e_launches = sum(sh.env.launch_count for sh in shards) - e2e_launches0
     env = shards[0].env                             # step_cost below is per environment
 
@@ -583,7 +600,11 @@ def run_ours(args):
             "dtype": args.dtype, "data": "synthetic", "config": config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "shards": n_sh, "launches": int(e2e_launches), "host_threads": args.e2e_driver, "cpu_binding": numa,
-                    "call_sequence": ("per shard and step: pdeb200_act_step_host = policy(env) -> action to the host [D2H] -> env(action) "
+                    "call_sequence": ("per shard and step: ONE call pdeb200_act_step_host = host-drawn exploration noise in [H2D] -> "
+                                      "policy(env) on the device -> env(action) -> [reward | state | done] to the host in one packed copy "
+                                      "[D2H]; one synchronisation; pinned host buffers; action and replay stay on the device "
+                                      "(DevicePolicyForward / DeviceTrajectory of the Julia shim)") if args.e2e_calls == "device-agent" else
+                                     ("per shard and step: pdeb200_act_step_host = policy(env) -> action to the host [D2H] -> env(action) "
                                       "from the host [H2D] -> [reward | state | done] to the host in one packed copy [D2H]; one "
                                       "synchronisation; pinned host buffers") if args.e2e_calls == "fused" else
                                      ("per shard and step: pdeb200_policy_act -> pdeb200_get(ACTION_IN) [D2H] -> "

@@ -14,9 +14,11 @@
 
 // fused = 1: the same two reference-side calls as ONE C call with one synchronisation and one packed result copy
 // (pdeb200_act_step_host); h_packed[k] then receives [reward | state | done] (pdeb200_result_layout).
+// h_noise != NULL: exploration noise drawn on the host (the reference's randn(policy.rng, ...), PDEagent.jl:201) goes in with
+// every step; h_act == NULL: the action stays on the device (device policy + device trajectory).
 extern "C" int32_t pdeb200_host_drive2(int32_t n_shards, pdeb200_ctx** ctxs, int32_t steps, void** h_act, void** h_packed, double act_limit,
-                                       double* seconds_out) {
-    if (n_shards < 1 || !ctxs || steps < 0 || !h_act || !h_packed || !seconds_out) return PDEB200_EINVAL;
+                                       double* seconds_out, const double** h_noise, double act_noise) {
+    if (n_shards < 1 || !ctxs || steps < 0 || !h_packed || !seconds_out) return PDEB200_EINVAL;
     std::atomic<int> ready{0}, failed{0};
     std::atomic<bool> go{false};
     std::vector<std::thread> th;
@@ -24,7 +26,8 @@ extern "C" int32_t pdeb200_host_drive2(int32_t n_shards, pdeb200_ctx** ctxs, int
         ready.fetch_add(1);
         while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
         for (int i = 0; i < steps; ++i) {
-            const int32_t rc = pdeb200_act_step_host(ctxs[k], nullptr, 0.0, act_limit, h_act[k], nullptr, h_packed[k], nullptr, nullptr, nullptr);
+            const int32_t rc = pdeb200_act_step_host(ctxs[k], h_noise ? h_noise[k] : nullptr, h_noise ? act_noise : 0.0, act_limit,
+                                                     h_act ? h_act[k] : nullptr, nullptr, h_packed[k], nullptr, nullptr, nullptr);
             if (rc) { failed.store(rc); return; }
         }
     };

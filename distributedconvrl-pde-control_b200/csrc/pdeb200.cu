@@ -652,7 +652,7 @@ int32_t pdeb200_result_layout(const pdeb200_ctx* c, size_t* reward_off, size_t* 
 
 int32_t pdeb200_act_step_host(pdeb200_ctx* c, const double* noise_host, double act_noise, double act_limit, void* action_out,
                               void* y_out, void* result_packed, void* reward_out, void* state_out, uint8_t* done_out) {
-    if (!c || !action_out) return fail(c, PDEB200_EINVAL, "act_step_host: null argument");
+    if (!c) return fail(c, PDEB200_EINVAL, "act_step_host: null argument");
     cudaSetDevice(c->device);
     const void* dn = nullptr;
     std::vector<float> tmp;
@@ -670,9 +670,12 @@ int32_t pdeb200_act_step_host(pdeb200_ctx* c, const double* noise_host, double a
     int32_t rc = policy_launch(c, dn, 0, 0, 0, act_noise, act_limit);
     if (rc) return rc;
     // policy(env) hands the action to the host; env(action) takes it from there (stream order: D2H, then H2D of the same buffer)
+    // action_out == NULL: the action never leaves the device (device policy + device trajectory: no host consumer)
     const size_t abytes = (size_t)c->cfg.n_envs * c->cfg.n_actuators * c->a_rows * c->esz;
-    PDEB_CUDA(c, cudaMemcpyAsync(action_out, c->action_in, abytes, cudaMemcpyDeviceToHost, c->stream));
-    PDEB_CUDA(c, cudaMemcpyAsync(c->action_in, action_out, abytes, cudaMemcpyHostToDevice, c->stream));
+    if (action_out) {
+        PDEB_CUDA(c, cudaMemcpyAsync(action_out, c->action_in, abytes, cudaMemcpyDeviceToHost, c->stream));
+        PDEB_CUDA(c, cudaMemcpyAsync(c->action_in, action_out, abytes, cudaMemcpyHostToDevice, c->stream));
+    }
     if ((rc = do_step(c, c->action_in, 1, 0, 0.0, nullptr))) return rc;
     if (y_out) PDEB_CUDA(c, cudaMemcpyAsync(y_out, c->y, (size_t)c->cfg.n_envs * c->y_elems * c->esz, cudaMemcpyDeviceToHost, c->stream));
     if (result_packed) PDEB_CUDA(c, cudaMemcpyAsync(result_packed, c->result_block, c->res_bytes, cudaMemcpyDeviceToHost, c->stream));

@@ -167,7 +167,8 @@ int32_t pdeb200_step_host(pdeb200_ctx* ctx, const void* actions_host, void* y_ou
                           void* state_out, uint8_t* done_out);
 /* `action = policy(env); env(action)` with HOST buffers as ONE call with ONE synchronisation (the drop-in closures' two calls
  * back to back): actor forward (+ optional host noise, as pdeb200_policy_act) -> the action is copied to action_out (HOST) and
- * taken back from that buffer as the step's input (stream-ordered D2H then H2D) -> env step -> results to the host.
+ * taken back from that buffer as the step's input (stream-ordered D2H then H2D; action_out = NULL: the action stays on the
+ * device, for hosts whose trajectory and hooks live on the device too) -> env step -> results to the host.
  * result_packed: optional HOST buffer of pdeb200_result_layout's total_bytes receiving [reward | state | done] in ONE copy
  * (they share one device allocation); reward_out / state_out / done_out: optional separate destinations instead. */
 int32_t pdeb200_act_step_host(pdeb200_ctx* ctx, const double* noise_host, double act_noise, double act_limit, void* action_out,
