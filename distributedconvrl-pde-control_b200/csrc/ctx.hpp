@@ -78,6 +78,8 @@ struct pdeb200_ctx {
     // KS sensor gather: layout permutation of the natural-order state in shared memory and the sensor table's
     // indices under it (ks.cu::sensor_layout); rebuilt after pdeb200_set_bases
     int *ks_perm = nullptr, *ks_sens_idx = nullptr; bool ks_layout_dirty = true, ks_layout_on = false;
+    // KS sensors as ONE spectral multiply + inverse transform (shift-invariant, equally spaced sensor bases; ks.cu::ks_bases_changed)
+    void* ks_sens_hat = nullptr; int ks_sens_sp = 0;
 
     // problem-specific opaque state (KSeg / NS translation units)
     void* prob = nullptr;
@@ -151,6 +153,7 @@ inline ObsRewardParams<T> make_obs_params(const pdeb200_ctx* c) {
 int32_t ks_setup(pdeb200_ctx* c);
 int32_t ks_core(pdeb200_ctx* c);
 int32_t ks_cost(const pdeb200_ctx* c, double* bytes, double* flops);
+int32_t ks_bases_changed(pdeb200_ctx* c, const double* sensor_basis);   // dense [n_sensors][nx] float64, as given to set_bases
 void ks_free(pdeb200_ctx* c);
 
 int32_t kseg_setup(pdeb200_ctx* c);

@@ -166,11 +166,16 @@ int32_t launch(pdeb200_ctx* c) {
     }
     A.sens = EllTable<T>{c->ks_layout_on ? c->ks_sens_idx : c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows};
     A.perm = c->ks_layout_on ? c->ks_perm : nullptr;
+    A.sens_hat = (const C*)c->ks_sens_hat; A.sens_sp = c->ks_sens_sp;
     A.y = (T*)c->y; A.p = (const T*)c->p; A.sensors_out = (T*)c->sensors; A.vmax_out = (T*)c->vmax;
     const int n_pairs = (g.n_envs + 1) / 2;
     const int grid = (n_pairs + PAIRS - 1) / PAIRS;
     const size_t smem = ks_smem_bytes<T, N1, N2>(PAIRS, g.oversampling > 1);
-    auto kern = lowreg ? ks_step_kernel<T, N1, N2, true> : ks_step_kernel<T, N1, N2, false>;
+    // spectral sensor dots where they pay (few substeps); PDEB200_KS_SPECTRAL_SENSORS=2 forces them at any oversampling
+    static const int spec_mode = [] { const char* e = getenv("PDEB200_KS_SPECTRAL_SENSORS"); return e ? atoi(e) : 1; }();
+    const bool spec = c->ks_sens_hat != nullptr && (spec_mode == 2 || g.oversampling <= 4);
+    auto kern = lowreg ? (spec ? ks_step_kernel<T, N1, N2, true, true> : ks_step_kernel<T, N1, N2, true, false>)
+                       : (spec ? ks_step_kernel<T, N1, N2, false, true> : ks_step_kernel<T, N1, N2, false, false>);
     PDEB_CUDA(c, ensure_dyn_smem(kern, smem, c->device));
     kern<<<grid, warps * 32, smem, c->stream>>>(A);
     PDEB_CUDA(c, cudaGetLastError());
@@ -208,6 +213,55 @@ int32_t ks_setup(pdeb200_ctx* c) {
     return c->cfg.dtype == PDEB200_F64 ? setup_t<double>(c) : setup_t<float>(c);
 }
 
+// Equally spaced, shift-invariant sensor bases (every shipped KS script: periodic Gaussians at every k-th grid point,
+// KSSetup.jl:82-113): <y, g_i> = s(sp * i) with s = ifft(fft(y) . conj(fft(g_0))) -- ONE more inverse transform of the spectrum
+// the kernel already holds, instead of a 21-tap gather per sensor through shared memory (a third of the kernel's shared-memory
+// wavefronts at oversampling 1, profiles/r2_ks_S1.md).  Detected here from the dense basis the host hands to set_bases; rows that
+// are not shifted copies of row 0 to 1e-14 (or PDEB200_KS_SPECTRAL_SENSORS=0) keep the gather.
+int32_t ks_bases_changed(pdeb200_ctx* c, const double* sb) {
+    const int N = c->cfg.nx, ns = c->cfg.n_sensors;
+    if (c->ks_sens_hat) { cudaFree(c->ks_sens_hat); c->ks_sens_hat = nullptr; }
+    c->ks_sens_sp = 0;
+    static const bool off = [] { const char* e = getenv("PDEB200_KS_SPECTRAL_SENSORS"); return e && atoi(e) == 0; }();
+    if (off || ns < 2 || !sb) return PDEB200_OK;
+    auto peak = [&](int i) {
+        int best = 0;
+        for (int n = 1; n < N; ++n) if (sb[(size_t)i * N + n] > sb[(size_t)i * N + best]) best = n;
+        return best;
+    };
+    const int p0 = peak(0), sp = ((peak(1) - p0) % N + N) % N;
+    if (sp < 1 || (long long)sp * ns > N) return PDEB200_OK;
+    double gmax = 0;
+    for (int n = 0; n < N; ++n) gmax = std::max(gmax, std::fabs(sb[n]));
+    for (int i = 1; i < ns; ++i)
+        for (int n = 0; n < N; ++n)
+            if (std::fabs(sb[(size_t)i * N + n] - sb[(((n - sp * i) % N) + N) % N]) > 1e-14 * gmax) return PDEB200_OK;
+    // H[k] = conj(sum_n g_0[n] exp(-2 pi i n k / N)), naive DFT in long double
+    const long double two_pi = 6.283185307179586476925286766559L;
+    std::vector<double> hr(N), hi(N);
+    for (int k = 0; k < N; ++k) {
+        long double sr = 0, si = 0;
+        for (int n = 0; n < N; ++n) {
+            const long double a = -two_pi * (long double)((long long)k * n % N) / N;
+            sr += (long double)sb[n] * cosl(a); si += (long double)sb[n] * sinl(a);
+        }
+        hr[k] = (double)sr; hi[k] = (double)(-si);
+    }
+    if (c->cfg.dtype == PDEB200_F64) {
+        std::vector<double2> h(N);
+        for (int k = 0; k < N; ++k) h[k] = make_double2(hr[k], hi[k]);
+        PDEB_CUDA(c, cudaMalloc(&c->ks_sens_hat, N * sizeof(double2)));
+        PDEB_CUDA(c, cudaMemcpy(c->ks_sens_hat, h.data(), N * sizeof(double2), cudaMemcpyHostToDevice));
+    } else {
+        std::vector<float2> h(N);
+        for (int k = 0; k < N; ++k) h[k] = make_float2((float)hr[k], (float)hi[k]);
+        PDEB_CUDA(c, cudaMalloc(&c->ks_sens_hat, N * sizeof(float2)));
+        PDEB_CUDA(c, cudaMemcpy(c->ks_sens_hat, h.data(), N * sizeof(float2), cudaMemcpyHostToDevice));
+    }
+    c->ks_sens_sp = sp;
+    return PDEB200_OK;
+}
+
 int32_t ks_core(pdeb200_ctx* c) { return c->cfg.dtype == PDEB200_F64 ? dispatch<double>(c) : dispatch<float>(c); }
 
 // Algorithmic cost of one env step (SURVEY.md 8d / DESIGN.md):
@@ -226,7 +280,7 @@ int32_t ks_cost(const pdeb200_ctx* c, double* bytes, double* flops) {
 }
 
 void ks_free(pdeb200_ctx* c) {
-    for (void** p : {&c->tw12, &c->tw21, &c->c1, &c->cN, &c->ainvh, &c->hm, (void**)&c->ks_perm, (void**)&c->ks_sens_idx}) {
+    for (void** p : {&c->tw12, &c->tw21, &c->c1, &c->cN, &c->ainvh, &c->hm, (void**)&c->ks_perm, (void**)&c->ks_sens_idx, &c->ks_sens_hat}) {
         if (*p) cudaFree(*p);
         *p = nullptr;
     }

@@ -45,6 +45,8 @@ struct KsArgs {
     T third, inv_n;                    // (h/2)/(3h/2); 1/N
     EllTable<T> sens;                  // rows: sensors, gather over grid points (indices already under `perm`)
     const int* perm;                   // position of grid point n in the natural-order shared line, or nullptr (identity)
+    const C* sens_hat;                 // conj(fft(g_0)) when the sensor bases are equally spaced shifted copies of g_0, else nullptr
+    int sens_sp;                       // their spacing in grid points: <y, g_i> = ifft(u_hat . sens_hat)[sens_sp * i]
     T* y;                              // [B][N] in/out
     const T* p;                        // [B][N] actuation field (physical)
     T* sensors_out;                    // [B][n_sensors] raw <y, g_i>
@@ -82,7 +84,11 @@ __host__ __device__ inline size_t ks_smem_bytes(int pairs_per_cta, bool with_pre
 // much as the transforms and latency hiding matters more than the 64 shared-memory wavefronts F costs per substep.
 template <typename T, bool LOWREG = false> struct KsMaxWarps { static constexpr int value = sizeof(T) == 8 ? (LOWREG ? 12 : 8) : 16; };
 
-template <typename T, int N1, int N2, bool LOWREG = false>
+// SPEC: the sensor dots come from one more inverse transform after the job loop (u_hat . conj(fft(g_0)); ks.cu::ks_bases_changed)
+// instead of the gather epilogue.  A compile-time switch: keeping u_hat alive past the loop costs the many-substep kernel 24 more
+// spilled bytes in its hot loop (183 -> 195 us at oversampling 30), so only the few-substep launches (oversampling <= 4) use it
+// (414 -> 392 us at oversampling 1, 131 072 environments).  Doing it as an extra job INSIDE the loop was worse on both (217 / 458 us).
+template <typename T, int N1, int N2, bool LOWREG = false, bool SPEC = false>
 __global__ void __launch_bounds__(KsMaxWarps<T, LOWREG>::value * 32, 1)
 ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
     using G = KsGeom<N1, N2>;
@@ -201,6 +207,50 @@ ks_step_kernel(const __grid_constant__ KsArgs<T> A) {
     // apart), which ncu showed as ~10 us of shared-memory time per launch at 8192 environments ----
     // the sensor table's entries are requested now (u_hat / F registers are dead) and stored into the dead PREV / F
     // region after the barrier below: their L2 latency hides behind the epilogue instead of heading the sensor phase
+    if (SPEC) {
+        // ---- sensors in spectral space: y first, then ONE more inverse transform of u_hat . conj(fft(g_0)) ------------------
+        T vmax_a = T(0), vmax_b = T(0);
+        if (t < N2) {
+#pragma unroll
+            for (int r = 0; r < N1; ++r) {
+                const int n = t + N2 * r;
+                const T ya = zr[r] * A.inv_n, yb = zi[r] * A.inv_n;
+                if (va) A.y[(size_t)ea * N + n] = ya;
+                if (vb) A.y[(size_t)eb * N + n] = yb;
+                vmax_a = fmax(vmax_a, fabs(ya)); vmax_b = fmax(vmax_b, fabs(yb));
+            }
+        }
+#pragma unroll
+        for (int o = TP / 2; o > 0; o >>= 1) {
+            vmax_a = fmax(vmax_a, __shfl_xor_sync(0xffffffffu, vmax_a, o, TP));
+            vmax_b = fmax(vmax_b, __shfl_xor_sync(0xffffffffu, vmax_b, o, TP));
+        }
+        if (t == 0) {
+            if (va) A.vmax_out[ea] = vmax_a;
+            if (vb) A.vmax_out[eb] = vmax_b;
+        }
+        if (t < N1) {
+#pragma unroll
+            for (int r = 0; r < N2; ++r) {
+                const C h = __ldg(A.sens_hat + t + N1 * r);
+                zr[r] = ur[r] * h.x - ui[r] * h.y;
+                zi[r] = ur[r] * h.y + ui[r] * h.x;
+            }
+        }
+        fft_pass<T, N2, N1, +1>(zr, zi, xb, s_tw12, t);
+        if (t < N2) {
+#pragma unroll
+            for (int r = 0; r < N1; ++r) {
+                const int n = t + N2 * r;
+                const int i = n / A.sens_sp;
+                if (i * A.sens_sp == n && i < n_s) {
+                    if (va) A.sensors_out[(size_t)ea * n_s + i] = zr[r] * A.inv_n;
+                    if (vb) A.sensors_out[(size_t)eb * n_s + i] = zi[r] * A.inv_n;
+                }
+            }
+        }
+        return;
+    }
     const size_t n_tab = (size_t)A.sens.nnz_max * n_s;
     const bool staged = n_tab * (sizeof(T) + sizeof(int)) <= dead_bytes;       // CTA-uniform
     constexpr int PF = 8;

@@ -174,6 +174,7 @@ int32_t set_bases_t(pdeb200_ctx* c, const double* sb, const double* ab, const in
     PDEB_CUDA(c, cudaMemcpy(c->d_sens_sum, ssum.data(), ssum.size() * sizeof(T), cudaMemcpyHostToDevice));
     c->bases_set = true;
     c->ks_layout_dirty = true;
+    if (c->cfg.problem == PDEB200_KS) return ks_bases_changed(c, sb);
     return PDEB200_OK;
 }
 
