@@ -6,6 +6,7 @@
 
 #include "ctx.hpp"
 #include "ks_step.cuh"
+#include "ks_step_tm.cuh"
 
 namespace pdeb200 {
 
@@ -141,6 +142,35 @@ int32_t sensor_layout(pdeb200_ctx* c) {
     return PDEB200_OK;
 }
 
+// fp64 N = 256: the tensor-memory variant (ks_step_tm.cuh).  One CTA of up to 8 warps per SM (512 TMEM columns), or two CTAs of
+// up to 4 warps (256 columns each); the CTA size is chosen like in plan() so that the grid fills whole waves.
+int32_t launch_tm(pdeb200_ctx* c, const KsArgs<double>& A, int n_sm, bool spec) {
+    const int n_pairs = (c->cfg.n_envs + 1) / 2;
+    static const int forced = [] { const char* e = getenv("PDEB200_KS_WARPS"); return e ? atoi(e) : 0; }();
+    double best = 1e300; int bw = 1;
+    for (int w = 1; w <= 8; ++w) {
+        if (forced && w != forced) continue;
+        const int ppc = 2 * w;
+        const int n_ctas = (n_pairs + ppc - 1) / ppc;
+        const int per_sm = (n_ctas + n_sm - 1) / n_sm;
+        const int cps = std::min(w <= 4 ? 2 : 1, per_sm);
+        const int rounds = (per_sm + cps - 1) / cps;
+        const double cost = (double)rounds * cps * ppc * (1.0 + 0.02 * (8 - cps * w));
+        if (cost < best - 1e-9) { best = cost; bw = w; }
+    }
+    const int PAIRS = 2 * bw;
+    const size_t n_tab = spec ? 0 : (size_t)A.sens.nnz_max * A.n_sensors;
+    const size_t smem = ks_tm_smem_bytes(PAIRS, n_tab);
+    if (smem > 227 * 1024) return PDEB200_EUNSUPPORTED;
+    auto kern = spec ? ks_step_tm_kernel<true> : ks_step_tm_kernel<false>;
+    PDEB_CUDA(c, ensure_dyn_smem(kern, smem, c->device));
+    kern<<<(n_pairs + PAIRS - 1) / PAIRS, bw * 32, smem, c->stream>>>(A);
+    PDEB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    return PDEB200_OK;
+}
+template <typename T> int32_t launch_tm(pdeb200_ctx*, const KsArgs<T>&, int, bool) { return PDEB200_EUNSUPPORTED; }
+
 template <typename T, int N1, int N2>
 int32_t launch(pdeb200_ctx* c) {
     using G = KsGeom<N1, N2>;
@@ -173,6 +203,12 @@ int32_t launch(pdeb200_ctx* c) {
     const size_t smem = ks_smem_bytes<T, N1, N2>(PAIRS, g.oversampling > 1);
     // spectral sensor dots where they pay (few substeps); PDEB200_KS_SPECTRAL_SENSORS=2 forces them at any oversampling
     static const int spec_mode = [] { const char* e = getenv("PDEB200_KS_SPECTRAL_SENSORS"); return e ? atoi(e) : 1; }();
+    // tensor-memory variant: fp64, 16 x 16, many substeps (PDEB200_KS_TMEM=0 off, 2 = at any oversampling)
+    static const int tm_mode = [] { const char* e = getenv("PDEB200_KS_TMEM"); return e ? atoi(e) : 1; }();
+    if (sizeof(T) == 8 && N1 == 16 && N2 == 16 && tm_mode && (tm_mode == 2 || g.oversampling > 4)) {
+        const int32_t rc = launch_tm(c, A, n_sm, c->ks_sens_hat != nullptr && spec_mode != 0);
+        if (rc != PDEB200_EUNSUPPORTED) return rc;
+    }
     const bool spec = c->ks_sens_hat != nullptr && (spec_mode == 2 || g.oversampling <= 4);
     auto kern = lowreg ? (spec ? ks_step_kernel<T, N1, N2, true, true> : ks_step_kernel<T, N1, N2, true, false>)
                        : (spec ? ks_step_kernel<T, N1, N2, false, true> : ks_step_kernel<T, N1, N2, false, false>);

@@ -30,10 +30,13 @@ __global__ void __launch_bounds__(256, 1) probe(int mode, int iters, long long* 
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t base = slot + ((uint32_t)(32 * (warp % 4)) << 16) + (warp / 4) * 256;
     uint32_t r[4][16];
+#pragma unroll
     for (int q = 0; q < 4; ++q)
+#pragma unroll
         for (int i = 0; i < 16; ++i) r[q][i] = threadIdx.x * 64 + q * 16 + i;
     uint4* sm = reinterpret_cast<uint4*>(dyn) + threadIdx.x * 17;     // 16 x 16 B per thread, odd stride
     for (int i = 0; i < 16; ++i) sm[i] = make_uint4(i, lane, warp, 0);
+#pragma unroll
     for (int q = 0; q < 4; ++q) ST16(r[q], base + q * 16);
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     __syncthreads();
@@ -41,11 +44,13 @@ __global__ void __launch_bounds__(256, 1) probe(int mode, int iters, long long* 
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
         if (mode == 0 || mode == 2 || mode == 4) {
-            for (int q = 0; q < 4; ++q) LD16(r[q], base + q * 16);
+            _Pragma("unroll") for (int q = 0; q < 4; ++q) LD16(r[q], base + q * 16);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            for (int q = 0; q < 4; ++q) acc ^= r[q][it & 15];
+_Pragma("unroll")
+            for (int q = 0; q < 4; ++q) acc ^= r[q][3] + r[q][12];
         }
         if (mode == 1 || mode == 2) {
+_Pragma("unroll")
             for (int q = 0; q < 4; ++q) { r[q][0] += it; ST16(r[q], base + q * 16); }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         }
