@@ -147,8 +147,11 @@ int32_t sensor_layout(pdeb200_ctx* c) {
 int32_t launch_tm(pdeb200_ctx* c, const KsArgs<double>& A, int n_sm, bool spec) {
     const int n_pairs = (c->cfg.n_envs + 1) / 2;
     static const int forced = [] { const char* e = getenv("PDEB200_KS_WARPS"); return e ? atoi(e) : 0; }();
-    double best = 1e300; int bw = 1;
-    for (int w = 1; w <= 8; ++w) {
+    // A CTA of up to 4 warps holds 256 of the SM's 512 TMEM columns whatever its size, so 4-warp CTAs are the smallest that
+    // let two launches of different env shards (bench.py's e2e leg) fill an SM together: smaller ones only for tiny batches.
+    double best = 1e300; int bw = std::min(4, (n_pairs + 1) / 2);
+    for (int w = 8; w >= 4; --w) {
+        if (n_pairs < 8 && !forced) break;
         if (forced && w != forced) continue;
         const int ppc = 2 * w;
         const int n_ctas = (n_pairs + ppc - 1) / ppc;
@@ -158,6 +161,7 @@ int32_t launch_tm(pdeb200_ctx* c, const KsArgs<double>& A, int n_sm, bool spec) 
         const double cost = (double)rounds * cps * ppc * (1.0 + 0.02 * (8 - cps * w));
         if (cost < best - 1e-9) { best = cost; bw = w; }
     }
+    if (forced && forced >= 1 && forced <= 8) bw = forced;
     const int PAIRS = 2 * bw;
     const size_t n_tab = spec ? 0 : (size_t)A.sens.nnz_max * A.n_sensors;
     const size_t smem = ks_tm_smem_bytes(PAIRS, n_tab);
