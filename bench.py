@@ -57,6 +57,9 @@ def parse():
                          "[H2D], [reward | state | done] out in one packed copy [D2H], one C call, one sync; fused: the same call "
                          "with the action additionally round-tripping through the host; split: policy_act -> get(ACTION_IN) -> "
                          "step_host (three syncs, four copies; round 1's sequence)")
+    ap.add_argument("--e2e-noise", default="prefetch", choices=["prefetch", "inline"],
+                    help="device-agent flow: prefetch = step i+1's host noise is handed to pdeb200_noise_prefetch before the call for "
+                         "step i (its upload overlaps step i's kernels); inline = uploaded at the head of its own call")
     ap.add_argument("--e2e-shards", type=int, default=4,
                     help="the e2e leg drives the batch as this many env shards (own context + stream + host thread each) "
                          "so that one shard's PCIe copies overlap another shard's kernels")
@@ -471,6 +474,7 @@ def run_ours(args):
             self.h_packed = torch.empty(tot.value, dtype=torch.uint8).pin_memory()      # [reward | state | done], one D2H
             # exploration noise drawn on the host like the reference's randn(policy.rng, ...) (PDEagent.jl:201): always float64
             self.h_noise = torch.from_numpy(np.random.default_rng(7 + k).standard_normal(self.n_act)).pin_memory()
+            self.primed = False
 
         def step(self):
             lib, ctx = self.env._lib, self.env._ctx
@@ -479,6 +483,13 @@ def run_ours(args):
                                                   C.c_void_p(self.h_packed.data_ptr()), None, None, None), ctx)
                 return
             if args.e2e_calls == "device-agent":
+                if args.e2e_noise == "prefetch":
+                    if not self.primed:
+                        L.check(lib.pdeb200_noise_prefetch(ctx, C.c_void_p(self.h_noise.data_ptr())), ctx)
+                        self.primed = True
+                    L.check(lib.pdeb200_noise_prefetch(ctx, C.c_void_p(self.h_noise.data_ptr())), ctx)
+                    L.check(lib.pdeb200_act_step_host(ctx, None, 0.05, 1.0, None, None, C.c_void_p(self.h_packed.data_ptr()), None, None, None), ctx)
+                    return
                 L.check(lib.pdeb200_act_step_host(ctx, C.c_void_p(self.h_noise.data_ptr()), 0.05, 1.0, None, None,
                                                   C.c_void_p(self.h_packed.data_ptr()), None, None, None), ctx)
                 return
@@ -517,7 +528,7 @@ def run_ours(args):
                                                   None, C.c_double(0.0))
             elif args.e2e_calls == "device-agent":
                 rc = host_lib.pdeb200_host_drive2(C.c_int32(n_sh), ctxs, C.c_int32(n), None, packs, C.c_double(1.0), C.byref(secs),
-                                                  noises, C.c_double(0.05))
+                                                  noises, C.c_double(-0.05 if args.e2e_noise == "prefetch" else 0.05))
             else:
                 rc = host_lib.pdeb200_host_drive(C.c_int32(n_sh), ctxs, C.c_int32(n), acts, nbytes, rews, sts, dns, C.c_double(1.0),
                                                  C.byref(secs))
@@ -600,7 +611,8 @@ def run_ours(args):
             "dtype": args.dtype, "data": "synthetic", "config": config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "shards": n_sh, "launches": int(e2e_launches), "host_threads": args.e2e_driver, "cpu_binding": numa,
-                    "call_sequence": ("per shard and step: ONE call pdeb200_act_step_host = host-drawn exploration noise in [H2D] -> "
+                    "call_sequence": (("per shard and step: pdeb200_noise_prefetch(next step's host noise) [H2D, overlapping this step's kernels] + " if args.e2e_noise == "prefetch" else "per shard and step: ") +
+                                      "ONE call pdeb200_act_step_host = host-drawn exploration noise in [H2D] -> "
                                       "policy(env) on the device -> env(action) -> [reward | state | done] to the host in one packed copy "
                                       "[D2H]; one synchronisation; pinned host buffers; action and replay stay on the device "
                                       "(DevicePolicyForward / DeviceTrajectory of the Julia shim)") if args.e2e_calls == "device-agent" else

@@ -25,8 +25,14 @@ extern "C" int32_t pdeb200_host_drive2(int32_t n_shards, pdeb200_ctx** ctxs, int
     auto work = [&](int k) {
         ready.fetch_add(1);
         while (!go.load(std::memory_order_acquire)) std::this_thread::yield();
+        // prefetch (act_noise < 0 selects it): step i+1's noise is handed over before the call for step i, so that its upload
+        // overlaps step i's kernels (pdeb200_noise_prefetch); the noise of every step still crosses PCIe inside the timed region
+        const bool prefetch = h_noise && act_noise < 0.0;
+        const double sigma = act_noise < 0.0 ? -act_noise : act_noise;
+        if (prefetch && steps > 0 && pdeb200_noise_prefetch(ctxs[k], h_noise[k])) { failed.store(PDEB200_ESTATE); return; }
         for (int i = 0; i < steps; ++i) {
-            const int32_t rc = pdeb200_act_step_host(ctxs[k], h_noise ? h_noise[k] : nullptr, h_noise ? act_noise : 0.0, act_limit,
+            if (prefetch && i + 1 < steps && pdeb200_noise_prefetch(ctxs[k], h_noise[k])) { failed.store(PDEB200_ESTATE); return; }
+            const int32_t rc = pdeb200_act_step_host(ctxs[k], (h_noise && !prefetch) ? h_noise[k] : nullptr, h_noise ? sigma : 0.0, act_limit,
                                                      h_act ? h_act[k] : nullptr, nullptr, h_packed[k], nullptr, nullptr, nullptr);
             if (rc) { failed.store(rc); return; }
         }

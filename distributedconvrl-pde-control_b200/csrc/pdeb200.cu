@@ -1,5 +1,9 @@
 // libpdeb200.so -- C ABI (include/pdeb200.h): context, constants, environment entry points.
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <map>
+#include <mutex>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -523,6 +527,11 @@ int32_t pdeb200_destroy(pdeb200_ctx* c) {
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->evc0) cudaEventDestroy(c->evc0);
     if (c->evc1) cudaEventDestroy(c->evc1);
+    for (int i = 0; i < 2; ++i) {
+        if (c->d_noise_q[i]) cudaFree(c->d_noise_q[i]);
+        if (c->noise_ready[i]) cudaEventDestroy(c->noise_ready[i]);
+    }
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return PDEB200_OK;
@@ -651,10 +660,72 @@ int32_t pdeb200_result_layout(const pdeb200_ctx* c, size_t* reward_off, size_t* 
     return PDEB200_OK;
 }
 
+static size_t policy_noise_count(const pdeb200_ctx* c) {
+    const int n_out = c->cfg.mono ? c->cfg.n_actuators * c->a_rows : c->a_rows;
+    return (size_t)c->cfg.n_envs * c->n_cols * (n_out - (c->cfg.mono ? 0 : c->cfg.memory_size));
+}
+
+int32_t pdeb200_noise_prefetch(pdeb200_ctx* c, const double* noise_host) {
+    if (!c || !noise_host) return fail(c, PDEB200_EINVAL, "noise_prefetch: null argument");
+    if (c->noise_put - c->noise_got >= 2) return fail(c, PDEB200_ESTATE, "noise_prefetch: two prefetches are already waiting for their policy calls");
+    cudaSetDevice(c->device);
+    const size_t n = policy_noise_count(c);
+    if (!c->copy_stream) {
+        PDEB_CUDA(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            PDEB_CUDA(c, cudaEventCreateWithFlags(&c->noise_ready[i], cudaEventDisableTiming));
+            PDEB_CUDA(c, cudaMalloc(&c->d_noise_q[i], n * c->esz));
+        }
+    }
+    // slot s was last read by the policy kernel of consumption (put - 2); put - got < 2 means that call has been made, and every
+    // consuming call synchronises before it returns, so the buffer is free: no ordering against c->stream is needed
+    const int s = (int)(c->noise_put & 1);
+    if (c->esz == 8) PDEB_CUDA(c, cudaMemcpyAsync(c->d_noise_q[s], noise_host, n * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    else {
+        std::vector<float> tmp(n);
+        for (size_t i = 0; i < n; ++i) tmp[i] = (float)noise_host[i];
+        PDEB_CUDA(c, cudaMemcpyAsync(c->d_noise_q[s], tmp.data(), n * 4, cudaMemcpyHostToDevice, c->copy_stream));
+        PDEB_CUDA(c, cudaStreamSynchronize(c->copy_stream));          // tmp is pageable and local
+    }
+    PDEB_CUDA(c, cudaEventRecord(c->noise_ready[s], c->copy_stream));
+    c->noise_put += 1;
+    return PDEB200_OK;
+}
+
+// PDEB200_E2E_TRACE=<file prefix>: per call, stream events at {entry, noise on the device, kernels done, results on the host} and
+// host clock at {entry, return}, appended to <prefix>.<ctx>.csv by the calling thread (tools/e2e_timeline.py draws the shards'
+// overlap from these).  Off (one getenv per process) in normal use.
+namespace {
+struct E2eTrace {
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    FILE* f = nullptr;
+};
+cudaEvent_t g_trace_base = nullptr;
+std::mutex g_trace_mu;
+std::map<pdeb200_ctx*, E2eTrace> g_traces;
+const char* trace_prefix() { static const char* p = getenv("PDEB200_E2E_TRACE"); return p; }
+E2eTrace* trace_get(pdeb200_ctx* c) {
+    std::lock_guard<std::mutex> lock(g_trace_mu);
+    if (!g_trace_base) { cudaEventCreate(&g_trace_base); cudaEventRecord(g_trace_base, c->stream); cudaEventSynchronize(g_trace_base); }
+    E2eTrace& t = g_traces[c];
+    if (!t.f) {
+        for (auto& e : t.ev) cudaEventCreate(&e);
+        char name[512];
+        snprintf(name, sizeof name, "%s.%p.csv", trace_prefix(), (void*)c);
+        t.f = fopen(name, "w");
+    }
+    return &t;
+}
+double host_now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace
+
 int32_t pdeb200_act_step_host(pdeb200_ctx* c, const double* noise_host, double act_noise, double act_limit, void* action_out,
                               void* y_out, void* result_packed, void* reward_out, void* state_out, uint8_t* done_out) {
     if (!c) return fail(c, PDEB200_EINVAL, "act_step_host: null argument");
     cudaSetDevice(c->device);
+    E2eTrace* tr = trace_prefix() ? trace_get(c) : nullptr;
+    const double h0 = tr ? host_now_ms() : 0.0;
+    if (tr) cudaEventRecord(tr->ev[0], c->stream);
     const void* dn = nullptr;
     std::vector<float> tmp;
     if (noise_host) {
@@ -667,7 +738,14 @@ int32_t pdeb200_act_step_host(pdeb200_ctx* c, const double* noise_host, double a
             PDEB_CUDA(c, cudaMemcpyAsync(c->d_noise, tmp.data(), n * 4, cudaMemcpyHostToDevice, c->stream));
         }
         dn = c->d_noise;
+    } else if (c->noise_put > c->noise_got && act_noise > 0.0) {
+        // noise uploaded by pdeb200_noise_prefetch while the previous step ran: wait for that copy, use its buffer
+        const int s = (int)(c->noise_got & 1);
+        PDEB_CUDA(c, cudaStreamWaitEvent(c->stream, c->noise_ready[s], 0));
+        c->noise_got += 1;
+        dn = c->d_noise_q[s];
     }
+    if (tr) cudaEventRecord(tr->ev[1], c->stream);
     int32_t rc = policy_launch(c, dn, 0, 0, 0, act_noise, act_limit);
     if (rc) return rc;
     // policy(env) hands the action to the host; env(action) takes it from there (stream order: D2H, then H2D of the same buffer)
@@ -678,6 +756,7 @@ int32_t pdeb200_act_step_host(pdeb200_ctx* c, const double* noise_host, double a
         PDEB_CUDA(c, cudaMemcpyAsync(c->action_in, action_out, abytes, cudaMemcpyHostToDevice, c->stream));
     }
     if ((rc = do_step(c, c->action_in, 1, 0, 0.0, nullptr))) return rc;
+    if (tr) cudaEventRecord(tr->ev[2], c->stream);
     if (y_out) PDEB_CUDA(c, cudaMemcpyAsync(y_out, c->y, (size_t)c->cfg.n_envs * c->y_elems * c->esz, cudaMemcpyDeviceToHost, c->stream));
     if (result_packed) PDEB_CUDA(c, cudaMemcpyAsync(result_packed, c->result_block, c->res_bytes, cudaMemcpyDeviceToHost, c->stream));
     auto back = [&](int which, void* dst) -> cudaError_t {
@@ -688,7 +767,14 @@ int32_t pdeb200_act_step_host(pdeb200_ctx* c, const double* noise_host, double a
     PDEB_CUDA(c, back(PDEB200_ARR_REWARD, reward_out));
     PDEB_CUDA(c, back(PDEB200_ARR_STATE, state_out));
     PDEB_CUDA(c, back(PDEB200_ARR_DONE, done_out));
+    if (tr) cudaEventRecord(tr->ev[3], c->stream);
     PDEB_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (tr && tr->f) {
+        float t[4];
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&t[i], g_trace_base, tr->ev[i]);
+        fprintf(tr->f, "%.4f,%.4f,%.4f,%.4f,%.4f,%.4f\n", t[0], t[1], t[2], t[3], h0, host_now_ms());
+        fflush(tr->f);
+    }
     return PDEB200_OK;
 }
 

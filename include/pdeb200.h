@@ -173,6 +173,13 @@ int32_t pdeb200_step_host(pdeb200_ctx* ctx, const void* actions_host, void* y_ou
  * (they share one device allocation); reward_out / state_out / done_out: optional separate destinations instead. */
 int32_t pdeb200_act_step_host(pdeb200_ctx* ctx, const double* noise_host, double act_noise, double act_limit, void* action_out,
                               void* y_out, void* result_packed, void* reward_out, void* state_out, uint8_t* done_out);
+/* Exploration noise never depends on the environment, so a host can hand over the NEXT step's noise before it makes the
+ * (synchronous) call for the current step -- the reference draws it inside the policy call, src/PDEagent.jl:201.  This enqueues
+ * the upload on a copy stream of the context's own and returns; pdeb200_act_step_host calls with noise_host = NULL and
+ * act_noise > 0 consume the prefetches in order.  At most two may be outstanding (PDEB200_ESTATE otherwise), which is what the
+ * pipelined loop needs:   prefetch(noise[0]);  for i = 0, 1, ...: { prefetch(noise[i+1]); act_step_host(NULL, ...) }   -- the
+ * upload of step i+1's noise then runs under step i's kernels instead of in front of its own. */
+int32_t pdeb200_noise_prefetch(pdeb200_ctx* ctx, const double* noise_host);
 int32_t pdeb200_result_layout(const pdeb200_ctx* ctx, size_t* reward_off, size_t* state_off, size_t* done_off, size_t* total_bytes);
 int32_t pdeb200_get(pdeb200_ctx* ctx, int32_t which, void* host_dst, size_t bytes);
 /* One environment's slice of a per-environment array (PDEhook's tracked environment: src/PDEhook.jl:54-62). */

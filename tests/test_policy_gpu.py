@@ -131,3 +131,37 @@ def test_act_step_host_equals_policy_act_then_step_host(pkg, golden):
         assert np.array_equal(a.get(L.ARR_Y), b.get(L.ARR_Y))
     for e in envs:
         e.close()
+
+
+def test_prefetched_noise_gives_the_same_steps_as_noise_handed_over_with_the_call(pkg, golden):
+    """pdeb200_noise_prefetch: step i+1's host noise is handed over BEFORE the call for step i (two outstanding at most) and
+    consumed in order; results must equal the calls that carry their noise themselves (randn inside the policy call,
+    PDEagent.jl:201), and a third outstanding prefetch is refused."""
+    import ctypes as C
+    A = _agent_mod(pkg)
+    L = pkg.lib
+    g = golden("ks200_hook")
+    chain = A.Chain(A.Dense(g["best_W1"], g["best_b1"], "relu"), A.Dense(g["best_W2"], g["best_b2"], "tanh"))
+    setup = pkg.setups.KSSetup.ks200()
+    B, steps = 4, 5
+    y0 = setup.generate_random_init(np.random.default_rng(5), B)
+    a, b = [setup.make_env(n_envs=B, dtype="f64", y0=y0) for _ in range(2)]
+    for e in (a, b):
+        A.CustomNeuralNetworkApproximator(e, L.NET_BEHAVIOR_ACTOR, chain.copy())
+    noise = np.random.default_rng(6).standard_normal((steps, B * 80))
+    tot = C.c_size_t()
+    L.check(a._lib.pdeb200_result_layout(a._ctx, None, None, None, C.byref(tot)), a._ctx)
+    pa, pb = np.zeros(tot.value, dtype=np.uint8), np.zeros(tot.value, dtype=np.uint8)
+    lib = a._lib
+    L.check(lib.pdeb200_noise_prefetch(a._ctx, noise[0].ctypes.data), a._ctx)
+    for i in range(steps):
+        if i + 1 < steps:
+            L.check(lib.pdeb200_noise_prefetch(a._ctx, noise[i + 1].ctypes.data), a._ctx)
+            assert lib.pdeb200_noise_prefetch(a._ctx, noise[i + 1].ctypes.data) == -4          # PDEB200_ESTATE: two are outstanding
+        L.check(lib.pdeb200_act_step_host(a._ctx, None, 0.3, 1.0, None, None, pa.ctypes.data, None, None, None), a._ctx)
+        L.check(lib.pdeb200_act_step_host(b._ctx, noise[i].ctypes.data, 0.3, 1.0, None, None, pb.ctypes.data, None, None, None), b._ctx)
+        assert np.array_equal(pa, pb)
+        assert np.array_equal(a.get(L.ARR_Y), b.get(L.ARR_Y))
+        assert np.array_equal(a.get(L.ARR_ACTION_IN), b.get(L.ARR_ACTION_IN))
+    for e in (a, b):
+        e.close()
