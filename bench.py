@@ -580,23 +580,24 @@ def run_ours(args):
     esz_ = 8 if args.dtype == "f64" else 4
     core_bytes_env = (3 * 256 + 64) * esz_
     achieved = core_bytes_env * B / (core_ms * 1e-3) / 1e9
+    core_kernel = (env._lib.pdeb200_last_core_kernel(env._ctx) or b"").decode() or "ks_step_kernel"
     traffic = None
     tp = ROOT / "profiles" / "traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get("ks_step_%s_S%d" % (args.dtype, args.oversampling))
+            traffic = json.loads(tp.read_text()).get("%s|%s|S%d|%d envs" % (core_kernel.split("<")[0], args.dtype, args.oversampling, B))
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_source": "profiles/traffic.json (one ncu --set full capture of this kernel and config; "
-                "not re-measured in this run)" if traffic is not None else None, "peak_source": peak_src, "kernel": "ks_step_kernel<%s,16,16>" % args.dtype,
+                "not re-measured in this run)" if traffic is not None else None, "peak_source": peak_src, "kernel": core_kernel,
                 "algorithmic_bytes_per_launch": core_bytes_env * B, "kernel_ms": core_ms,
                 "kernel_share_of_step": core_ms / avg_ms,
                 "phase_ms": {"actuate": phases[0], "core": phases[1], "observe": phases[2]},
                 "step": {"algorithmic_bytes_per_env_step": bytes_env, "ms": avg_ms,
                          "achieved_gbs": bytes_env * B / (avg_ms * 1e-3) / 1e9, "frac": bytes_env * B / (avg_ms * 1e-3) / 1e9 / peak},
-                "note": "at oversampling=30 the step is FP64-pipe/shared-memory bound (arithmetic intensity ~%d flop/B), "
-                        "so the HBM fraction is small by construction; see fp_pipe" % round(flops_env / bytes_env),
+                "note": "at oversampling=%d the step is FP64-pipe/shared-memory bound (arithmetic intensity ~%d flop/B against a ridge of "
+                        "~5.6), so the HBM fraction is small by construction; see fp_pipe" % (args.oversampling, round(flops_env / bytes_env)),
                 "binding_roof": "fp_pipe (%s CUDA-core FMA)" % args.dtype,
                 "fp_pipe": {"algorithmic_flops_per_env_step": flops_env,
                             "achieved_tflops": flops_env * B / (core_ms * 1e-3) / 1e12,

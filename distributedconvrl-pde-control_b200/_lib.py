@@ -109,6 +109,7 @@ _PROTOS = {
     "pdeb200_last_step_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
     "pdeb200_last_phase_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
     "pdeb200_last_core_ms": (C.c_int32, [C.c_void_p, C.POINTER(C.c_float)]),
+    "pdeb200_last_core_kernel": (C.c_char_p, [C.c_void_p]),
     "pdeb200_enable_step_timing": (C.c_int32, [C.c_void_p, C.c_int32]),
     "pdeb200_measure_fma_peak": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_double)]),
     "pdeb200_debug_timeline": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_int32, C.POINTER(C.c_int32)]),

@@ -95,6 +95,7 @@ struct pdeb200_ctx {
     void* comm = nullptr;           // pdeb200::Comm (comm.cu) after pdeb200_comm_init
 
     // timing
+    const char* core_kernel = "";  // name of the core kernel the most recent step launched (pdeb200_last_core_kernel)
     bool timing = false; cudaEvent_t ev0 = nullptr, ev1 = nullptr, evc0 = nullptr, evc1 = nullptr; bool timed = false;
 };
 

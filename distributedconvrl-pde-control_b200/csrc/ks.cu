@@ -167,6 +167,7 @@ int32_t launch_tm(pdeb200_ctx* c, const KsArgs<double>& A, int n_sm, bool spec) 
     const size_t smem = ks_tm_smem_bytes(PAIRS, n_tab);
     if (smem > 227 * 1024) return PDEB200_EUNSUPPORTED;
     auto kern = spec ? ks_step_tm_kernel<true> : ks_step_tm_kernel<false>;
+    c->core_kernel = spec ? "ks_step_tm_kernel<spectral sensors>" : "ks_step_tm_kernel<gather sensors>";
     PDEB_CUDA(c, ensure_dyn_smem(kern, smem, c->device));
     kern<<<(n_pairs + PAIRS - 1) / PAIRS, bw * 32, smem, c->stream>>>(A);
     PDEB_CUDA(c, cudaGetLastError());
@@ -207,15 +208,17 @@ int32_t launch(pdeb200_ctx* c) {
     const size_t smem = ks_smem_bytes<T, N1, N2>(PAIRS, g.oversampling > 1);
     // spectral sensor dots where they pay (few substeps); PDEB200_KS_SPECTRAL_SENSORS=2 forces them at any oversampling
     static const int spec_mode = [] { const char* e = getenv("PDEB200_KS_SPECTRAL_SENSORS"); return e ? atoi(e) : 1; }();
-    // tensor-memory variant: fp64, 16 x 16, many substeps (PDEB200_KS_TMEM=0 off, 2 = at any oversampling)
+    // tensor-memory variant: fp64, 16 x 16, three or more substeps (measured: 165 vs 194 us at oversampling 4 and 32768 envs, 410 vs
+    // 386 us at oversampling 1 and 131072 envs; PDEB200_KS_TMEM=0 off, 2 = at any oversampling)
     static const int tm_mode = [] { const char* e = getenv("PDEB200_KS_TMEM"); return e ? atoi(e) : 1; }();
-    if (sizeof(T) == 8 && N1 == 16 && N2 == 16 && tm_mode && (tm_mode == 2 || g.oversampling > 4)) {
+    if (sizeof(T) == 8 && N1 == 16 && N2 == 16 && tm_mode && (tm_mode == 2 || g.oversampling > 2)) {
         const int32_t rc = launch_tm(c, A, n_sm, c->ks_sens_hat != nullptr && spec_mode != 0);
         if (rc != PDEB200_EUNSUPPORTED) return rc;
     }
     const bool spec = c->ks_sens_hat != nullptr && (spec_mode == 2 || g.oversampling <= 4);
     auto kern = lowreg ? (spec ? ks_step_kernel<T, N1, N2, true, true> : ks_step_kernel<T, N1, N2, true, false>)
                        : (spec ? ks_step_kernel<T, N1, N2, false, true> : ks_step_kernel<T, N1, N2, false, false>);
+    c->core_kernel = sizeof(T) == 8 ? (lowreg ? "ks_step_kernel<f64, low-register>" : "ks_step_kernel<f64>") : "ks_step_kernel<f32>";
     PDEB_CUDA(c, ensure_dyn_smem(kern, smem, c->device));
     kern<<<grid, warps * 32, smem, c->stream>>>(A);
     PDEB_CUDA(c, cudaGetLastError());

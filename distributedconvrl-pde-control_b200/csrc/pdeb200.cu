@@ -1057,6 +1057,8 @@ int32_t pdeb200_last_core_ms(pdeb200_ctx* c, float* ms) {
     return PDEB200_OK;
 }
 
+const char* pdeb200_last_core_kernel(const pdeb200_ctx* c) { return c ? c->core_kernel : ""; }
+
 int32_t pdeb200_step_cost(const pdeb200_ctx* c, double* bytes, double* flops) {
     if (!c) return PDEB200_EINVAL;
     switch (c->cfg.problem) {

@@ -315,6 +315,8 @@ int32_t pdeb200_enable_step_timing(pdeb200_ctx* ctx, int32_t on);
 /* Device time of the problem's core kernel(s) -- (y, p) -> (y', sensor dots): the dominant kernel of a step -- in the
  * most recent env step, from CUDA events recorded around it on the context's stream (needs step timing enabled). */
 int32_t pdeb200_last_core_ms(pdeb200_ctx* ctx, float* ms);
+/* Name of the core kernel the most recent env step launched (KS: which ks_step variant the dispatch chose); "" if none. */
+const char* pdeb200_last_core_kernel(const pdeb200_ctx* ctx);
 /* The three phases of the most recent single env step {actuation, core, observe} in ms (events on the stream). */
 int32_t pdeb200_last_phase_ms(pdeb200_ctx* ctx, float* ms3);
 /* Measured CUDA-core FMA peak of this GPU (TFLOP/s, 2 flops per FMA) for dtype PDEB200_F32 / F64: the roofline
