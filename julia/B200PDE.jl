@@ -142,6 +142,18 @@ policy_act!(c::Ctx; act_noise = 0.0, act_limit = 1.0, noise = nothing) =
     check(ccall((:pdeb200_policy_act, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64),
                 c.ptr, isnothing(noise) ? C_NULL : noise, act_noise, act_limit), c.ptr)
 
+# Exploration noise one step ahead (pdeb200_noise_prefetch): its upload runs on a copy stream under the current step's kernels.
+# `noise` must stay referenced until the consuming act_step! has returned (the copy reads it asynchronously).
+noise_prefetch!(c::Ctx, noise::Matrix{Float64}) =
+    check(ccall((:pdeb200_noise_prefetch, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), c.ptr, noise), c.ptr)
+
+# `action = policy(env); env(action)` as ONE call with one synchronisation (pdeb200_act_step_host); packed receives
+# [reward | state | done] (result_layout).  noise = nothing with act_noise > 0 consumes the oldest prefetched noise.
+act_step!(c::Ctx, packed::Vector{UInt8}; act_noise = 0.0, act_limit = 1.0, noise = nothing) =
+    check(ccall((:pdeb200_act_step_host, LIB), Int32,
+                (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}),
+                c.ptr, isnothing(noise) ? C_NULL : noise, act_noise, act_limit, C_NULL, C_NULL, packed, C_NULL, C_NULL, C_NULL), c.ptr)
+
 ddpg_update!(c::Ctx; γ = 0.99, p = 0.995, lr_actor = 5e-4, lr_critic = 1e-3, literal_q1 = true) =
     check(ccall((:pdeb200_ddpg_update, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Float64, Float64, Int32),
                 c.ptr, γ, p, lr_actor, lr_critic, Int32(literal_q1)), c.ptr)
