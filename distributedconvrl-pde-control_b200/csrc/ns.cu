@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "ctx.hpp"
+#include "fft_batch.cuh"
 #include "fft_pass.cuh"
 #include "glue.cuh"
 
@@ -44,7 +45,8 @@ template <int P1, int P2> struct NsGeom {
 
 
 struct NsProb {
-    int N = 0, NP = 0, NH = 0, NHP = 0, chunk = 0;
+    int N = 0, NP = 0, NH = 0, NHP = 0, chunk = 0, n_sm = 148;
+    bool legacy = false;
     int n1 = 0, n2 = 0, p1 = 0, p2 = 0;
     void *tw_inv = nullptr, *tw_fwd = nullptr, *tw_n = nullptr;
     void *kx = nullptr, *ky = nullptr;
@@ -305,6 +307,198 @@ ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
     }
 }
 
+// ---- A and B, batched form (fft_batch.cuh): a warp owns FOUR lines in shared memory ------------------------
+// A4: one warp = one kx >= 0 column, its four fields are the four lines.  The column pair (kx, -kx) is read
+//     straight from global memory into registers (16 independent 16-byte loads per lane, no staging table), each
+//     entry is divided by k^2 once (as a reciprocal) and the four symmetrised spectra are written in natural
+//     layout; after the batched inverse transform the CTA stores all four fields as COLS-column tiles.
+template <typename T, int P1, int P2, int NN, int COLS>
+__global__ void __launch_bounds__(COLS * 32)
+ns_ypass_inv4_kernel(const __grid_constant__ NsArgs<T> A) {
+    using G = BatchLayout<P1, P2>;
+    using C = typename V2<T>::type;
+    constexpr int NP = G::N, N = NN, NH = NN / 2 + 1, NHP = (NH + 3) / 4 * 4;
+    constexpr int WS = 4 * G::LS + 2;                            // per-warp stride: == 2 (mod 8) entries, see tile store
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* s_tw = reinterpret_cast<C*>(smem_raw);
+    C* s_xb0 = s_tw + NP;
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+    const int env = blockIdx.y, a0 = blockIdx.x * COLS, a = a0 + w;
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) s_tw[i] = A.tw_inv[i];
+    C* xb = s_xb0 + w * WS;
+    if (a < NH) {
+        const int ib = (N - a) % N;                               // column of -kx in the unpadded array
+        const bool xpartner = unpad_idx((NP - a) % NP, NP, N) >= 0;   // pad() keeps (-kx) ?
+        const T kxa = A.kx[a], kxb = A.kx[ib];
+        const C* srcA = A.fin + (size_t)env * N * N + (size_t)a * N;
+        const C* srcB = A.fin + (size_t)env * N * N + (size_t)ib * N;
+        constexpr int NB = (NP + 31) / 32;
+        C c1[NB], c2[NB];
+        T k1[NB], k2[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int kyp = i * 32 + t;
+            c1[i] = c2[i] = V2<T>::make(T(0), T(0)); k1[i] = k2[i] = T(0);
+            if (i * 32 > N / 2 && i * 32 + 31 < NP - N / 2) continue;     // all-zero block of pad()
+            if (NP % 32 != 0 && kyp >= NP) continue;
+            const int j1 = unpad_idx(kyp, NP, N);
+            const int j2 = xpartner ? unpad_idx((NP - kyp) % NP, NP, N) : -1;
+            if (j1 >= 0) { c1[i] = srcA[j1]; k1[i] = A.ky[j1]; }
+            if (j2 >= 0) { c2[i] = srcB[j2]; k2[i] = A.ky[j2]; }
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int kyp = i * 32 + t;
+            if (NP % 32 != 0 && kyp >= NP) continue;
+            C* o = xb + G::nat(kyp);
+            if (i * 32 > N / 2 && i * 32 + 31 < NP - N / 2) {
+                const C z = V2<T>::make(T(0), T(0));
+                o[0] = z; o[G::LS] = z; o[2 * G::LS] = z; o[3 * G::LS] = z;
+                continue;
+            }
+            // psi_hat = omega_hat ./ kx2ky2, psi_hat[1,1] = 0   (fluid_rk4.jl:152-153); absent entries are 0 / 1
+            const T qa = k1[i] * k1[i] + kxa * kxa, qb = k2[i] * k2[i] + kxb * kxb;
+            const T ra = qa > T(0) ? T(1) / qa : T(0), rb = qb > T(0) ? T(1) / qb : T(0);
+            const C p1 = V2<T>::make(c1[i].x * ra, c1[i].y * ra), p2 = V2<T>::make(c2[i].x * rb, c2[i].y * rb);
+            // X_h = (X(k) + conj(X(-k))) / 2 with X = i m c:   u = i ky psi, v = -i kx psi, w_x = i kx omega, w_y = i ky omega
+            o[0]         = V2<T>::make(T(0.5) * (-k1[i] * p1.y - k2[i] * p2.y), T(0.5) * (k1[i] * p1.x - k2[i] * p2.x));
+            o[G::LS]     = V2<T>::make(T(0.5) * (kxa * p1.y + kxb * p2.y),      T(0.5) * (-kxa * p1.x + kxb * p2.x));
+            o[2 * G::LS] = V2<T>::make(T(0.5) * (-kxa * c1[i].y - kxb * c2[i].y), T(0.5) * (kxa * c1[i].x - kxb * c2[i].x));
+            o[3 * G::LS] = V2<T>::make(T(0.5) * (-k1[i] * c1[i].y - k2[i] * c2[i].y), T(0.5) * (k1[i] * c1[i].x - k2[i] * c2[i].x));
+        }
+    }
+    __syncthreads();                                             // twiddles staged; xb written by its own warp
+    if (a < NH) fft_batch_nt<T, P1, P2, 4, +1>(xb, s_tw, t);
+    __syncthreads();
+    {
+        // COLS-column tile store: thread -> (column c, row y); consecutive lanes = COLS columns x 32/COLS rows.
+        // Row y of the transposed layout sits at (y % P2) * S + y / P2; the per-warp stride WS shifts column c by
+        // 2c entries, so the 8 lanes of a quarter warp (COLS = 4: 4 columns x 2 rows) hit 32 distinct banks.
+        const int c = threadIdx.x % COLS, y0 = threadIdx.x / COLS;
+        if (a0 + c < NH) {
+            const C* src = s_xb0 + c * WS;
+#pragma unroll 1
+            for (int f = 0; f < 4; ++f) {
+                C* dst = A.W + ((size_t)(env * 4 + f) * NP + y0) * NHP + a0 + c;
+                int ym = y0 % P2, yd = y0 / P2;
+#pragma unroll 4
+                for (int y = y0; y < NP; y += 32) {
+                    *dst = src[f * G::LS + ym * G::S + yd];
+                    dst += (size_t)32 * NHP;
+                    ym += 32 % P2; yd += 32 / P2;
+                    if (ym >= P2) { ym -= P2; ++yd; }
+                }
+            }
+        }
+    }
+}
+
+// B4: one warp = two y-lines per job, persistent over jobs.  The four inverse transforms along x (u + i v and
+//     w_x + i w_y of both lines) are ONE batch; the two real products are packed into one forward transform.
+//     The raw half-spectrum rows of W are staged by 1-D bulk copies (cp.async.bulk, one mbarrier per line) INTO the
+//     line buffer they will be expanded in (U at entry 0, V at entry NHP), and the copies of the next job are issued
+//     as soon as a line buffer is dead (lines 1-3 after the product, line 0 after the split), so that they run under
+//     the forward transform and the stores.
+template <typename T, int P1, int P2, int NN, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+ns_xpass4_kernel(const __grid_constant__ NsArgs<T> A, int n_jobs) {
+    using G = BatchLayout<P1, P2>;
+    using C = typename V2<T>::type;
+    constexpr int NP = G::N, N = NN, NH = NN / 2 + 1, NHP = (NH + 3) / 4 * 4;
+    static_assert(2 * NHP <= G::LS, "raw rows must fit the line buffer");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* s_twi = reinterpret_cast<C*>(smem_raw);
+    C* s_twf = s_twi + NP;
+    C* s_xb0 = s_twf + NP;
+    uint64_t* s_bar0 = reinterpret_cast<uint64_t*>(s_xb0 + (size_t)WARPS * 4 * G::LS);
+    const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+    C* xb = s_xb0 + (size_t)w * 4 * G::LS;
+    uint64_t* bar = s_bar0 + w * 4;
+    constexpr uint32_t row_bytes = (uint32_t)(NHP * sizeof(C));
+    constexpr int JPE = NP / 2;                                   // jobs per environment
+    const int stride = gridDim.x * WARPS;
+    int job = blockIdx.x * WARPS + w;
+    // line l of a job: y-line y0 + (l >> 1), fields (2h, 2h + 1) with h = l & 1
+    auto issue = [&](int jb, int l) {
+        const int env = jb / JPE, y = (jb % JPE) * 2 + (l >> 1);
+        const C* Wu = A.W + ((size_t)(env * 4 + 2 * (l & 1)) * NP + y) * NHP;
+        mbar_expect_tx(bar + l, 2 * row_bytes);
+        bulk_g2s(xb + l * G::LS, Wu, row_bytes, bar + l);
+        bulk_g2s(xb + l * G::LS + NHP, Wu + (size_t)NP * NHP, row_bytes, bar + l);
+    };
+    if (t == 0) {
+        for (int l = 0; l < 4; ++l) mbar_init(bar + l, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (job < n_jobs) for (int l = 0; l < 4; ++l) issue(job, l);
+    }
+    for (int i = threadIdx.x; i < NP; i += blockDim.x) { s_twi[i] = A.tw_inv[i]; s_twf[i] = A.tw_fwd[i]; }
+    __syncthreads();
+    constexpr int NA = (NH + 31) / 32;
+    uint32_t ph = 0;
+#pragma unroll 1
+    for (; job < n_jobs; job += stride, ph ^= 1) {
+        const int env = job / JPE, y0 = (job % JPE) * 2;
+        // expand the raw rows in place: Z = U + i V on kx >= 0, conj(U) + i conj(V) on kx < 0, zero band between
+#pragma unroll 1
+        for (int l = 0; l < 4; ++l) {
+            C* ln = xb + l * G::LS;
+            mbar_wait(bar + l, ph);
+            C U[NA], V[NA];
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                const int a = i * 32 + t;
+                if (a < NH) { U[i] = ln[a]; V[i] = ln[NHP + a]; }
+            }
+            __syncwarp();
+            for (int e = N / 2 + 1 + t; e < NP - N / 2; e += 32) ln[G::nat(e)] = V2<T>::make(T(0), T(0));
+#pragma unroll
+            for (int i = 0; i < NA; ++i) {
+                const int a = i * 32 + t;
+                if (a < NH) {
+                    ln[G::nat(a)] = V2<T>::make(U[i].x - V[i].y, U[i].y + V[i].x);
+                    if (a > 0) ln[G::nat(NP - a)] = V2<T>::make(U[i].x + V[i].y, V[i].x - U[i].y);
+                }
+            }
+        }
+        __syncwarp();
+        fft_batch_nt<T, P1, P2, 4, +1>(xb, s_twi, t);
+        // q = -u w_x - v w_y  (fluid_rk4.jl:175), both lines packed into one complex line; same (transposed) positions
+        for (int i = t; i < NP; i += 32) {
+            const int pos = (i / P1) * G::S + i % P1;
+            const C g0 = xb[pos], z0 = xb[G::LS + pos], g1 = xb[2 * G::LS + pos], z1 = xb[3 * G::LS + pos];
+            xb[pos] = V2<T>::make(-(g0.x * z0.x + g0.y * z0.y) * A.scale, -(g1.x * z1.x + g1.y * z1.y) * A.scale);
+        }
+        __syncwarp();
+        const bool more = job + stride < n_jobs;
+        if (t == 0 && more) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (int l = 1; l < 4; ++l) issue(job + stride, l);
+        }
+        fft_batch_tn<T, P1, P2, 1, -1>(xb, s_twf, t);
+        C za[NA], zb[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const int a = i * 32 + t;
+            if (a < NH) { za[i] = xb[G::nat(a)]; zb[i] = xb[G::nat((NP - a) % NP)]; }
+        }
+        __syncwarp();
+        if (t == 0 && more) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue(job + stride, 0);
+        }
+        C* Qa = A.Q + ((size_t)env * NP + y0) * NHP;
+        C* Qb = Qa + NHP;
+#pragma unroll
+        for (int i = 0; i < NA; ++i) {
+            const int a = i * 32 + t;
+            if (a < NH) {
+                Qa[a] = V2<T>::make(T(0.5) * (za[i].x + zb[i].x), T(0.5) * (za[i].y - zb[i].y));
+                Qb[a] = V2<T>::make(T(0.5) * (za[i].y + zb[i].y), T(-0.5) * (za[i].x - zb[i].x));
+            }
+        }
+    }
+}
+
 // ---- C: forward transform along y, chop, RK4 stage update ---------------------------------------------------
 // RK4 stage update of U entries at once: all loads are issued before the first store (the arrays may alias
 // from the compiler's point of view, so it cannot do this reordering itself).
@@ -556,6 +750,16 @@ int32_t rk4_t(pdeb200_ctx* c) {
     const size_t sa = smem_a<T, P1, P2>(N), sb = smem_b<T, P1, P2>(P->NHP), sc = smem_c<T, P1, P2>(N);
     int32_t rc;
     if ((rc = set_smem(c, kA, sa)) || (rc = set_smem(c, kB, sb)) || (rc = set_smem(c, kC, sc))) return rc;
+    // batched form of A and B (fft_batch.cuh); PDEB200_NS_LEGACY=1 keeps the one-line-per-warp kernels
+    constexpr int COLS_A4 = 4, WARPS_B4 = sizeof(T) == 8 ? 8 : 8;
+    auto kA4 = ns_ypass_inv4_kernel<T, P1, P2, NN, COLS_A4>;
+    auto kB4 = ns_xpass4_kernel<T, P1, P2, NN, WARPS_B4>;
+    using BL = BatchLayout<P1, P2>;
+    const size_t sa4 = ((size_t)BL::N + COLS_A4 * (4 * BL::LS + 2)) * sizeof(C);
+    const size_t sb4 = ((size_t)2 * BL::N + (size_t)WARPS_B4 * 4 * BL::LS) * sizeof(C) + (size_t)WARPS_B4 * 4 * sizeof(uint64_t);
+    const bool batched = !P->legacy;
+    const int b4_ctas = std::max<int>(1, (int)((227 * 1024) / (sb4 + 1024)));   // resident CTAs per SM
+    if (batched && ((rc = set_smem(c, kA4, sa4)) || (rc = set_smem(c, kB4, sb4)))) return rc;
     NsArgs<T> A;
     A.N = N; A.NH = P->NH; A.NHP = P->NHP;
     A.tw_inv = (const C*)P->tw_inv; A.tw_fwd = (const C*)P->tw_fwd;
@@ -573,8 +777,13 @@ int32_t rk4_t(pdeb200_ctx* c) {
             for (int stage = 1; stage <= 4; ++stage) {
                 A.stage = stage;
                 A.fin = stage == 1 ? A.y : A.fst;
-                kA<<<dim3((P->NH + COLS_A - 1) / COLS_A, ne), COLS_A * 32, sa, c->stream>>>(A);
-                kB<<<dim3((NP / 2 + COLS_B - 1) / COLS_B, ne), COLS_B * 32, sb, c->stream>>>(A);
+                if (batched) {
+                    kA4<<<dim3((P->NH + COLS_A4 - 1) / COLS_A4, ne), COLS_A4 * 32, sa4, c->stream>>>(A);
+                    kB4<<<std::min(P->n_sm * b4_ctas, (ne * (NP / 2) + WARPS_B4 - 1) / WARPS_B4), WARPS_B4 * 32, sb4, c->stream>>>(A, ne * (NP / 2));
+                } else {
+                    kA<<<dim3((P->NH + COLS_A - 1) / COLS_A, ne), COLS_A * 32, sa, c->stream>>>(A);
+                    kB<<<dim3((NP / 2 + COLS_B - 1) / COLS_B, ne), COLS_B * 32, sb, c->stream>>>(A);
+                }
                 kC<<<dim3((P->NH + COLS_C - 1) / COLS_C, ne), COLS_C * 32, sc, c->stream>>>(A);
                 c->launches += 3;
             }
@@ -676,6 +885,9 @@ int32_t ns_setup(pdeb200_ctx* c) {
     const char* e = getenv("PDEB200_NS_CHUNK");
     P->chunk = e ? std::max(1, atoi(e)) : g.n_envs;
     P->chunk = std::min(P->chunk, g.n_envs);
+    cudaDeviceGetAttribute(&P->n_sm, cudaDevAttrMultiProcessorCount, c->device);
+    e = getenv("PDEB200_NS_LEGACY");
+    P->legacy = e && atoi(e) != 0;
     return g.dtype == PDEB200_F64 ? setup_t<double>(c) : setup_t<float>(c);
 }
 
