@@ -47,6 +47,7 @@ template <int P1, int P2> struct NsGeom {
 struct NsProb {
     int N = 0, NP = 0, NH = 0, NHP = 0, chunk = 0, n_sm = 148;
     bool legacy = false;
+    int b4_mode = 0;             // kernel B4: bit 0 = twiddles in shared memory
     int n1 = 0, n2 = 0, p1 = 0, p2 = 0;
     void *tw_inv = nullptr, *tw_fwd = nullptr, *tw_n = nullptr;
     void *kx = nullptr, *ky = nullptr;
@@ -312,18 +313,24 @@ ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
 //     straight from global memory into registers (16 independent 16-byte loads per lane, no staging table), each
 //     entry is divided by k^2 once (as a reciprocal) and the four symmetrised spectra are written in natural
 //     layout; after the batched inverse transform the CTA stores all four fields as COLS-column tiles.
-template <typename T, int P1, int P2, int NN, int COLS>
-__global__ void __launch_bounds__(COLS * 32)
+//     Measured and dropped: twiddles in registers (230 registers: 175 -> 193 us per 148 environments) and a
+//     persistent CTA that issues the next job's column loads before its tile store (222-255 registers: 198-216 us).
+//     FPW = fields per warp: 4 (one warp per column) or 2 (two warps per column: psi-based u, v and omega-based
+//     w_x, w_y; half the shared memory per warp, i.e. twice the resident warps, for a row pass with 48 tasks on
+//     2 x 32 lanes).
+template <typename T, int P1, int P2, int NN, int COLS, int FPW>
+__global__ void __launch_bounds__(COLS * (4 / FPW) * 32, FPW == 2 ? 2 : 1)
 ns_ypass_inv4_kernel(const __grid_constant__ NsArgs<T> A) {
     using G = BatchLayout<P1, P2>;
     using C = typename V2<T>::type;
     constexpr int NP = G::N, N = NN, NH = NN / 2 + 1, NHP = (NH + 3) / 4 * 4;
-    constexpr int WS = 4 * G::LS + 2;                            // per-warp stride: == 2 (mod 8) entries, see tile store
+    constexpr int WS = FPW * G::LS + 2;                          // per-warp stride: == 2 (mod 8) entries, see tile store
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* s_tw = reinterpret_cast<C*>(smem_raw);
     C* s_xb0 = s_tw + NP;
     const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
-    const int env = blockIdx.y, a0 = blockIdx.x * COLS, a = a0 + w;
+    const int wc = w % COLS, half = w / COLS;                    // FPW == 2: half 0 = psi-based fields 0, 1; half 1 = fields 2, 3
+    const int env = blockIdx.y, a0 = blockIdx.x * COLS, a = a0 + wc;
     for (int i = threadIdx.x; i < NP; i += blockDim.x) s_tw[i] = A.tw_inv[i];
     C* xb = s_xb0 + w * WS;
     if (a < NH) {
@@ -346,44 +353,57 @@ ns_ypass_inv4_kernel(const __grid_constant__ NsArgs<T> A) {
             if (j1 >= 0) { c1[i] = srcA[j1]; k1[i] = A.ky[j1]; }
             if (j2 >= 0) { c2[i] = srcB[j2]; k2[i] = A.ky[j2]; }
         }
+        const bool psi = FPW == 4 || half == 0, omg = FPW == 4 || half == 1;
+        C* opsi = xb;
+        C* oomg = xb + (FPW == 4 ? 2 * G::LS : 0);
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
             const int kyp = i * 32 + t;
             if (NP % 32 != 0 && kyp >= NP) continue;
-            C* o = xb + G::nat(kyp);
+            const int o = G::nat(kyp);
             if (i * 32 > N / 2 && i * 32 + 31 < NP - N / 2) {
                 const C z = V2<T>::make(T(0), T(0));
-                o[0] = z; o[G::LS] = z; o[2 * G::LS] = z; o[3 * G::LS] = z;
+#pragma unroll
+                for (int f = 0; f < FPW; ++f) xb[f * G::LS + o] = z;
                 continue;
             }
-            // psi_hat = omega_hat ./ kx2ky2, psi_hat[1,1] = 0   (fluid_rk4.jl:152-153); absent entries are 0 / 1
-            const T qa = k1[i] * k1[i] + kxa * kxa, qb = k2[i] * k2[i] + kxb * kxb;
-            const T ra = qa > T(0) ? T(1) / qa : T(0), rb = qb > T(0) ? T(1) / qb : T(0);
-            const C p1 = V2<T>::make(c1[i].x * ra, c1[i].y * ra), p2 = V2<T>::make(c2[i].x * rb, c2[i].y * rb);
             // X_h = (X(k) + conj(X(-k))) / 2 with X = i m c:   u = i ky psi, v = -i kx psi, w_x = i kx omega, w_y = i ky omega
-            o[0]         = V2<T>::make(T(0.5) * (-k1[i] * p1.y - k2[i] * p2.y), T(0.5) * (k1[i] * p1.x - k2[i] * p2.x));
-            o[G::LS]     = V2<T>::make(T(0.5) * (kxa * p1.y + kxb * p2.y),      T(0.5) * (-kxa * p1.x + kxb * p2.x));
-            o[2 * G::LS] = V2<T>::make(T(0.5) * (-kxa * c1[i].y - kxb * c2[i].y), T(0.5) * (kxa * c1[i].x - kxb * c2[i].x));
-            o[3 * G::LS] = V2<T>::make(T(0.5) * (-k1[i] * c1[i].y - k2[i] * c2[i].y), T(0.5) * (k1[i] * c1[i].x - k2[i] * c2[i].x));
+            if (psi) {
+                // psi_hat = omega_hat ./ kx2ky2, psi_hat[1,1] = 0   (fluid_rk4.jl:152-153); absent entries are 0
+                const T qa = k1[i] * k1[i] + kxa * kxa, qb = k2[i] * k2[i] + kxb * kxb;
+                const T ra = qa > T(0) ? T(1) / qa : T(0), rb = qb > T(0) ? T(1) / qb : T(0);
+                const C p1 = V2<T>::make(c1[i].x * ra, c1[i].y * ra), p2 = V2<T>::make(c2[i].x * rb, c2[i].y * rb);
+                opsi[o]         = V2<T>::make(T(0.5) * (-k1[i] * p1.y - k2[i] * p2.y), T(0.5) * (k1[i] * p1.x - k2[i] * p2.x));
+                opsi[G::LS + o] = V2<T>::make(T(0.5) * (kxa * p1.y + kxb * p2.y),      T(0.5) * (-kxa * p1.x + kxb * p2.x));
+            }
+            if (omg) {
+                oomg[o]         = V2<T>::make(T(0.5) * (-kxa * c1[i].y - kxb * c2[i].y), T(0.5) * (kxa * c1[i].x - kxb * c2[i].x));
+                oomg[G::LS + o] = V2<T>::make(T(0.5) * (-k1[i] * c1[i].y - k2[i] * c2[i].y), T(0.5) * (k1[i] * c1[i].x - k2[i] * c2[i].x));
+            }
         }
     }
     __syncthreads();                                             // twiddles staged; xb written by its own warp
-    if (a < NH) fft_batch_nt<T, P1, P2, 4, +1>(xb, s_tw, t);
+    if (a < NH)
+        fft_batch_nt<T, P1, P2, FPW, +1, false, BatchNoSync>(
+            xb, s_tw, BatchTwiddles<T, P1, P2>(), t, [&](int line, int col, int r) { return xb[line * G::LS + r * G::S + col]; },
+            [](int) {});
     __syncthreads();
     {
         // COLS-column tile store: thread -> (column c, row y); consecutive lanes = COLS columns x 32/COLS rows.
-        // Row y of the transposed layout sits at (y % P2) * S + y / P2; the per-warp stride WS shifts column c by
+        // Row y of the transposed layout sits at (y % P2) * S + y / P2; the per-warp stride shifts column c by
         // 2c entries, so the 8 lanes of a quarter warp (COLS = 4: 4 columns x 2 rows) hit 32 distinct banks.
-        const int c = threadIdx.x % COLS, y0 = threadIdx.x / COLS;
+        constexpr int TPF = COLS * 32;                            // threads per tile-store group
+        const int grp = threadIdx.x / TPF, tid = threadIdx.x % TPF;
+        const int c = tid % COLS, y0 = tid / COLS;
         if (a0 + c < NH) {
-            const C* src = s_xb0 + c * WS;
 #pragma unroll 1
-            for (int f = 0; f < 4; ++f) {
+            for (int f = grp * FPW; f < grp * FPW + FPW; ++f) {
+                const C* src = s_xb0 + ((f / FPW) * COLS + c) * WS + (f % FPW) * G::LS;
                 C* dst = A.W + ((size_t)(env * 4 + f) * NP + y0) * NHP + a0 + c;
                 int ym = y0 % P2, yd = y0 / P2;
 #pragma unroll 4
                 for (int y = y0; y < NP; y += 32) {
-                    *dst = src[f * G::LS + ym * G::S + yd];
+                    *dst = src[ym * G::S + yd];
                     dst += (size_t)32 * NHP;
                     ym += 32 % P2; yd += 32 / P2;
                     if (ym >= P2) { ym -= P2; ++yd; }
@@ -399,7 +419,7 @@ ns_ypass_inv4_kernel(const __grid_constant__ NsArgs<T> A) {
 //     line buffer they will be expanded in (U at entry 0, V at entry NHP), and the copies of the next job are issued
 //     as soon as a line buffer is dead (lines 1-3 after the product, line 0 after the split), so that they run under
 //     the forward transform and the stores.
-template <typename T, int P1, int P2, int NN, int WARPS>
+template <typename T, int P1, int P2, int NN, int WARPS, bool TWR>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 ns_xpass4_kernel(const __grid_constant__ NsArgs<T> A, int n_jobs) {
     using G = BatchLayout<P1, P2>;
@@ -408,8 +428,8 @@ ns_xpass4_kernel(const __grid_constant__ NsArgs<T> A, int n_jobs) {
     static_assert(2 * NHP <= G::LS, "raw rows must fit the line buffer");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     C* s_twi = reinterpret_cast<C*>(smem_raw);
-    C* s_twf = s_twi + NP;
-    C* s_xb0 = s_twf + NP;
+    C* s_twf = s_twi + (TWR ? 0 : NP);
+    C* s_xb0 = s_twf + (TWR ? 0 : NP);
     uint64_t* s_bar0 = reinterpret_cast<uint64_t*>(s_xb0 + (size_t)WARPS * 4 * G::LS);
     const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
     C* xb = s_xb0 + (size_t)w * 4 * G::LS;
@@ -431,50 +451,51 @@ ns_xpass4_kernel(const __grid_constant__ NsArgs<T> A, int n_jobs) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (job < n_jobs) for (int l = 0; l < 4; ++l) issue(job, l);
     }
-    for (int i = threadIdx.x; i < NP; i += blockDim.x) { s_twi[i] = A.tw_inv[i]; s_twf[i] = A.tw_fwd[i]; }
+    BatchTwiddles<T, P1, P2> tw;
+    if (TWR) tw.load(A.tw_inv, t);
+    else for (int i = threadIdx.x; i < NP; i += blockDim.x) { s_twi[i] = A.tw_inv[i]; s_twf[i] = A.tw_fwd[i]; }
     __syncthreads();
     constexpr int NA = (NH + 31) / 32;
+    constexpr int LPR = 32 / P1;                                  // lines per column-pass round
     uint32_t ph = 0;
 #pragma unroll 1
     for (; job < n_jobs; job += stride, ph ^= 1) {
         const int env = job / JPE, y0 = (job % JPE) * 2;
-        // expand the raw rows in place: Z = U + i V on kx >= 0, conj(U) + i conj(V) on kx < 0, zero band between
-#pragma unroll 1
-        for (int l = 0; l < 4; ++l) {
-            C* ln = xb + l * G::LS;
-            mbar_wait(bar + l, ph);
-            C U[NA], V[NA];
-#pragma unroll
-            for (int i = 0; i < NA; ++i) {
-                const int a = i * 32 + t;
-                if (a < NH) { U[i] = ln[a]; V[i] = ln[NHP + a]; }
-            }
-            __syncwarp();
-            for (int e = N / 2 + 1 + t; e < NP - N / 2; e += 32) ln[G::nat(e)] = V2<T>::make(T(0), T(0));
-#pragma unroll
-            for (int i = 0; i < NA; ++i) {
-                const int a = i * 32 + t;
-                if (a < NH) {
-                    ln[G::nat(a)] = V2<T>::make(U[i].x - V[i].y, U[i].y + V[i].x);
-                    if (a > 0) ln[G::nat(NP - a)] = V2<T>::make(U[i].x + V[i].y, V[i].x - U[i].y);
-                }
-            }
-        }
-        __syncwarp();
-        fft_batch_nt<T, P1, P2, 4, +1>(xb, s_twi, t);
-        // q = -u w_x - v w_y  (fluid_rk4.jl:175), both lines packed into one complex line; same (transposed) positions
-        for (int i = t; i < NP; i += 32) {
-            const int pos = (i / P1) * G::S + i % P1;
-            const C g0 = xb[pos], z0 = xb[G::LS + pos], g1 = xb[2 * G::LS + pos], z1 = xb[3 * G::LS + pos];
-            xb[pos] = V2<T>::make(-(g0.x * z0.x + g0.y * z0.y) * A.scale, -(g1.x * z1.x + g1.y * z1.y) * A.scale);
-        }
-        __syncwarp();
+        // inverse batch; its column pass expands the raw rows while loading: Z = U + i V on kx >= 0,
+        // conj(U) + i conj(V) on kx < 0 (G(y, -kx) = conj(G(y, kx)) for a real field), pad()'s zero band between
+        fft_batch_nt<T, P1, P2, 4, +1, TWR, BatchSync>(
+            xb, s_twi, tw, t,
+            [&](int line, int col, int r) {
+                const C* ln = xb + line * G::LS;
+                const int e = col + P1 * r, lo = P1 * r, hi = P1 * r + P1 - 1;     // lo, hi fold after unrolling
+                bool pos, neg;
+                if (hi <= N / 2) { pos = true; neg = false; }
+                else if (lo >= NP - N / 2 && lo > N / 2) { pos = false; neg = true; }
+                else if (lo > N / 2 && hi < NP - N / 2) { pos = false; neg = false; }
+                else { pos = e <= N / 2; neg = !pos && e >= NP - N / 2; }
+                if (pos) { const C U = ln[e], V = ln[NHP + e]; return V2<T>::make(U.x - V.y, U.y + V.x); }
+                if (neg) { const C U = ln[NP - e], V = ln[NHP + NP - e]; return V2<T>::make(U.x + V.y, V.x - U.y); }
+                return V2<T>::make(T(0), T(0));
+            },
+            [&](int round) {
+                for (int l = round * LPR; l < round * LPR + LPR; ++l) mbar_wait(bar + l, ph);
+            });
         const bool more = job + stride < n_jobs;
-        if (t == 0 && more) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            for (int l = 1; l < 4; ++l) issue(job + stride, l);
-        }
-        fft_batch_tn<T, P1, P2, 1, -1>(xb, s_twf, t);
+        // forward transform of the two real products packed into one complex line; its row pass forms
+        // q = -u w_x - v w_y  (fluid_rk4.jl:175) from the four lines at the same (transposed) positions
+        fft_batch_tn<T, P1, P2, 1, -1, TWR>(
+            xb, s_twf, tw, t,
+            [&](int, int row, int r) {
+                const int pos = row * G::S + r;
+                const C g0 = xb[pos], z0 = xb[G::LS + pos], g1 = xb[2 * G::LS + pos], z1 = xb[3 * G::LS + pos];
+                return V2<T>::make(-(g0.x * z0.x + g0.y * z0.y) * A.scale, -(g1.x * z1.x + g1.y * z1.y) * A.scale);
+            },
+            [&]() {
+                if (t == 0 && more) {                              // lines 1-3 are dead: next job's rows
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    for (int l = 1; l < 4; ++l) issue(job + stride, l);
+                }
+            });
         C za[NA], zb[NA];
 #pragma unroll
         for (int i = 0; i < NA; ++i) {
@@ -752,14 +773,23 @@ int32_t rk4_t(pdeb200_ctx* c) {
     if ((rc = set_smem(c, kA, sa)) || (rc = set_smem(c, kB, sb)) || (rc = set_smem(c, kC, sc))) return rc;
     // batched form of A and B (fft_batch.cuh); PDEB200_NS_LEGACY=1 keeps the one-line-per-warp kernels
     constexpr int COLS_A4 = 4, WARPS_B4 = sizeof(T) == 8 ? 8 : 8;
-    auto kA4 = ns_ypass_inv4_kernel<T, P1, P2, NN, COLS_A4>;
-    auto kB4 = ns_xpass4_kernel<T, P1, P2, NN, WARPS_B4>;
     using BL = BatchLayout<P1, P2>;
-    const size_t sa4 = ((size_t)BL::N + COLS_A4 * (4 * BL::LS + 2)) * sizeof(C);
-    const size_t sb4 = ((size_t)2 * BL::N + (size_t)WARPS_B4 * 4 * BL::LS) * sizeof(C) + (size_t)WARPS_B4 * 4 * sizeof(uint64_t);
-    const bool batched = !P->legacy;
-    const int b4_ctas = std::max<int>(1, (int)((227 * 1024) / (sb4 + 1024)));   // resident CTAs per SM
+    // 192 = 12 x 16 points: P1 does not divide 32, those grids keep the one-line-per-warp kernels
+    constexpr int BP1 = BL::TWREG ? P1 : 16, BP2 = BL::TWREG ? P2 : 16;
+    constexpr int FPW_A4 = 4;      // 2 (two warps per column, 16 resident warps) measured slower: 205 vs 173 us per 148 environments
+    auto kA4 = ns_ypass_inv4_kernel<T, BP1, BP2, NN, COLS_A4, FPW_A4>;
+    auto kB4r = ns_xpass4_kernel<T, BP1, BP2, NN, WARPS_B4, true>;
+    auto kB4s = ns_xpass4_kernel<T, BP1, BP2, NN, WARPS_B4, false>;
+    auto kB4 = (P->b4_mode & 1) ? kB4s : kB4r;
+    const size_t sa4 = ((size_t)BL::N + COLS_A4 * (4 / FPW_A4) * (FPW_A4 * BL::LS + 2)) * sizeof(C);
+    const size_t sb4 = ((size_t)((P->b4_mode & 1) ? 2 * BL::N : 0) + (size_t)WARPS_B4 * 4 * BL::LS) * sizeof(C) + (size_t)WARPS_B4 * 4 * sizeof(uint64_t);
+    const bool batched = !P->legacy && BL::TWREG;
     if (batched && ((rc = set_smem(c, kA4, sa4)) || (rc = set_smem(c, kB4, sb4)))) return rc;
+    int b4_ctas = 1;                                              // resident CTAs per SM of the persistent kernel B
+    if (batched) {
+        PDEB_CUDA(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b4_ctas, kB4, WARPS_B4 * 32, sb4));
+        b4_ctas = std::max(1, b4_ctas);
+    }
     NsArgs<T> A;
     A.N = N; A.NH = P->NH; A.NHP = P->NHP;
     A.tw_inv = (const C*)P->tw_inv; A.tw_fwd = (const C*)P->tw_fwd;
@@ -778,7 +808,7 @@ int32_t rk4_t(pdeb200_ctx* c) {
                 A.stage = stage;
                 A.fin = stage == 1 ? A.y : A.fst;
                 if (batched) {
-                    kA4<<<dim3((P->NH + COLS_A4 - 1) / COLS_A4, ne), COLS_A4 * 32, sa4, c->stream>>>(A);
+                    kA4<<<dim3((P->NH + COLS_A4 - 1) / COLS_A4, ne), COLS_A4 * (4 / FPW_A4) * 32, sa4, c->stream>>>(A);
                     kB4<<<std::min(P->n_sm * b4_ctas, (ne * (NP / 2) + WARPS_B4 - 1) / WARPS_B4), WARPS_B4 * 32, sb4, c->stream>>>(A, ne * (NP / 2));
                 } else {
                     kA<<<dim3((P->NH + COLS_A - 1) / COLS_A, ne), COLS_A * 32, sa, c->stream>>>(A);
@@ -886,6 +916,8 @@ int32_t ns_setup(pdeb200_ctx* c) {
     P->chunk = e ? std::max(1, atoi(e)) : g.n_envs;
     P->chunk = std::min(P->chunk, g.n_envs);
     cudaDeviceGetAttribute(&P->n_sm, cudaDevAttrMultiProcessorCount, c->device);
+    e = getenv("PDEB200_NS_B4");
+    if (e) P->b4_mode = atoi(e);
     e = getenv("PDEB200_NS_LEGACY");
     P->legacy = e && atoi(e) != 0;
     return g.dtype == PDEB200_F64 ? setup_t<double>(c) : setup_t<float>(c);
