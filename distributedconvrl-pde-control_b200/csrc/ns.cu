@@ -53,6 +53,7 @@ struct NsProb {
     void *kx = nullptr, *ky = nullptr;
     void *fst = nullptr, *acc = nullptr, *W = nullptr, *Q = nullptr;
     void *p_phys = nullptr, *om_phys = nullptr, *tmpc = nullptr;
+    void *y2 = nullptr, *ad_state = nullptr; int* ad_active = nullptr; int* h_active = nullptr;   // adaptive mode
 };
 
 template <typename T>
@@ -62,7 +63,9 @@ struct NsArgs {
     const C* tw_inv; const C* tw_fwd;
     const T* kx; const T* ky;
     const C* fin;              // stage input (y at stage 1, fst afterwards)
-    C* y; C* fst; C* acc;
+    C* y; C* fst; C* acc;      // y: the step's base state (read by stages 2-4)
+    C* yout;                   // stage 4 writes the step's result here (== y for the in-place fixed-step path)
+    const T* dt_env;           // adaptive mode: per-environment step size (nullptr: dt)
     const C* phat;
     C* W;                      // [env][4][NP][NHP]
     C* Q;                      // [env][NP][NHP]
@@ -524,7 +527,7 @@ ns_xpass4_kernel(const __grid_constant__ NsArgs<T> A, int n_jobs) {
 // RK4 stage update of U entries at once: all loads are issued before the first store (the arrays may alias
 // from the compiler's point of view, so it cannot do this reordering itself).
 template <typename T, int U>
-__device__ __forceinline__ void rk_update(const NsArgs<T>& A, const size_t* idx, const T* k2, const typename V2<T>::type* nl) {
+__device__ __forceinline__ void rk_update(const NsArgs<T>& A, const T dt, const size_t* idx, const T* k2, const typename V2<T>::type* nl) {
     using C = typename V2<T>::type;
     C fs[U], ph[U], f0[U], ac[U];
 #pragma unroll
@@ -540,12 +543,12 @@ __device__ __forceinline__ void rk_update(const NsArgs<T>& A, const size_t* idx,
         const T ki = (-A.nu * (k2[u] * fs[u].y) + nl[u].y) + ph[u].y;
         if (A.stage == 1) {
             A.acc[idx[u]] = V2<T>::make(kr, ki);
-            A.fst[idx[u]] = V2<T>::make(fs[u].x + (T(0.5) * A.dt) * kr, fs[u].y + (T(0.5) * A.dt) * ki);
+            A.fst[idx[u]] = V2<T>::make(fs[u].x + (T(0.5) * dt) * kr, fs[u].y + (T(0.5) * dt) * ki);
         } else if (A.stage == 4) {
-            A.y[idx[u]] = V2<T>::make(f0[u].x + (A.dt / T(6)) * (ac[u].x + kr), f0[u].y + (A.dt / T(6)) * (ac[u].y + ki));
+            A.yout[idx[u]] = V2<T>::make(f0[u].x + (dt / T(6)) * (ac[u].x + kr), f0[u].y + (dt / T(6)) * (ac[u].y + ki));
         } else {
             A.acc[idx[u]] = V2<T>::make(ac[u].x + T(2) * kr, ac[u].y + T(2) * ki);
-            const T c = A.stage == 2 ? T(0.5) * A.dt : A.dt;
+            const T c = A.stage == 2 ? T(0.5) * dt : dt;
             A.fst[idx[u]] = V2<T>::make(f0[u].x + c * kr, f0[u].y + c * ki);
         }
     }
@@ -593,6 +596,7 @@ ns_ypass_fwd_kernel(const __grid_constant__ NsArgs<T> A) {
     const int ib = (N - a) % N;
     const bool two = ib != a;
     const T kxa = A.kx[a], kxb = A.kx[ib];
+    const T dt = A.dt_env ? A.dt_env[env] : A.dt;
     const size_t base = (size_t)env * N * N;
     constexpr int U = 2;                                          // rows per lane in flight (N / 32 is even)
     for (int j0 = t; j0 < N; j0 += 32 * U) {
@@ -610,8 +614,8 @@ ns_ypass_fwd_kernel(const __grid_constant__ NsArgs<T> A) {
             v.y = -v.y;
             idx[U + u] = base + (size_t)ib * N + j; k2[U + u] = kyv * kyv + kxb * kxb; nl[U + u] = v;
         }
-        if (two) rk_update<T, 2 * U>(A, idx, k2, nl);
-        else rk_update<T, U>(A, idx, k2, nl);
+        if (two) rk_update<T, 2 * U>(A, dt, idx, k2, nl);
+        else rk_update<T, U>(A, dt, idx, k2, nl);
     }
 }
 
@@ -666,6 +670,94 @@ __global__ void __launch_bounds__(256) ns_vmax_kernel(const typename V2<T>::type
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x == 0) { for (int i = 1; i < 8; ++i) m = fmax(m, s[i]); vmax[blockIdx.x] = m; }
+}
+
+// ---- adaptive-step parity mode (FluidSetup.jl:178-186) ---------------------------------------------
+// The shipped Fluid scripts wire do_step2 = solve(ODEProblem(f, y, (t, t + dt), p), RK4(), reltol = tol, abstol = tol).
+// OrdinaryDiffEq's controller is third-party and unpinned, so -- like the Keller-Segel adaptive mode (kseg.cu) -- this is
+// an error-controlled integrator of the SAME tableau: classical RK4 with step doubling per ENVIRONMENT (one step of h
+// against two of h/2, e = (y2 - y1)/15, the extrapolated y2 + e kept, the 16x larger error of the single full step held
+// below the tolerance; RMS norm over the N^2 complex entries of |16 e| / (atol + rtol max(|y|, |y_new|)); factor
+// 0.9 err^(-1/5) in [0.2, 5]; first trial step dt / oversampling or the previous env step's last accepted size).
+// The environments advance in lock step through ATTEMPTS (3 RK4 steps = 12 rhs launches for all of them); each has its
+// own t, h and accept / reject decision, a finished one rides along with step size 0.
+constexpr int kNsMaxAttempts = 2000;
+
+template <typename T>
+struct NsAdapt {
+    T* t; T* h; T* hs; T* hh;       // [B] time inside the env step, natural step, this attempt's step and its half
+    T* hlast; int* nsub;            // context arrays: warm start, {accepted, rejected}
+    int* n_active;                  // environments that need another attempt
+    T dt, h0, rtol, atol;
+};
+
+template <typename T>
+__global__ void ns_adapt_begin_kernel(NsAdapt<T> D, int B) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B) return;
+    const T h = D.hlast[e] > T(0) ? D.hlast[e] : D.h0;
+    const T hs = h >= D.dt ? D.dt : h;
+    D.t[e] = T(0); D.h[e] = h; D.hs[e] = hs; D.hh[e] = T(0.5) * hs;
+    D.nsub[2 * e] = 0; D.nsub[2 * e + 1] = 0;
+}
+
+// one CTA per environment: error norm of the attempt, accept / reject, controller, next attempt's step
+template <typename T>
+__global__ void __launch_bounds__(1024) ns_adapt_finish_kernel(NsAdapt<T> D, typename V2<T>::type* __restrict__ y,
+                                                               const typename V2<T>::type* __restrict__ y1,
+                                                               const typename V2<T>::type* __restrict__ y2, int n) {
+    using C = typename V2<T>::type;
+    const int e = blockIdx.x;
+    const T hs = D.hs[e];
+    if (!(hs > T(0))) return;                                    // finished earlier
+    C* ye = y + (size_t)e * n;
+    const C* y1e = y1 + (size_t)e * n;
+    const C* y2e = y2 + (size_t)e * n;
+    double e2 = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const C a = ye[i], b1 = y1e[i], b2 = y2e[i];
+        const double ex = ((double)b2.x - (double)b1.x) / 15.0, ey = ((double)b2.y - (double)b1.y) / 15.0;
+        const double nx = (double)b2.x + ex, ny = (double)b2.y + ey;
+        const double sc = (double)D.atol + (double)D.rtol * fmax(hypot((double)a.x, (double)a.y), hypot(nx, ny));
+        e2 += 256.0 * (ex * ex + ey * ey) / (sc * sc);
+    }
+    __shared__ double s_red[32];
+    __shared__ int s_ok;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = e2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < (int)((blockDim.x + 31) >> 5); ++w) tot += s_red[w];
+        const double err = sqrt(tot / n);
+        const bool ok = err <= 1.0;                              // NaN compares false: rejected, step shrinks
+        const T h = D.h[e];
+        T t = D.t[e];
+        const bool last = t + h >= D.dt;
+        if (ok) { t = last ? D.dt : t + hs; ++D.nsub[2 * e]; }
+        else ++D.nsub[2 * e + 1];
+        double fac = err == err ? (err > 0.0 ? 0.9 * pow(err, -0.2) : 5.0) : 0.2;
+        fac = fmin(5.0, fmax(0.2, fac));
+        // an accepted step that was truncated to land on t + dt says nothing about the natural step size: keep h
+        const T hn = (ok && hs < h) ? h : (T)((double)hs * fac);
+        // give up (state left at the last accepted value, warm start forgotten) when the step underflows -- a state that
+        // is already non-finite rejects every attempt -- or after kNsMaxAttempts attempts
+        const bool stuck = !(hn > D.dt * T(1e-10)) || D.nsub[2 * e] + D.nsub[2 * e + 1] >= kNsMaxAttempts;
+        const bool done = !(t < D.dt) || stuck;
+        const T hsn = done ? T(0) : (t + hn >= D.dt ? D.dt - t : hn);
+        D.t[e] = t; D.h[e] = hn; D.hs[e] = hsn; D.hh[e] = T(0.5) * hsn;
+        if (done) D.hlast[e] = stuck ? T(0) : hn; else atomicAdd(D.n_active, 1);
+        s_ok = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_ok) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            const C b1 = y1e[i], b2 = y2e[i];
+            ye[i] = V2<T>::make((T)((double)b2.x + ((double)b2.x - (double)b1.x) / 15.0),
+                                (T)((double)b2.y + ((double)b2.y - (double)b1.y) / 15.0));
+        }
+    }
 }
 
 struct Fact { int n, n1, n2; };
@@ -723,6 +815,12 @@ int32_t setup_t(pdeb200_ctx* c) {
     PDEB_CUDA(c, cudaMalloc(&P->W, (size_t)P->chunk * 4 * P->NP * P->NHP * sizeof(C)));
     PDEB_CUDA(c, cudaMalloc(&P->Q, (size_t)P->chunk * P->NP * P->NHP * sizeof(C)));
     c->prob_p_phys = P->p_phys;
+    if (g.adaptive) {
+        PDEB_CUDA(c, cudaMalloc(&P->y2, B * nn * sizeof(C)));
+        PDEB_CUDA(c, cudaMalloc(&P->ad_state, B * 4 * sizeof(T)));
+        PDEB_CUDA(c, cudaMalloc((void**)&P->ad_active, sizeof(int)));
+        PDEB_CUDA(c, cudaMallocHost((void**)&P->h_active, sizeof(int)));
+    }
     return PDEB200_OK;
 }
 
@@ -799,24 +897,53 @@ int32_t rk4_t(pdeb200_ctx* c) {
     // ifft normalisation of the two factors (1/NP^2 each) and the 1.5*1.5 of fluid_rk4.jl:178
     const double np2 = (double)NP * NP;
     A.scale = (T)((g.ifpad ? 2.25 : 1.0) / (np2 * np2));
+    A.dt_env = nullptr;
+    // one classical RK4 step (4 rhs evaluations) of `ne` environments: A.y -> A.yout
+    auto rk4_step = [&](int ne) {
+        for (int stage = 1; stage <= 4; ++stage) {
+            A.stage = stage;
+            A.fin = stage == 1 ? A.y : A.fst;
+            if (batched) {
+                kA4<<<dim3((P->NH + COLS_A4 - 1) / COLS_A4, ne), COLS_A4 * (4 / FPW_A4) * 32, sa4, c->stream>>>(A);
+                kB4<<<std::min(P->n_sm * b4_ctas, (ne * (NP / 2) + WARPS_B4 - 1) / WARPS_B4), WARPS_B4 * 32, sb4, c->stream>>>(A, ne * (NP / 2));
+            } else {
+                kA<<<dim3((P->NH + COLS_A - 1) / COLS_A, ne), COLS_A * 32, sa, c->stream>>>(A);
+                kB<<<dim3((NP / 2 + COLS_B - 1) / COLS_B, ne), COLS_B * 32, sb, c->stream>>>(A);
+            }
+            kC<<<dim3((P->NH + COLS_C - 1) / COLS_C, ne), COLS_C * 32, sc, c->stream>>>(A);
+            c->launches += 3;
+        }
+    };
+    if (g.adaptive) {
+        const int B = g.n_envs;
+        NsAdapt<T> D;
+        T* st = (T*)P->ad_state;
+        D.t = st; D.h = st + B; D.hs = st + 2 * (size_t)B; D.hh = st + 3 * (size_t)B;
+        D.hlast = (T*)c->d_hlast; D.nsub = c->d_nsub; D.n_active = P->ad_active;
+        D.dt = (T)g.dt; D.h0 = (T)(g.dt / g.oversampling); D.rtol = (T)g.rtol; D.atol = (T)g.atol;
+        A.fst = (C*)P->fst; A.acc = (C*)P->acc; A.phat = (const C*)c->p;
+        C* y = (C*)c->y; C* y1 = (C*)P->tmpc; C* y2 = (C*)P->y2;
+        ns_adapt_begin_kernel<T><<<(B + 255) / 256, 256, 0, c->stream>>>(D, B);
+        c->launches += 1;
+        for (int attempt = 0; attempt <= kNsMaxAttempts; ++attempt) {
+            A.y = y;  A.yout = y1; A.dt_env = D.hs; rk4_step(B);          // one step of h
+            A.y = y;  A.yout = y2; A.dt_env = D.hh; rk4_step(B);          // two steps of h/2
+            A.y = y2; A.yout = y2; A.dt_env = D.hh; rk4_step(B);
+            PDEB_CUDA(c, cudaMemsetAsync(P->ad_active, 0, sizeof(int), c->stream));
+            ns_adapt_finish_kernel<T><<<B, 1024, 0, c->stream>>>(D, y, y1, y2, (int)nn);
+            c->launches += 1;
+            PDEB_CUDA(c, cudaMemcpyAsync(P->h_active, P->ad_active, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            PDEB_CUDA(c, cudaStreamSynchronize(c->stream));          // the host decides whether another attempt is needed
+            if (*P->h_active == 0) break;
+        }
+        PDEB_CUDA(c, cudaGetLastError());
+        return PDEB200_OK;
+    }
     for (int e0 = 0; e0 < g.n_envs; e0 += P->chunk) {
         const int ne = std::min(P->chunk, g.n_envs - e0);
-        A.y = (C*)c->y + (size_t)e0 * nn; A.fst = (C*)P->fst + (size_t)e0 * nn; A.acc = (C*)P->acc + (size_t)e0 * nn;
+        A.y = (C*)c->y + (size_t)e0 * nn; A.yout = A.y; A.fst = (C*)P->fst + (size_t)e0 * nn; A.acc = (C*)P->acc + (size_t)e0 * nn;
         A.phat = (const C*)c->p + (size_t)e0 * nn;
-        for (int s = 0; s < g.oversampling; ++s)
-            for (int stage = 1; stage <= 4; ++stage) {
-                A.stage = stage;
-                A.fin = stage == 1 ? A.y : A.fst;
-                if (batched) {
-                    kA4<<<dim3((P->NH + COLS_A4 - 1) / COLS_A4, ne), COLS_A4 * (4 / FPW_A4) * 32, sa4, c->stream>>>(A);
-                    kB4<<<std::min(P->n_sm * b4_ctas, (ne * (NP / 2) + WARPS_B4 - 1) / WARPS_B4), WARPS_B4 * 32, sb4, c->stream>>>(A, ne * (NP / 2));
-                } else {
-                    kA<<<dim3((P->NH + COLS_A - 1) / COLS_A, ne), COLS_A * 32, sa, c->stream>>>(A);
-                    kB<<<dim3((NP / 2 + COLS_B - 1) / COLS_B, ne), COLS_B * 32, sb, c->stream>>>(A);
-                }
-                kC<<<dim3((P->NH + COLS_C - 1) / COLS_C, ne), COLS_C * 32, sc, c->stream>>>(A);
-                c->launches += 3;
-            }
+        for (int s = 0; s < g.oversampling; ++s) rk4_step(ne);
     }
     PDEB_CUDA(c, cudaGetLastError());
     return PDEB200_OK;
@@ -954,6 +1081,8 @@ void ns_free(pdeb200_ctx* c) {
     if (!P) return;
     for (void* p : {P->tw_inv, P->tw_fwd, P->tw_n, P->kx, P->ky, P->fst, P->acc, P->W, P->Q, P->p_phys, P->om_phys, P->tmpc})
         if (p) cudaFree(p);
+    for (void* p : {P->y2, P->ad_state, (void*)P->ad_active}) if (p) cudaFree(p);
+    if (P->h_active) cudaFreeHost(P->h_active);
     delete P;
     c->prob = nullptr;
     c->prob_p_phys = nullptr;

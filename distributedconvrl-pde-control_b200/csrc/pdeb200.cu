@@ -436,8 +436,8 @@ int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** 
         cfg->window_size % 2 == 0 || cfg->temporal_steps < 1 || cfg->memory_size < 0)
         return fail(nullptr, PDEB200_EINVAL, "create: bad sizes (n_envs/nx/n_sensors/n_actuators/window/temporal/memory)");
     if (cfg->dtype != PDEB200_F32 && cfg->dtype != PDEB200_F64) return fail(nullptr, PDEB200_EINVAL, "create: bad dtype");
-    if (cfg->adaptive && cfg->problem != PDEB200_KSEG1D)
-        return fail(nullptr, PDEB200_EUNSUPPORTED, "create: adaptive = 1 exists for PDEB200_KSEG1D only");
+    if (cfg->adaptive && cfg->problem != PDEB200_KSEG1D && cfg->problem != PDEB200_NS2D)
+        return fail(nullptr, PDEB200_EUNSUPPORTED, "create: adaptive = 1 exists for PDEB200_KSEG1D and PDEB200_NS2D only");
     if (cfg->adaptive && !(cfg->rtol > 0.0 && cfg->atol > 0.0)) return fail(nullptr, PDEB200_EINVAL, "create: adaptive needs rtol, atol > 0");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)

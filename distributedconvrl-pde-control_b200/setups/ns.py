@@ -5,8 +5,9 @@ from `taylorvtx`, src/fluid_rk4.jl:54-69) and of initial conditions (`ic`, fluid
 to the library as arrays in Julia's column-major flattening of the (ny, nx) matrices.  The wavenumber tables
 (FluidSetup.jl:103-124) are derived inside libpdeb200 from (nx, Lx, Ly).
 
-The env steps with the FIXED-step `do_step` (RK4 x oversampling, FluidSetup.jl:163-172), the path named by
-BASELINE.json; the shipped scripts wire the adaptive `do_step2` (quirk Q9).
+By default the env steps with the FIXED-step `do_step` (RK4 x oversampling, FluidSetup.jl:163-172), the path named by
+BASELINE.json.  The shipped scripts wire the adaptive `do_step2` (quirk Q9): `make_env(adaptive=True, rtol, atol)`
+selects the error-controlled mode (per-environment step control; the reference's tolerance is 1e0, FluidSetup.jl:178-179).
 """
 import numpy as np
 
@@ -99,12 +100,14 @@ class FluidSetup:
         a = np.asarray(a)
         return np.ascontiguousarray(np.swapaxes(a, -1, -2)).reshape(a.shape[:-2] + (-1,))
 
-    def make_env(self, n_envs=1, dtype="f64", device=0, y0=None, drop_tol=0.0):
-        """initialize_setup(), FluidSetup.jl:330-343 -- the PDEenv part."""
+    def make_env(self, n_envs=1, dtype="f64", device=0, y0=None, drop_tol=0.0, adaptive=False, rtol=1.0, atol=1.0):
+        """initialize_setup(), FluidSetup.jl:330-343 -- the PDEenv part.  adaptive=True: `do_step2`'s role
+        (FluidSetup.jl:181-186), error-controlled RK4 with step doubling per environment at (rtol, atol)."""
         y0 = self.ic(2) if y0 is None else np.asarray(y0)
         if y0.ndim == 3:                      # (B, ny, nx) -> reference shape (ny, nx, B)
             y0 = y0.transpose(1, 2, 0)
-        return PDEenv(problem=L.NS2D, n_envs=n_envs, dtype=dtype, device=device,
+        return PDEenv(problem=L.NS2D, adaptive=int(bool(adaptive)), rtol=float(rtol), atol=float(atol), n_envs=n_envs,
+                      dtype=dtype, device=device,
                       sensor_basis=self._julia_flat(self.gaussians),
                       actuator_basis=self._julia_flat(self.gaussians_actuators),
                       actuators_to_sensors=self.actuators_to_sensors, y0=y0, drop_tol=drop_tol,

@@ -119,7 +119,11 @@ typedef struct pdeb200_config {
     /* Adaptive-step parity mode.  The reference's ACTIVE Keller-Segel stepper is OrdinaryDiffEq's
      * adaptive RK4() at reltol = abstol = 1e-8 (KellerSegelSetup.jl:234-239): adaptive = 1 integrates each environment
      * with its own error-controlled step sequence (classical RK4 + step doubling, RMS error norm like OrdinaryDiffEq's
-     * default) instead of `oversampling` fixed substeps.  KSEG1D only. */
+     * default) instead of `oversampling` fixed substeps.  For PDEB200_NS2D the same controller takes the role of the wired-in
+     * `do_step2` (FluidSetup.jl:178-186, reltol = abstol = 1e0 as shipped): the environments advance through attempts
+     * (3 RK4 steps each) in lock step, each with its own step size and accept / reject decision.  `oversampling` gives
+     * the first trial step dt / oversampling; PDEB200_ARR_NSUB reports {accepted, rejected} per environment.
+     * KSEG1D and NS2D. */
     double rtol, atol;
     int32_t adaptive;
     int32_t reserved0;

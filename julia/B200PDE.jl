@@ -40,7 +40,7 @@ Base.@kwdef mutable struct Config
     obs_scale::Float64 = 0
     reward_gain::Float64 = 0; reward_pow::Float64 = 0; reward_div::Float64 = 0; reward_offset::Float64 = 0
     action_punish::Float64 = 0; delta_action_punish::Float64 = 0
-    rtol::Float64 = 1e-8; atol::Float64 = 1e-8       # adaptive-step parity mode (KellerSegelSetup.jl:234-239)
+    rtol::Float64 = 1e-8; atol::Float64 = 1e-8       # adaptive-step parity mode (KellerSegelSetup.jl:234-239; FluidSetup.jl:178-186)
     adaptive::Int32 = 0; reserved0::Int32 = 0
 end
 

@@ -272,6 +272,39 @@ def from_julia_memory(flat, ny, nx):
     return np.asarray(flat).reshape(nx, ny).T
 
 
+def do_step_adaptive(cfg, ops, y, p, rtol=1.0, atol=1.0, h0=None, return_stats=False):
+    """Error-controlled RK4 over [t, t + dt] in the role of the WIRED-IN `do_step2` (FluidSetup.jl:178-186, :333:
+    `solve(ODEProblem(f, env.y, tspan, env.p), RK4(), reltol=tol, abstol=tol)`, tol = 1e0 as shipped, 1e-8 commented).
+    OrdinaryDiffEq's controller is third-party and unpinned; this is the controller of the CUDA adaptive mode
+    (same rules as kseg_oracle.do_step_adaptive): step doubling with the classical tableau rk4(), e = (y2 - y1)/15, the
+    extrapolated y2 + e kept, the 16x larger error of the single full step controlled, RMS norm over the complex entries
+    against atol + rtol max(|y|, |y_new|) (complex moduli, like OrdinaryDiffEq's default norm), factor 0.9 err^(-1/5)
+    clamped to [0.2, 5], first trial step dt / oversampling (or h0 = the previous env step's last accepted size)."""
+    y = np.array(y, dtype=np.complex128)
+    t, h = 0.0, (cfg.dt / cfg.oversampling if h0 is None else h0)
+    acc = rej = 0
+    while t < cfg.dt:
+        last = t + h >= cfg.dt
+        hs = cfg.dt - t if last else h
+        y1 = rk4(cfg, ops, y, p, hs)
+        y2 = rk4(cfg, ops, rk4(cfg, ops, y, p, 0.5 * hs), p, 0.5 * hs)
+        e = (y2 - y1) / 15
+        yn = y2 + e
+        sc = atol + rtol * np.maximum(np.abs(y), np.abs(yn))
+        err = float(np.sqrt(np.sum((16 * np.abs(e) / sc) ** 2) / e.size))
+        ok = err <= 1.0
+        if ok:
+            y, t = yn, (cfg.dt if last else t + hs)
+            acc += 1
+        else:
+            rej += 1
+        fac = (0.9 * err ** -0.2 if err > 0 else 5.0) if err == err else 0.2
+        fac = min(5.0, max(0.2, fac))
+        if not (ok and hs < h):
+            h = hs * fac
+    return (y, h, acc, rej) if return_stats else y
+
+
 @dataclass
 class NSEnv:
     """PDEenv restated for the Fluid setup (src/PDEenv.jl:64-241, FluidSetup.jl:330-343)."""

@@ -131,3 +131,54 @@ def test_fused_actor_rollout_matches_host_loop(pkg):
     assert np.array_equal(envs[0].state, envs[1].state)
     for e in envs:
         e.close()
+
+
+def test_adaptive_mode_matches_its_oracle_and_the_fixed_step_path(pkg):
+    """SURVEY 8f row 4, Fluid: per-environment error-controlled RK4 in the role of the wired-in `do_step2`
+    (FluidSetup.jl:178-186).  (1) at the shipped tolerance 1e0 the device takes the same step decisions as
+    oracle/ns_oracle.py::do_step_adaptive (a handful of steps instead of `oversampling`), lands on its state to 1e-12, and
+    warm-starts the next env step from the last accepted size; (2) at a tight tolerance the same holds with hundreds of
+    steps and a few rejections, the faster environment takes more steps than its neighbours (per-environment control), and
+    the result agrees with a finely resolved fixed-step run of the same ODE."""
+    nx, spa, var, B = 64, 8, 0.08, 3
+    cfg = NS.NSConfig(nx=nx, sensors_per_axis=spa, variance=var, oversampling=20)
+    ops = NS.NSOperators(cfg)
+    setup = pkg.setups.FluidSetup(nx=nx, sensors_per_axis=spa, variance=var, oversampling=20)
+    rng = np.random.default_rng(11)
+    y0 = setup.generate_random_init(rng, B, caseno=3)
+    y0[1] *= 4.0                                       # a faster flow: needs smaller steps
+    n_a = cfg.n_actuators
+    a = rng.uniform(-1, 1, (1, B * n_a))
+    g_act = NS.prepare_gaussians(cfg, ops, 2)
+    p = [NS.prepare_action(cfg, g_act, a[:, b * n_a:(b + 1) * n_a]) for b in range(B)]
+    # (1) the reference's tolerance, two env steps (the second one warm-started)
+    env = setup.make_env(n_envs=B, dtype="f64", y0=y0, adaptive=True, rtol=1.0, atol=1.0)
+    env(a)
+    y_dev, nsub = env.y, env.substeps
+    mid = []
+    for b in range(B):
+        yo, h, acc, rej = NS.do_step_adaptive(cfg, ops, y0[b], p[b], rtol=1.0, atol=1.0, return_stats=True)
+        assert (nsub[b, 0], nsub[b, 1]) == (acc, rej), (b, nsub[b], acc, rej)
+        assert acc < 20 and relerr(y_dev[:, :, b], yo) < 1e-12
+        mid.append((yo, h))
+    env(a)
+    y_dev, nsub = env.y, env.substeps
+    for b in range(B):
+        yo, h, acc, rej = NS.do_step_adaptive(cfg, ops, mid[b][0], p[b], rtol=1.0, atol=1.0, h0=mid[b][1], return_stats=True)
+        assert (nsub[b, 0], nsub[b, 1]) == (acc, rej) and acc <= 4, (b, nsub[b], acc, rej)
+        assert relerr(y_dev[:, :, b], yo) < 1e-12
+    env.close()
+    # (2) tight tolerance; fixed-step comparison run with 4x the substeps (its own error is then ~1e-8 of the fast flow)
+    tol = 1e-9
+    env_a = setup.make_env(n_envs=B, dtype="f64", y0=y0, adaptive=True, rtol=tol, atol=tol)
+    fine = pkg.setups.FluidSetup(nx=nx, sensors_per_axis=spa, variance=var, oversampling=80)
+    env_f = fine.make_env(n_envs=B, dtype="f64", y0=y0)
+    env_a(a); env_f(a)
+    ya, yf, ns_ = env_a.y, env_f.y, env_a.substeps
+    for b in range(B):
+        yo, h, acc, rej = NS.do_step_adaptive(cfg, ops, y0[b], p[b], rtol=tol, atol=tol, return_stats=True)
+        assert (ns_[b, 0], ns_[b, 1]) == (acc, rej), (b, ns_[b], acc, rej)
+        assert relerr(ya[:, :, b], yo) < 1e-11
+        assert relerr(ya[:, :, b], yf[:, :, b]) < 1e-7
+    assert ns_[1, 0] > 2 * ns_[0, 0] and ns_[:, 1].sum() > 0       # per-environment control, some rejected attempts
+    env_a.close(); env_f.close()
