@@ -101,3 +101,24 @@ def test_env_step_runs_and_julia_memory_round_trip():
     assert np.all(np.isfinite(env.y.view(np.float64)))
     flat = NS.to_julia_memory(env.y)
     assert flat[1] == env.y[1, 0] and np.array_equal(NS.from_julia_memory(flat, 32, 32), env.y)
+
+
+def test_adaptive_controller_meets_its_tolerance():
+    """do_step_adaptive (the role of FluidSetup.jl's do_step2): the error against a finely resolved fixed-step run of the
+    same ODE shrinks with the tolerance and stays below it (relative to the state), the step count grows, and the warm start
+    returns the last natural step."""
+    cfg = _cfg(32, dt=0.02)
+    ops = NS.NSOperators(cfg)
+    y0 = 3.0 * NS.ic(cfg, ops, 3, np.random.default_rng(4))
+    p = np.zeros_like(y0)
+    fine = y0
+    for _ in range(400):
+        fine = NS.rk4(cfg, ops, fine, p, cfg.dt / 400)
+    prev_acc, prev_err = 0, None
+    for tol in (1e-4, 1e-6, 1e-8):
+        y, h, acc, rej = NS.do_step_adaptive(cfg, ops, y0, p, rtol=tol, atol=tol, return_stats=True)
+        err = np.abs(y - fine).max() / np.abs(fine).max()
+        assert err < tol and acc >= prev_acc and 0 < h
+        assert prev_err is None or err < prev_err
+        prev_acc, prev_err = acc, err
+    assert prev_acc > 3
