@@ -311,6 +311,19 @@ ns_xpass_kernel(const __grid_constant__ NsArgs<T> A) {
     }
 }
 
+// 1 / q for q > 0, normal range: hardware seed + two Newton steps (4 DFMA; the IEEE division is ~25 instructions and was
+// 10 % of kernel A4's samples).  Within 1-2 ulp of the quotient -- the psi_hat = omega_hat ./ kx2ky2 of fluid_rk4.jl:152
+// is then a multiplication; far inside the 1e-12 parity bound.
+__device__ __forceinline__ double fast_rcp(double q) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(q));
+    double e = fma(-q, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-q, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ float fast_rcp(float q) { return 1.0f / q; }
+
 // ---- A and B, batched form (fft_batch.cuh): a warp owns FOUR lines in shared memory ------------------------
 // A4: one warp = one kx >= 0 column, its four fields are the four lines.  The column pair (kx, -kx) is read
 //     straight from global memory into registers (16 independent 16-byte loads per lane, no staging table), each
@@ -334,7 +347,22 @@ ns_ypass_inv4_kernel(const __grid_constant__ NsArgs<T> A) {
     const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
     const int wc = w % COLS, half = w / COLS;                    // FPW == 2: half 0 = psi-based fields 0, 1; half 1 = fields 2, 3
     const int env = blockIdx.y, a0 = blockIdx.x * COLS, a = a0 + wc;
-    for (int i = threadIdx.x; i < NP; i += blockDim.x) s_tw[i] = A.tw_inv[i];
+    // twiddle table: the global loads are issued here, the shared-memory stores after the column loads below, so that
+    // the two latencies overlap (a load-store loop up front was 8 % of the samples, all of them waiting)
+    constexpr int NTW = (NP + COLS * (4 / FPW) * 32 - 1) / (COLS * (4 / FPW) * 32);
+    C twv[NTW];
+#pragma unroll
+    for (int i = 0; i < NTW; ++i) {
+        const int q = i * (int)blockDim.x + threadIdx.x;
+        twv[i] = q < NP ? A.tw_inv[q] : V2<T>::make(T(0), T(0));
+    }
+    auto stage_tw = [&]() {
+#pragma unroll
+        for (int i = 0; i < NTW; ++i) {
+            const int q = i * (int)blockDim.x + threadIdx.x;
+            if (q < NP) s_tw[q] = twv[i];
+        }
+    };
     C* xb = s_xb0 + w * WS;
     if (a < NH) {
         const int ib = (N - a) % N;                               // column of -kx in the unpadded array
@@ -356,6 +384,7 @@ ns_ypass_inv4_kernel(const __grid_constant__ NsArgs<T> A) {
             if (j1 >= 0) { c1[i] = srcA[j1]; k1[i] = A.ky[j1]; }
             if (j2 >= 0) { c2[i] = srcB[j2]; k2[i] = A.ky[j2]; }
         }
+        stage_tw();
         const bool psi = FPW == 4 || half == 0, omg = FPW == 4 || half == 1;
         C* opsi = xb;
         C* oomg = xb + (FPW == 4 ? 2 * G::LS : 0);
@@ -374,7 +403,7 @@ ns_ypass_inv4_kernel(const __grid_constant__ NsArgs<T> A) {
             if (psi) {
                 // psi_hat = omega_hat ./ kx2ky2, psi_hat[1,1] = 0   (fluid_rk4.jl:152-153); absent entries are 0
                 const T qa = k1[i] * k1[i] + kxa * kxa, qb = k2[i] * k2[i] + kxb * kxb;
-                const T ra = qa > T(0) ? T(1) / qa : T(0), rb = qb > T(0) ? T(1) / qb : T(0);
+                const T ra = qa > T(0) ? fast_rcp(qa) : T(0), rb = qb > T(0) ? fast_rcp(qb) : T(0);
                 const C p1 = V2<T>::make(c1[i].x * ra, c1[i].y * ra), p2 = V2<T>::make(c2[i].x * rb, c2[i].y * rb);
                 opsi[o]         = V2<T>::make(T(0.5) * (-k1[i] * p1.y - k2[i] * p2.y), T(0.5) * (k1[i] * p1.x - k2[i] * p2.x));
                 opsi[G::LS + o] = V2<T>::make(T(0.5) * (kxa * p1.y + kxb * p2.y),      T(0.5) * (-kxa * p1.x + kxb * p2.x));
@@ -385,6 +414,7 @@ ns_ypass_inv4_kernel(const __grid_constant__ NsArgs<T> A) {
             }
         }
     }
+    if (a >= NH) stage_tw();
     __syncthreads();                                             // twiddles staged; xb written by its own warp
     if (a < NH)
         fft_batch_nt<T, P1, P2, FPW, +1, false, BatchNoSync>(

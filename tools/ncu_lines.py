@@ -4,6 +4,7 @@
 import collections
 import csv
 import io
+import os
 import subprocess
 import sys
 
@@ -20,23 +21,25 @@ top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass", "--launch-skip", str(skip),
                       "--launch-count", "1"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-# find header rows
-views = [i for i, r in enumerate(rows) if "# Samples" in r]
-for vi, start in enumerate(views):
-    h = rows[start]
-    sx = {x: i for i, x in enumerate(h)}
-    end = views[vi + 1] - 1 if vi + 1 < len(views) else len(rows)
-    data = [r for r in rows[start + 1:end] if len(r) >= len(h)]
-    tot = sum(num(r[sx["# Samples"]]) for r in data) or 1
-    if "Address" in sx and vi == 0 and len(views) > 1:
-        continue        # SASS view first; the CUDA-C view follows
-    print("view %d: %d rows, %d samples" % (vi, len(data), tot))
-    key = "Source"
-    agg = collections.Counter()
-    ins = collections.Counter()
-    for r in data:
-        agg[r[sx[key]].strip()[:110]] += num(r[sx["# Samples"]])
-        ins[r[sx[key]].strip()[:110]] += num(r[sx["Instructions Executed"]])
-    ti = sum(ins.values()) or 1
-    for s, v in agg.most_common(top):
-        print("%5.1f%% samples %5.1f%% inst | %s" % (100.0 * v / tot, 100.0 * ins[s] / ti, s))
+agg, ins, text, stalls = collections.Counter(), collections.Counter(), {}, collections.defaultdict(collections.Counter)
+fname, hdr = "?", None
+for r in rows:
+    if len(r) == 2 and r[0] == "File Name":
+        fname = os.path.basename(r[1]); hdr = None
+        continue
+    if "# Samples" in r:
+        hdr = r
+        si, ii = r.index("# Samples"), r.index("Instructions Executed")
+        st_cols = [(i, x) for i, x in enumerate(r) if x.startswith("stall_") and "Not Issued" not in x]
+        continue
+    if hdr is None or len(r) < len(hdr):
+        continue
+    key = (fname, r[0])
+    agg[key] += num(r[si]); ins[key] += num(r[ii]); text[key] = r[1].strip()[:90]
+    for i, x in st_cols:
+        stalls[key][x] += num(r[i])
+tot, ti = sum(agg.values()) or 1, sum(ins.values()) or 1
+print("samples %d, warp instructions %d" % (tot, ti))
+for key, v in agg.most_common(top):
+    s2 = ", ".join("%s %.0f%%" % (k[6:], 100.0 * c / max(v, 1)) for k, c in stalls[key].most_common(2))
+    print("%5.1f%% smp %5.1f%% ins | %-14s:%-4s | %-90s | %s" % (100.0 * v / tot, 100.0 * ins[key] / ti, key[0], key[1], text[key], s2))
