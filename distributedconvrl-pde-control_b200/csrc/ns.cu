@@ -47,9 +47,8 @@ template <int P1, int P2> struct NsGeom {
 struct NsProb {
     int N = 0, NP = 0, NH = 0, NHP = 0, chunk = 0, n_sm = 148;
     bool legacy = false;
-    int b4_mode = 0;             // kernel B4: bit 0 = twiddles in shared memory
     int n1 = 0, n2 = 0, p1 = 0, p2 = 0;
-    void *tw_inv = nullptr, *tw_fwd = nullptr, *tw_n = nullptr;
+    void *tw_inv = nullptr, *tw_fwd = nullptr, *tw_n = nullptr, *tw_b = nullptr;
     void *kx = nullptr, *ky = nullptr;
     void *fst = nullptr, *acc = nullptr, *W = nullptr, *Q = nullptr;
     void *p_phys = nullptr, *om_phys = nullptr, *tmpc = nullptr;
@@ -61,6 +60,7 @@ struct NsArgs {
     using C = typename V2<T>::type;
     int N, NH, NHP, stage;
     const C* tw_inv; const C* tw_fwd;
+    const C* tw_b;             // batched kernels: table of fft_pass<BP2, BP1> for THEIR factorisation (tw_b[n*BP2 + k] = W^(n k))
     const T* kx; const T* ky;
     const C* fin;              // stage input (y at stage 1, fst afterwards)
     C* y; C* fst; C* acc;      // y: the step's base state (read by stages 2-4)
@@ -354,7 +354,7 @@ ns_ypass_inv4_kernel(const __grid_constant__ NsArgs<T> A) {
 #pragma unroll
     for (int i = 0; i < NTW; ++i) {
         const int q = i * (int)blockDim.x + threadIdx.x;
-        twv[i] = q < NP ? A.tw_inv[q] : V2<T>::make(T(0), T(0));
+        twv[i] = q < NP ? A.tw_b[q] : V2<T>::make(T(0), T(0));
     }
     auto stage_tw = [&]() {
 #pragma unroll
@@ -452,7 +452,7 @@ ns_ypass_inv4_kernel(const __grid_constant__ NsArgs<T> A) {
 //     line buffer they will be expanded in (U at entry 0, V at entry NHP), and the copies of the next job are issued
 //     as soon as a line buffer is dead (lines 1-3 after the product, line 0 after the split), so that they run under
 //     the forward transform and the stores.
-template <typename T, int P1, int P2, int NN, int WARPS, bool TWR>
+template <typename T, int P1, int P2, int NN, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 ns_xpass4_kernel(const __grid_constant__ NsArgs<T> A, int n_jobs) {
     using G = BatchLayout<P1, P2>;
@@ -460,9 +460,11 @@ ns_xpass4_kernel(const __grid_constant__ NsArgs<T> A, int n_jobs) {
     constexpr int NP = G::N, N = NN, NH = NN / 2 + 1, NHP = (NH + 3) / 4 * 4;
     static_assert(2 * NHP <= G::LS, "raw rows must fit the line buffer");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    C* s_twi = reinterpret_cast<C*>(smem_raw);
-    C* s_twf = s_twi + (TWR ? 0 : NP);
-    C* s_xb0 = s_twf + (TWR ? 0 : NP);
+    constexpr bool TWR = true;                                    // twiddles in registers (shared-memory tables measured slower: 195 vs 180 us)
+    static_assert(G::TWREG, "kernel B4 needs a factorisation with P1 | 32");
+    C* s_twi = nullptr;
+    C* s_twf = nullptr;
+    C* s_xb0 = reinterpret_cast<C*>(smem_raw);
     uint64_t* s_bar0 = reinterpret_cast<uint64_t*>(s_xb0 + (size_t)WARPS * 4 * G::LS);
     const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
     C* xb = s_xb0 + (size_t)w * 4 * G::LS;
@@ -485,8 +487,7 @@ ns_xpass4_kernel(const __grid_constant__ NsArgs<T> A, int n_jobs) {
         if (job < n_jobs) for (int l = 0; l < 4; ++l) issue(job, l);
     }
     BatchTwiddles<T, P1, P2> tw;
-    if (TWR) tw.load(A.tw_inv, t);
-    else for (int i = threadIdx.x; i < NP; i += blockDim.x) { s_twi[i] = A.tw_inv[i]; s_twf[i] = A.tw_fwd[i]; }
+    tw.load(A.tw_b, t);
     __syncthreads();
     constexpr int NA = (NH + 31) / 32;
     constexpr int LPR = 32 / P1;                                  // lines per column-pass round
@@ -826,6 +827,10 @@ int32_t setup_t(pdeb200_ctx* c) {
     if ((rc = upload<C>(c, &P->tw_inv, twiddles<T>(P->p2, P->p1)))) return rc;    // fft_pass<P2, P1>
     if ((rc = upload<C>(c, &P->tw_fwd, twiddles<T>(P->p1, P->p2)))) return rc;    // fft_pass<P1, P2>
     if ((rc = upload<C>(c, &P->tw_n, twiddles<T>(P->n1, P->n2)))) return rc;      // fft_pass<N1, N2>
+    {
+        const int bp1 = 32 % P->p1 == 0 ? P->p1 : 16, bp2 = P->NP / bp1;            // the batched kernels' factorisation
+        if ((rc = upload<C>(c, &P->tw_b, twiddles<T>(bp2, bp1)))) return rc;        // fft_pass<BP2, BP1>
+    }
     // kx = [0:(nx/2); (-nx/2+1):(-1)] / Lx * 2pi  (Nyquist kept, positive side; FluidSetup.jl:106-107)
     std::vector<T> kx(N), ky(N);
     for (int i = 0; i < N; ++i) {
@@ -902,16 +907,15 @@ int32_t rk4_t(pdeb200_ctx* c) {
     // batched form of A and B (fft_batch.cuh); PDEB200_NS_LEGACY=1 keeps the one-line-per-warp kernels
     constexpr int COLS_A4 = 4, WARPS_B4 = sizeof(T) == 8 ? 8 : 8;
     using BL = BatchLayout<P1, P2>;
-    // 192 = 12 x 16 points: P1 does not divide 32, those grids keep the one-line-per-warp kernels
-    constexpr int BP1 = BL::TWREG ? P1 : 16, BP2 = BL::TWREG ? P2 : 16;
+    // the batched kernels need P1 | 32: 192 points are 16 x 12 there (12 x 16 in the one-line-per-warp kernels)
+    constexpr int BP1 = BL::TWREG ? P1 : 16, BP2 = BL::TWREG ? P2 : BL::N / 16;
+    using BLB = BatchLayout<BP1, BP2>;
     constexpr int FPW_A4 = 4;      // 2 (two warps per column, 16 resident warps) measured slower: 205 vs 173 us per 148 environments
     auto kA4 = ns_ypass_inv4_kernel<T, BP1, BP2, NN, COLS_A4, FPW_A4>;
-    auto kB4r = ns_xpass4_kernel<T, BP1, BP2, NN, WARPS_B4, true>;
-    auto kB4s = ns_xpass4_kernel<T, BP1, BP2, NN, WARPS_B4, false>;
-    auto kB4 = (P->b4_mode & 1) ? kB4s : kB4r;
-    const size_t sa4 = ((size_t)BL::N + COLS_A4 * (4 / FPW_A4) * (FPW_A4 * BL::LS + 2)) * sizeof(C);
-    const size_t sb4 = ((size_t)((P->b4_mode & 1) ? 2 * BL::N : 0) + (size_t)WARPS_B4 * 4 * BL::LS) * sizeof(C) + (size_t)WARPS_B4 * 4 * sizeof(uint64_t);
-    const bool batched = !P->legacy && BL::TWREG;
+    auto kB4 = ns_xpass4_kernel<T, BP1, BP2, NN, WARPS_B4>;
+    const size_t sa4 = ((size_t)BLB::N + COLS_A4 * (4 / FPW_A4) * (FPW_A4 * BLB::LS + 2)) * sizeof(C);
+    const size_t sb4 = ((size_t)WARPS_B4 * 4 * BLB::LS) * sizeof(C) + (size_t)WARPS_B4 * 4 * sizeof(uint64_t);
+    const bool batched = !P->legacy;
     if (batched && ((rc = set_smem(c, kA4, sa4)) || (rc = set_smem(c, kB4, sb4)))) return rc;
     int b4_ctas = 1;                                              // resident CTAs per SM of the persistent kernel B
     if (batched) {
@@ -920,7 +924,7 @@ int32_t rk4_t(pdeb200_ctx* c) {
     }
     NsArgs<T> A;
     A.N = N; A.NH = P->NH; A.NHP = P->NHP;
-    A.tw_inv = (const C*)P->tw_inv; A.tw_fwd = (const C*)P->tw_fwd;
+    A.tw_inv = (const C*)P->tw_inv; A.tw_fwd = (const C*)P->tw_fwd; A.tw_b = (const C*)P->tw_b;
     A.kx = (const T*)P->kx; A.ky = (const T*)P->ky;
     A.W = (C*)P->W; A.Q = (C*)P->Q;
     A.nu = (T)g.nu; A.dt = (T)(g.dt / g.oversampling);
@@ -1073,8 +1077,6 @@ int32_t ns_setup(pdeb200_ctx* c) {
     P->chunk = e ? std::max(1, atoi(e)) : g.n_envs;
     P->chunk = std::min(P->chunk, g.n_envs);
     cudaDeviceGetAttribute(&P->n_sm, cudaDevAttrMultiProcessorCount, c->device);
-    e = getenv("PDEB200_NS_B4");
-    if (e) P->b4_mode = atoi(e);
     e = getenv("PDEB200_NS_LEGACY");
     P->legacy = e && atoi(e) != 0;
     return g.dtype == PDEB200_F64 ? setup_t<double>(c) : setup_t<float>(c);
@@ -1109,7 +1111,7 @@ int32_t ns_cost(const pdeb200_ctx* c, double* bytes, double* flops) {
 void ns_free(pdeb200_ctx* c) {
     NsProb* P = prob(c);
     if (!P) return;
-    for (void* p : {P->tw_inv, P->tw_fwd, P->tw_n, P->kx, P->ky, P->fst, P->acc, P->W, P->Q, P->p_phys, P->om_phys, P->tmpc})
+    for (void* p : {P->tw_inv, P->tw_fwd, P->tw_n, P->tw_b, P->kx, P->ky, P->fst, P->acc, P->W, P->Q, P->p_phys, P->om_phys, P->tmpc})
         if (p) cudaFree(p);
     for (void* p : {P->y2, P->ad_state, (void*)P->ad_active}) if (p) cudaFree(p);
     if (P->h_active) cudaFreeHost(P->h_active);
