@@ -15,7 +15,7 @@ const LIB = get(ENV, "PDEB200_LIB", joinpath(@__DIR__, "..", "distributedconvrl-
 const KS, KSEG1D, NS2D, KSEG2D = Int32(0), Int32(1), Int32(2), Int32(3)
 const F32, F64 = Int32(0), Int32(1)
 const ARR_Y, ARR_P, ARR_STATE, ARR_ACTION, ARR_DELTA_ACTION, ARR_REWARD, ARR_DONE, ARR_TIME, ARR_STEPS, ARR_Y0, ARR_GRADS,
-      ARR_LOSSES, ARR_SENSORS, ARR_ACTION_IN, ARR_STATS = Int32.(0:14)
+      ARR_LOSSES, ARR_SENSORS, ARR_ACTION_IN, ARR_STATS, ARR_NSUB = Int32.(0:15)
 const NET_BEHAVIOR_ACTOR, NET_BEHAVIOR_CRITIC, NET_TARGET_ACTOR, NET_TARGET_CRITIC = Int32.(0:3)
 const ACT_IDENTITY, ACT_RELU, ACT_TANH = Int32.(0:2)
 
