@@ -80,8 +80,7 @@ __device__ __forceinline__ int unpad_idx(int kp, int NP, int N) {
 }
 
 template <typename T> struct NsMinCtas { static constexpr int value = sizeof(T) == 8 ? 1 : 2; };
-// Kernel A is latency bound at one 8-warp CTA per SM (fp64: ~180 registers/thread): 12 columns per CTA is what the
-// register file allows (fp32 runs two 8-warp CTAs per SM instead).
+// Round-1 kernels (one line per warp; PDEB200_NS_LEGACY=1): kernel A ran best as three 4-warp CTAs per SM in fp64.
 template <typename T> struct NsColsA { static constexpr int value = 4; };
 template <typename T> struct NsColsC { static constexpr int value = 8; };
 // Kernel B: a ninth warp fits 227 KB of shared memory in fp64 (24.2 KB per warp + 12 KB of twiddles) but measured
@@ -905,7 +904,7 @@ int32_t rk4_t(pdeb200_ctx* c) {
     int32_t rc;
     if ((rc = set_smem(c, kA, sa)) || (rc = set_smem(c, kB, sb)) || (rc = set_smem(c, kC, sc))) return rc;
     // batched form of A and B (fft_batch.cuh); PDEB200_NS_LEGACY=1 keeps the one-line-per-warp kernels
-    constexpr int COLS_A4 = 4, WARPS_B4 = sizeof(T) == 8 ? 8 : 8;
+    constexpr int COLS_A4 = 4, WARPS_B4 = 8;
     using BL = BatchLayout<P1, P2>;
     // the batched kernels need P1 | 32: 192 points are 16 x 12 there (12 x 16 in the one-line-per-warp kernels)
     constexpr int BP1 = BL::TWREG ? P1 : 16, BP2 = BL::TWREG ? P2 : BL::N / 16;
