@@ -54,9 +54,14 @@ def parse():
                     help="host threads of the e2e leg: native std::threads calling the C ABI (libpdeb200_host.so) or Python threads")
     ap.add_argument("--e2e-calls", default="device-agent", choices=["device-agent", "fused", "split"],
                     help="device-agent: the drop-in as deployed (policy and trajectory on the device): per step host noise in "
-                         "[H2D], [reward | state | done] out in one packed copy [D2H], one C call, one sync; fused: the same call "
+                         "[H2D], the packed result block (--e2e-result) out in one copy [D2H], one C call, one sync; fused: the same call "
                          "with the action additionally round-tripping through the host; split: policy_act -> get(ACTION_IN) -> "
                          "step_host (three syncs, four copies; round 1's sequence)")
+    ap.add_argument("--e2e-result", default="reward+done", choices=["reward+done", "full"],
+                    help="device-agent flow: what the packed per-step D2H copy carries.  reward+done: what host code reads every "
+                         "step when policy and trajectory are on the device (the hook reads env.reward, the run loop env.done; "
+                         "pdeb200_result_select(ctx, 0)); full: [reward | done | state].  The other one is measured too and "
+                         "reported as e2e.other_result")
     ap.add_argument("--e2e-noise", default="prefetch", choices=["prefetch", "inline"],
                     help="device-agent flow: prefetch = step i+1's host noise is handed to pdeb200_noise_prefetch before the call for "
                          "step i (its upload overlaps step i's kernels); inline = uploaded at the head of its own call")
@@ -471,7 +476,7 @@ def run_ours(args):
             tot = C.c_size_t()
             L.check(self.env._lib.pdeb200_result_layout(self.env._ctx, None, None, None, C.byref(tot)), self.env._ctx)
             self.packed_bytes = tot.value
-            self.h_packed = torch.empty(tot.value, dtype=torch.uint8).pin_memory()      # [reward | state | done], one D2H
+            self.h_packed = torch.empty(tot.value, dtype=torch.uint8).pin_memory()      # [reward | done | state], one D2H
             # exploration noise drawn on the host like the reference's randn(policy.rng, ...) (PDEagent.jl:201): always float64
             self.h_noise = torch.from_numpy(np.random.default_rng(7 + k).standard_normal(self.n_act)).pin_memory()
             self.primed = False
@@ -499,7 +504,6 @@ def run_ours(args):
                                           C.c_void_p(self.h_state.data_ptr()), C.c_void_p(self.h_done.data_ptr())), ctx)
 
     shards = [Shard(k) for k in range(n_sh)]
-    e2e_launches0 = sum(sh.env.launch_count for sh in shards)
 
     host_lib = None
     if args.e2e_driver == "native":
@@ -550,22 +554,37 @@ def run_ours(args):
                 th.join()
         return time.perf_counter() - t_
 
-    drive(3)
-    barrier()
-    t0 = time.perf_counter()
-    drive(args.steps)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    def timed_e2e(with_state):
+        """-> (env-steps/s over all ranks, packed D2H bytes per step and GPU) with the packed copy carrying the whole
+        [reward | done | state] block or its [reward | done] prefix"""
+        tot = C.c_size_t()
+        for sh in shards:
+            L.check(sh.env._lib.pdeb200_result_select(sh.env._ctx, 1 if with_state else 0), sh.env._ctx)
+            L.check(sh.env._lib.pdeb200_result_layout(sh.env._ctx, None, None, None, C.byref(tot)), sh.env._ctx)
+            sh.packed_bytes = tot.value
+        drive(3)
+        barrier()
+        t0_ = time.perf_counter()
+        drive(args.steps)
+        torch.cuda.synchronize()
+        t_ = torch.tensor([time.perf_counter() - t0_], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return B * world * args.steps / float(t_.item()), sum(sh.packed_bytes for sh in shards)
+
+    primary_full = args.e2e_result == "full" or args.e2e_calls != "device-agent"
+    other_result = None
+    if args.e2e_calls == "device-agent":
+        ov, ob = timed_e2e(not primary_full)
+        other_result = {"result": "[reward | done | state]" if not primary_full else "[reward | done]", "value": ov, "d2h_bytes_per_step": ob}
+    e2e_launches0 = sum(sh.env.launch_count for sh in shards)
+    e2e_value, packed_total = timed_e2e(primary_full)
     clk = clocks.stop()
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = B * world * args.steps / float(t.item())
     n_act = B * shards[0].env.n_actuators
     ns_rows = shards[0].env.ns
     if args.e2e_calls == "device-agent":
         h2d = n_act * 8                                           # exploration noise (float64 like the reference's randn)
-        d2h = sum(sh.packed_bytes for sh in shards)                # [reward | state | done] blocks (256-byte aligned parts)
+        d2h = packed_total                                         # packed blocks (256-byte aligned parts)
     else:
         h2d = n_act * esz
         d2h = n_act * esz + n_act * esz + n_act * ns_rows * esz + B
@@ -612,13 +631,18 @@ def run_ours(args):
             "dtype": args.dtype, "data": "synthetic", "config": config_dict(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "shards": n_sh, "launches": int(e2e_launches), "host_threads": args.e2e_driver, "cpu_binding": numa,
+                    "result": ("[reward | done | state]" if primary_full else "[reward | done]") if args.e2e_calls == "device-agent" else "reward, state, done",
+                    "other_result": other_result,
+                    "note": "the shards step continuously, so one shard's actuation / observation kernels and copies run under another "
+                            "shard's core kernel; `value` times isolated steps of one 8192-environment context (L2 flushed in between), "
+                            "which is why this leg can exceed it when its copies are small",
                     "call_sequence": (("per shard and step: pdeb200_noise_prefetch(next step's host noise) [H2D, overlapping this step's kernels] + " if args.e2e_noise == "prefetch" else "per shard and step: ") +
                                       "ONE call pdeb200_act_step_host = host-drawn exploration noise in [H2D] -> "
-                                      "policy(env) on the device -> env(action) -> [reward | state | done] to the host in one packed copy "
+                                      "policy(env) on the device -> env(action) -> " + ("[reward | done | state]" if primary_full else "[reward | done] (what host code reads per step: the hook env.reward, the run loop env.done; the observation is consumed by the device policy and pushed to the device trajectory)") + " to the host in one packed copy "
                                       "[D2H]; one synchronisation; pinned host buffers; action and replay stay on the device "
                                       "(DevicePolicyForward / DeviceTrajectory of the Julia shim)") if args.e2e_calls == "device-agent" else
                                      ("per shard and step: pdeb200_act_step_host = policy(env) -> action to the host [D2H] -> env(action) "
-                                      "from the host [H2D] -> [reward | state | done] to the host in one packed copy [D2H]; one "
+                                      "from the host [H2D] -> [reward | done | state] to the host in one packed copy [D2H]; one "
                                       "synchronisation; pinned host buffers") if args.e2e_calls == "fused" else
                                      ("per shard and step: pdeb200_policy_act -> pdeb200_get(ACTION_IN) [D2H] -> "
                                       "pdeb200_step_host [H2D action; D2H reward, state, done], pinned host buffers")},

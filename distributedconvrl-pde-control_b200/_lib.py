@@ -59,6 +59,7 @@ _PROTOS = {
                                           C.c_void_p, C.c_void_p]),
     "pdeb200_noise_prefetch": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "pdeb200_result_layout": (C.c_int32, [C.c_void_p] + [C.POINTER(C.c_size_t)] * 4),
+    "pdeb200_result_select": (C.c_int32, [C.c_void_p, C.c_int32]),
     "pdeb200_get": (C.c_int32, [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t]),
     "pdeb200_get_env": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t]),
     "pdeb200_reset_diverged": (C.c_int32, [C.c_void_p, C.c_void_p]),

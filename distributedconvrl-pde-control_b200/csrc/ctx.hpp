@@ -62,8 +62,9 @@ struct pdeb200_ctx {
     void *y = nullptr, *y0 = nullptr, *p = nullptr, *state = nullptr, *action = nullptr, *action_in = nullptr,
          *delta_action = nullptr, *reward = nullptr, *sensors = nullptr;
     uint8_t* done = nullptr; double* time = nullptr; int* steps = nullptr;
-    void* result_block = nullptr;   // [reward | state | done] in one allocation (reward / state / done point into it)
+    void* result_block = nullptr;   // [reward | done | state] in one allocation (reward / done / state point into it)
     size_t res_reward_off = 0, res_state_off = 0, res_done_off = 0, res_bytes = 0;
+    size_t res_copy_bytes = 0;      // what result_packed receives: res_bytes, or the [reward | done] prefix (pdeb200_result_select)
     int* d_nsub = nullptr;           // adaptive mode: {accepted, rejected} substeps per environment
     void* d_hlast = nullptr;         // adaptive mode: last accepted step size per environment (warm start of the controller)
     uint8_t* d_mask = nullptr; int* d_counts = nullptr; double* d_rsum = nullptr; void* d_noise = nullptr; void* vmax = nullptr;

@@ -13,7 +13,7 @@
 #include "../../../include/pdeb200.h"
 
 // fused = 1: the same two reference-side calls as ONE C call with one synchronisation and one packed result copy
-// (pdeb200_act_step_host); h_packed[k] then receives [reward | state | done] (pdeb200_result_layout).
+// (pdeb200_act_step_host); h_packed[k] then receives [reward | done | state] or its [reward | done] prefix (pdeb200_result_layout).
 // h_noise != NULL: exploration noise drawn on the host (the reference's randn(policy.rng, ...), PDEagent.jl:201) goes in with
 // every step; h_act == NULL: the action stays on the device (device policy + device trajectory).
 extern "C" int32_t pdeb200_host_drive2(int32_t n_shards, pdeb200_ctx** ctxs, int32_t steps, void** h_act, void** h_packed, double act_limit,

@@ -479,12 +479,15 @@ int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** 
         return cudaMemset(*p, 0, bytes ? bytes : 16) == cudaSuccess;
     };
     const size_t nact = B * cfg->n_actuators * c->a_rows;
-    // what a host reads back after every env step lives in ONE block [reward | state | done]: a single D2H copy
+    // what a host reads back after every env step lives in ONE block [reward | done | state]: a single D2H copy of the
+    // whole block, or of its [reward | done] prefix when the policy and the trajectory live on the device and no host
+    // code consumes the observation (pdeb200_result_select)
     auto up256 = [](size_t b) { return (b + 255) / 256 * 256; };
     c->res_reward_off = 0;
-    c->res_state_off = up256(B * c->n_rew * e);
-    c->res_done_off = c->res_state_off + up256(B * c->n_cols * c->obs_rows * e);
-    c->res_bytes = c->res_done_off + up256(B);
+    c->res_done_off = up256(B * c->n_rew * e);
+    c->res_state_off = c->res_done_off + up256(B);
+    c->res_bytes = c->res_state_off + up256(B * c->n_cols * c->obs_rows * e);
+    c->res_copy_bytes = c->res_bytes;
     bool ok = alloc(&c->y, B * c->y_elems * e) && alloc(&c->y0, B * c->y_elems * e) && alloc(&c->p, B * c->p_elems * e) &&
               alloc(&c->result_block, c->res_bytes) && alloc(&c->action, nact * e) &&
               alloc(&c->action_in, nact * e) && alloc(&c->delta_action, nact * e) &&
@@ -656,7 +659,13 @@ int32_t pdeb200_result_layout(const pdeb200_ctx* c, size_t* reward_off, size_t* 
     if (reward_off) *reward_off = c->res_reward_off;
     if (state_off) *state_off = c->res_state_off;
     if (done_off) *done_off = c->res_done_off;
-    if (total_bytes) *total_bytes = c->res_bytes;
+    if (total_bytes) *total_bytes = c->res_copy_bytes;
+    return PDEB200_OK;
+}
+
+int32_t pdeb200_result_select(pdeb200_ctx* c, int32_t with_state) {
+    if (!c) return PDEB200_EINVAL;
+    c->res_copy_bytes = with_state ? c->res_bytes : c->res_state_off;
     return PDEB200_OK;
 }
 
@@ -758,7 +767,7 @@ int32_t pdeb200_act_step_host(pdeb200_ctx* c, const double* noise_host, double a
     if ((rc = do_step(c, c->action_in, 1, 0, 0.0, nullptr))) return rc;
     if (tr) cudaEventRecord(tr->ev[2], c->stream);
     if (y_out) PDEB_CUDA(c, cudaMemcpyAsync(y_out, c->y, (size_t)c->cfg.n_envs * c->y_elems * c->esz, cudaMemcpyDeviceToHost, c->stream));
-    if (result_packed) PDEB_CUDA(c, cudaMemcpyAsync(result_packed, c->result_block, c->res_bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (result_packed) PDEB_CUDA(c, cudaMemcpyAsync(result_packed, c->result_block, c->res_copy_bytes, cudaMemcpyDeviceToHost, c->stream));
     auto back = [&](int which, void* dst) -> cudaError_t {
         if (!dst) return cudaSuccess;
         ArrInfo a = arr_info(c, which);

@@ -173,8 +173,9 @@ int32_t pdeb200_step_host(pdeb200_ctx* ctx, const void* actions_host, void* y_ou
  * back to back): actor forward (+ optional host noise, as pdeb200_policy_act) -> the action is copied to action_out (HOST) and
  * taken back from that buffer as the step's input (stream-ordered D2H then H2D; action_out = NULL: the action stays on the
  * device, for hosts whose trajectory and hooks live on the device too) -> env step -> results to the host.
- * result_packed: optional HOST buffer of pdeb200_result_layout's total_bytes receiving [reward | state | done] in ONE copy
- * (they share one device allocation); reward_out / state_out / done_out: optional separate destinations instead. */
+ * result_packed: optional HOST buffer of pdeb200_result_layout's total_bytes receiving [reward | done | state] in ONE copy
+ * (they share one device allocation; pdeb200_result_select(ctx, 0) shortens the copy to the [reward | done] prefix);
+ * reward_out / state_out / done_out: optional separate destinations instead. */
 int32_t pdeb200_act_step_host(pdeb200_ctx* ctx, const double* noise_host, double act_noise, double act_limit, void* action_out,
                               void* y_out, void* result_packed, void* reward_out, void* state_out, uint8_t* done_out);
 /* Exploration noise never depends on the environment, so a host can hand over the NEXT step's noise before it makes the
@@ -185,6 +186,11 @@ int32_t pdeb200_act_step_host(pdeb200_ctx* ctx, const double* noise_host, double
  * upload of step i+1's noise then runs under step i's kernels instead of in front of its own. */
 int32_t pdeb200_noise_prefetch(pdeb200_ctx* ctx, const double* noise_host);
 int32_t pdeb200_result_layout(const pdeb200_ctx* ctx, size_t* reward_off, size_t* state_off, size_t* done_off, size_t* total_bytes);
+/* with_state = 0: result_packed receives only [reward | done] (total_bytes of pdeb200_result_layout shrinks accordingly).  For
+ * hosts whose policy and trajectory are on the device (DevicePolicyForward / DeviceTrajectory of the Julia shim): nothing on the
+ * host reads env.state then -- the hook reads env.reward (src/PDEhook.jl:66-76), the run loop env.done (PDEenv.jl:226-240) --
+ * and pdeb200_get(PDEB200_ARR_STATE) still fetches it on demand.  Default: with_state = 1. */
+int32_t pdeb200_result_select(pdeb200_ctx* ctx, int32_t with_state);
 int32_t pdeb200_get(pdeb200_ctx* ctx, int32_t which, void* host_dst, size_t bytes);
 /* One environment's slice of a per-environment array (PDEhook's tracked environment: src/PDEhook.jl:54-62). */
 int32_t pdeb200_get_env(pdeb200_ctx* ctx, int32_t which, int32_t env_index, void* host_dst, size_t bytes);

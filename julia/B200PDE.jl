@@ -148,7 +148,10 @@ noise_prefetch!(c::Ctx, noise::Matrix{Float64}) =
     check(ccall((:pdeb200_noise_prefetch, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), c.ptr, noise), c.ptr)
 
 # `action = policy(env); env(action)` as ONE call with one synchronisation (pdeb200_act_step_host); packed receives
-# [reward | state | done] (result_layout).  noise = nothing with act_noise > 0 consumes the oldest prefetched noise.
+# [reward | done | state] (result_layout), or only [reward | done] after result_select!(c, false) -- enough for a host whose
+# policy and trajectory are on the device.  noise = nothing with act_noise > 0 consumes the oldest prefetched noise.
+result_select!(c::Ctx, with_state::Bool) =
+    check(ccall((:pdeb200_result_select, LIB), Int32, (Ptr{Cvoid}, Int32), c.ptr, Int32(with_state)), c.ptr)
 act_step!(c::Ctx, packed::Vector{UInt8}; act_noise = 0.0, act_limit = 1.0, noise = nothing) =
     check(ccall((:pdeb200_act_step_host, LIB), Int32,
                 (Ptr{Cvoid}, Ptr{Float64}, Float64, Float64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}),

@@ -129,6 +129,20 @@ def test_act_step_host_equals_policy_act_then_step_host(pkg, golden):
         assert np.array_equal(packed[s_off:s_off + B * 80 * 8].view(np.float64), b.get(L.ARR_STATE))
         assert np.array_equal(packed[d_off:d_off + B], b.get(L.ARR_DONE))
         assert np.array_equal(a.get(L.ARR_Y), b.get(L.ARR_Y))
+    # pdeb200_result_select(ctx, 0): the packed copy shrinks to the [reward | done] prefix of the same block
+    assert r_off < d_off < s_off
+    L.check(a._lib.pdeb200_result_select(a._ctx, 0), a._ctx)
+    short = C.c_size_t()
+    L.check(a._lib.pdeb200_result_layout(a._ctx, None, None, None, C.byref(short)), a._ctx)
+    assert short.value == s_off
+    packed[:] = 0xAB
+    L.check(a._lib.pdeb200_act_step_host(a._ctx, noise.ctypes.data, 0.3, 1.0, None, None, packed.ctypes.data, None, None, None), a._ctx)
+    b.policy_act(noise, 0.3, 1.0)
+    b(b.get(L.ARR_ACTION_IN).reshape(1, -1))
+    assert np.array_equal(packed[r_off:r_off + B * 80 * 8].view(np.float64), b.reward)
+    assert np.array_equal(packed[d_off:d_off + B], b.get(L.ARR_DONE))
+    assert np.all(packed[s_off:] == 0xAB)                                   # the observation stayed on the device ...
+    assert np.array_equal(a.get(L.ARR_STATE), b.get(L.ARR_STATE))           # ... and is still there on demand
     for e in envs:
         e.close()
 
