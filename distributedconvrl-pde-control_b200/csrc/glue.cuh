@@ -31,6 +31,9 @@ struct ActuateArgs {
     const T* state;                // [B][n_cols][obs_rows]
     T* action; T* delta_action;    // [B][n_act][a_rows]
     T* p;                          // [B][npts] physical actuation field
+    // fused actor of actuate_conv_kernel only: exploration noise [B][n_act] added before the clamp (PDEagent.jl:201-202),
+    // and the policy's output array (ARR_ACTION_IN) kept up to date
+    const T* noise; T act_noise; T* action_in_out;
 };
 
 // Shared memory: s_a [E][n_act] T | staged table (w, idx) | actor params | activations [2][wmax][blockDim] f32
@@ -276,12 +279,13 @@ __global__ void __launch_bounds__(256, 3) actuate_conv_kernel(const __grid_const
     const int ce = tid / A.n_act, cj = tid - ce * A.n_act;          // this thread's column slot (fixed for all groups)
     const bool col_on = tid < ncol;
     constexpr int NX = NIN > 0 ? NIN : (NIN < 0 ? 8 : 1);
-    T prev, xin[NX];
+    T prev, xin[NX], nz = T(0);
     auto request = [&](int env0n) {
         const int envn = env0n + ce;
         const bool onn = col_on && envn < A.n_envs;
         const size_t coln = onn ? (size_t)envn * A.n_act + cj : 0;
         prev = onn ? A.action[coln] : T(0);
+        if (NIN != 0 && A.noise) nz = onn ? A.noise[coln] : T(0);
         if (NIN == 0) xin[0] = onn ? A.actions_in[coln] : T(0);
         else {
             const T* srcn = A.state + coln * A.obs_rows;
@@ -313,9 +317,12 @@ __global__ void __launch_bounds__(256, 3) actuate_conv_kernel(const __grid_const
                             if (r < A.obs_rows) xa[r * BD] = (float)xin[r];
                         o = mlp_forward_smem(A.actor, s_par, xa, xh, BD)[0];
                     }
-                    v = clamp_t<T>((T)o, A.act_limit);
+                    T vv = (T)o;
+                    if (A.noise) vv += nz * A.act_noise;
+                    v = clamp_t<T>(vv, A.act_limit);
                 }
                 const size_t col = (size_t)env * A.n_act + cj;
+                if (NIN != 0 && A.action_in_out) A.action_in_out[col] = v;
                 A.delta_action[col] = v - prev;
                 A.action[col] = v;
             }

@@ -220,8 +220,10 @@ ActuateFn<T> conv_kernel_for(int nnz, int mode) {
 }
 
 template <typename T>
-int32_t actuate_t(pdeb200_ctx* c, const void* actions_dev, int use_actor, double act_limit) {
+int32_t actuate_t(pdeb200_ctx* c, const void* actions_dev, int use_actor, double act_limit, const void* d_noise = nullptr,
+                  double act_noise = 0.0, bool want_policy_out = false) {
     ActuateArgs<T> A;
+    A.noise = nullptr; A.act_noise = T(0); A.action_in_out = nullptr;
     const HostNet& net = c->nets[PDEB200_NET_BEHAVIOR_ACTOR];
     A.n_envs = c->cfg.n_envs;
     A.n_act = c->cfg.n_actuators; A.a_rows = c->a_rows; A.obs_rows = c->obs_rows; A.mono = c->cfg.mono;
@@ -257,6 +259,11 @@ int32_t actuate_t(pdeb200_ctx* c, const void* actions_dev, int use_actor, double
         kern = conv_kernel_for<T>(A.act_nnz, mode);
         smem = (((size_t)2 * E * A.n_act * sizeof(T) + 15) & ~(size_t)15) + (size_t)((A.actor_np + 3) & ~3) * sizeof(float) +
                (mode == -1 ? (size_t)2 * A.actor_wmax * tpb * sizeof(float) : 0);
+        if (use_actor && want_policy_out) {
+            A.noise = (const T*)d_noise; A.act_noise = (T)act_noise; A.action_in_out = (T*)c->action_in;
+        }
+    } else if (want_policy_out) {
+        return 1;                        // the policy-with-noise fusion exists in the shape-specialised kernel only: caller falls back
     }
     if (smem > 200 * 1024) return fail(c, PDEB200_EUNSUPPORTED, "actuate: actor too large for shared memory");
     PDEB_CUDA(c, ensure_dyn_smem(kern, smem, c->device));
@@ -309,7 +316,8 @@ int32_t core_step(pdeb200_ctx* c) {
 
 // env(action) for all environments: actuate -> core -> observe, `n_steps` times (n_steps > 1 only with
 // the fused actor).  Everything is enqueued on the context's stream; no host synchronisation.
-int32_t do_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum) {
+int32_t do_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_actor, double act_limit, double* d_rsum,
+                const void* d_noise = nullptr, double act_noise = 0.0, bool policy_fused = false) {
     if (!c->bases_set) return fail(c, PDEB200_ESTATE, "step: call pdeb200_set_bases first");
     if (!c->y0_set) return fail(c, PDEB200_ESTATE, "step: call pdeb200_set_y0 + pdeb200_reset first");
     if (use_actor) {
@@ -324,8 +332,9 @@ int32_t do_step(pdeb200_ctx* c, const void* actions_dev, int n_steps, int use_ac
     const bool f64 = c->cfg.dtype == PDEB200_F64;
     if (c->timing) cudaEventRecord(c->ev0, c->stream);
     for (int s = 0; s < n_steps; ++s) {
-        int32_t rc = f64 ? actuate_t<double>(c, actions_dev, use_actor, act_limit) : actuate_t<float>(c, actions_dev, use_actor, act_limit);
-        if (rc) return rc;
+        int32_t rc = f64 ? actuate_t<double>(c, actions_dev, use_actor, act_limit, d_noise, act_noise, policy_fused)
+                         : actuate_t<float>(c, actions_dev, use_actor, act_limit, d_noise, act_noise, policy_fused);
+        if (rc) return rc;               // 1: policy fusion not available for this shape (nothing was launched)
         const bool tc = c->timing && s == n_steps - 1;            // CUDA events around the core (dominant) kernel
         if (tc) cudaEventRecord(c->evc0, c->stream);
         if ((rc = core_step(c))) return rc;
@@ -755,8 +764,18 @@ int32_t pdeb200_act_step_host(pdeb200_ctx* c, const double* noise_host, double a
         dn = c->d_noise_q[s];
     }
     if (tr) cudaEventRecord(tr->ev[1], c->stream);
-    int32_t rc = policy_launch(c, dn, 0, 0, 0, act_noise, act_limit);
-    if (rc) return rc;
+    // host does not want the action: policy(env) (actor + noise + clamp) runs inside the actuation kernel when the
+    // shape-specialised one applies (one launch and one pass over the state fewer per step); otherwise policy kernel first
+    int32_t rc = 1;
+    if (!action_out) {
+        const HostNet& pa = c->nets[PDEB200_NET_BEHAVIOR_ACTOR];
+        bool narrow = pa.n_layers > 0 && c->cfg.memory_size == 0;
+        for (int l = 0; narrow && l <= pa.n_layers; ++l) narrow = pa.sizes[l] <= kFusedActorMaxWidth;
+        if (narrow) rc = do_step(c, nullptr, 1, 1, act_limit, nullptr, dn, act_noise, true);
+        if (rc < 0) return rc;
+    }
+    const bool fused_policy = rc == 0;
+    if (!fused_policy && (rc = policy_launch(c, dn, 0, 0, 0, act_noise, act_limit))) return rc;
     // policy(env) hands the action to the host; env(action) takes it from there (stream order: D2H, then H2D of the same buffer)
     // action_out == NULL: the action never leaves the device (device policy + device trajectory: no host consumer)
     const size_t abytes = (size_t)c->cfg.n_envs * c->cfg.n_actuators * c->a_rows * c->esz;
@@ -764,7 +783,7 @@ int32_t pdeb200_act_step_host(pdeb200_ctx* c, const double* noise_host, double a
         PDEB_CUDA(c, cudaMemcpyAsync(action_out, c->action_in, abytes, cudaMemcpyDeviceToHost, c->stream));
         PDEB_CUDA(c, cudaMemcpyAsync(c->action_in, action_out, abytes, cudaMemcpyHostToDevice, c->stream));
     }
-    if ((rc = do_step(c, c->action_in, 1, 0, 0.0, nullptr))) return rc;
+    if (!fused_policy && (rc = do_step(c, c->action_in, 1, 0, 0.0, nullptr))) return rc;
     if (tr) cudaEventRecord(tr->ev[2], c->stream);
     if (y_out) PDEB_CUDA(c, cudaMemcpyAsync(y_out, c->y, (size_t)c->cfg.n_envs * c->y_elems * c->esz, cudaMemcpyDeviceToHost, c->stream));
     if (result_packed) PDEB_CUDA(c, cudaMemcpyAsync(result_packed, c->result_block, c->res_copy_bytes, cudaMemcpyDeviceToHost, c->stream));
