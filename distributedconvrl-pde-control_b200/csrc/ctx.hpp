@@ -67,7 +67,7 @@ struct pdeb200_ctx {
     size_t res_copy_bytes = 0;      // what result_packed receives: res_bytes, or the [reward | done] prefix (pdeb200_result_select)
     int* d_nsub = nullptr;           // adaptive mode: {accepted, rejected} substeps per environment
     void* d_hlast = nullptr;         // adaptive mode: last accepted step size per environment (warm start of the controller)
-    uint8_t* d_mask = nullptr; int* d_counts = nullptr; double* d_rsum = nullptr; void* d_noise = nullptr; void* vmax = nullptr;
+    uint8_t* d_mask = nullptr; int* d_list = nullptr; int* d_counts = nullptr; double* d_rsum = nullptr; void* d_noise = nullptr; void* vmax = nullptr;
     // pdeb200_noise_prefetch: the NEXT policy call's host noise, uploaded on its own stream while the current step runs
     void* d_noise_q[2] = {nullptr, nullptr}; cudaStream_t copy_stream = nullptr; cudaEvent_t noise_ready[2] = {nullptr, nullptr};
     unsigned long long noise_put = 0, noise_got = 0;     // prefetches issued / consumed (at most two outstanding)

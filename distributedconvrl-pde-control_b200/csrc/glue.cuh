@@ -358,6 +358,7 @@ struct ObserveArgs {
     const T* vmax;                 // [B] max |y| (CHECK_Y)
     T* state; T* action; T* delta_action; T* action_in; T* reward;
     uint8_t* done; double* time; int* steps; double* reward_sum;
+    const int* list; const int* list_n;   // optional: only these environments (see observe_kernel)
 };
 
 // One WARP per environment: lanes stride over the actuator columns, the sensor dots are read straight from global
@@ -368,11 +369,8 @@ struct ObserveArgs {
 // PLAIN = the 1-D conv agent without temporal stacking or action memory (one field, window <= n_sensors): the column
 // loop then has no runtime-shaped inner loops and no integer division (every shipped KS script).
 template <typename T, bool PLAIN>
-__global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ ObserveArgs<T> A) {
+__device__ __forceinline__ void observe_env(const ObserveArgs<T>& A, const int env, const int lane) {
     const ObsRewardParams<T>& P = A.P;
-    const int lane = threadIdx.x & 31;
-    const int env = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (env >= A.n_envs) return;
     if (A.mask && !A.mask[env]) return;
     const bool fresh = A.fresh != 0;
     double tm0 = 0.0; T vm = T(0); int st = 0; double rs0 = 0.0;
@@ -459,25 +457,45 @@ __global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ Ob
     }
 }
 
+// one warp per environment; A.list != nullptr: the warps of a small grid walk the environments list[0 .. *list_n)
+// (pdeb200_reset_diverged: usually none -- a full-size grid of early-exiting CTAs costs ~8 us, this one ~2)
+template <typename T, bool PLAIN>
+__global__ void __launch_bounds__(128) observe_kernel(const __grid_constant__ ObserveArgs<T> A) {
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (A.list) {
+        const int n = *A.list_n, nw = gridDim.x * (blockDim.x >> 5);
+        for (int k = w; k < n; k += nw) observe_env<T, PLAIN>(A, A.list[k], lane);
+        return;
+    }
+    if (w < A.n_envs) observe_env<T, PLAIN>(A, w, lane);
+}
+
 // Sensor dots straight from physical fields in global memory (reset! / set_state path; the core
 // kernels produce them from on-chip state).  One CTA per environment.
 template <typename T>
 __global__ void __launch_bounds__(128) sensors_phys_kernel(int fields, int npts, int n_sensors, EllTable<T> sens,
                                                            const uint8_t* __restrict__ mask, const T* __restrict__ y,
-                                                           int interleaved, T* sensors_out, T* vmax_out) {
-    const int env = blockIdx.x;
-    if (mask && !mask[env]) return;
-    const T* ye = y + (size_t)env * fields * npts;
-    for (int q = threadIdx.x; q < fields * n_sensors; q += blockDim.x) {
-        const int f = q / n_sensors, i = q % n_sensors;
-        T acc = T(0);
-        for (int j = 0; j < sens.nnz_max; ++j) {
-            const int n = sens.idx[j * n_sensors + i];
-            acc += (interleaved ? ye[n * fields + f] : ye[f * npts + n]) * sens.w[j * n_sensors + i];
+                                                           int interleaved, T* sensors_out, T* vmax_out,
+                                                           const int* __restrict__ list = nullptr,
+                                                           const int* __restrict__ list_n = nullptr) {
+    // list != nullptr: a small grid walks the environments list[0 .. *list_n) (pdeb200_reset_diverged: usually none)
+    const int n_items = list ? *list_n : (int)gridDim.x;
+    for (int k = blockIdx.x; k < n_items; k += gridDim.x) {
+        const int env = list ? list[k] : k;
+        if (mask && !mask[env]) continue;
+        const T* ye = y + (size_t)env * fields * npts;
+        for (int q = threadIdx.x; q < fields * n_sensors; q += blockDim.x) {
+            const int f = q / n_sensors, i = q % n_sensors;
+            T acc = T(0);
+            for (int j = 0; j < sens.nnz_max; ++j) {
+                const int n = sens.idx[j * n_sensors + i];
+                acc += (interleaved ? ye[n * fields + f] : ye[f * npts + n]) * sens.w[j * n_sensors + i];
+            }
+            sensors_out[(size_t)env * fields * n_sensors + q] = acc;
         }
-        sensors_out[(size_t)env * fields * n_sensors + q] = acc;
+        if (vmax_out && threadIdx.x == 0) vmax_out[env] = T(0);
     }
-    if (vmax_out && threadIdx.x == 0) vmax_out[env] = T(0);
 }
 
 }  // namespace pdeb200

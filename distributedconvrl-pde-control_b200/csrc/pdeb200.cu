@@ -18,27 +18,34 @@ thread_local std::string g_last_error;
 
 namespace {
 
+constexpr int kListGrid = 296;      // CTAs of the list-driven reset kernels (two per SM)
+
 // reset!: y = y0, p = prepare_action(action0) = 0 for the masked environments (src/PDEenv.jl:183-193)
 template <typename T>
 __global__ void reset_copy_kernel(int y_elems, int p_elems, const uint8_t* __restrict__ mask, const T* __restrict__ y0,
-                                  T* y, T* p) {
-    const int env = blockIdx.x;
-    if (mask && !mask[env]) return;
-    for (int i = threadIdx.x; i < y_elems; i += blockDim.x) y[(size_t)env * y_elems + i] = y0[(size_t)env * y_elems + i];
-    for (int i = threadIdx.x; i < p_elems; i += blockDim.x) p[(size_t)env * p_elems + i] = T(0);
+                                  T* y, T* p, const int* __restrict__ list, const int* __restrict__ list_n) {
+    // list != nullptr: a small grid walks the environments list[0 .. *list_n)
+    const int n_items = list ? *list_n : (int)gridDim.x;
+    for (int k = blockIdx.x; k < n_items; k += gridDim.x) {
+        const int env = list ? list[k] : k;
+        if (mask && !mask[env]) continue;
+        for (int i = threadIdx.x; i < y_elems; i += blockDim.x) y[(size_t)env * y_elems + i] = y0[(size_t)env * y_elems + i];
+        for (int i = threadIdx.x; i < p_elems; i += blockDim.x) p[(size_t)env * p_elems + i] = T(0);
+    }
 }
 
 // Batched termination: mask[b] = done[b] although the clock of b has not reached te, i.e. b diverged (PDEenv.jl:226-237);
 // counts = {done, time limit, diverged}
+// list[0 .. counts[2]) = the diverged environments (any order): the reset kernels that follow walk it with small grids
 __global__ void diverged_mask_kernel(int n_envs, const uint8_t* __restrict__ done, const double* __restrict__ time, double te,
-                                     uint8_t* mask, int* counts) {
+                                     uint8_t* mask, int* counts, int* list) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= n_envs) return;
     const bool dn = done[b] != 0, tl = time[b] >= te;
     mask[b] = dn && !tl;
     if (dn) atomicAdd(counts + 0, 1);
     if (dn && tl) atomicAdd(counts + 1, 1);
-    if (dn && !tl) atomicAdd(counts + 2, 1);
+    if (dn && !tl) list[atomicAdd(counts + 2, 1)] = b;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -183,8 +190,10 @@ int32_t set_bases_t(pdeb200_ctx* c, const double* sb, const double* ab, const in
 }
 
 template <typename T>
-int32_t observe_t(pdeb200_ctx* c, int fresh, const uint8_t* d_mask, double* d_rsum) {
+int32_t observe_t(pdeb200_ctx* c, int fresh, const uint8_t* d_mask, double* d_rsum, const int* list = nullptr,
+                  const int* list_n = nullptr) {
     ObserveArgs<T> O;
+    O.list = list; O.list_n = list_n;
     O.P = make_obs_params<T>(c);
     O.n_envs = c->cfg.n_envs; O.fresh = fresh; O.mask = d_mask; O.sensors = (const T*)c->sensors; O.vmax = (const T*)c->vmax;
     O.state = (T*)c->state; O.action = (T*)c->action; O.delta_action = (T*)c->delta_action; O.action_in = (T*)c->action_in;
@@ -193,7 +202,8 @@ int32_t observe_t(pdeb200_ctx* c, int fresh, const uint8_t* d_mask, double* d_rs
     const bool plain = !O.P.mono && O.P.spa == 0 && O.P.temporal == 1 && O.P.memory == 0 && O.P.fields == 1 &&
                        O.P.a_rows == 1 && O.P.window <= O.P.n_sensors && O.P.obs_rows == O.P.window;
     auto kern = plain ? observe_kernel<T, true> : observe_kernel<T, false>;
-    kern<<<(c->cfg.n_envs + tpb / 32 - 1) / (tpb / 32), tpb, 0, c->stream>>>(O);
+    const int full = (c->cfg.n_envs + tpb / 32 - 1) / (tpb / 32);
+    kern<<<list ? std::min(full, kListGrid) : full, tpb, 0, c->stream>>>(O);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     return PDEB200_OK;
@@ -285,23 +295,26 @@ int32_t actuate_t(pdeb200_ctx* c, const void* actions_dev, int use_actor, double
 }
 
 template <typename T>
-int32_t reset_t(pdeb200_ctx* c, const uint8_t* d_mask) {
-    reset_copy_kernel<T><<<c->cfg.n_envs, 256, 0, c->stream>>>(c->y_elems, c->p_elems, d_mask, (const T*)c->y0,
-                                                              (T*)c->y, (T*)c->p);
+int32_t reset_t(pdeb200_ctx* c, const uint8_t* d_mask, const int* list = nullptr, const int* list_n = nullptr) {
+    if (c->cfg.problem == PDEB200_NS2D) list = list_n = nullptr;       // the NS sensor path (2-D transforms) is mask driven
+    const int lg = list ? std::min(c->cfg.n_envs, kListGrid) : c->cfg.n_envs;
+    reset_copy_kernel<T><<<lg, 256, 0, c->stream>>>(c->y_elems, c->p_elems, d_mask, (const T*)c->y0,
+                                                   (T*)c->y, (T*)c->p, list, list_n);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
     if (c->cfg.problem == PDEB200_NS2D) {
         int32_t rc = ns_sensors(c, d_mask);
         if (rc) return rc;
     } else {
-        sensors_phys_kernel<T><<<c->cfg.n_envs, 128, 0, c->stream>>>(
+        sensors_phys_kernel<T><<<lg, 128, 0, c->stream>>>(
             c->fields, c->npts, c->cfg.n_sensors,
             EllTable<T>{c->sens.d_idx, (const T*)c->sens.d_w, c->sens.nnz_max, c->sens.n_rows}, d_mask, (const T*)c->y,
-            (c->cfg.problem == PDEB200_KSEG1D || c->cfg.problem == PDEB200_KSEG2D) ? 1 : 0, (T*)c->sensors, (T*)c->vmax);
+            (c->cfg.problem == PDEB200_KSEG1D || c->cfg.problem == PDEB200_KSEG2D) ? 1 : 0, (T*)c->sensors, (T*)c->vmax,
+            list, list_n);
         PDEB_CUDA(c, cudaGetLastError());
         c->launches += 1;
     }
-    return observe_t<T>(c, 1, d_mask, nullptr);
+    return observe_t<T>(c, 1, d_mask, nullptr, list, list_n);
 }
 
 int32_t core_step(pdeb200_ctx* c) {
@@ -501,7 +514,7 @@ int32_t pdeb200_create(const pdeb200_config* cfg, int32_t device, pdeb200_ctx** 
               alloc(&c->result_block, c->res_bytes) && alloc(&c->action, nact * e) &&
               alloc(&c->action_in, nact * e) && alloc(&c->delta_action, nact * e) &&
               alloc(&c->sensors, B * c->fields * cfg->n_sensors * e) &&
-              alloc((void**)&c->time, B * 8) && alloc((void**)&c->steps, B * 4) && alloc((void**)&c->d_mask, B) &&
+              alloc((void**)&c->time, B * 8) && alloc((void**)&c->steps, B * 4) && alloc((void**)&c->d_mask, B) && alloc((void**)&c->d_list, B * 4) &&
               alloc((void**)&c->d_rsum, B * 8) && alloc(&c->d_noise, nact * e) && alloc(&c->vmax, B * e) &&
               alloc((void**)&c->d_a2s, cfg->n_actuators * 4) && alloc(&c->d_sens_sum, cfg->n_sensors * e) &&
               alloc((void**)&c->d_losses, 8) && alloc((void**)&c->d_counts, 16) && alloc((void**)&c->d_nsub, B * 8) &&
@@ -528,7 +541,7 @@ int32_t pdeb200_destroy(pdeb200_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     ks_free(c); kseg_free(c); ns_free(c); agent_free(c); comm_free(c);
     for (void* p : {c->y, c->y0, c->p, c->result_block, c->action, c->action_in, c->delta_action, c->sensors,
-                    (void*)c->time, (void*)c->steps, (void*)c->d_mask, (void*)c->d_rsum, c->d_noise, c->vmax,
+                    (void*)c->time, (void*)c->steps, (void*)c->d_mask, (void*)c->d_list, (void*)c->d_rsum, c->d_noise, c->vmax,
                     (void*)c->d_a2s, c->d_sens_sum, (void*)c->sens.d_idx, c->sens.d_w, (void*)c->actT.d_idx, c->actT.d_w,
                     (void*)c->d_grads, (void*)c->d_losses, (void*)c->d_counts, (void*)c->d_nsub, c->d_hlast})
         if (p) cudaFree(p);
@@ -610,10 +623,13 @@ int32_t pdeb200_reset_diverged(pdeb200_ctx* c, int32_t* counts) {
     cudaSetDevice(c->device);
     PDEB_CUDA(c, cudaMemsetAsync(c->d_counts, 0, 4 * sizeof(int), c->stream));
     diverged_mask_kernel<<<(c->cfg.n_envs + 255) / 256, 256, 0, c->stream>>>(c->cfg.n_envs, c->done, c->time, c->cfg.te, c->d_mask,
-                                                                               c->d_counts);
+                                                                               c->d_counts, c->d_list);
     PDEB_CUDA(c, cudaGetLastError());
     c->launches += 1;
-    int32_t rc = c->cfg.dtype == PDEB200_F64 ? reset_t<double>(c, c->d_mask) : reset_t<float>(c, c->d_mask);
+    // the reset kernels walk the list of diverged environments (usually empty) with small grids instead of launching one
+    // early-exiting CTA / warp per environment
+    int32_t rc = c->cfg.dtype == PDEB200_F64 ? reset_t<double>(c, c->d_mask, c->d_list, c->d_counts + 2)
+                                             : reset_t<float>(c, c->d_mask, c->d_list, c->d_counts + 2);
     if (rc) return rc;
     if (counts) {
         PDEB_CUDA(c, cudaMemcpyAsync(counts, c->d_counts, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
