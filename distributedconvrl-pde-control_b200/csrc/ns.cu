@@ -20,6 +20,9 @@
 //                     update for column kx and (by conjugate symmetry of the FFT of a real field) column -kx:
 //                     k = -nu k^2 f + nonlin + p_hat;  stage combinations of rk4().
 // Arrays are env-major, Julia column-major inside an environment: y[env][i (kx)][j (ky)] complex.
+// A and B exist in two forms: the round-1 kernels keep one line per warp in registers (fft_pass.cuh; PDEB200_NS_LEGACY=1),
+// the default ones (ns_ypass_inv4_kernel, ns_xpass4_kernel) transform four lines per warp in place in shared memory
+// (fft_batch.cuh).  adaptive = 1 adds per-environment step control on top of the same kernels (ns_adapt_*).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
