@@ -182,3 +182,23 @@ def test_adaptive_mode_matches_its_oracle_and_the_fixed_step_path(pkg):
         assert relerr(ya[:, :, b], yf[:, :, b]) < 1e-7
     assert ns_[1, 0] > 2 * ns_[0, 0] and ns_[:, 1].sum() > 0       # per-environment control, some rejected attempts
     env_a.close(); env_f.close()
+
+
+def test_round1_kernels_stay_in_step_with_the_batched_ones(pkg, monkeypatch):
+    """PDEB200_NS_LEGACY=1 selects the one-line-per-warp kernels A / B (fft_pass.cuh); the default batched in-place kernels
+    (fft_batch.cuh) must give the same states up to summation order, on a padded 16 x 12 (192-point) and a 8 x 12 grid."""
+    for nx, spa, var in ((128, 16, 0.04), (64, 8, 0.08)):
+        setup = pkg.setups.FluidSetup(nx=nx, sensors_per_axis=spa, variance=var)     # the scripts' substep count (a
+        rng = np.random.default_rng(21)                                                 # marginal one amplifies round-off)
+        y0 = setup.generate_random_init(rng, 2, caseno=3)
+        a = rng.uniform(-1, 1, (1, 2 * spa * spa))
+        out = []
+        for legacy in ("1", "0"):
+            monkeypatch.setenv("PDEB200_NS_LEGACY", legacy)
+            env = setup.make_env(n_envs=2, dtype="f64", y0=y0)
+            env(a); env(a)
+            out.append((env.y.copy(), env.reward.copy(), env.state.copy()))
+            env.close()
+        assert relerr(out[0][0], out[1][0]) < 1e-12
+        assert np.allclose(out[0][1], out[1][1], rtol=1e-11, atol=1e-13)
+        assert relerr(out[0][2], out[1][2]) < 1e-12
